@@ -194,3 +194,27 @@ uint64_t refh_extend(void *_h, uint8_t const *a, uint32_t alen, uint8_t const *b
 	lmm_free(h->lmm, (void *)al);
 	return(n);
 }
+
+/* refh_extend_dump: the seed-chain-extend loop of mm_align_seq (minialign.c:4444-4449) WITHOUT the post-processing;
+ * dumps n_res then per result {score, iid, n_aln, plen, lb, ub} (6 x u32) so the extend state machine can be compared
+ * before pruning / MAPQ.  Alignments are left to the arena. */
+uint64_t refh_extend_dump(void *_h, uint8_t const *seq, uint32_t len, uint32_t *out, uint64_t cap)
+{
+	refh_t *h = (refh_t *)_h;
+	mm_tbuf_t *t = h->aln->t[0];
+	mm_tbuf_clear(t, h->lmm);
+	mm_init_query(t, len, seq, 0, 0);
+	for(uint64_t i = 0; i < t->mi.n_occ; i++) {
+		if(mm_seed(t, i) == 0) { continue; }
+		if(mm_chain(t, i) == 0) { continue; }
+		if(mm_extend(t, i) > 0) { break; }
+	}
+	uint64_t n = 1;
+	out[0] = t->n_res;
+	mm_res_t *r = (mm_res_t *)t->root.a;
+	for(uint32_t i = 0; i < t->n_res && n + 6 <= cap; i++) {
+		mm_bin_t *bin = (mm_bin_t *)&t->bin.a[r[i].iid];
+		out[n++] = r[i].score; out[n++] = r[i].iid; out[n++] = bin->n_aln; out[n++] = bin->plen; out[n++] = bin->lb; out[n++] = bin->ub;
+	}
+	return(n);
+}
