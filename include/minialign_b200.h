@@ -1,0 +1,113 @@
+/*
+ * minialign_b200.h -- C ABI of the B200-native read->reference mapping hot path (drop-in for minialign's
+ * per-batch mapper).  Plain pointers and sizes only; no CUDA or torch types cross this boundary.
+ *
+ * What each entry point replaces in the reference (ocxtal/minialign @ /root/reference):
+ *
+ *   mab_init / mab_destroy      mm_align_init / mm_align_destroy            minialign.c:4671-4718, 4651-4664
+ *                               (+ gaba_init / gaba_dp_init,                gaba_wrap.h:245-295, gaba.c:3848-3928)
+ *   mab_map_batch               pt_worker_t mm_align_worker: for each read  minialign.c:4589-4601
+ *                               of a bseq_t batch call mm_align_seq          minialign.c:4427-4474
+ *   mab_result_* / release      mm_reg_t / mm_aln_t / gaba_alignment_t views minialign.c:3260-3267, gaba.h:193-219
+ *                               that mm_align_drain_intl hands the printer   minialign.c:4607-4626
+ *   mab_sketch                  mm_sketch                                   minialign.c:2410-2435
+ *   mab_seed_chain              mm_seed + mm_chain                          minialign.c:3500-3541, 3702-3721
+ *   mab_extend_pair             the body of the mm_extend loop:             minialign.c:4134-4154
+ *                               gaba_dp_fill_root/fill/search_max/trace     gaba.c:2110-2203, 2776-2817, 3372-3393
+ *
+ * Ownership mirrors the reference: the caller owns the index blob and the read block; results of one batch live in
+ * the context until mab_release_batch (the reference frees its lmm arena in the drain, minialign.c:4615-4623).
+ * One context per GPU, one host thread per context.  Errors are negative return codes; nothing aborts.
+ * There is NO CPU fallback: every call fails with MAB_ENODEV when no sm_100 device is usable.
+ */
+#ifndef MINIALIGN_B200_H
+#define MINIALIGN_B200_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAB_OK        0
+#define MAB_ENODEV   -1		/* no usable CUDA device / CUDA runtime error (message via mab_last_error) */
+#define MAB_EINVAL   -2		/* bad argument / unsupported parameter set (e.g. non-combined gap model) */
+#define MAB_ENOMEM   -3		/* device or host allocation failed */
+#define MAB_EOVERFLOW -4	/* a per-read device workspace overflowed even after the retry */
+
+/* mapping parameters: the subset of mm_align_params_t (minialign.c:2517-2524) + gaba_params_t (gaba.h:90-110) the hot
+ * path reads.  k, w, b, occ[] come from the index itself. */
+typedef struct {
+	int32_t wlen, glen;			/* chainable window edge length, linkable gap length (-W, -G; default 7000) */
+	uint32_t min_score;			/* -s */
+	float min_ratio;			/* -m */
+	int8_t score_matrix[16];	/* [a | b << 2] */
+	int8_t gi, ge, gfa, gfb;	/* positive penalties; combined (piecewise-affine) model: all non-zero */
+	int8_t xdrop;				/* -Y */
+	uint8_t _pad[3];
+	uint32_t flags;				/* reserved, must be 0 */
+} mab_params_t;
+
+typedef struct mab_ctx mab_ctx;
+
+/* blob = raw (inflated) .mai payload after the 12-byte {magic,size} header: the relocatable mm_idx_t image
+ * (minialign.c:3070-3167).  Copied to HBM; the host copy is only read during the call. device = CUDA ordinal. */
+mab_ctx *mab_init(const void *mai_blob, uint64_t size, const mab_params_t *params, int device);
+void mab_destroy(mab_ctx *ctx);
+const char *mab_last_error(void);
+
+/* index facts the host printer needs (mm_idx_seq_t, minialign.c:2464-2470) */
+uint32_t mab_n_ref(const mab_ctx *ctx);
+int mab_ref_info(const mab_ctx *ctx, uint32_t rid, const char **name, uint32_t *l_name, uint32_t *l_seq, const uint8_t **seq);
+int mab_index_params(const mab_ctx *ctx, uint32_t *k, uint32_t *w, uint32_t *b, uint32_t *n_occ, uint32_t *occ /* [7] */);
+
+/* Map one batch.  seq_block holds n_seq reads, 1 byte/base codes A,C,G,T = 0..3, N = 4 (minialign.c:214-232), read i at
+ * seq_block[seq_ofs[i] .. seq_ofs[i] + seq_len[i]).  Host memory (pinned or pageable).
+ * On success the batch's results are readable through mab_result() until mab_release_batch(). */
+int mab_map_batch(mab_ctx *ctx, const uint8_t *seq_block, uint64_t block_size,
+	const uint64_t *seq_ofs, const uint32_t *seq_len, uint32_t n_seq);
+
+/* Result of read i as a flat little-endian u32 stream, the same layout the reference harness and the oracle dump:
+ *   [0] n_all  [1] n_uniq   then n_all alignments, each
+ *   16 x u32 header : score(lo,hi) identity(double bits lo,hi) agcnt bgcnt dcnt slen plen npathwords rank mapq 0 0 0 0
+ *   slen x 8 x u32  : aid bid apos bpos alen blen ppos(lo,hi)          (gaba_segment_s, gaba.h:193-198)
+ *   npathwords x u32: path bit string, LSB first, sentinel bit at plen (gaba.h:205-219)
+ * Returns the number of u32 words (0 = unmapped, the reference's NULL mm_reg_t). */
+uint64_t mab_result(const mab_ctx *ctx, uint32_t i, const uint32_t **words);
+void mab_release_batch(mab_ctx *ctx);
+
+/* device-side statistics of the last batch (for bench.py / roofline): kernel milliseconds measured with CUDA events
+ * on the context's stream, DP vectors filled, bytes moved each way */
+typedef struct {
+	float ms_total, ms_h2d, ms_seed, ms_sortchain, ms_extend, ms_d2h, ms_post;
+	uint64_t n_vectors;			/* anti-diagonal vectors filled (down + up + replays) */
+	uint64_t n_fill_calls, n_trace;
+	uint64_t h2d_bytes, d2h_bytes;
+	uint32_t n_launches;		/* kernels launched */
+	uint32_t n_retry;
+} mab_stats_t;
+int mab_last_stats(const mab_ctx *ctx, mab_stats_t *out);
+
+/* When set, mab_map_batch takes seq_block as a DEVICE pointer already resident in HBM (bench.py's kernel-only arm). */
+int mab_set_device_input(mab_ctx *ctx, int on);
+
+/* ---- stage-level entry points (parity tests; same semantics as the reference functions named above) ---- */
+/* sketch of one read: writes the minimizer words followed by the 4-word cap; returns #words (may exceed cap) */
+uint64_t mab_sketch(mab_ctx *ctx, const uint8_t *seq, uint32_t len, uint64_t *out, uint64_t cap);
+/* seeds (+ leaves) and roots after rounds 0..round of mm_seed + mm_chain; returns n_seed */
+uint64_t mab_seed_chain(mab_ctx *ctx, const uint8_t *seq, uint32_t len, uint32_t round,
+	uint32_t *seeds, uint64_t seed_cap, uint64_t *n_total, uint32_t *roots, uint64_t root_cap, uint64_t *n_root);
+/* n independent extension problems: pair i = (a_i, b_i, apos, bpos, brev, narrow); res = 16 u32 per pair, alignment in
+ * the flat layout above at aln_out + aln_ofs[i] (aln_ofs[n] = total).  See oracle/ref_harness.c refh_extend. */
+typedef struct {
+	uint64_t a_ofs, b_ofs;		/* offsets into seq_block */
+	uint32_t alen, blen, apos, bpos, brev, narrow;
+	int64_t min_score;
+} mab_pair_t;
+int mab_extend_pairs(mab_ctx *ctx, const uint8_t *seq_block, uint64_t block_size, const mab_pair_t *pairs, uint32_t n,
+	uint32_t *res /* 16 x n */, uint32_t *aln_out, uint64_t aln_cap, uint64_t *aln_ofs /* n + 1 */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

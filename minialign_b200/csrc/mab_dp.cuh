@@ -1,0 +1,773 @@
+/*
+ * mab_dp.cuh -- warp-parallel GABA engine (adaptive-banded, difference-recurrence, piecewise-affine SW-Gotoh) for sm_100a.
+ *
+ * One warp owns one band.  A band of W cells (W = 64, or 32 / 16 for the reference's "narrow" retries) is spread over the
+ * warp two cells per lane, each cell a signed 16-bit half of a 32-bit register, so the whole recurrence runs on
+ * Blackwell's native packed-16x2 integer SIMD (VIADD.16x2 / VIMNMX.S16x2 / VIMNMX3.S16x2 / VIADDMNMX.S16x2); the
+ * reference's int8 wrap-around is re-imposed only where it is observable (the per-block delta accumulator and the
+ * saturating drop vector).  Band shifts are one SHFL + one PRMT per shifted vector, the direction accumulator is a single
+ * REDUX per anti-diagonal.  Semantics follow gaba.c (COMBINED model) and are checked against oracle/gaba_oracle.c;
+ * citations are into /root/reference/gaba.c.
+ *
+ * Everything here is executed by all 32 lanes with warp-uniform control flow.
+ */
+#pragma once
+#include "mab_types.h"
+#include "mab_scalar.cuh"
+
+namespace mab {
+
+#define MAB_FULL 0xffffffffu
+
+__device__ __forceinline__ uint32_t pack2(int v) { uint32_t x = (uint32_t)(uint16_t)(int16_t)v; return x | (x << 16); }
+__device__ __forceinline__ uint32_t sext8x2(uint32_t x) { return __byte_perm(x, 0, 0xA280); }		/* int8 wrap of both halves */
+__device__ __forceinline__ uint32_t unpack8(uint32_t v) { return __byte_perm(v, 0, 0x9180); }		/* {b0,b1} -> s16x2 */
+__device__ __forceinline__ uint32_t pack8(uint32_t x) { return __byte_perm(x, 0, 0x4420); }			/* s16x2 -> {b0,b1} */
+/* "H8" form: the int8 value sits in the HIGH byte of its 16-bit half (low byte zero), so VIADD.16x2 wraps exactly like the
+ * reference's int8 lanes (observable at the band edges, where dv/de run away) while signed 16-bit max/compare keep order */
+__device__ __forceinline__ uint32_t unpack8h(uint32_t v) { return __byte_perm(v, 0, 0x1404); }		/* {b0,b1} -> H8 */
+__device__ __forceinline__ uint32_t pack8h(uint32_t x) { return __byte_perm(x, 0, 0x4431); }			/* H8 -> {b0,b1} */
+__device__ __forceinline__ uint32_t h8_to_s16(uint32_t x) { return __byte_perm(x, 0, 0xB391); }		/* H8 -> sign-extended s16x2 */
+__device__ __forceinline__ uint32_t pack2h(int v) { uint32_t x = ((uint32_t)(uint8_t)(int8_t)v) << 8; return x | (x << 16); }
+__device__ __forceinline__ int lo16(uint32_t x) { return (int)(int16_t)(x & 0xffff); }
+__device__ __forceinline__ int hi16(uint32_t x) { return (int)(int16_t)(x >> 16); }
+__device__ __forceinline__ uint32_t clamp8x2(uint32_t x) { return __vmaxs2(__vmins2(x, 0x007f007fu), 0xff80ff80u); }
+
+/* warp-uniform DP context: arena pointers + band geometry */
+struct DpCtx {
+	const DevParams *P;
+	BlkEntry *blk; uint32_t blk_cap;
+	uint32_t *masks;				/* 256 u32 per entry (only written by traced fills) */
+	TailRec *tails;
+	const uint32_t *lut;			/* 256-entry packed score LUT in shared memory */
+	uint32_t nblk, ntail;
+	int W, nl, lane, widx;			/* band width, active lanes (W/2), lane id, root template index */
+	uint32_t err;
+	uint64_t n_vectors;
+};
+
+struct Vec {
+	uint32_t dh, dv, de, df, delta, drop, md, wa, wb;
+	int32_t acc; uint32_t dir;
+};
+
+/* reader work (gaba_reader_work_s, gaba.c:400-423), warp-uniform */
+struct FillWork {
+	SecDesc sec[2];
+	uint32_t rem[2], sridx[2], pridx;
+	int32_t ofsd;
+	int32_t wtail;
+};
+
+/* sequence fetch with the reference's code tables (gaba.c:864-879, 957-1118); `rev` replaces the mirrored pointers */
+__device__ __forceinline__ uint32_t fetch_a(const SecDesc &s, uint32_t i)
+{
+	const uint8_t *b = (const uint8_t *)s.base;
+	if(!s.rev) { return b[i]; }
+	uint32_t c = b[s.len - 1 - i];
+	return c < 4 ? 3 - c : 4;
+}
+__device__ __forceinline__ uint32_t fetch_b(const SecDesc &s, uint32_t i)
+{
+	const uint8_t *b = (const uint8_t *)s.base;
+	uint32_t c = s.rev ? b[s.len - 1 - i] : b[i];
+	if(c >= 4) { return 2; }
+	return (s.rev ? 3 - c : c) << 2;
+}
+
+/* build the 256-entry LUT: index = idx(cell 2l) | idx(cell 2l+1) << 4, value = packed sb[] pair (gaba.c:1612, 3657) */
+__device__ __forceinline__ void build_lut(const DevParams &P, uint32_t *lut, int tid, int nthreads)
+{
+	for(int i = tid; i < 256; i += nthreads) {
+		uint32_t lo = (uint32_t)(uint8_t)P.sb[i & 15] << 8, hi = (uint32_t)(uint8_t)P.sb[i >> 4] << 8;
+		lut[i] = lo | (hi << 16);
+	}
+}
+
+/* ---------------------------------------------------------------- one anti-diagonal (gaba.c:1604-1699) */
+template <bool MASKS>
+__device__ __forceinline__ void vec_step(const DpCtx &c, Vec &v, int down, uint32_t newch, uint32_t &mbits, int slot)
+{
+	const DevParams &P = *c.P;
+	if(!down) {			/* _fill_right: bsl dh, df; a new a-base enters at cell 0 */
+		uint32_t uh = __shfl_up_sync(MAB_FULL, v.dh, 1), uf = __shfl_up_sync(MAB_FULL, v.df, 1), ua = __shfl_up_sync(MAB_FULL, v.wa, 1);
+		if(c.lane == 0) { uh = 0; uf = 0; ua = newch << 16; }
+		v.dh = __byte_perm(uh, v.dh, 0x5432); v.df = __byte_perm(uf, v.df, 0x5432); v.wa = __byte_perm(ua, v.wa, 0x5432);
+	} else {			/* _fill_down: bsr dv, de; a new b-base enters at cell W-1 */
+		uint32_t nv = __shfl_down_sync(MAB_FULL, v.dv, 1), ne = __shfl_down_sync(MAB_FULL, v.de, 1), nb = __shfl_down_sync(MAB_FULL, v.wb, 1);
+		if(c.lane == c.nl - 1) { nv = 0; ne = 0; nb = newch; }
+		v.dv = __byte_perm(v.dv, nv, 0x5432); v.de = __byte_perm(v.de, ne, 0x5432); v.wb = __byte_perm(v.wb, nb, 0x5432);
+	}
+	uint32_t idx = v.wa | v.wb;
+	uint32_t t = c.lut[(idx & 0xf) | ((idx >> 12) & 0xf0)];
+	uint32_t dfh = __vadd2(v.dv, pack2h(P.gfh)), dfv = __vsub2(pack2h(P.gfv), v.dh);
+	t = __vimax3_s16x2(t, dfv, __vimax3_s16x2(v.de, v.df, dfh));
+	uint32_t te = __viaddmax_s16x2(v.de, pack2h(P.adjh), t);
+	uint32_t tf = __viaddmax_s16x2(v.df, pack2h(P.adjv), t);
+	if(MASKS) {
+		/* t is the (int8) maximum, so t - x is 0..255 in the high byte: min.u16 against 0x0100 leaves bit 8 set <=> "not equal" */
+		const uint32_t one = 0x01000100u;
+		uint32_t n_fh = __vminu2(__vsub2(t, dfh), one), n_e = __vminu2(__vsub2(t, v.de), one);
+		uint32_t n_fv = __vminu2(__vsub2(t, dfv), one), n_f = __vminu2(__vsub2(t, v.df), one);
+		uint32_t g_e = __vminu2(__vsub2(te, t), one), g_f = __vminu2(__vsub2(tf, t), one);		/* set <=> te != t */
+		uint32_t NH = n_fh & n_e, NV = n_fv & n_f;								/* ~h, ~v */
+		uint32_t NE = (n_e | ~n_fh) & g_e, NF = (n_f | ~n_fv) & g_f;			/* ~e, ~f */
+		uint32_t bits = ((NH >> 8) & 0x00010001u) | ((NV >> 7) & 0x00020002u) | ((NE >> 6) & 0x00040004u) | ((NF >> 5) & 0x00080008u);
+		mbits |= bits << (4 * slot);
+	}
+	uint32_t de = __vadd2(te, v.dh), dh = __vadd2(v.dh, t);
+	uint32_t df = __vsub2(tf, v.dv); t = __vsub2(v.dv, t);
+	v.dv = dh; v.dh = t; v.de = de; v.df = df;
+	uint32_t dH = down ? __vadd2(pack2h(P.ofsv), v.dv) : __vsub2(pack2h(P.ofsh), v.dh);	/* _fill_update_delta */
+	v.delta = __vadd2(v.delta, dH);											/* wraps like int8 */
+	uint32_t d = h8_to_s16(dH);
+	v.drop = clamp8x2(__vsub2(v.drop, d));									/* saturating */
+	int contrib = (c.lane == 0 ? lo16(d) : 0) - (c.lane == c.nl - 1 ? hi16(d) : 0);
+	v.acc += __reduce_add_sync(MAB_FULL, contrib);								/* _dir_update */
+}
+
+/* load the vector registers from the entry physically before a block (_fill_load_context, gaba.c:1527-1550) */
+__device__ __forceinline__ void vec_load(const DpCtx &c, Vec &v, const BlkEntry *prev, uint32_t xd)
+{
+	int l = c.lane;
+	v.dh = unpack8h(prev->dh[l]); v.dv = unpack8h(prev->dv[l]); v.de = unpack8h(prev->de[l]); v.df = unpack8h(prev->df[l]);
+	v.delta = 0; v.drop = xd;
+	v.acc = prev->acc; v.dir = 0;
+}
+
+/* ---------------------------------------------------------------- tails, sections */
+__device__ __forceinline__ int32_t push_tail(DpCtx &c)
+{
+	if(c.ntail >= MAB_MAX_TAILS) { c.err |= MAB_ERR_TAIL_OVF; return (int32_t)c.ntail - 1; }
+	return (int32_t)c.ntail++;
+}
+__device__ __forceinline__ int32_t push_blk(DpCtx &c)
+{
+	if(c.nblk >= c.blk_cap) { c.err |= MAB_ERR_DP_OVF; return (int32_t)c.nblk - 1; }
+	return (int32_t)c.nblk++;
+}
+
+/* gaba_dp_flush (gaba.c:3969-4002): entry 0 / tail 0 are the root templates of the current band width */
+__device__ inline void dp_flush(DpCtx &c, int widx)
+{
+	const DevParams &P = *c.P;
+	const RootTpl &R = P.root[widx];
+	c.widx = widx; c.W = 64 >> widx; c.nl = c.W / 2;
+	int l = c.lane;
+	BlkEntry *b = &c.blk[0]; TailRec *t = &c.tails[0];
+	if(l < c.nl) {
+		b->dh[l] = (uint16_t)((uint8_t)R.dh[2 * l] | ((uint8_t)R.dh[2 * l + 1] << 8));
+		b->dv[l] = (uint16_t)((uint8_t)R.dv[2 * l] | ((uint8_t)R.dv[2 * l + 1] << 8));
+		b->de[l] = (uint16_t)((uint8_t)R.de[2 * l] | ((uint8_t)R.de[2 * l + 1] << 8));
+		b->df[l] = (uint16_t)((uint8_t)R.df[2 * l] | ((uint8_t)R.df[2 * l + 1] << 8));
+		t->cha[l] = (l == 0) ? 0x000c : 0;								/* ch.w[0] = 0x0c (gaba.c:3780) */
+		t->chb[l] = (l == c.nl - 1) ? 0x0300 : 0;						/* ch.w[W-1] = 0x03 << 4 */
+		t->xd[l] = 0x8080;												/* -128 */
+		t->md[2 * l] = R.md[2 * l]; t->md[2 * l + 1] = R.md[2 * l + 1];
+	}
+	if(l == 0) {
+		b->acc = 0; b->xstat = MAB_X_ROOT; b->acnt = 0; b->bcnt = 0; b->link = -1; b->dir_mask = 0; b->mm_lo = b->mm_hi = 0;
+		t->mdrop = R.mdrop; t->istat = 0; t->pridx = 0;
+		t->ridx[0] = t->ridx[1] = 0; t->adv[0] = t->adv[1] = 0; t->tail = -1; t->last_blk = 0;
+		t->aid = t->bid = 0; t->ascnt = t->bscnt = 0;
+		t->apos = -(c.W / 2); t->bpos = -(c.W / 2); t->max = R.init_max; t->status = MAB_UPDATE_A | MAB_UPDATE_B;
+	}
+	c.nblk = 1; c.ntail = 1;
+	__syncwarp();
+}
+
+/* fill_load_section (gaba.c:1269-1308); breakpoint masks are always zero on minialign's path */
+__device__ __forceinline__ void load_section(DpCtx &c, FillWork &w, int32_t tail, const SecDesc &a, const SecDesc &b, uint32_t pridx)
+{
+	const TailRec *t = &c.tails[tail];
+	w.sec[0] = a; w.sec[1] = b;
+	uint32_t ra = t->ridx[0], rb = t->ridx[1];
+	w.rem[0] = w.sridx[0] = ra == 0 ? a.len : ra;
+	w.rem[1] = w.sridx[1] = rb == 0 ? b.len : rb;
+	w.pridx = pridx; w.ofsd = 0; w.wtail = tail;
+}
+
+/* fill_load_vectors + fill_create_phantom (gaba.c:1315-1332, 1376-1399); returns the head entry index.
+ * The char windows, xd and md of the tail are returned in registers. */
+__device__ __forceinline__ int32_t load_vectors(DpCtx &c, int32_t tail, Vec &v, uint32_t &xd)
+{
+	const TailRec *t = &c.tails[tail];
+	int l = c.lane, ls = l < c.nl ? l : 0;
+	v.wa = (uint32_t)(t->cha[ls] & 0xff) | ((uint32_t)(t->cha[ls] >> 8) << 16);
+	v.wb = (uint32_t)(t->chb[ls] & 0xff) | ((uint32_t)(t->chb[ls] >> 8) << 16);
+	xd = unpack8(t->xd[ls]);
+	v.md = (uint32_t)(uint16_t)t->md[2 * ls] | ((uint32_t)(uint16_t)t->md[2 * ls + 1] << 16);
+	int32_t prev = t->last_blk;
+	int32_t ph = push_blk(c);
+	BlkEntry *p = &c.blk[ph]; const BlkEntry *pb = &c.blk[prev];
+	if(l < c.nl) { p->dh[l] = pb->dh[l]; p->dv[l] = pb->dv[l]; p->de[l] = pb->de[l]; p->df[l] = pb->df[l]; }
+	if(l == 0) {
+		p->acc = pb->acc; p->xstat = (int8_t)((pb->xstat & MAB_X_ROOT) | MAB_X_HEAD);
+		p->acnt = 0; p->bcnt = 0; p->link = prev; p->dir_mask = 0; p->mm_lo = p->mm_hi = 0; p->tail = (uint32_t)tail;
+	}
+	__syncwarp();
+	return ph;
+}
+
+/* shift `n` freshly fetched bases of one side into the window registers without a DP step (init fetch) */
+__device__ __forceinline__ void window_consume(const DpCtx &c, Vec &v, const FillWork &w, int side, uint32_t n)
+{
+	const SecDesc &s = w.sec[side];
+	for(uint32_t k = 0; k < n; k++) {
+		uint32_t pos = s.len - w.rem[side] + k;
+		if(side == 0) {
+			uint32_t ch = fetch_a(s, pos);
+			uint32_t ua = __shfl_up_sync(MAB_FULL, v.wa, 1);
+			if(c.lane == 0) { ua = ch << 16; }
+			v.wa = __byte_perm(ua, v.wa, 0x5432);
+		} else {
+			uint32_t ch = fetch_b(s, pos);
+			uint32_t nb = __shfl_down_sync(MAB_FULL, v.wb, 1);
+			if(c.lane == c.nl - 1) { nb = ch; }
+			v.wb = __byte_perm(v.wb, nb, 0x5432);
+		}
+	}
+}
+
+/* fill_init_fetch (gaba.c:1168-1210) */
+__device__ __forceinline__ int64_t init_fetch(DpCtx &c, FillWork &w, Vec &v, int32_t ph, int64_t apos, int64_t bpos)
+{
+	int32_t irem[2] = { (int32_t)(-1 - (int32_t)apos), (int32_t)(-1 - (int32_t)bpos) };
+	int32_t srem[2] = { (int32_t)w.rem[0], (int32_t)w.rem[1] };
+	int32_t len[2];
+	for(int i = 0; i < 2; i++) {
+		int32_t x = irem[i] < srem[i] ? irem[i] : srem[i];
+		int32_t y = (srem[1 - i] - irem[1 - i]) + ((i == 0 ? 1 : 0) + irem[i]);
+		len[i] = x < y ? x : y;
+	}
+	window_consume(c, v, w, 0, (uint32_t)len[0]); window_consume(c, v, w, 1, (uint32_t)len[1]);
+	if(c.lane == 0) { c.blk[ph].acnt = (int8_t)len[0]; c.blk[ph].bcnt = (int8_t)len[1]; }
+	w.rem[0] = (uint32_t)(srem[0] - len[0]); w.rem[1] = (uint32_t)(srem[1] - len[1]);
+	__syncwarp();
+	return bpos + len[1];
+}
+
+/* fill_create_tail (gaba.c:1405-1499); `last` = last processed entry */
+__device__ __forceinline__ int32_t create_tail(DpCtx &c, FillWork &w, const Vec &v, uint32_t xd, int32_t last)
+{
+	const BlkEntry *b = &c.blk[last];
+	int xstat = b->xstat;
+	int cnt = ((uint8_t)b->acnt) | (((uint8_t)b->bcnt) << 8);
+	if(cnt == 0 && !(xstat & MAB_X_HEAD)) { c.nblk = (uint32_t)last; last--; }		/* squash the empty block */
+	else if(cnt == 0) { last--; }
+	int32_t ti = push_tail(c);
+	TailRec *t = &c.tails[ti];
+	const TailRec *prev = &c.tails[w.wtail];
+	int l = c.lane;
+	/* fill_save_vectors: mdrop = hmax(md + xd) */
+	int m0 = (int)(int16_t)(lo16(v.md) + lo16(xd)), m1 = (int)(int16_t)(hi16(v.md) + hi16(xd));
+	int mx = l < c.nl ? (m0 > m1 ? m0 : m1) : -32768;
+	int mdrop = __reduce_max_sync(MAB_FULL, mx);
+	if(l < c.nl) {
+		t->cha[l] = (uint16_t)((v.wa & 0xff) | ((v.wa >> 16) << 8));
+		t->chb[l] = (uint16_t)((v.wb & 0xff) | ((v.wb >> 16) << 8));
+		t->xd[l] = (uint16_t)pack8(xd);
+		t->md[2 * l] = (int16_t)lo16(v.md); t->md[2 * l + 1] = (int16_t)hi16(v.md);
+	}
+	if(l == 0) {
+		t->mdrop = mdrop; t->istat = 0; t->pridx = w.pridx;
+		uint32_t upd = 0;
+		for(int i = 0; i < 2; i++) {
+			t->ridx[i] = w.rem[i]; t->adv[i] = w.sridx[i] - w.rem[i];
+			if(w.rem[i] == 0) { upd |= i == 0 ? MAB_UPDATE_A : MAB_UPDATE_B; }
+		}
+		t->tail = w.wtail; t->last_blk = last;
+		t->aid = w.sec[0].id; t->bid = w.sec[1].id;
+		t->ascnt = prev->ascnt + (w.rem[0] == 0); t->bscnt = prev->bscnt + (w.rem[1] == 0);
+		t->apos = prev->apos + (w.sridx[0] - w.rem[0]); t->bpos = prev->bpos + (w.sridx[1] - w.rem[1]);
+		t->max = (prev->max - prev->mdrop) + w.ofsd + mdrop;
+		t->status = ((uint32_t)(xstat & MAB_X_TERM) << 8) | upd;
+		t->sec[0] = w.sec[0]; t->sec[1] = w.sec[1];
+	}
+	__syncwarp();
+	return ti;
+}
+
+/* ---------------------------------------------------------------- block loop (gaba.c:1821-2103) */
+template <bool MASKS>
+__device__ inline int32_t fill_blocks(DpCtx &c, FillWork &w, Vec &v, uint32_t &xd, int32_t cur)
+{
+	const DevParams &P = *c.P;
+	int cap = 0;
+	int l = c.lane;
+	while(1) {
+		if(c.blk[cur].xstat < 0) { break; }											/* TERM */
+		if(!cap && (w.rem[0] < MAB_BLK || w.rem[1] < MAB_BLK || w.pridx < MAB_BLK)) { cap = 1; }
+		int32_t bi = push_blk(c);
+		if(c.err) { break; }
+		BlkEntry *b = &c.blk[bi];
+		/* prefetch up to 32 bases of each side, one per lane (fill_fetch_core, gaba.c:1125-1144) */
+		uint32_t an = 0, bn = 0;
+		if((uint32_t)l < w.rem[0]) { an = fetch_a(w.sec[0], w.sec[0].len - w.rem[0] + l); }
+		if((uint32_t)l < w.rem[1]) { bn = fetch_b(w.sec[1], w.sec[1].len - w.rem[1] + l); }
+		if(l < c.nl) {
+			b->cha[l] = (uint16_t)((v.wa & 0xff) | ((v.wa >> 16) << 8));
+			b->chb[l] = (uint16_t)((v.wb & 0xff) | ((v.wb >> 16) << 8));
+		}
+		vec_load(c, v, &c.blk[bi - 1], xd);
+		uint32_t *mrow = c.masks + 256ull * bi + l;
+		uint32_t mbits = 0;
+		int acnt = 0, bcnt = 0, i = 0;
+		for(; i < MAB_BLK; i++) {
+			v.dir = (v.dir << 1) | (uint32_t)(v.acc < 0);								/* _dir_fetch */
+			int down = (int)(v.dir & 1);
+			if(cap) {																/* _fill_cap_test_idx */
+				int64_t ar = (int64_t)w.rem[0] - (acnt + !down), br = (int64_t)w.rem[1] - (bcnt + down);
+				int64_t pr = ar + br + (int64_t)w.pridx;
+				if((ar | br | pr) < 0) { v.dir >>= 1; break; }
+			}
+			uint32_t newch = down ? __shfl_sync(MAB_FULL, bn, bcnt) : __shfl_sync(MAB_FULL, an, acnt);
+			if(down) { bcnt++; } else { acnt++; }
+			vec_step<MASKS>(c, v, down, newch, mbits, i & 3);
+			if(MASKS && (i & 3) == 3) { mrow[32 * (i >> 2)] = mbits; mbits = 0; }
+		}
+		if(MASKS && (i & 3) != 0) { mrow[32 * (i >> 2)] = mbits; }
+		c.n_vectors += (uint64_t)i;
+		w.pridx -= (uint32_t)i;
+		if(i < MAB_BLK && i != 0) { v.dir <<= (MAB_BLK - i); }						/* _dir_adjust_remainder */
+		/* _fill_store_context (gaba.c:1734-1778) */
+		int ctr = c.W / 4;															/* lane holding cell W/2 (low half) */
+		uint32_t dl = h8_to_s16(v.delta);										/* delta as sign-extended int8 */
+		int dropc = lo16(__shfl_sync(MAB_FULL, v.drop, ctr)), cofs = lo16(__shfl_sync(MAB_FULL, dl, ctr));
+		int xstat = (P.tx - dropc) & MAB_X_TERM;
+		uint32_t sum = sext8x2(__vadd2(v.drop, dl));
+		uint32_t mlo = __ballot_sync(MAB_FULL, l < c.nl && lo16(sum) > lo16(xd));
+		uint32_t mhi = __ballot_sync(MAB_FULL, l < c.nl && hi16(sum) > hi16(xd));
+		/* middle delta with the overflow / underflow rescue terms */
+		uint32_t md = __vadd2(v.md, dl);
+		uint32_t ov = sext8x2(~sum & (v.drop & dl));
+		md = __vadd2(md, ov & 0x01000100u);
+		uint32_t uv = sext8x2(clamp8x2(__vsub2(dl, 0x00400040u)) | v.drop);
+		md = __vadd2(md, uv & 0x01000100u);
+		md = __vsub2(md, pack2(cofs + 0x0100));
+		v.md = md; xd = v.drop;
+		w.ofsd += cofs; w.rem[0] -= (uint32_t)acnt; w.rem[1] -= (uint32_t)bcnt;
+		if(l < c.nl) {
+			b->dh[l] = (uint16_t)pack8h(v.dh); b->dv[l] = (uint16_t)pack8h(v.dv); b->de[l] = (uint16_t)pack8h(v.de); b->df[l] = (uint16_t)pack8h(v.df);
+		}
+#ifdef MAB_DEBUG_BLK
+		{ int d0 = lo16(__shfl_sync(MAB_FULL, dl, 0)), dW = hi16(__shfl_sync(MAB_FULL, dl, c.nl - 1));
+		if(l == 0 && getenv("ORA_DEBUG")) { fprintf(stderr, "GPU blk acnt %d bcnt %d dir %08x acc %d drop_c %d delta_c %d d0 %d dW %d\n", acnt, bcnt, v.dir, v.acc, dropc, cofs, d0, dW); } }
+#endif
+		if(l == 0) {
+			b->acc = (int8_t)v.acc; b->xstat = (int8_t)xstat; b->acnt = (int8_t)acnt; b->bcnt = (int8_t)bcnt;
+			b->dir_mask = v.dir; b->mm_lo = mlo; b->mm_hi = mhi; b->link = -1;
+			b->arem = w.rem[0] + (uint32_t)acnt; b->brem = w.rem[1] + (uint32_t)bcnt; b->tail = (uint32_t)c.ntail;	/* the tail created next */
+		}
+		__syncwarp();
+		cur = bi;
+		if(i != MAB_BLK) { break; }
+	}
+	return cur;
+}
+
+/* gaba_dp_fill_root (gaba.c:2110-2154) */
+template <bool MASKS>
+__device__ inline int32_t dp_fill_root(DpCtx &c, const SecDesc &a, uint32_t apos, const SecDesc &b, uint32_t bpos)
+{
+	/* fill_create_bridge (gaba.c:1339-1369) */
+	int32_t bi = push_tail(c);
+	TailRec *brg = &c.tails[bi]; const TailRec *rt = &c.tails[0];
+	int l = c.lane;
+	if(l < c.nl) { brg->cha[l] = rt->cha[l]; brg->chb[l] = rt->chb[l]; brg->xd[l] = rt->xd[l]; brg->md[2 * l] = rt->md[2 * l]; brg->md[2 * l + 1] = rt->md[2 * l + 1]; }
+	if(l == 0) {
+		brg->mdrop = rt->mdrop; brg->istat = 1; brg->pridx = rt->pridx;
+		brg->ridx[0] = a.len - apos; brg->ridx[1] = b.len - bpos; brg->adv[0] = apos; brg->adv[1] = bpos;
+		brg->tail = 0; brg->last_blk = 0;
+		brg->aid = a.id; brg->bid = b.id; brg->ascnt = rt->ascnt; brg->bscnt = rt->bscnt;
+		brg->apos = rt->apos; brg->bpos = rt->bpos; brg->max = rt->max; brg->status = rt->status;
+		brg->sec[0] = a; brg->sec[1] = b;
+	}
+	__syncwarp();
+	FillWork w; Vec v; uint32_t xd;
+	load_section(c, w, bi, a, b, 0xffffffffu);
+	int32_t ph = load_vectors(c, 0, v, xd);
+	int64_t rapos = c.tails[0].apos, rbpos = c.tails[0].bpos;
+	if(init_fetch(c, w, v, ph, rapos, rbpos) < -1) { return create_tail(c, w, v, xd, ph); }
+	return create_tail(c, w, v, xd, fill_blocks<MASKS>(c, w, v, xd, ph));
+}
+
+/* gaba_dp_fill (gaba.c:2161-2203) */
+template <bool MASKS>
+__device__ inline int32_t dp_fill(DpCtx &c, int32_t prev, const SecDesc &a, const SecDesc &b)
+{
+	FillWork w; Vec v; uint32_t xd;
+	load_section(c, w, prev, a, b, c.tails[prev].pridx);
+	int32_t ph = load_vectors(c, prev, v, xd);
+	int64_t papos = c.tails[prev].apos, pbpos = c.tails[prev].bpos;
+	if(pbpos < -1) {
+		if(init_fetch(c, w, v, ph, papos, pbpos) < -1) { return create_tail(c, w, v, xd, ph); }
+	}
+	return create_tail(c, w, v, xd, fill_blocks<MASKS>(c, w, v, xd, ph));
+}
+
+/* mm_extend_core (minialign.c:4075-4112): fill_root, then keep filling over the N-tail sections until X-drop or a second
+ * section end; returns the tail with the largest max */
+template <bool MASKS>
+__device__ inline int32_t extend_core(DpCtx &c, SecDesc a, const SecDesc &at, SecDesc b, const SecDesc &bt, uint32_t apos, uint32_t bpos)
+{
+	int32_t f = dp_fill_root<MASKS>(c, a, apos, b, bpos);
+	int32_t m = f;
+	uint32_t flag = MAB_TERM;
+	while(c.err == 0) {
+		uint32_t st = c.tails[f].status;
+		if((flag & st) != 0) { break; }
+		if(st & MAB_UPDATE_A) { a = at; }
+		if(st & MAB_UPDATE_B) { b = bt; }
+		flag |= st & (MAB_UPDATE_A | MAB_UPDATE_B);
+		f = dp_fill<MASKS>(c, f, a, b);
+		m = c.tails[f].max > c.tails[m].max ? f : m;
+	}
+	return m;
+}
+
+/* ---------------------------------------------------------------- max search (gaba.c:2604-2817) */
+struct Leaf {
+	int32_t blk; uint32_t p, q;
+	int32_t gidx[2], sgidx[2];
+	uint64_t plen;
+};
+
+/* lowest set cell index of a two-plane mask (cell 2l = plane lo bit l, cell 2l+1 = plane hi bit l); 64 when empty */
+__device__ __forceinline__ uint32_t mask_tz(uint32_t lo, uint32_t hi)
+{
+	uint32_t a = lo ? 2u * (uint32_t)(__ffs((int)lo) - 1) : 64u, b = hi ? 2u * (uint32_t)(__ffs((int)hi) - 1) + 1u : 64u;
+	return a < b ? a : b;
+}
+
+__device__ inline void leaf_search(DpCtx &c, int32_t ti, Leaf &lf)
+{
+	const TailRec *t = &c.tails[ti];
+	int l = c.lane, ls = l < c.nl ? l : 0;
+	/* leaf_load_max_mask */
+	uint32_t xd = unpack8(t->xd[ls]);
+	int m0 = (int)(int16_t)(t->md[2 * ls] + lo16(xd)), m1 = (int)(int16_t)(t->md[2 * ls + 1] + hi16(xd));
+	int mdrop = (int)(int16_t)t->mdrop;
+	uint32_t mlo = __ballot_sync(MAB_FULL, l < c.nl && m0 == mdrop), mhi = __ballot_sync(MAB_FULL, l < c.nl && m1 == mdrop);
+	int32_t b = t->last_blk + 1;
+	int32_t ridx[2] = { (int32_t)t->ridx[0], (int32_t)t->ridx[1] };
+	lf.plen = 0; lf.blk = 0; lf.p = 0; lf.q = 0; lf.gidx[0] = lf.gidx[1] = lf.sgidx[0] = lf.sgidx[1] = 0;
+	while(1) {
+		--b;
+		if((c.blk[b].xstat & MAB_X_ROOT) == MAB_X_ROOT) { return; }
+		while(c.blk[b].xstat & MAB_X_HEAD) { b = c.blk[b].link; }
+		ridx[0] += c.blk[b].acnt; ridx[1] += c.blk[b].bcnt;
+		uint32_t blo = c.blk[b].mm_lo, bhi = c.blk[b].mm_hi;
+		if(((mlo & ~blo) | (mhi & ~bhi)) == 0) { break; }
+		mlo &= ~blo; mhi &= ~bhi;
+	}
+	/* leaf_detect_pos: replay the block, lane i keeps the update mask of vector i */
+	const BlkEntry *blk = &c.blk[b];
+	int n = blk->acnt + blk->bcnt;
+	uint32_t my_lo = 0, my_hi = 0;
+	{
+		const TailRec *bt = &c.tails[blk->tail];
+		SecDesc sa = bt->sec[0], sb = bt->sec[1];
+		uint32_t arem = blk->arem, brem = blk->brem;
+		Vec v;
+		v.wa = (uint32_t)(blk->cha[ls] & 0xff) | ((uint32_t)(blk->cha[ls] >> 8) << 16);
+		v.wb = (uint32_t)(blk->chb[ls] & 0xff) | ((uint32_t)(blk->chb[ls] >> 8) << 16);
+		v.md = 0;
+		vec_load(c, v, &c.blk[b - 1], 0);
+		uint32_t an = 0, bn = 0;
+		if((uint32_t)l < arem) { an = fetch_a(sa, sa.len - arem + l); }
+		if((uint32_t)l < brem) { bn = fetch_b(sb, sb.len - brem + l); }
+		uint32_t mx = 0, dummy = 0;
+		int acnt = 0, bcnt = 0;
+		for(int i = 0; i < n; i++) {
+			v.dir = (v.dir << 1) | (uint32_t)(v.acc < 0);
+			int down = (int)(v.dir & 1);
+			uint32_t newch = down ? __shfl_sync(MAB_FULL, bn, bcnt) : __shfl_sync(MAB_FULL, an, acnt);
+			if(down) { bcnt++; } else { acnt++; }
+			vec_step<false>(c, v, down, newch, dummy, 0);
+			uint32_t ulo = __ballot_sync(MAB_FULL, l < c.nl && lo16(v.delta) > lo16(mx));
+			uint32_t uhi = __ballot_sync(MAB_FULL, l < c.nl && hi16(v.delta) > hi16(mx));
+			mx = __vmaxs2(mx, v.delta);
+			if(l == i) { my_lo = ulo; my_hi = uhi; }
+		}
+		c.n_vectors += (uint64_t)n;
+	}
+	/* leaf_search_pos: while(m > mask_arr && (max_mask & ~(--m)->all) != 0) { max_mask &= ~m->all; } */
+	int m = n;
+	uint32_t clo = 0, chi = 0;
+	for(;;) {
+		if(!(m > 0)) { break; }
+		m--;
+		clo = __shfl_sync(MAB_FULL, my_lo, m); chi = __shfl_sync(MAB_FULL, my_hi, m);
+		if(((mlo & ~clo) | (mhi & ~chi)) == 0) { break; }
+		mlo &= ~clo; mhi &= ~chi;
+	}
+	if(n == 0) { clo = chi = 0; }
+	uint32_t p = (uint32_t)m, q = mask_tz(clo & mlo, chi & mhi);
+	lf.blk = b; lf.p = p & 0xff; lf.q = q & 0xff;
+	int32_t fcnt = (int32_t)p + 1;
+	uint32_t dir_mask = blk->dir_mask >> (MAB_BLK - fcnt);
+	ridx[0] -= (int32_t)((uint32_t)(fcnt - __popc(dir_mask)) - (1 + q));
+	ridx[1] -= (int32_t)((uint32_t)(0 + __popc(dir_mask)) - ((uint32_t)c.W - q));
+	for(int i = 0; i < 2; i++) { lf.gidx[i] = lf.sgidx[i] = 1 - ridx[i] + (int32_t)t->ridx[i]; }
+	int32_t rem0 = ridx[0] - (int32_t)t->ridx[0], rem1 = ridx[1] - (int32_t)t->ridx[1];
+	lf.plen = (uint64_t)t->apos + (uint64_t)t->bpos + 2 + (uint64_t)c.W - (uint64_t)(int64_t)rem1 - (uint64_t)(int64_t)rem0;
+}
+
+struct PosPair { uint32_t aid, bid, apos, bpos; uint64_t plen; };
+
+/* gaba_dp_search_max (gaba.c:2776-2817) */
+__device__ inline PosPair dp_search_max(DpCtx &c, int32_t ti)
+{
+	Leaf lf; leaf_search(c, ti, lf);
+	PosPair pos; pos.plen = lf.plen;
+	int32_t gidx[2] = { lf.gidx[0], lf.gidx[1] }, acc[2] = { 0, 0 };
+	const TailRec *t = &c.tails[ti];
+	uint32_t id[2] = { t->aid, t->bid };
+	while(t->tail >= 0) {
+		int upd0 = 1 > gidx[0], upd1 = 1 > gidx[1];
+		if(!upd0 && !upd1) { break; }
+		uint32_t nid0 = t->aid, nid1 = t->bid;
+		acc[0] += (int32_t)t->adv[0]; acc[1] += (int32_t)t->adv[1];
+		t = &c.tails[t->tail];
+		if(upd0 && t->ridx[0] == 0) { gidx[0] += acc[0]; id[0] = nid0; acc[0] = 0; }
+		if(upd1 && t->ridx[1] == 0) { gidx[1] += acc[1]; id[1] = nid1; acc[1] = 0; }
+	}
+	pos.aid = id[0]; pos.bid = id[1]; pos.apos = (uint32_t)gidx[0]; pos.bpos = (uint32_t)gidx[1];
+	return pos;
+}
+
+/* ---------------------------------------------------------------- traceback (gaba.c:2820-3393) */
+#define MAB_TS_H 1
+#define MAB_TS_V 2
+#define MAB_TS_S 4
+enum { mab_ts_d = 3, mab_ts_v0 = 2, mab_ts_v1 = 6, mab_ts_h0 = 1, mab_ts_h1 = 5 };
+enum { MP_D_HEAD, MP_D_MID, MP_D_TAIL, MP_H_HEAD, MP_H_BODY, MP_H_TAIL, MP_V_HEAD, MP_V_BODY, MP_V_TAIL };
+
+struct Trace {
+	int32_t blk, mi; uint32_t q, state;
+	int32_t gidx[2], sgidx[2]; uint32_t ofs[2], id[2];
+	int32_t tail[2];
+	uint32_t gi[2], ge[2], gf[2];
+	uint64_t npop, plen;
+	uint32_t *path;				/* path words in the result pool */
+	uint32_t cur_word; int64_t cur_idx;
+};
+
+/* stage the 1 KB mask block of entry b into this warp's shared-memory tile (coalesced 128 B rows) */
+__device__ __forceinline__ void stage_masks(const DpCtx &c, int32_t b, uint32_t *tile)
+{
+	const uint32_t *src = c.masks + 256ull * b;
+	__syncwarp();				/* every lane is done reading the previous tile (lanes are not lock-stepped on sm_70+) */
+	for(int g = 0; g < 8; g++) { tile[32 * g + c.lane] = src[32 * g + c.lane]; }
+	__syncwarp();
+}
+
+/* nibble of (vector mi, cell q): bit0 = ~h, bit1 = ~v, bit2 = ~e, bit3 = ~f.  q is taken modulo the mask word width like
+ * the reference's `mask->x.all >> q` on x86 (gaba.c:2952-2973) */
+__device__ __forceinline__ uint32_t mask_nib(const DpCtx &c, const uint32_t *tile, int32_t mi, uint32_t q)
+{
+	uint32_t qq;
+	if(c.W == 64) { qq = q & 63; } else if(c.W == 32) { qq = q & 31; } else { qq = q & 31; if(qq >= 16) { return 0xfu; } }
+	uint32_t wd = tile[32 * (mi >> 2) + (qq >> 1)];
+	return (wd >> (16 * (qq & 1) + 4 * (mi & 3))) & 0xfu;
+}
+
+__device__ __forceinline__ void trace_pop(Trace &w, int v, int lane)
+{
+	int64_t bit = (int64_t)w.plen - 1 - (int64_t)w.npop;
+	int64_t wi = bit >> 5;
+	if(wi != w.cur_idx) {
+		if(lane == 0) { w.path[w.cur_idx] = w.cur_word; }
+		w.cur_idx = wi; w.cur_word = 0;
+	}
+	w.cur_word |= (uint32_t)v << (bit & 31);
+	w.npop++;
+}
+
+/* trace_reload_section (gaba.c:2826-2859) */
+__device__ __forceinline__ void trace_reload_section(const DpCtx &c, Trace &w, int i)
+{
+	int32_t tail = w.tail[i], prev = tail;
+	int32_t gidx = w.gidx[i];
+	while(gidx <= 0) {
+		do {
+			gidx += c.tails[tail].istat ? 0 : (int32_t)c.tails[tail].adv[i];
+			prev = tail; tail = c.tails[tail].tail;
+		} while(c.tails[tail].ridx[i] != 0);
+	}
+	w.tail[i] = tail;
+	w.id[i] = i == 0 ? c.tails[prev].aid : c.tails[prev].bid;
+	w.ofs[i] = c.tails[prev].istat ? c.tails[prev].adv[i] : 0;
+	w.gidx[i] = gidx; w.sgidx[i] = gidx;
+}
+
+/* trace_core (gaba.c:3111-3232) as an explicit state machine with the reference's bulk / tail modes */
+__device__ inline void trace_core(DpCtx &c, Trace &w, uint32_t *tile)
+{
+	const int W = c.W;
+	const uint32_t HEAD_CNT = (uint32_t)(W / MAB_BLK + (W == 16));
+	int32_t b = w.blk, mi = w.mi; uint32_t q = w.q, save = HEAD_CNT;
+	uint32_t dir = c.blk[b].dir_mask >> (MAB_BLK - (mi + 1));
+	int bulk = 0, pos;
+	switch(w.state) {
+		case mab_ts_d:  pos = MP_D_HEAD; break;
+		case mab_ts_v0: pos = MP_V_HEAD; break;
+		case mab_ts_v1: pos = MP_V_TAIL; break;
+		case mab_ts_h0: pos = MP_H_HEAD; break;
+		case mab_ts_h1: pos = MP_H_TAIL; break;
+		default: return;
+	}
+	stage_masks(c, b, tile);
+	#define NIB()			mask_nib(c, tile, mi, q)
+	#define TEST_BULK(_ok) { \
+		int32_t _ga = w.gidx[0] - c.blk[b].acnt, _gb = w.gidx[1] - c.blk[b].bcnt; \
+		_ok = !(W > _ga) && !(W > _gb); \
+		if(_ok) { w.gidx[0] = _ga; w.gidx[1] = _gb; } \
+	}
+	#define RELOAD_BLOCK() { \
+		b--; mi = MAB_BLK - 1; dir = c.blk[b].dir_mask; \
+		if(c.blk[b].xstat & MAB_X_HEAD) { \
+			do { b = c.blk[b].link; } while(c.blk[b].xstat & MAB_X_HEAD); \
+			int _cnt = c.blk[b].acnt + c.blk[b].bcnt; \
+			mi = _cnt - 1; dir = c.blk[b].dir_mask >> (MAB_BLK - _cnt); \
+		} \
+	}
+	#define POP(_v) { \
+		if(!bulk) { w.gidx[_v]--; } \
+		trace_pop(w, _v, c.lane); mi--; \
+		q += (dir & 1) - (uint32_t)(_v); dir >>= 1; \
+		if(mi < 0) { \
+			int _term = 0; \
+			if(bulk) { \
+				RELOAD_BLOCK(); \
+				int _ok; TEST_BULK(_ok); \
+				if(!_ok) { \
+					if(q >= (uint32_t)W) { _term = 1; } \
+					else { w.gidx[1] += (int32_t)(q - save); w.gidx[0] += (int32_t)(save - q); save = HEAD_CNT; bulk = 0; } \
+				} \
+			} else { \
+				if(c.blk[b - 1].xstat & MAB_X_HEAD) { \
+					b--; do { b = c.blk[b].link; } while(c.blk[b].xstat & MAB_X_HEAD); \
+					int _cnt = c.blk[b].acnt + c.blk[b].bcnt; \
+					mi = _cnt - 1; dir = c.blk[b].dir_mask >> (MAB_BLK - _cnt); \
+				} else { \
+					RELOAD_BLOCK(); \
+					if(--save >= HEAD_CNT) { int _ok; TEST_BULK(_ok); if(_ok) { save = q; bulk = 1; } } \
+				} \
+			} \
+			if(_term) { goto term; } \
+			stage_masks(c, b, tile); \
+		} \
+	}
+	while(1) {
+		uint32_t nb;
+		switch(pos) {
+		case MP_D_HEAD:
+			nb = NIB();
+			if(!(nb & 1)) { pos = MP_H_HEAD; break; }								/* h bit set */
+			if(!bulk && (w.gidx[0] == 0 || w.gidx[1] == 0)) { w.state = mab_ts_d; goto term; }
+			POP(0); pos = MP_D_MID; break;
+		case MP_D_MID:
+			POP(1); pos = MP_D_TAIL; break;
+		case MP_D_TAIL:
+			nb = NIB();
+			if(!(nb & 2)) { pos = MP_V_HEAD; break; }
+			pos = MP_D_HEAD; break;
+		case MP_H_HEAD:
+			nb = NIB();
+			if(nb & 4) {															/* e bit clear: short gap */
+				if(!bulk && w.gidx[0] == 0) { w.state = mab_ts_h0; goto term; }
+				w.gf[0]++; POP(0); pos = MP_D_HEAD; break;
+			}
+			w.gi[0]++; pos = MP_H_BODY; break;
+		case MP_H_BODY:
+			if(!bulk && w.gidx[0] == 0) { w.state = mab_ts_h1; goto term; }
+			w.ge[0]++; POP(0); pos = MP_H_TAIL; break;
+		case MP_H_TAIL:
+			nb = NIB();
+			/* (~h & e) bit clear <=> !(~h set && e set) <=> !((nb & 1) && !(nb & 4)) */
+			pos = !((nb & 1) && !(nb & 4)) ? MP_H_BODY : MP_D_HEAD; break;
+		case MP_V_HEAD:
+			nb = NIB();
+			if(nb & 8) {
+				if(!bulk && w.gidx[1] == 0) { w.state = mab_ts_v0; goto term; }
+				w.gf[1]++; POP(1); pos = MP_D_TAIL; break;
+			}
+			w.gi[1]++; pos = MP_V_BODY; break;
+		case MP_V_BODY:
+			if(!bulk && w.gidx[1] == 0) { w.state = mab_ts_v1; goto term; }
+			w.ge[1]++; POP(1); pos = MP_V_TAIL; break;
+		case MP_V_TAIL:
+			nb = NIB();
+			pos = !((nb & 2) && !(nb & 8)) ? MP_V_BODY : MP_D_TAIL; break;
+		}
+	}
+term:
+	w.blk = b; w.mi = mi; w.q = q & 0xff;
+	__syncwarp();
+	#undef NIB
+	#undef TEST_BULK
+	#undef RELOAD_BLOCK
+	#undef POP
+}
+
+/* gaba_dp_trace (gaba.c:3244-3393).  Allocates the alignment record from the result pool (lane 0 bumps the pointer),
+ * returns its word offset or UINT64_MAX when the path left the band / the pool is full (err set in that case). */
+__device__ inline uint64_t dp_trace(DpCtx &c, int32_t ti, uint32_t *pool, uint64_t pool_cap, BatchCounters *ctr, uint32_t *tile)
+{
+	const DevParams &P = *c.P;
+	const TailRec *t = &c.tails[ti];
+	Leaf lf; lf.plen = 0; lf.blk = 0; lf.p = 0; lf.q = 0; lf.gidx[0] = lf.gidx[1] = lf.sgidx[0] = lf.sgidx[1] = 0;
+	if(!(t->bpos < -1)) { leaf_search(c, ti, lf); }
+	uint64_t plen = lf.plen;
+	uint32_t sn = t->ascnt + t->bscnt + 2, npw = (uint32_t)((plen + 31) / 32 + 1);
+	uint64_t words = MAB_ALN_HDR + 8ull * sn + npw + 1;
+	unsigned long long ofs = 0;
+	if(c.lane == 0) { ofs = atomicAdd(&ctr->pool_top, (unsigned long long)words); }
+	ofs = __shfl_sync(MAB_FULL, ofs, 0);
+	if(ofs + words > pool_cap) { c.err |= MAB_ERR_POOL_OVF; return 0xffffffffffffffffull; }
+	uint32_t *rec = pool + ofs;
+	Trace w;
+	w.blk = lf.blk; w.mi = (int32_t)lf.p; w.q = lf.q; w.state = mab_ts_d;
+	for(int i = 0; i < 2; i++) { w.gidx[i] = lf.gidx[i]; w.sgidx[i] = lf.sgidx[i]; w.tail[i] = ti; w.ofs[i] = 0; w.id[i] = 0; w.gi[i] = w.ge[i] = w.gf[i] = 0; }
+	w.npop = 0; w.plen = plen; w.path = rec + MAB_ALN_HDR + 8ull * sn;
+	w.cur_idx = (int64_t)(plen >> 5); w.cur_word = 1u << (plen & 31);				/* sentinel (gaba.c:3287) */
+	if(c.lane == 0) { w.path[(plen >> 5) + 1] = 0; }
+	uint32_t nseg = 0;
+	while(w.npop < plen) {
+		if(w.gidx[0] < (int32_t)((w.state & MAB_TS_H) != 0)) { trace_reload_section(c, w, 0); }
+		if(w.gidx[1] < (int32_t)((w.state & MAB_TS_V) != 0)) { trace_reload_section(c, w, 1); }
+		trace_core(c, w, tile);
+		if(w.q >= (uint32_t)c.W) { return 0xffffffffffffffffull; }					/* out of band: abort (gaba.c:3324-3328) */
+		/* trace_push_segment (gaba.c:2865-2895): slots fill from the back */
+		if(c.lane == 0 && nseg < sn) {
+			uint32_t *s = rec + MAB_ALN_HDR + 8ull * (sn - 1 - nseg);
+			uint64_t ppos = plen - w.npop;
+			s[0] = w.id[0]; s[1] = w.id[1];
+			s[2] = w.ofs[0] + (uint32_t)w.gidx[0]; s[3] = w.ofs[1] + (uint32_t)w.gidx[1];
+			s[4] = (uint32_t)(w.sgidx[0] - w.gidx[0]); s[5] = (uint32_t)(w.sgidx[1] - w.gidx[1]);
+			s[6] = (uint32_t)ppos; s[7] = (uint32_t)(ppos >> 32);
+		}
+		nseg++;
+		w.sgidx[0] = w.gidx[0]; w.sgidx[1] = w.gidx[1];
+	}
+	if(c.lane == 0) {
+		w.path[w.cur_idx] = w.cur_word;
+		/* identity (gaba.c:3334-3355): only the a-side counters enter the sum (_mm_mul_epi32 multiplies the low lane) */
+		uint32_t gc0 = w.ge[0] + w.gf[0], gc1 = w.ge[1] + w.gf[1];
+		int32_t g0 = (int32_t)((uint32_t)P.gi * w.gi[0] + (uint32_t)P.ge * w.ge[0] + (uint32_t)P.gfa * w.gf[0]);
+		uint64_t dlen = ((uint32_t)plen - gc1 - gc0) >> 1;
+		int64_t score = t->max, dsc = score + g0;
+		double identity = dlen == 0 ? 0.0 : __dsub_rn(__dmul_rn(__ddiv_rn((double)dsc, (double)dlen), P.imx), P.xmx);
+		unsigned long long ib; memcpy(&ib, &identity, 8);
+		rec[0] = (uint32_t)score; rec[1] = (uint32_t)((uint64_t)score >> 32); rec[2] = (uint32_t)ib; rec[3] = (uint32_t)(ib >> 32);
+		rec[4] = gc0; rec[5] = gc1; rec[6] = (uint32_t)dlen; rec[7] = nseg < sn ? nseg : sn; rec[8] = (uint32_t)plen; rec[9] = npw; rec[10] = sn;
+		rec[11] = rec[12] = rec[13] = rec[14] = rec[15] = 0;
+	}
+	if(nseg > sn) { c.err |= MAB_ERR_POOL_OVF; }
+	__syncwarp();
+	return (uint64_t)ofs;
+}
+
+}  // namespace mab

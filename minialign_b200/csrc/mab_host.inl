@@ -1,0 +1,552 @@
+/*
+ * mab_host.inl -- host driver behind the C ABI (include/minialign_b200.h): context setup, batch orchestration, D2H and the
+ * floating-point post-processing (pruning, supplementary/secondary split, MAPQ: minialign.c:4175-4396) that the reference
+ * also runs on the CPU.  Included by mab_cuda.cu (real CUDA runtime) and by tests/emu/mab_emu.cpp (CUDA-on-CPU shim used by
+ * the "not gpu" tests); the RT_* macros are the only difference between the two builds.
+ */
+#include "../../include/minialign_b200.h"
+#include "mab_kernels.cuh"
+#include <vector>
+#include <string>
+#include <cmath>
+#include <cstring>
+#include <cstdlib>
+#include <algorithm>
+
+using namespace mab;
+
+static thread_local std::string g_err;
+extern "C" const char *mab_last_error(void) { return g_err.c_str(); }
+
+struct mab_ctx {
+	int device;
+	DevParams P;
+	std::vector<uint8_t> blob;			/* host copy of the index image (reference names / sequences for the printer) */
+	uint8_t *d_idx = nullptr, *d_ntail = nullptr;
+	uint32_t n_sm = 0, n_slots = 0;
+	mab_params_t prm;
+	double xcoef;
+	/* batch buffers (grown on demand) */
+	uint8_t *d_seq = nullptr; uint64_t seq_cap = 0;
+	ReadRec *d_reads = nullptr; uint64_t reads_cap = 0;
+	uint8_t *d_ws = nullptr; uint64_t ws_cap = 0;
+	uint32_t *d_frames = nullptr; uint64_t frames_cap = 0;
+	uint8_t *d_arenas = nullptr; uint64_t arenas_cap = 0;
+	uint32_t *d_pool = nullptr; uint64_t pool_cap = 0;
+	BatchCounters *d_ctr = nullptr;
+	RT_STREAM stream;
+	RT_EVENT ev[8];
+	int device_input = 0;
+	/* results of the last batch */
+	std::vector<uint32_t> res_words; std::vector<uint64_t> res_ofs;
+	std::vector<uint32_t> h_pool; std::vector<ReadRec> h_reads;
+	mab_stats_t stats;
+};
+
+/* ---------------------------------------------------------------- GABA constants (gaba.c:3613-3842) */
+namespace {
+struct GapModel {
+	int M, gi, ge, gfa, gfb;
+	int gap_h(int l) const { return std::max(-1 * (l > 0) * gi - ge * l, -1 * gfb * l); }
+	int gap_v(int l) const { return std::max(-1 * (l > 0) * gi - ge * l, -1 * gfa * l); }
+	int gap_e(int l) const { return -1 * (l > 0) * gi - ge * l; }
+};
+
+int check_params(const mab_params_t *p)
+{
+	int M = -128, X = 127;
+	for(int i = 0; i < 16; i++) { M = std::max(M, (int)p->score_matrix[i]); X = std::min(X, (int)p->score_matrix[i]); }
+	if(p->gi == 0 || p->gfa == 0 || p->gfb == 0) { return -1; }				/* combined model only */
+	if(M <= 0 || M > 6 || X >= 0 || X < -7) { return -1; }
+	if(X < -2 * (p->gi + p->ge)) { return -1; }
+	if(X <= -1 * (p->gfa + p->gfb)) { return -1; }
+	if(p->ge <= 0 || p->gi < 0) { return -1; }
+	if(p->gfa <= p->ge || p->gfb <= p->ge) { return -1; }
+	GapModel g = { M, p->gi, p->ge, p->gfa, p->gfb };
+	int ofs = p->gi + p->ge;
+	for(int i = 0; i < 8; i++) {											/* the wrapper validates with the 16-cell object */
+		int t1 = ofs + g.gap_h(i * 2 + 1) - g.gap_h(i * 2);
+		int t2 = ofs + (M + g.gap_v(i * 2 + 1)) - g.gap_v((i + 1) * 2);
+		int t3 = ofs + (M + g.gap_h(i * 2 + 1)) - g.gap_h((i + 1) * 2);
+		if(std::max(std::max(t1, t2), t3) > 127) { return -1; }
+		if(std::min(std::min(t2, t3), t1) < 0) { return -1; }
+	}
+	return 0;
+}
+
+void init_gaba_consts(DevParams &P, const mab_params_t *p)
+{
+	int M = -128;
+	for(int i = 0; i < 16; i++) { M = std::max(M, (int)p->score_matrix[i]); }
+	GapModel g = { M, p->gi, p->ge, p->gfa, p->gfb };
+	int ofs = p->gi + p->ge;
+	for(int i = 0; i < 16; i++) { P.sb[i] = (int8_t)(p->score_matrix[i] + 2 * ofs); }
+	P.adjh = P.adjv = p->gi; P.ofsh = P.ofsv = -ofs; P.gfh = ofs - p->gfb; P.gfv = ofs - p->gfa;
+	P.tx = (int8_t)(p->xdrop - 128);
+	P.gi = p->gi; P.ge = p->ge; P.gfa = p->gfa; P.gfb = p->gfb;
+	long long diag = 0, off = 0;
+	for(int i = 0; i < 16; i++) { if((i & 3) == (i >> 2)) { diag += p->score_matrix[i]; } else { off += p->score_matrix[i]; } }
+	double m = (double)diag / 4.0, x = (double)off / 12.0;
+	P.imx = 1 / (m - x); P.xmx = x / (m - x);
+	for(int wi = 0; wi < 3; wi++) {
+		int W = 64 >> wi;
+		RootTpl &R = P.root[wi];
+		memset(&R, 0, sizeof(R));
+		for(int i = 0; i < W / 2; i++) {
+			int lo = W / 2 - 1 - i, hi = W / 2 + i;
+			uint8_t dh_lo = (uint8_t)(ofs + g.gap_h(i * 2 + 1) - g.gap_h(i * 2));
+			uint8_t dh_hi = (uint8_t)(ofs + M + g.gap_v(i * 2 + 1) - g.gap_v((i + 1) * 2));
+			uint8_t dv_lo = (uint8_t)(ofs + M + g.gap_h(i * 2 + 1) - g.gap_h((i + 1) * 2));
+			uint8_t dv_hi = (uint8_t)(ofs + g.gap_v(i * 2 + 1) - g.gap_v(i * 2));
+			R.dh[lo] = (int8_t)(uint8_t)(0 - dh_lo); R.dh[hi] = (int8_t)(uint8_t)(0 - dh_hi);		/* dh is kept negated */
+			R.dv[lo] = (int8_t)dv_lo; R.dv[hi] = (int8_t)dv_hi;
+			R.de[lo] = (int8_t)(uint8_t)(p->gi + dv_lo + g.gap_e(i * 2 + 1) - g.gap_h(i * 2 + 1));
+			R.de[hi] = (int8_t)(uint8_t)(p->gi + dv_hi - p->gi);
+			R.df[lo] = (int8_t)(uint8_t)(p->gi + dh_lo - p->gi);
+			R.df[hi] = (int8_t)(uint8_t)(p->gi + dh_hi + g.gap_e(i * 2 + 1) - g.gap_v(i * 2 + 1));
+			R.md[lo] = (int16_t)(-(i + 1) * M + g.gap_h(i * 2 + 1));
+			R.md[hi] = (int16_t)(-(i + 1) * M + g.gap_v(i * 2 + 1));
+		}
+		R.init_max = -(M + g.gap_h(1));
+		R.mdrop = (int16_t)(R.init_max - 128);
+	}
+}
+
+inline uint64_t rd64(const uint8_t *p) { uint64_t v; memcpy(&v, p, 8); return v; }
+inline uint32_t rd32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
+inline uint16_t rd16(const uint8_t *p) { uint16_t v; memcpy(&v, p, 2); return v; }
+}  // namespace
+
+#define CK(call) do { if(!RT_OK(call)) { g_err = std::string(#call) + ": " + RT_ERRSTR(); return MAB_ENODEV; } } while(0)
+#define CKP(call) do { if(!RT_OK(call)) { g_err = std::string(#call) + ": " + RT_ERRSTR(); mab_destroy(ctx); return nullptr; } } while(0)
+
+extern "C" mab_ctx *mab_init(const void *mai_blob, uint64_t size, const mab_params_t *params, int device)
+{
+	if(mai_blob == nullptr || size < 64 || params == nullptr) { g_err = "mab_init: bad arguments"; return nullptr; }
+	if(check_params(params) != 0) { g_err = "mab_init: unsupported scoring parameters (combined gap model with validated ranges only)"; return nullptr; }
+	mab_ctx *ctx = new mab_ctx();
+	ctx->device = device; ctx->prm = *params;
+	memset(&ctx->stats, 0, sizeof(ctx->stats));
+	if(!RT_OK(RT_SET_DEVICE(device))) { g_err = std::string("no usable CUDA device: ") + RT_ERRSTR(); delete ctx; return nullptr; }
+	ctx->n_sm = RT_SM_COUNT(device);
+	const uint8_t *b = (const uint8_t *)mai_blob;
+	ctx->blob.assign(b, b + size);
+	DevParams &P = ctx->P;
+	memset(&P, 0, sizeof(P));
+	P.bkt_ofs = rd64(b); P.bkt_mask = rd64(b + 8);
+	P.b = b[16]; P.w = b[17]; P.k = b[18]; P.n_occ = b[19];
+	for(int i = 0; i < 7; i++) { P.occ[i] = rd32(b + 20 + 4 * i); }
+	P.n_ref = rd32(b + 48); P.seq_ofs = rd64(b + 56);
+	if(P.n_occ == 0 || P.n_occ > 7 || P.w == 0 || P.w >= 32 || P.k == 0 || P.k > 31 || P.bkt_ofs >= size || P.seq_ofs >= size) { g_err = "mab_init: malformed index image"; delete ctx; return nullptr; }
+	P.twlen = (uint32_t)((params->wlen << 1) - params->wlen); P.tglen = (uint32_t)((params->glen << 1) - params->glen);
+	P.min_score = params->min_score; P.min_ratio = params->min_ratio;
+	double mc = 0.0, xc = 0.0;																/* minialign.c:4676-4681 */
+	for(int i = 0; i < 16; i++) { if((i & 3) == (i >> 3)) { mc += params->score_matrix[0]; } else { xc += params->score_matrix[0]; } }
+	P.mcoef = mc / 4.0; ctx->xcoef = xc / 12.0;
+	init_gaba_consts(P, params);
+	CKP(RT_MALLOC(&ctx->d_idx, size + 256));
+	CKP(RT_MEMCPY_H2D(ctx->d_idx, b, size));
+	P.idx = ctx->d_idx;
+	uint8_t nt[128]; memset(nt, 4, sizeof(nt));
+	CKP(RT_MALLOC(&ctx->d_ntail, 256));
+	CKP(RT_MEMCPY_H2D(ctx->d_ntail, nt, 128));
+	CKP(RT_MALLOC(&ctx->d_ctr, sizeof(BatchCounters)));
+	CKP(RT_STREAM_CREATE(&ctx->stream));
+	for(int i = 0; i < 8; i++) { CKP(RT_EVENT_CREATE(&ctx->ev[i])); }
+	ctx->n_slots = RT_EXTEND_SLOTS(ctx->n_sm);
+	return ctx;
+}
+
+extern "C" void mab_destroy(mab_ctx *ctx)
+{
+	if(ctx == nullptr) { return; }
+	RT_FREE(ctx->d_idx); RT_FREE(ctx->d_ntail); RT_FREE(ctx->d_ctr); RT_FREE(ctx->d_seq); RT_FREE(ctx->d_reads); RT_FREE(ctx->d_ws);
+	RT_FREE(ctx->d_frames); RT_FREE(ctx->d_arenas); RT_FREE(ctx->d_pool);
+	delete ctx;
+}
+
+extern "C" uint32_t mab_n_ref(const mab_ctx *ctx) { return ctx->P.n_ref; }
+extern "C" int mab_ref_info(const mab_ctx *ctx, uint32_t rid, const char **name, uint32_t *l_name, uint32_t *l_seq, const uint8_t **seq)
+{
+	if(rid >= ctx->P.n_ref) { return MAB_EINVAL; }
+	const uint8_t *b = ctx->blob.data(), *s = b + ctx->P.seq_ofs + 24ull * rid;
+	if(seq) { *seq = b + rd64(s); }
+	if(name) { *name = (const char *)(b + rd64(s + 8)); }
+	if(l_seq) { *l_seq = rd32(s + 16); }
+	if(l_name) { *l_name = rd16(s + 20); }
+	return MAB_OK;
+}
+extern "C" int mab_index_params(const mab_ctx *ctx, uint32_t *k, uint32_t *w, uint32_t *b, uint32_t *n_occ, uint32_t *occ)
+{
+	if(k) { *k = ctx->P.k; } if(w) { *w = ctx->P.w; } if(b) { *b = ctx->P.b; } if(n_occ) { *n_occ = ctx->P.n_occ; }
+	if(occ) { for(int i = 0; i < 7; i++) { occ[i] = ctx->P.occ[i]; } }
+	return MAB_OK;
+}
+extern "C" int mab_set_device_input(mab_ctx *ctx, int on) { ctx->device_input = on; return MAB_OK; }
+extern "C" int mab_last_stats(const mab_ctx *ctx, mab_stats_t *out) { *out = ctx->stats; return MAB_OK; }
+
+template <class T> static int grow(T **p, uint64_t *cap, uint64_t need_bytes)
+{
+	if(need_bytes <= *cap && *p != nullptr) { return MAB_OK; }
+	RT_FREE(*p); *p = nullptr;
+	uint64_t nb = need_bytes + need_bytes / 4 + 4096;
+	if(!RT_OK(RT_MALLOC(p, nb))) { g_err = std::string("device allocation failed: ") + RT_ERRSTR(); *cap = 0; return MAB_ENOMEM; }
+	*cap = nb;
+	return MAB_OK;
+}
+
+/* ---------------------------------------------------------------- host post-processing (minialign.c:4175-4396) */
+namespace {
+/* the reference's radix_sort_64x on {score, idx} pairs: same unstable algorithm as on the device (ksort.h:82-131) */
+void rs_insertion64(uint32_t *a, uint32_t n)
+{
+	for(uint32_t i = 1; i < n; i++) {
+		if(a[2 * i] < a[2 * (i - 1)]) {
+			uint32_t t0 = a[2 * i], t1 = a[2 * i + 1], j;
+			for(j = i; j > 0 && t0 < a[2 * (j - 1)]; j--) { a[2 * j] = a[2 * (j - 1)]; a[2 * j + 1] = a[2 * (j - 1) + 1]; }
+			a[2 * j] = t0; a[2 * j + 1] = t1;
+		}
+	}
+}
+void rs_sort64(uint32_t *a, uint32_t n, int s)
+{
+	uint32_t head[256], end[256];
+	memset(end, 0, sizeof(end));
+	for(uint32_t i = 0; i < n; i++) { end[(a[2 * i] >> s) & 0xff]++; }
+	head[0] = 0;
+	for(int k = 1; k < 256; k++) { end[k] += end[k - 1]; head[k] = end[k - 1]; }
+	for(int k = 0; k < 256;) {
+		if(head[k] != end[k]) {
+			int l = (a[2 * head[k]] >> s) & 0xff;
+			if(l != k) {
+				uint32_t t0 = a[2 * head[k]], t1 = a[2 * head[k] + 1];
+				do {
+					uint32_t s0 = t0, s1 = t1; t0 = a[2 * head[l]]; t1 = a[2 * head[l] + 1]; a[2 * head[l]] = s0; a[2 * head[l] + 1] = s1; head[l]++;
+					l = (t0 >> s) & 0xff;
+				} while(l != k);
+				a[2 * head[k]] = t0; a[2 * head[k] + 1] = t1; head[k]++;
+			} else { head[k]++; }
+		} else { k++; }
+	}
+	if(s) {
+		s = s > 8 ? s - 8 : 0;
+		uint32_t beg = 0;
+		for(int k = 0; k < 256; k++) {
+			uint32_t sz = end[k] - beg;
+			if(sz > 64) { rs_sort64(a + 2 * beg, sz, s); } else if(sz > 1) { rs_insertion64(a + 2 * beg, sz); }
+			beg = end[k];
+		}
+	}
+}
+void radix_sort_64x(uint32_t *a, uint32_t n) { if(n <= 64) { rs_insertion64(a, n); } else { rs_sort64(a, n, 24); } }
+
+struct HRes { uint32_t score, n_aln, plen, lb, ub; const uint32_t *alns; };		/* alns: n_aln x (lo, hi) pool offsets */
+
+inline int32_t SC(uint32_t x) { return (int32_t)0x40000000 - (int32_t)x; }
+inline uint32_t clip_mapq(double x) { uint32_t v = (uint32_t)x; return std::min(v, 60u * 16); }
+}  // namespace
+
+/* sort, prune, supplementary/secondary split, MAPQ, pack into the flat layout */
+static void post_process(mab_ctx *ctx, const uint32_t *pool, const uint32_t *rec, std::vector<uint32_t> &out)
+{
+	uint32_t n_res = rec[0];
+	std::vector<HRes> bins(n_res);
+	std::vector<uint32_t> res(2 * (size_t)n_res);
+	const uint32_t *p = rec + 1;
+	for(uint32_t i = 0; i < n_res; i++) {
+		bins[i].score = p[0]; bins[i].n_aln = p[1]; bins[i].plen = p[2]; bins[i].lb = p[3]; bins[i].ub = p[4]; bins[i].alns = p + 5;
+		res[2 * i] = p[0]; res[2 * i + 1] = i;
+		p += 5 + 2 * (size_t)p[1];
+	}
+	radix_sort_64x(res.data(), n_res);															/* minialign.c:4452 */
+	/* mm_prune_regs (4185-4207) */
+	uint32_t q = n_res;
+	uint32_t minv = (uint32_t)SC((uint32_t)(SC(res[0]) * ctx->prm.min_ratio));
+	while(res[2 * --q] > minv) {}
+	n_res = q + 1;
+	/* mm_collect_supp (4214-4263) */
+	auto swap_res = [&](uint64_t x, uint64_t y) { std::swap(res[2 * x], res[2 * y]); std::swap(res[2 * x + 1], res[2 * y + 1]); };
+	uint64_t pp, qq;
+	for(pp = 1, qq = n_res; pp < qq; pp++) {
+		uint64_t mx = 0;
+		for(uint64_t i = pp; i < qq; i++) {
+			const HRes &s = bins[res[2 * i + 1]];
+			int64_t lb = s.lb, ub = s.ub, span = ub - lb;
+			bool covered = false;
+			for(uint64_t j = 0; j < pp; j++) {
+				const HRes &t = bins[res[2 * j + 1]];
+				if(t.ub < ub) { lb = std::max(lb, (int64_t)t.ub); } else { ub = std::min(ub, (int64_t)t.lb); }
+				if(1.2 * (ub - lb) < span) { qq--; swap_res(i, qq); i--; covered = true; break; }
+			}
+			if(covered) { continue; }
+			mx = std::max(mx, ((uint64_t)(2 * (ub - lb) - span) << 32) | i);
+		}
+		if(mx & 0xffffffff) { swap_res(pp, mx & 0xffffffff); }
+	}
+	uint64_t n_uniq = std::min(pp, qq);
+	/* mm_post_map (4270-4325) */
+	auto aln_at = [&](const HRes &h, uint32_t j) { return pool + ((uint64_t)h.alns[2 * j] | (uint64_t)h.alns[2 * j + 1] << 32); };
+	int64_t usc = 0, lsc = INT64_MAX, tsc = 0;
+	for(uint64_t i = n_uniq; i < n_res; i++) { usc = std::max(usc, (int64_t)SC(res[2 * i])); lsc = std::min(lsc, (int64_t)SC(res[2 * i])); tsc += SC(res[2 * i]); }
+	lsc = (lsc == INT32_MAX) ? 0 : lsc;
+	double tpc = 1.0, x = ctx->xcoef, mxc = ctx->P.mcoef + ctx->xcoef;
+	std::vector<uint32_t> mapq(bins.size(), 0);
+	for(uint64_t i = 0; i < n_uniq; i++) {
+		uint32_t score = (uint32_t)SC(res[2 * i]); const HRes &h = bins[res[2 * i + 1]];
+		double pid = 0.0; uint64_t len = 0;
+		for(uint32_t j = 0; j < h.n_aln; j++) {
+			const uint32_t *a = aln_at(h, j);
+			double identity; uint64_t ib = (uint64_t)a[2] | (uint64_t)a[3] << 32; memcpy(&identity, &ib, 8);
+			len += a[8]; pid += (double)a[8] * identity;
+		}
+		pid /= (double)len;
+		double ec = 2.0 / (pid * mxc - x);
+		double ulen = ec * std::max((int64_t)score - usc, (int64_t)0), pe = 1.0 / (ulen * ulen + 1);
+		mapq[res[2 * i + 1]] = clip_mapq(-10.0 * 16 * log10(pe));
+		tpc *= 1.0 - pe;
+	}
+	double tpe = std::min(1.0 - tpc, 1.0);
+	for(uint64_t i = n_uniq; i < n_res; i++) {
+		mapq[res[2 * i + 1]] = clip_mapq(-10.0 * 16 * log10(1.0 - tpe * (double)(res[2 * i] - lsc + 1) / (double)tsc));
+	}
+	/* mm_pack_reg (4364-4396) into the flat layout */
+	size_t base = out.size();
+	out.push_back(0); out.push_back(0);
+	uint32_t cnt = 0, uniq = 0;
+	for(uint64_t i = 0; i < n_res; i++) {
+		const HRes &h = bins[res[2 * i + 1]];
+		for(uint32_t j = 0; j < h.n_aln; j++) {
+			const uint32_t *a = aln_at(h, j);
+			uint32_t slen = a[7], npw = a[9], sn = a[10];
+			for(int t = 0; t < 10; t++) { out.push_back(a[t]); }
+			out.push_back((uint32_t)i); out.push_back(mapq[res[2 * i + 1]]);
+			out.push_back(0); out.push_back(0); out.push_back(0); out.push_back(0);
+			const uint32_t *seg = a + MAB_ALN_HDR + 8ull * (sn - slen);
+			out.insert(out.end(), seg, seg + 8ull * slen);
+			const uint32_t *path = a + MAB_ALN_HDR + 8ull * sn;
+			out.insert(out.end(), path, path + npw);
+			cnt++;
+		}
+		if(i == n_uniq - 1) { uniq = cnt; }
+	}
+	out[base] = cnt; out[base + 1] = uniq;
+}
+
+/* ---------------------------------------------------------------- batch driver */
+static uint32_t dp_blk_cap(uint32_t maxlen) { return (uint32_t)((4ull * ((uint64_t)maxlen + 512)) / 32 + 64); }
+
+extern "C" int mab_map_batch(mab_ctx *ctx, const uint8_t *seq_block, uint64_t block_size, const uint64_t *seq_ofs, const uint32_t *seq_len, uint32_t n_seq)
+{
+	const DevParams &P = ctx->P;
+	mab_stats_t &S = ctx->stats;
+	memset(&S, 0, sizeof(S));
+	ctx->res_words.clear(); ctx->res_ofs.assign((size_t)n_seq + 1, 0);
+	if(n_seq == 0) { return MAB_OK; }
+	CK(RT_SET_DEVICE(ctx->device));
+	RT_EVENT_RECORD(ctx->ev[0], ctx->stream);
+	/* 1. reads to HBM */
+	const uint8_t *d_base;
+	if(ctx->device_input) { d_base = seq_block; }
+	else {
+		int rc = grow(&ctx->d_seq, &ctx->seq_cap, block_size + 256); if(rc) { return rc; }
+		CK(RT_MEMCPY_H2D_ASYNC(ctx->d_seq, seq_block, block_size, ctx->stream));
+		d_base = ctx->d_seq; S.h2d_bytes += block_size;
+	}
+	std::vector<ReadRec> &hr = ctx->h_reads;
+	hr.assign(n_seq, ReadRec());
+	uint32_t maxlen = 0; uint64_t tot_len = 0;
+	for(uint32_t i = 0; i < n_seq; i++) { memset(&hr[i], 0, sizeof(ReadRec)); hr[i].seq_ofs = seq_ofs[i]; hr[i].len = seq_len[i]; maxlen = std::max(maxlen, seq_len[i]); tot_len += seq_len[i]; }
+	{ int rc = grow(&ctx->d_reads, &ctx->reads_cap, sizeof(ReadRec) * (uint64_t)n_seq); if(rc) { return rc; } }
+	CK(RT_MEMCPY_H2D_ASYNC(ctx->d_reads, hr.data(), sizeof(ReadRec) * (uint64_t)n_seq, ctx->stream));
+	S.h2d_bytes += sizeof(ReadRec) * (uint64_t)n_seq;
+	RT_EVENT_RECORD(ctx->ev[1], ctx->stream);
+	/* 2. count pass, workspace sizing */
+	uint32_t seed_ctas = std::min<uint32_t>((n_seq + MAB_WARPS_PER_CTA - 1) / MAB_WARPS_PER_CTA, ctx->n_sm * 8);
+	RT_LAUNCH((k_seed<true>), seed_ctas, 32 * MAB_WARPS_PER_CTA, 512 * MAB_WARPS_PER_CTA, ctx->stream, P, d_base, ctx->d_reads, n_seq, (uint8_t *)nullptr);
+	S.n_launches++;
+	CK(RT_MEMCPY_D2H_ASYNC(hr.data(), ctx->d_reads, sizeof(ReadRec) * (uint64_t)n_seq, ctx->stream));
+	CK(RT_STREAM_SYNC(ctx->stream));
+	S.d2h_bytes += sizeof(ReadRec) * (uint64_t)n_seq;
+	uint64_t ws_total = 0;
+	for(uint32_t i = 0; i < n_seq; i++) {
+		ReadRec &r = hr[i];
+		if(r.state != 0) { continue; }
+		r.seed_cap = 2 * (r.tot_seeds + 1) + 8; r.root_cap = r.tot_seeds + 8; r.resc_cap = r.tot_resc + 4; r.bin_cap = 2 * r.tot_seeds + 128;
+		r.ws_ofs = ws_total;
+		ws_total += ws_layout(r.seed_cap, r.root_cap, r.resc_cap, r.bin_cap).total;
+	}
+	{ int rc = grow(&ctx->d_ws, &ctx->ws_cap, ws_total + 256); if(rc) { return rc; } }
+	{ int rc = grow(&ctx->d_frames, &ctx->frames_cap, 4ull * 8 * MAB_RS_FRAME * n_seq); if(rc) { return rc; } }
+	uint32_t blk_cap = dp_blk_cap(maxlen);
+	ArenaLayout AL = arena_layout(blk_cap);
+	uint32_t ext_ctas = std::max<uint32_t>(1, std::min<uint32_t>(ctx->n_slots / MAB_WARPS_PER_CTA, (n_seq + MAB_WARPS_PER_CTA - 1) / MAB_WARPS_PER_CTA));
+	{ int rc = grow(&ctx->d_arenas, &ctx->arenas_cap, AL.total * (uint64_t)ext_ctas * MAB_WARPS_PER_CTA); if(rc) { return rc; } }
+	uint64_t pool_need = tot_len / 4 + 64ull * n_seq + (1u << 16);				/* ~2 bits per base and alignment, x4 head room */
+	int rc_final = MAB_OK;
+	for(int attempt = 0; attempt < 3; attempt++) {
+		{ int rc = grow(&ctx->d_pool, &ctx->pool_cap, 4 * pool_need); if(rc) { return rc; } }
+		uint64_t pool_words = ctx->pool_cap / 4;
+		CK(RT_MEMCPY_H2D_ASYNC(ctx->d_reads, hr.data(), sizeof(ReadRec) * (uint64_t)n_seq, ctx->stream));
+		BatchCounters zero; memset(&zero, 0, sizeof(zero));
+		CK(RT_MEMCPY_H2D_ASYNC(ctx->d_ctr, &zero, sizeof(zero), ctx->stream));
+		RT_EVENT_RECORD(ctx->ev[2], ctx->stream);
+		/* 3. seeds */
+		RT_LAUNCH((k_seed<false>), seed_ctas, 32 * MAB_WARPS_PER_CTA, 512 * MAB_WARPS_PER_CTA, ctx->stream, P, d_base, ctx->d_reads, n_seq, ctx->d_ws);
+		S.n_launches++;
+		RT_EVENT_RECORD(ctx->ev[3], ctx->stream);
+		/* 4. rounds of sort+chain / extend (minialign.c:4444-4448) */
+		for(uint32_t round = 0; round < P.n_occ; round++) {
+			RT_LAUNCH(k_sortchain, (n_seq + 63) / 64, 64, 0, ctx->stream, P, ctx->d_reads, n_seq, ctx->d_ws, ctx->d_frames, round);
+			RT_MEMSET_ASYNC(&ctx->d_ctr->work_next, 0, sizeof(unsigned int), ctx->stream);
+			RT_LAUNCH(k_extend, ext_ctas, 32 * MAB_WARPS_PER_CTA, 1024 + 1024 * MAB_WARPS_PER_CTA, ctx->stream, P, d_base, ctx->d_ntail, ctx->d_reads, n_seq, ctx->d_ws,
+				ctx->d_arenas, AL.total, blk_cap, ctx->d_pool, pool_words, ctx->d_ctr, round, P.n_occ - 1);
+			S.n_launches += 2;
+		}
+		RT_EVENT_RECORD(ctx->ev[4], ctx->stream);
+		/* 5. results back */
+		BatchCounters hc;
+		CK(RT_MEMCPY_D2H_ASYNC(&hc, ctx->d_ctr, sizeof(hc), ctx->stream));
+		CK(RT_MEMCPY_D2H_ASYNC(hr.data(), ctx->d_reads, sizeof(ReadRec) * (uint64_t)n_seq, ctx->stream));
+		CK(RT_STREAM_SYNC(ctx->stream));
+		uint32_t err = 0;
+		for(uint32_t i = 0; i < n_seq; i++) { err |= hr[i].err; }
+		S.n_vectors = hc.n_vectors; S.n_fill_calls = hc.n_fill; S.n_trace = hc.n_trace;
+		if((err & MAB_ERR_POOL_OVF) || hc.pool_top > pool_words) {
+			pool_need *= 4; S.n_retry++;
+			for(uint32_t i = 0; i < n_seq; i++) { ReadRec &r = hr[i]; if(r.len >= P.k && (double)r.len * P.mcoef >= (double)P.min_score) { r.state = 0; } r.err = 0; r.result_words = 0; r.n_res = 0; r.nbin = 0; }
+			rc_final = MAB_EOVERFLOW;
+			continue;
+		}
+		if(err) { g_err = "device workspace overflow (error bits " + std::to_string(err) + ")"; return MAB_EOVERFLOW; }
+		uint64_t top = hc.pool_top;
+		ctx->h_pool.resize((size_t)top + 4);
+		if(top) { CK(RT_MEMCPY_D2H_ASYNC(ctx->h_pool.data(), ctx->d_pool, 4 * top, ctx->stream)); }
+		RT_EVENT_RECORD(ctx->ev[5], ctx->stream);
+		CK(RT_STREAM_SYNC(ctx->stream));
+		S.d2h_bytes += 4 * top + sizeof(ReadRec) * (uint64_t)n_seq + sizeof(hc);
+		rc_final = MAB_OK;
+		break;
+	}
+	if(rc_final != MAB_OK) { g_err = "result pool overflow after retries"; return rc_final; }
+	/* 6. host post-processing */
+	double t0 = RT_WALL_MS();
+	for(uint32_t i = 0; i < n_seq; i++) {
+		ctx->res_ofs[i] = ctx->res_words.size();
+		if(hr[i].result_words != 0) { post_process(ctx, ctx->h_pool.data(), ctx->h_pool.data() + hr[i].result_ofs, ctx->res_words); }
+	}
+	ctx->res_ofs[n_seq] = ctx->res_words.size();
+	S.ms_post = (float)(RT_WALL_MS() - t0);
+	S.ms_h2d = RT_EVENT_MS(ctx->ev[0], ctx->ev[1]);
+	S.ms_seed = RT_EVENT_MS(ctx->ev[2], ctx->ev[3]);
+	S.ms_extend = RT_EVENT_MS(ctx->ev[3], ctx->ev[4]);
+	S.ms_d2h = RT_EVENT_MS(ctx->ev[4], ctx->ev[5]);
+	S.ms_total = RT_EVENT_MS(ctx->ev[0], ctx->ev[5]);
+	return MAB_OK;
+}
+
+extern "C" uint64_t mab_result(const mab_ctx *ctx, uint32_t i, const uint32_t **words)
+{
+	if((size_t)i + 1 >= ctx->res_ofs.size()) { return 0; }
+	uint64_t n = ctx->res_ofs[i + 1] - ctx->res_ofs[i];
+	if(words) { *words = n ? ctx->res_words.data() + ctx->res_ofs[i] : nullptr; }
+	return n;
+}
+extern "C" void mab_release_batch(mab_ctx *ctx) { ctx->res_words.clear(); ctx->res_ofs.clear(); }
+
+/* ---------------------------------------------------------------- stage-level entry points */
+extern "C" uint64_t mab_sketch(mab_ctx *ctx, const uint8_t *seq, uint32_t len, uint64_t *out, uint64_t cap)
+{
+	uint8_t *d_seq = nullptr; uint64_t *d_out = nullptr, *d_n = nullptr;
+	uint64_t n = 0, dcap = (uint64_t)len + 8;
+	if(!RT_OK(RT_MALLOC(&d_seq, (uint64_t)len + 64)) || !RT_OK(RT_MALLOC(&d_out, 8 * dcap)) || !RT_OK(RT_MALLOC(&d_n, 8))) { return 0; }
+	RT_MEMCPY_H2D(d_seq, seq, len);
+	RT_LAUNCH(k_sketch_words, 1, 32, 512, ctx->stream, ctx->P, (const uint8_t *)d_seq, len, d_out, dcap, d_n);
+	RT_STREAM_SYNC(ctx->stream);
+	RT_MEMCPY_D2H(&n, d_n, 8);
+	if(n <= cap) { RT_MEMCPY_D2H(out, d_out, 8 * n); }
+	RT_FREE(d_seq); RT_FREE(d_out); RT_FREE(d_n);
+	return n;
+}
+
+extern "C" uint64_t mab_seed_chain(mab_ctx *ctx, const uint8_t *seq, uint32_t len, uint32_t round,
+	uint32_t *seeds, uint64_t seed_cap, uint64_t *n_total, uint32_t *roots, uint64_t root_cap, uint64_t *n_root)
+{
+	const DevParams &P = ctx->P;
+	*n_total = 0; *n_root = 0;
+	uint8_t *d_seq = nullptr; ReadRec *d_r = nullptr; uint8_t *d_ws = nullptr; uint32_t *d_fr = nullptr;
+	if(!RT_OK(RT_MALLOC(&d_seq, (uint64_t)len + 256)) || !RT_OK(RT_MALLOC(&d_r, sizeof(ReadRec))) || !RT_OK(RT_MALLOC(&d_fr, 4ull * 8 * MAB_RS_FRAME))) { return 0; }
+	RT_MEMCPY_H2D(d_seq, seq, len);
+	ReadRec r; memset(&r, 0, sizeof(r)); r.len = len;
+	RT_MEMCPY_H2D(d_r, &r, sizeof(r));
+	RT_LAUNCH((k_seed<true>), 1, 32, 512, ctx->stream, P, (const uint8_t *)d_seq, d_r, 1u, (uint8_t *)nullptr);
+	RT_STREAM_SYNC(ctx->stream);
+	RT_MEMCPY_D2H(&r, d_r, sizeof(r));
+	uint64_t ns = 0;
+	if(r.state == 0) {
+		r.seed_cap = 2 * (r.tot_seeds + 1) + 8; r.root_cap = r.tot_seeds + 8; r.resc_cap = r.tot_resc + 4; r.bin_cap = 2 * r.tot_seeds + 128; r.ws_ofs = 0;
+		WsLayout L = ws_layout(r.seed_cap, r.root_cap, r.resc_cap, r.bin_cap);
+		RT_MALLOC(&d_ws, L.total + 256);
+		RT_MEMCPY_H2D(d_r, &r, sizeof(r));
+		RT_LAUNCH((k_seed<false>), 1, 32, 512, ctx->stream, P, (const uint8_t *)d_seq, d_r, 1u, d_ws);
+		for(uint32_t i = 0; i <= round && i < P.n_occ; i++) { RT_LAUNCH(k_sortchain, 1, 32, 0, ctx->stream, P, d_r, 1u, d_ws, d_fr, i); }
+		RT_STREAM_SYNC(ctx->stream);
+		RT_MEMCPY_D2H(&r, d_r, sizeof(r));
+		if(r.n_seed) {
+			ns = r.n_seed; *n_total = r.seed_n; *n_root = r.n_root;
+			if(r.seed_n <= seed_cap) { RT_MEMCPY_D2H(seeds, d_ws + L.seed, 16ull * r.seed_n); }
+			if(r.n_root && r.n_root <= root_cap) { RT_MEMCPY_D2H(roots, d_ws + L.root, 8ull * r.n_root); }
+		}
+		RT_FREE(d_ws);
+	}
+	RT_FREE(d_seq); RT_FREE(d_r); RT_FREE(d_fr);
+	return ns;
+}
+
+extern "C" int mab_extend_pairs(mab_ctx *ctx, const uint8_t *seq_block, uint64_t block_size, const mab_pair_t *pairs, uint32_t n,
+	uint32_t *res, uint32_t *aln_out, uint64_t aln_cap, uint64_t *aln_ofs)
+{
+	const DevParams &P = ctx->P;
+	if(n == 0) { aln_ofs[0] = 0; return MAB_OK; }
+	uint32_t maxlen = 0; uint64_t tot = 0;
+	for(uint32_t i = 0; i < n; i++) { maxlen = std::max(maxlen, std::max(pairs[i].alen, pairs[i].blen)); tot += pairs[i].alen + pairs[i].blen; }
+	uint32_t blk_cap = dp_blk_cap(maxlen);
+	ArenaLayout AL = arena_layout(blk_cap);
+	uint32_t ctas = std::max<uint32_t>(1, std::min<uint32_t>(ctx->n_slots / MAB_WARPS_PER_CTA, (n + MAB_WARPS_PER_CTA - 1) / MAB_WARPS_PER_CTA));
+	uint64_t pool_words = tot / 2 + 256ull * n + 4096;
+	uint8_t *d_seq = nullptr, *d_ar = nullptr; PairIn *d_p = nullptr; uint32_t *d_res = nullptr, *d_pool = nullptr; uint64_t *d_ao = nullptr;
+	static_assert(sizeof(PairIn) == sizeof(mab_pair_t), "pair layout");
+	CK(RT_MALLOC(&d_seq, block_size + 256)); CK(RT_MALLOC(&d_ar, AL.total * (uint64_t)ctas * MAB_WARPS_PER_CTA)); CK(RT_MALLOC(&d_p, sizeof(PairIn) * (uint64_t)n));
+	CK(RT_MALLOC(&d_res, 64ull * n)); CK(RT_MALLOC(&d_pool, 4 * pool_words)); CK(RT_MALLOC(&d_ao, 8ull * n));
+	CK(RT_MEMCPY_H2D(d_seq, seq_block, block_size)); CK(RT_MEMCPY_H2D(d_p, pairs, sizeof(PairIn) * (uint64_t)n));
+	BatchCounters zero; memset(&zero, 0, sizeof(zero));
+	CK(RT_MEMCPY_H2D(ctx->d_ctr, &zero, sizeof(zero)));
+	RT_LAUNCH(k_extend_pairs, ctas, 32 * MAB_WARPS_PER_CTA, 1024 + 1024 * MAB_WARPS_PER_CTA, ctx->stream, P, (const uint8_t *)d_seq, (const uint8_t *)ctx->d_ntail, (const PairIn *)d_p, n, d_res, d_ao,
+		d_ar, AL.total, blk_cap, d_pool, pool_words, ctx->d_ctr);
+	CK(RT_STREAM_SYNC(ctx->stream));
+	BatchCounters hc; CK(RT_MEMCPY_D2H(&hc, ctx->d_ctr, sizeof(hc)));
+	std::vector<uint32_t> pool((size_t)std::min<uint64_t>(hc.pool_top, pool_words) + 4);
+	std::vector<uint64_t> ao(n);
+	CK(RT_MEMCPY_D2H(res, d_res, 64ull * n)); CK(RT_MEMCPY_D2H(ao.data(), d_ao, 8ull * n));
+	if(hc.pool_top) { CK(RT_MEMCPY_D2H(pool.data(), d_pool, 4 * std::min<uint64_t>(hc.pool_top, pool_words))); }
+	ctx->stats.n_vectors = hc.n_vectors;
+	uint64_t o = 0;
+	int rc = (hc.err_any || hc.pool_top > pool_words) ? MAB_EOVERFLOW : MAB_OK;
+	for(uint32_t i = 0; i < n; i++) {
+		aln_ofs[i] = o;
+		if(ao[i] == 0xffffffffffffffffull || rc != MAB_OK) { continue; }
+		const uint32_t *a = pool.data() + ao[i];
+		uint32_t slen = a[7], npw = a[9], sn = a[10];
+		uint64_t need = 16 + 8ull * slen + npw;
+		if(o + need > aln_cap) { rc = MAB_ENOMEM; break; }
+		uint32_t *w = aln_out + o;
+		for(int t = 0; t < 10; t++) { w[t] = a[t]; }
+		for(int t = 10; t < 16; t++) { w[t] = 0; }
+		memcpy(w + 16, a + MAB_ALN_HDR + 8ull * (sn - slen), 32ull * slen);
+		memcpy(w + 16 + 8ull * slen, a + MAB_ALN_HDR + 8ull * sn, 4ull * npw);
+		o += need;
+	}
+	aln_ofs[n] = o;
+	RT_FREE(d_seq); RT_FREE(d_ar); RT_FREE(d_p); RT_FREE(d_res); RT_FREE(d_pool); RT_FREE(d_ao);
+	if(rc == MAB_EOVERFLOW) { g_err = "extend_pairs: device workspace overflow"; }
+	return rc;
+}

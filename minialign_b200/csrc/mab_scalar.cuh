@@ -1,0 +1,309 @@
+/*
+ * mab_scalar.cuh -- single-thread device routines of the mapper: index probe, exact radix sort, array chaining, the
+ * position hash.  These are the data-dependent, branchy parts of minialign's map.c (minialign.c:3171-4067); they run on
+ * one lane per read (thousands of reads in flight) because their control flow is strictly sequential per read and
+ * bit-exactness depends on reproducing it step by step.
+ */
+#pragma once
+#include "mab_types.h"
+
+namespace mab {
+
+#define MAB_OFS0 0x40000000u
+
+__device__ __forceinline__ uint64_t ldg64(const uint8_t *p) { return *(const uint64_t *)p; }
+__device__ __forceinline__ uint32_t ldg32(const uint8_t *p) { return *(const uint32_t *)p; }
+__device__ __forceinline__ uint16_t ldg16(const uint8_t *p) { return *(const uint16_t *)p; }
+
+/* reference sequence descriptor (mm_idx_seq_t, minialign.c:2464-2470) */
+struct RefSeq { const uint8_t *seq; uint32_t l_seq; uint32_t circular; };
+__device__ __forceinline__ RefSeq ref_seq(const DevParams &P, uint32_t rid)
+{
+	const uint8_t *s = P.idx + P.seq_ofs + 24ull * rid;
+	RefSeq r; r.seq = P.idx + ldg64(s); r.l_seq = ldg32(s + 16); r.circular = ldg16(s + 22);
+	return r;
+}
+
+/* CRC32C step of the minimizer hash (minialign.c:2353).  The same 64-bit word is both the seed (low half) and the data,
+ * so for k <= 16 the result is 0; the loop is only reached for k >= 17. */
+__device__ __forceinline__ uint32_t crc32c_u64(uint32_t crc, uint64_t data)
+{
+	if((uint32_t)data == crc && (data >> 32) == 0) { return 0; }
+	for(int i = 0; i < 64; i++) {
+		uint32_t bit = (crc ^ (uint32_t)(data >> i)) & 1u;
+		crc = (crc >> 1) ^ (0x82f63b78u & (0u - bit));
+	}
+	return crc;
+}
+
+/* mm_idx_get (minialign.c:2727-2748) + kh_get_ptr (634-643): 2-level probe.  Returns the occurrence array (8 B each)
+ * and n; the dependent loads are bucket header -> hash slot(s) -> value array. */
+__device__ __forceinline__ const uint8_t *idx_get(const DevParams &P, uint64_t minier, uint32_t *n)
+{
+	const uint8_t *bk = P.idx + P.bkt_ofs + 32ull * (minier & P.bkt_mask);
+	uint64_t hmask = ldg32(bk), a = ldg64(bk + 16), pofs = ldg64(bk + 24);
+	*n = 0;
+	if(a == 0) { return nullptr; }
+	uint64_t key = minier >> P.b, pos = key & hmask, kk;
+	const uint8_t *val = nullptr;
+	do {
+		const uint8_t *slot = P.idx + a + 16ull * pos;
+		kk = ldg64(slot);
+		if(kk == key) { val = slot + 8; break; }
+		pos = hmask & (pos + 1);
+	} while(kk + 1 != 0);
+	if(val == nullptr) { return nullptr; }
+	uint64_t v = ldg64(val);
+	if((int64_t)v >= 0) { *n = 1; return val; }
+	*n = (uint32_t)v;
+	return P.idx + pofs + 8ull * ((v >> 32) & 0x7fffffff);
+}
+
+/* ---------------------------------------------------------------- exact radix sort (ksort.h:82-131) */
+/* In-place American-flag sort on 8-bit digits, insertion sort at <= 64 elements.  The reference's sort is unstable and
+ * the order it leaves equal keys in is observable downstream (chaining walks the array in order), so the permutation
+ * cycles are followed in exactly the reference's order.  Iterative, with an explicit frame stack in `frames`
+ * (8 levels x 257 u32).  esz = element size in u32 words: 4 (key = words 1:0) or 2 (key = word 0). */
+__device__ __forceinline__ uint64_t rs_key(const uint32_t *e, int esz) { return esz == 4 ? ((uint64_t)e[1] << 32 | e[0]) : (uint64_t)e[0]; }
+
+__device__ inline void rs_copy(uint32_t *d, const uint32_t *s, int esz) { for(int i = 0; i < esz; i++) { d[i] = s[i]; } }
+
+__device__ inline void rs_insertion(uint32_t *a, uint32_t n, int esz)
+{
+	uint32_t tmp[4];
+	for(uint32_t i = 1; i < n; i++) {
+		if(rs_key(a + esz * i, esz) < rs_key(a + esz * (i - 1), esz)) {
+			rs_copy(tmp, a + esz * i, esz);
+			uint64_t tk = rs_key(tmp, esz);
+			uint32_t j;
+			for(j = i; j > 0 && tk < rs_key(a + esz * (j - 1), esz); j--) { rs_copy(a + esz * j, a + esz * (j - 1), esz); }
+			rs_copy(a + esz * j, tmp, esz);
+		}
+	}
+}
+
+/* frames: per level {beg, s, k, end[256]} as u32; at most 8 levels for a 64-bit key */
+#define MAB_RS_FRAME 260
+__device__ inline void radix_sort_exact(uint32_t *a, uint32_t n, int esz, uint32_t *frames)
+{
+	if(n <= 64) { rs_insertion(a, n, esz); return; }
+	int lvl = 0;
+	uint32_t *f = frames;
+	f[0] = 0; f[1] = (uint32_t)(esz == 4 ? 56 : 24); f[2] = 0xffffffffu; f[3] = n;		/* beg, s, k (unset), n */
+	while(lvl >= 0) {
+		f = frames + MAB_RS_FRAME * lvl;
+		uint32_t beg = f[0], s = f[1], cnt = f[3];
+		uint32_t *end = f + 4;
+		uint32_t *base = a + (uint64_t)esz * beg;
+		if(f[2] == 0xffffffffu) {
+			/* distribute this range by digit (s) */
+			uint32_t head[256];
+			for(int k = 0; k < 256; k++) { end[k] = 0; }
+			for(uint32_t i = 0; i < cnt; i++) { end[(rs_key(base + esz * i, esz) >> s) & 0xff]++; }
+			head[0] = 0;
+			for(int k = 1; k < 256; k++) { end[k] += end[k - 1]; head[k] = end[k - 1]; }
+			for(int k = 0; k < 256;) {
+				if(head[k] != end[k]) {
+					int l = (int)((rs_key(base + esz * head[k], esz) >> s) & 0xff);
+					if(l != k) {
+						uint32_t tmp[4], swp[4];
+						rs_copy(tmp, base + esz * head[k], esz);
+						do {
+							rs_copy(swp, tmp, esz); rs_copy(tmp, base + esz * head[l], esz); rs_copy(base + esz * head[l], swp, esz); head[l]++;
+							l = (int)((rs_key(tmp, esz) >> s) & 0xff);
+						} while(l != k);
+						rs_copy(base + esz * head[k], tmp, esz); head[k]++;
+					} else { head[k]++; }
+				} else { k++; }
+			}
+			if(s == 0) { lvl--; continue; }
+			f[2] = 0;
+		}
+		/* visit child buckets in order */
+		uint32_t ns = s > 8 ? s - 8 : 0;
+		int descended = 0;
+		while(f[2] < 256) {
+			uint32_t k = f[2]++;
+			uint32_t b0 = k == 0 ? 0 : end[k - 1], sz = end[k] - b0;
+			if(sz > 64) {
+				uint32_t *g = frames + MAB_RS_FRAME * (lvl + 1);
+				g[0] = beg + b0; g[1] = ns; g[2] = 0xffffffffu; g[3] = sz;
+				lvl++; descended = 1;
+				break;
+			} else if(sz > 1) {
+				rs_insertion(base + esz * b0, sz, esz);
+			}
+		}
+		if(!descended) { lvl--; }
+	}
+}
+
+/* ---------------------------------------------------------------- seeds and chaining (minialign.c:3340-3625) */
+__device__ __forceinline__ uint32_t u_of(uint32_t x, uint32_t y) { return ((x << 1) - y) + MAB_OFS0; }
+__device__ __forceinline__ uint32_t v_of(uint32_t x, uint32_t y) { return ((y << 1) - x) + MAB_OFS0; }
+__device__ __forceinline__ int32_t as_of(const uint32_t *s) { return (int32_t)(((s[0] - MAB_OFS0) << 1) + (s[2] - MAB_OFS0)) / 3; }
+__device__ __forceinline__ int32_t bs_of(const uint32_t *s) { return (int32_t)(((s[2] - MAB_OFS0) << 1) + (s[0] - MAB_OFS0)) / 3; }
+
+/* mm_expand (minialign.c:3420-3446) for one occurrence */
+__device__ __forceinline__ void make_seed(const DevParams &P, uint32_t *s, uint32_t rs, uint32_t rid, uint32_t qs)
+{
+	uint32_t rmask = 0u - (rid & 1);
+	uint32_t _rs = rs + (P.k & rmask), _qs = qs ^ rmask;
+	s[0] = u_of(_rs, _qs); s[1] = rid >> 1; s[2] = v_of(_rs, _qs); s[3] = 0x7fffffffu;
+}
+
+/* window vector lanes: (uub, rid, vub, vlb); position vector lanes: (upos, rid, vpos, vpos); signed compares
+ * (minialign.c:3372-3402) */
+struct V4 { int32_t l0, l1, l2, l3; };
+__device__ __forceinline__ V4 load_pv(const uint32_t *s) { V4 r; r.l0 = (int32_t)s[0]; r.l1 = (int32_t)s[1]; r.l2 = (int32_t)s[2]; r.l3 = (int32_t)s[2]; return r; }
+__device__ __forceinline__ V4 load_wv(const uint32_t *s, uint32_t len)
+{
+	V4 r = load_pv(s);
+	r.l0 = (int32_t)((uint32_t)r.l0 + len); r.l2 = (int32_t)((uint32_t)r.l2 + len);
+	return r;
+}
+__device__ __forceinline__ uint32_t inside_mask(const V4 &w, const V4 &d)
+{
+	return (d.l0 > w.l0 ? 0x000fu : 0) | (d.l1 > w.l1 ? 0x00f0u : 0) | (d.l2 > w.l2 ? 0x0f00u : 0) | (d.l3 > w.l3 ? 0xf000u : 0);
+}
+__device__ __forceinline__ bool inside_wv(const V4 &w, const V4 &d) { return inside_mask(w, d) == 0xf000u; }
+__device__ __forceinline__ bool inside_uub(const V4 &w, const V4 &d) { return (inside_mask(w, d) & 0xff) == 0; }
+__device__ __forceinline__ V4 update_wv(V4 w, const V4 &f)
+{
+	uint32_t d0 = (uint32_t)w.l0 - (uint32_t)f.l0, d2 = (uint32_t)w.l2 - (uint32_t)f.l2;
+	w.l0 = (int32_t)((uint32_t)w.l0 - d2); w.l2 = (int32_t)((uint32_t)w.l2 - d0);
+	return w;
+}
+__device__ __forceinline__ int32_t pdiff_wv(const V4 &w, const V4 &f)
+{
+	return (int32_t)(((uint32_t)w.l0 - (uint32_t)f.l0) + ((uint32_t)w.l2 - (uint32_t)f.l2));
+}
+
+/* mm_chain_seeds (minialign.c:3547-3625).  s = seed array ({upos, rid, vpos, lid} x n_seed, sentinel at n_seed, leaves
+ * appended behind it), c = root array ({plen, lid}).  Returns #chains, *seed_n = seeds + sentinel + leaves. */
+__device__ inline uint32_t chain_seeds(const DevParams &P, uint32_t *s, uint32_t n_seed, uint32_t *c, uint32_t *seed_n)
+{
+	uint32_t ncid = 0, nlid = n_seed + 1, nlsid = 0, tsid = n_seed;
+	while(nlsid < tsid) {
+		uint32_t lid = nlid++;
+		uint32_t *lf = s + 4ull * lid;							/* leaf: {rsid, rid, lsid, cid} */
+		lf[0] = nlsid; lf[2] = nlsid; lf[1] = s[4ull * nlsid + 1]; lf[3] = 0xffffffffu;
+		uint32_t plen = s[4ull * nlsid] + s[4ull * nlsid + 2], scnt = 1;
+		uint64_t nrsid = nlsid; nlsid = 0xffffffffu;
+		while(1) {
+			uint32_t rsid = (uint32_t)nrsid; nrsid = 0;
+			V4 wv = load_wv(s + 4ull * rsid, P.twlen);
+			for(uint32_t sid = rsid + 1; ; sid++) {
+				V4 fv = load_pv(s + 4ull * sid);
+				if(!inside_wv(wv, fv)) {
+					nlsid = nlsid < sid ? nlsid : sid;
+					if(inside_uub(wv, fv)) { continue; }
+					break;
+				}
+				wv = update_wv(wv, fv);
+				int64_t di = (int64_t)(((uint64_t)(int64_t)pdiff_wv(wv, fv) << 32) | sid);
+				nrsid = (uint64_t)((int64_t)nrsid > di ? (int64_t)nrsid : di);
+			}
+			if(nrsid == 0) { nrsid = rsid; break; }
+			if(s[4ull * (uint32_t)nrsid + 3] != 0x7fffffffu) { nrsid = (uint32_t)nrsid; break; }
+			s[4ull * (uint32_t)nrsid + 3] = lid; scnt++;
+			if((uint64_t)nlsid <= nrsid) { nlsid = 0xffffffffu; }
+		}
+		if(nrsid == lf[2]) { continue; }
+		uint32_t cid = 0xffffffffu;
+		if(s[4ull * nrsid + 3] < lid) {
+			nrsid = s[4ull * s[4ull * nrsid + 3] + 0];
+			cid = s[4ull * s[4ull * nrsid + 3] + 3];
+		}
+		if(cid == 0xffffffffu) { cid = ncid++; c[2ull * cid] = MAB_OFS0; c[2ull * cid + 1] = lid; }
+		lf[3] = cid; lf[0] = (uint32_t)nrsid;
+		uint32_t ps = s[4ull * nrsid] + s[4ull * nrsid + 2];
+		double frac = __dsub_rn(1.0, __ddiv_rn(1.0, (double)scnt));
+		double dl = __dmul_rn(frac, (double)(uint32_t)(ps - plen));
+		plen = (uint32_t)((int32_t)MAB_OFS0 - (int32_t)(uint32_t)(int64_t)__double2ll_rz(dl));
+		if(plen < c[2ull * cid]) { c[2ull * cid] = plen; c[2ull * cid + 1] = lid; }
+	}
+	*seed_n = nlid;
+	return ncid;
+}
+
+/* ---------------------------------------------------------------- position hash (kh_t, minialign.c:346-613) */
+#define MAB_KH_EMPTY	0xffffffffffffffffull
+#define MAB_KH_MOVED	0xfffffffffffffffeull
+#define MAB_KH_INIT		0xffffffffffffffffull
+
+__device__ inline void kh_reset(uint64_t *kh, ReadRec *r)								/* kh_clear (481-495) */
+{
+	r->kh_mask = 255; r->kh_cnt = 0; r->kh_ub = 102;									/* 256 * 0.4 */
+	for(uint32_t i = 0; i < 256; i++) { kh[2 * i] = MAB_KH_EMPTY; kh[2 * i + 1] = MAB_KH_INIT; }
+}
+
+__device__ inline uint64_t kh_poll(const uint64_t *a, uint64_t *pi, uint64_t b0, uint64_t mask)
+{
+	int64_t b = (int64_t)b0; uint64_t i = *pi, k1;
+	while(1) {
+		k1 = a[2 * i];
+		if(b <= (int64_t)(k1 & mask) + (int64_t)(k1 + 2 < 2)) { break; }
+		b -= (int64_t)((i + 1) & (mask + 1));
+		i = (i + 1) & mask;
+	}
+	*pi = i;
+	return k1;
+}
+
+/* kh_allocate (503-536): returns slot index, *isnew = 1 when a slot was taken */
+__device__ inline uint64_t kh_allocate(uint64_t *a, uint64_t k, uint64_t v, uint64_t mask, uint32_t *isnew)
+{
+	uint64_t i = k & mask, k0 = k, v0 = v;
+	uint64_t k1 = kh_poll(a, &i, i, mask);
+	if(k0 == k1) { *isnew = 0; return i; }
+	uint64_t j = i;
+	a[2 * i] = k0;
+	while(k1 + 2 >= 2) {
+		uint64_t v1 = a[2 * i + 1];
+		a[2 * i + 1] = v0;
+		k0 = k1; v0 = v1;
+		i = (i + 1) & mask;
+		k1 = kh_poll(a, &i, k0 & mask, mask);
+		a[2 * i] = k0;
+	}
+	a[2 * i + 1] = v0;
+	*isnew = 1;
+	return j;
+}
+
+__device__ inline int kh_extend(uint64_t *kh, ReadRec *r)								/* 543-579 */
+{
+	uint64_t prev_size = (uint64_t)r->kh_mask + 1, size = 2 * prev_size, mask = size - 1;
+	if(size > MAB_KH_CAP) { return -1; }
+	r->kh_mask = (uint32_t)mask; r->kh_ub = (uint32_t)((double)size * 0.4);
+	for(uint64_t i = 0; i < prev_size; i++) { kh[2 * (i + prev_size)] = MAB_KH_EMPTY; kh[2 * (i + prev_size) + 1] = MAB_KH_INIT; }
+	for(uint64_t i = 0; i < size; i++) {
+		uint64_t k = kh[2 * i];
+		if(k + 2 < 2 || (k & mask) == i) { continue; }
+		uint64_t v = kh[2 * i + 1];
+		kh[2 * i] = MAB_KH_MOVED; kh[2 * i + 1] = MAB_KH_INIT;
+		uint32_t dummy;
+		kh_allocate(kh, k, v, mask, &dummy);
+	}
+	return 0;
+}
+
+/* kh_put_ptr (604-613): returns the slot index of the value */
+__device__ inline uint64_t kh_put_ptr(uint64_t *kh, ReadRec *r, uint64_t key, int extend)
+{
+	if(extend && r->kh_cnt >= r->kh_ub) { if(kh_extend(kh, r) != 0) { r->err |= MAB_ERR_KH_OVF; r->kh_ub = 0xffffffffu; } }
+	uint32_t isnew;
+	uint64_t idx = kh_allocate(kh, key, MAB_KH_INIT, r->kh_mask, &isnew);
+	r->kh_cnt += isnew;
+	return idx;
+}
+
+__device__ __forceinline__ uint64_t bswap64(uint64_t x)
+{
+	uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+	return ((uint64_t)__byte_perm(lo, 0, 0x0123) << 32) | __byte_perm(hi, 0, 0x0123);
+}
+__device__ __forceinline__ uint64_t pos_key(uint64_t x, uint64_t y) { return x ^ (x >> 29) ^ y ^ bswap64(y); }		/* minialign.c:3362 */
+
+}  // namespace mab

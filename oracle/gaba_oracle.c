@@ -15,6 +15,7 @@
 #include "gaba_oracle.h"
 #include <stdlib.h>
 #include <string.h>
+#include <stdio.h>
 
 #define MAX2(a, b) ((a) > (b) ? (a) : (b))
 #define MIN2(a, b) ((a) < (b) ? (a) : (b))
@@ -193,6 +194,7 @@ static void vec_step(ora_dp_t *dp, vec_t *v, int down, ora_mask_t *m)
 		int8_t t = (idx & 0x80) ? 0 : dp->sb[idx & 15];						/* pshufb */
 		int8_t dh = v->dh[q], dv = v->dv[q], de = v->de[q], df = v->df[q];
 		int8_t dfh = w8(dv + dp->gfh), dfv = w8(dp->gfv - dh);
+		if(getenv("ORA_DEBUG2")) { int x1 = dv + dp->gfh, x2 = dp->gfv - dh, x3 = de + dp->adjh, x4 = df + dp->adjv; if(x1 != (int8_t)x1 || x2 != (int8_t)x2 || x3 != (int8_t)x3 || x4 != (int8_t)x4) fprintf(stderr, "WRAP q %d: %d %d %d %d (dh %d dv %d de %d df %d)\n", q, x1, x2, x3, x4, dh, dv, de, df); }
 		int8_t s = MAX2(de, df); s = MAX2(s, dfh); t = MAX2(t, dfv); t = MAX2(t, s);
 		uint64_t gfh = t == dfh, gh = t == de, gfv = t == dfv, gv = t == df;
 		mh |= (gfh | gh) << q; gh &= ~gfh;
@@ -230,6 +232,7 @@ static void blk_store(ora_dp_t *dp, ora_block_t *b, vec_t const *v, int acnt, in
 	memcpy(b->dh, v->dh, ORA_WMAX); memcpy(b->dv, v->dv, ORA_WMAX);
 	memcpy(b->de, v->de, ORA_WMAX); memcpy(b->df, v->df, ORA_WMAX);
 	b->dir_mask = v->dir; b->acc = (int8_t)v->acc;								/* _dir_save: int8 store */
+	if(getenv("ORA_DEBUG")) { fprintf(stderr, "ORA blk acnt %d bcnt %d dir %08x acc %d drop_c %d delta_c %d d0 %d dW %d\n", acnt, bcnt, v->dir, v->acc, v->drop[dp->W/2], v->delta[dp->W/2], v->delta[0], v->delta[dp->W-1]); }
 	b->xstat = (int8_t)(((int)dp->tx - (int)v->drop[W / 2]) & ORA_X_TERM);
 	int32_t cofs = v->delta[W / 2];
 	b->acnt = (int8_t)acnt; b->bcnt = (int8_t)bcnt;
