@@ -107,6 +107,9 @@ typedef struct {
 int mab_extend_pairs(mab_ctx *ctx, const uint8_t *seq_block, uint64_t block_size, const mab_pair_t *pairs, uint32_t n,
 	uint32_t *res /* 16 x n */, uint32_t *aln_out, uint64_t aln_cap, uint64_t *aln_ofs /* n + 1 */);
 
+/* runs every packed-SIMD / permute / warp primitive the DP uses on fixed inputs; out = 64 x 32 words (test hook) */
+int mab_selftest(mab_ctx *ctx, uint32_t *out);
+
 #ifdef __cplusplus
 }
 #endif

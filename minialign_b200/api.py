@@ -79,6 +79,8 @@ def load_library(lib_path: str | None = None):
     L.mab_seed_chain.argtypes = [C.c_void_p, u8p, C.c_uint32, C.c_uint32, u32p, C.c_uint64, u64p, u32p, C.c_uint64, u64p]
     L.mab_extend_pairs.restype = C.c_int
     L.mab_extend_pairs.argtypes = [C.c_void_p, u8p, C.c_uint64, C.POINTER(MabPair), C.c_uint32, u32p, u32p, C.c_uint64, u64p]
+    L.mab_selftest.restype = C.c_int
+    L.mab_selftest.argtypes = [C.c_void_p, u32p]
     return L
 
 
@@ -136,6 +138,13 @@ class Mapper:
         s = MabStats()
         self.lib.mab_last_stats(self.h, C.byref(s))
         return {k: getattr(s, k) for k, _ in MabStats._fields_}
+
+    def selftest(self) -> np.ndarray:
+        out = np.zeros(64 * 32, dtype=np.uint32)
+        rc = self.lib.mab_selftest(self.h, out.ctypes.data_as(C.POINTER(C.c_uint32)))
+        if rc != 0:
+            raise RuntimeError("mab_selftest failed: " + self.lib.mab_last_error().decode())
+        return out.reshape(64, 32)
 
     # ---- stage-level entry points (parity tests) ----
     def sketch(self, seq: np.ndarray) -> np.ndarray:

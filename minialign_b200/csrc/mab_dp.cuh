@@ -18,16 +18,33 @@
 namespace mab {
 
 #define MAB_FULL 0xffffffffu
+#ifdef MAB_DEBUG_DEV
+#define MAB_DBG(...) do { if(c.lane == 0) { printf(__VA_ARGS__); } } while(0)
+#else
+#define MAB_DBG(...) do {} while(0)
+#endif
 
+/* PTX prmt.b32 in default mode: selector nibble bit 3 replicates the sign bit of the selected byte.  (__byte_perm masks the
+ * selector with 0x7777, so the sign-extending permutes below have to be issued as PTX.) */
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+#ifdef MAB_EMU
+	return emu_prmt(a, b, sel);
+#else
+	uint32_t d;
+	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+	return d;
+#endif
+}
 __device__ __forceinline__ uint32_t pack2(int v) { uint32_t x = (uint32_t)(uint16_t)(int16_t)v; return x | (x << 16); }
-__device__ __forceinline__ uint32_t sext8x2(uint32_t x) { return __byte_perm(x, 0, 0xA280); }		/* int8 wrap of both halves */
-__device__ __forceinline__ uint32_t unpack8(uint32_t v) { return __byte_perm(v, 0, 0x9180); }		/* {b0,b1} -> s16x2 */
+__device__ __forceinline__ uint32_t sext8x2(uint32_t x) { return prmt(x, 0, 0xA280); }		/* int8 wrap of both halves */
+__device__ __forceinline__ uint32_t unpack8(uint32_t v) { return prmt(v, 0, 0x9180); }		/* {b0,b1} -> s16x2 */
 __device__ __forceinline__ uint32_t pack8(uint32_t x) { return __byte_perm(x, 0, 0x4420); }			/* s16x2 -> {b0,b1} */
 /* "H8" form: the int8 value sits in the HIGH byte of its 16-bit half (low byte zero), so VIADD.16x2 wraps exactly like the
  * reference's int8 lanes (observable at the band edges, where dv/de run away) while signed 16-bit max/compare keep order */
 __device__ __forceinline__ uint32_t unpack8h(uint32_t v) { return __byte_perm(v, 0, 0x1404); }		/* {b0,b1} -> H8 */
 __device__ __forceinline__ uint32_t pack8h(uint32_t x) { return __byte_perm(x, 0, 0x4431); }			/* H8 -> {b0,b1} */
-__device__ __forceinline__ uint32_t h8_to_s16(uint32_t x) { return __byte_perm(x, 0, 0xB391); }		/* H8 -> sign-extended s16x2 */
+__device__ __forceinline__ uint32_t h8_to_s16(uint32_t x) { return prmt(x, 0, 0xB391); }		/* H8 -> sign-extended s16x2 */
 __device__ __forceinline__ uint32_t pack2h(int v) { uint32_t x = ((uint32_t)(uint8_t)(int8_t)v) << 8; return x | (x << 16); }
 __device__ __forceinline__ int lo16(uint32_t x) { return (int)(int16_t)(x & 0xffff); }
 __device__ __forceinline__ int hi16(uint32_t x) { return (int)(int16_t)(x >> 16); }
@@ -152,6 +169,7 @@ __device__ inline void dp_flush(DpCtx &c, int widx)
 {
 	const DevParams &P = *c.P;
 	const RootTpl &R = P.root[widx];
+	__syncwarp();				/* nobody is still reading the previous extension's records */
 	c.widx = widx; c.W = 64 >> widx; c.nl = c.W / 2;
 	int l = c.lane;
 	BlkEntry *b = &c.blk[0]; TailRec *t = &c.tails[0];
@@ -240,6 +258,8 @@ __device__ __forceinline__ int64_t init_fetch(DpCtx &c, FillWork &w, Vec &v, int
 		int32_t y = (srem[1 - i] - irem[1 - i]) + ((i == 0 ? 1 : 0) + irem[i]);
 		len[i] = x < y ? x : y;
 	}
+	MAB_DBG("init_fetch apos %lld bpos %lld irem %d %d srem %d %d len %d %d\n", (long long)apos, (long long)bpos, irem[0], irem[1], srem[0], srem[1], len[0], len[1]);
+	if(len[0] < 0 || len[1] < 0 || len[0] > MAB_WMAX || len[1] > MAB_WMAX) { c.err |= MAB_ERR_DP_OVF; len[0] = len[1] = 0; }	/* cannot happen for non-empty sections */
 	window_consume(c, v, w, 0, (uint32_t)len[0]); window_consume(c, v, w, 1, (uint32_t)len[1]);
 	if(c.lane == 0) { c.blk[ph].acnt = (int8_t)len[0]; c.blk[ph].bcnt = (int8_t)len[1]; }
 	w.rem[0] = (uint32_t)(srem[0] - len[0]); w.rem[1] = (uint32_t)(srem[1] - len[1]);
@@ -285,6 +305,7 @@ __device__ __forceinline__ int32_t create_tail(DpCtx &c, FillWork &w, const Vec 
 		t->sec[0] = w.sec[0]; t->sec[1] = w.sec[1];
 	}
 	__syncwarp();
+	MAB_DBG("create_tail ti %d last %d xstat %d cnt %d rem %u %u sridx %u %u mdrop %d ofsd %d max %lld status %x nblk %u\n", ti, last, xstat, cnt, w.rem[0], w.rem[1], w.sridx[0], w.sridx[1], mdrop, w.ofsd, (long long)c.tails[ti].max, c.tails[ti].status, c.nblk);
 	return ti;
 }
 
@@ -296,6 +317,7 @@ __device__ inline int32_t fill_blocks(DpCtx &c, FillWork &w, Vec &v, uint32_t &x
 	int cap = 0;
 	int l = c.lane;
 	while(1) {
+		MAB_DBG("fill_blocks cur %d xstat %d rem %u %u pridx %u cap %d err %u nblk %u\n", cur, (int)c.blk[cur].xstat, w.rem[0], w.rem[1], w.pridx, cap, c.err, c.nblk);
 		if(c.blk[cur].xstat < 0) { break; }											/* TERM */
 		if(!cap && (w.rem[0] < MAB_BLK || w.rem[1] < MAB_BLK || w.pridx < MAB_BLK)) { cap = 1; }
 		int32_t bi = push_blk(c);
@@ -328,6 +350,7 @@ __device__ inline int32_t fill_blocks(DpCtx &c, FillWork &w, Vec &v, uint32_t &x
 		}
 		if(MASKS && (i & 3) != 0) { mrow[32 * (i >> 2)] = mbits; }
 		c.n_vectors += (uint64_t)i;
+		MAB_DBG(" block bi %d i %d acnt %d bcnt %d dir %08x acc %d\n", bi, i, acnt, bcnt, v.dir, v.acc);
 		w.pridx -= (uint32_t)i;
 		if(i < MAB_BLK && i != 0) { v.dir <<= (MAB_BLK - i); }						/* _dir_adjust_remainder */
 		/* _fill_store_context (gaba.c:1734-1778) */
@@ -389,7 +412,7 @@ __device__ inline int32_t dp_fill_root(DpCtx &c, const SecDesc &a, uint32_t apos
 	int32_t ph = load_vectors(c, 0, v, xd);
 	int64_t rapos = c.tails[0].apos, rbpos = c.tails[0].bpos;
 	if(init_fetch(c, w, v, ph, rapos, rbpos) < -1) { return create_tail(c, w, v, xd, ph); }
-	return create_tail(c, w, v, xd, fill_blocks<MASKS>(c, w, v, xd, ph));
+	{ int32_t last = fill_blocks<MASKS>(c, w, v, xd, ph); return create_tail(c, w, v, xd, last); }	/* sequenced: xd is updated by fill_blocks */
 }
 
 /* gaba_dp_fill (gaba.c:2161-2203) */
@@ -403,7 +426,7 @@ __device__ inline int32_t dp_fill(DpCtx &c, int32_t prev, const SecDesc &a, cons
 	if(pbpos < -1) {
 		if(init_fetch(c, w, v, ph, papos, pbpos) < -1) { return create_tail(c, w, v, xd, ph); }
 	}
-	return create_tail(c, w, v, xd, fill_blocks<MASKS>(c, w, v, xd, ph));
+	{ int32_t last = fill_blocks<MASKS>(c, w, v, xd, ph); return create_tail(c, w, v, xd, last); }	/* sequenced: xd is updated by fill_blocks */
 }
 
 /* mm_extend_core (minialign.c:4075-4112): fill_root, then keep filling over the N-tail sections until X-drop or a second
@@ -534,6 +557,7 @@ __device__ inline PosPair dp_search_max(DpCtx &c, int32_t ti)
 		if(upd1 && t->ridx[1] == 0) { gidx[1] += acc[1]; id[1] = nid1; acc[1] = 0; }
 	}
 	pos.aid = id[0]; pos.bid = id[1]; pos.apos = (uint32_t)gidx[0]; pos.bpos = (uint32_t)gidx[1];
+	__syncwarp();
 	return pos;
 }
 
@@ -590,11 +614,11 @@ __device__ __forceinline__ void trace_reload_section(const DpCtx &c, Trace &w, i
 {
 	int32_t tail = w.tail[i], prev = tail;
 	int32_t gidx = w.gidx[i];
-	while(gidx <= 0) {
+	while(gidx <= 0 && tail > 0) {
 		do {
 			gidx += c.tails[tail].istat ? 0 : (int32_t)c.tails[tail].adv[i];
 			prev = tail; tail = c.tails[tail].tail;
-		} while(c.tails[tail].ridx[i] != 0);
+		} while(tail > 0 && c.tails[tail].ridx[i] != 0);
 	}
 	w.tail[i] = tail;
 	w.id[i] = i == 0 ? c.tails[prev].aid : c.tails[prev].bid;
@@ -735,7 +759,9 @@ __device__ inline uint64_t dp_trace(DpCtx &c, int32_t ti, uint32_t *pool, uint64
 	w.cur_idx = (int64_t)(plen >> 5); w.cur_word = 1u << (plen & 31);				/* sentinel (gaba.c:3287) */
 	if(c.lane == 0) { w.path[(plen >> 5) + 1] = 0; }
 	uint32_t nseg = 0;
+	uint32_t fuel = sn + 8;
 	while(w.npop < plen) {
+		if(fuel-- == 0) { c.err |= MAB_ERR_DP_OVF; return 0xffffffffffffffffull; }		/* more segments than sections: cannot happen */
 		if(w.gidx[0] < (int32_t)((w.state & MAB_TS_H) != 0)) { trace_reload_section(c, w, 0); }
 		if(w.gidx[1] < (int32_t)((w.state & MAB_TS_V) != 0)) { trace_reload_section(c, w, 1); }
 		trace_core(c, w, tile);

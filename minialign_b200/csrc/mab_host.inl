@@ -37,6 +37,7 @@ struct mab_ctx {
 	RT_STREAM stream;
 	RT_EVENT ev[8];
 	int device_input = 0;
+	uint32_t rlen_last = 0;				/* the reference's self->rlen carried from read to read and batch to batch */
 	/* results of the last batch */
 	std::vector<uint32_t> res_words; std::vector<uint64_t> res_ofs;
 	std::vector<uint32_t> h_pool; std::vector<ReadRec> h_reads;
@@ -335,33 +336,21 @@ static void post_process(mab_ctx *ctx, const uint32_t *pool, const uint32_t *rec
 /* ---------------------------------------------------------------- batch driver */
 static uint32_t dp_blk_cap(uint32_t maxlen) { return (uint32_t)((4ull * ((uint64_t)maxlen + 512)) / 32 + 64); }
 
-extern "C" int mab_map_batch(mab_ctx *ctx, const uint8_t *seq_block, uint64_t block_size, const uint64_t *seq_ofs, const uint32_t *seq_len, uint32_t n_seq)
+/* one pass of the device pipeline over `hr` (seq_ofs / len / rlen_in filled in); on return hr holds the device-side
+ * records and ctx->h_pool the result pool */
+static int map_core(mab_ctx *ctx, const uint8_t *d_base, std::vector<ReadRec> &hr, bool timed)
 {
 	const DevParams &P = ctx->P;
 	mab_stats_t &S = ctx->stats;
-	memset(&S, 0, sizeof(S));
-	ctx->res_words.clear(); ctx->res_ofs.assign((size_t)n_seq + 1, 0);
-	if(n_seq == 0) { return MAB_OK; }
-	CK(RT_SET_DEVICE(ctx->device));
-	RT_EVENT_RECORD(ctx->ev[0], ctx->stream);
-	/* 1. reads to HBM */
-	const uint8_t *d_base;
-	if(ctx->device_input) { d_base = seq_block; }
-	else {
-		int rc = grow(&ctx->d_seq, &ctx->seq_cap, block_size + 256); if(rc) { return rc; }
-		CK(RT_MEMCPY_H2D_ASYNC(ctx->d_seq, seq_block, block_size, ctx->stream));
-		d_base = ctx->d_seq; S.h2d_bytes += block_size;
-	}
-	std::vector<ReadRec> &hr = ctx->h_reads;
-	hr.assign(n_seq, ReadRec());
+	uint32_t n_seq = (uint32_t)hr.size();
 	uint32_t maxlen = 0; uint64_t tot_len = 0;
-	for(uint32_t i = 0; i < n_seq; i++) { memset(&hr[i], 0, sizeof(ReadRec)); hr[i].seq_ofs = seq_ofs[i]; hr[i].len = seq_len[i]; maxlen = std::max(maxlen, seq_len[i]); tot_len += seq_len[i]; }
+	for(uint32_t i = 0; i < n_seq; i++) { maxlen = std::max(maxlen, hr[i].len); tot_len += hr[i].len; }
 	{ int rc = grow(&ctx->d_reads, &ctx->reads_cap, sizeof(ReadRec) * (uint64_t)n_seq); if(rc) { return rc; } }
 	CK(RT_MEMCPY_H2D_ASYNC(ctx->d_reads, hr.data(), sizeof(ReadRec) * (uint64_t)n_seq, ctx->stream));
 	S.h2d_bytes += sizeof(ReadRec) * (uint64_t)n_seq;
-	RT_EVENT_RECORD(ctx->ev[1], ctx->stream);
-	/* 2. count pass, workspace sizing */
-	uint32_t seed_ctas = std::min<uint32_t>((n_seq + MAB_WARPS_PER_CTA - 1) / MAB_WARPS_PER_CTA, ctx->n_sm * 8);
+	if(timed) { RT_EVENT_RECORD(ctx->ev[1], ctx->stream); }
+	/* count pass, workspace sizing */
+	uint32_t seed_ctas = std::max<uint32_t>(1, std::min<uint32_t>((n_seq + MAB_WARPS_PER_CTA - 1) / MAB_WARPS_PER_CTA, ctx->n_sm * 8));
 	RT_LAUNCH((k_seed<true>), seed_ctas, 32 * MAB_WARPS_PER_CTA, 512 * MAB_WARPS_PER_CTA, ctx->stream, P, d_base, ctx->d_reads, n_seq, (uint8_t *)nullptr);
 	S.n_launches++;
 	CK(RT_MEMCPY_D2H_ASYNC(hr.data(), ctx->d_reads, sizeof(ReadRec) * (uint64_t)n_seq, ctx->stream));
@@ -382,57 +371,106 @@ extern "C" int mab_map_batch(mab_ctx *ctx, const uint8_t *seq_block, uint64_t bl
 	uint32_t ext_ctas = std::max<uint32_t>(1, std::min<uint32_t>(ctx->n_slots / MAB_WARPS_PER_CTA, (n_seq + MAB_WARPS_PER_CTA - 1) / MAB_WARPS_PER_CTA));
 	{ int rc = grow(&ctx->d_arenas, &ctx->arenas_cap, AL.total * (uint64_t)ext_ctas * MAB_WARPS_PER_CTA); if(rc) { return rc; } }
 	uint64_t pool_need = tot_len / 4 + 64ull * n_seq + (1u << 16);				/* ~2 bits per base and alignment, x4 head room */
-	int rc_final = MAB_OK;
 	for(int attempt = 0; attempt < 3; attempt++) {
 		{ int rc = grow(&ctx->d_pool, &ctx->pool_cap, 4 * pool_need); if(rc) { return rc; } }
 		uint64_t pool_words = ctx->pool_cap / 4;
 		CK(RT_MEMCPY_H2D_ASYNC(ctx->d_reads, hr.data(), sizeof(ReadRec) * (uint64_t)n_seq, ctx->stream));
 		BatchCounters zero; memset(&zero, 0, sizeof(zero));
 		CK(RT_MEMCPY_H2D_ASYNC(ctx->d_ctr, &zero, sizeof(zero), ctx->stream));
-		RT_EVENT_RECORD(ctx->ev[2], ctx->stream);
-		/* 3. seeds */
+		if(timed) { RT_EVENT_RECORD(ctx->ev[2], ctx->stream); }
 		RT_LAUNCH((k_seed<false>), seed_ctas, 32 * MAB_WARPS_PER_CTA, 512 * MAB_WARPS_PER_CTA, ctx->stream, P, d_base, ctx->d_reads, n_seq, ctx->d_ws);
 		S.n_launches++;
-		RT_EVENT_RECORD(ctx->ev[3], ctx->stream);
-		/* 4. rounds of sort+chain / extend (minialign.c:4444-4448) */
+		if(timed) { RT_EVENT_RECORD(ctx->ev[3], ctx->stream); }
+		/* rounds of sort+chain / extend (minialign.c:4444-4448) */
 		for(uint32_t round = 0; round < P.n_occ; round++) {
 			RT_LAUNCH(k_sortchain, (n_seq + 63) / 64, 64, 0, ctx->stream, P, ctx->d_reads, n_seq, ctx->d_ws, ctx->d_frames, round);
 			RT_MEMSET_ASYNC(&ctx->d_ctr->work_next, 0, sizeof(unsigned int), ctx->stream);
-			RT_LAUNCH(k_extend, ext_ctas, 32 * MAB_WARPS_PER_CTA, 1024 + 1024 * MAB_WARPS_PER_CTA, ctx->stream, P, d_base, ctx->d_ntail, ctx->d_reads, n_seq, ctx->d_ws,
+			RT_LAUNCH(k_extend, ext_ctas, 32 * MAB_WARPS_PER_CTA, 1024 + 1024 * MAB_WARPS_PER_CTA, ctx->stream, P, d_base, (const uint8_t *)ctx->d_ntail, ctx->d_reads, n_seq, ctx->d_ws,
 				ctx->d_arenas, AL.total, blk_cap, ctx->d_pool, pool_words, ctx->d_ctr, round, P.n_occ - 1);
 			S.n_launches += 2;
 		}
-		RT_EVENT_RECORD(ctx->ev[4], ctx->stream);
-		/* 5. results back */
+		if(timed) { RT_EVENT_RECORD(ctx->ev[4], ctx->stream); }
 		BatchCounters hc;
 		CK(RT_MEMCPY_D2H_ASYNC(&hc, ctx->d_ctr, sizeof(hc), ctx->stream));
 		CK(RT_MEMCPY_D2H_ASYNC(hr.data(), ctx->d_reads, sizeof(ReadRec) * (uint64_t)n_seq, ctx->stream));
 		CK(RT_STREAM_SYNC(ctx->stream));
 		uint32_t err = 0;
 		for(uint32_t i = 0; i < n_seq; i++) { err |= hr[i].err; }
-		S.n_vectors = hc.n_vectors; S.n_fill_calls = hc.n_fill; S.n_trace = hc.n_trace;
+		S.n_vectors += hc.n_vectors; S.n_fill_calls += hc.n_fill; S.n_trace += hc.n_trace;
 		if((err & MAB_ERR_POOL_OVF) || hc.pool_top > pool_words) {
 			pool_need *= 4; S.n_retry++;
 			for(uint32_t i = 0; i < n_seq; i++) { ReadRec &r = hr[i]; if(r.len >= P.k && (double)r.len * P.mcoef >= (double)P.min_score) { r.state = 0; } r.err = 0; r.result_words = 0; r.n_res = 0; r.nbin = 0; }
-			rc_final = MAB_EOVERFLOW;
+			if(attempt == 2) { g_err = "result pool overflow after retries"; return MAB_EOVERFLOW; }
 			continue;
 		}
 		if(err) { g_err = "device workspace overflow (error bits " + std::to_string(err) + ")"; return MAB_EOVERFLOW; }
 		uint64_t top = hc.pool_top;
 		ctx->h_pool.resize((size_t)top + 4);
 		if(top) { CK(RT_MEMCPY_D2H_ASYNC(ctx->h_pool.data(), ctx->d_pool, 4 * top, ctx->stream)); }
-		RT_EVENT_RECORD(ctx->ev[5], ctx->stream);
+		if(timed) { RT_EVENT_RECORD(ctx->ev[5], ctx->stream); }
 		CK(RT_STREAM_SYNC(ctx->stream));
 		S.d2h_bytes += 4 * top + sizeof(ReadRec) * (uint64_t)n_seq + sizeof(hc);
-		rc_final = MAB_OK;
 		break;
 	}
-	if(rc_final != MAB_OK) { g_err = "result pool overflow after retries"; return rc_final; }
-	/* 6. host post-processing */
+	return MAB_OK;
+}
+
+extern "C" int mab_map_batch(mab_ctx *ctx, const uint8_t *seq_block, uint64_t block_size, const uint64_t *seq_ofs, const uint32_t *seq_len, uint32_t n_seq)
+{
+	mab_stats_t &S = ctx->stats;
+	memset(&S, 0, sizeof(S));
+	ctx->res_words.clear(); ctx->res_ofs.assign((size_t)n_seq + 1, 0);
+	if(n_seq == 0) { return MAB_OK; }
+	CK(RT_SET_DEVICE(ctx->device));
+	RT_EVENT_RECORD(ctx->ev[0], ctx->stream);
+	const uint8_t *d_base;
+	if(ctx->device_input) { d_base = seq_block; }
+	else {
+		int rc = grow(&ctx->d_seq, &ctx->seq_cap, block_size + 256); if(rc) { return rc; }
+		CK(RT_MEMCPY_H2D_ASYNC(ctx->d_seq, seq_block, block_size, ctx->stream));
+		d_base = ctx->d_seq; S.h2d_bytes += block_size;
+	}
+	std::vector<ReadRec> &hr = ctx->h_reads;
+	hr.assign(n_seq, ReadRec());
+	for(uint32_t i = 0; i < n_seq; i++) { memset(&hr[i], 0, sizeof(ReadRec)); hr[i].seq_ofs = seq_ofs[i]; hr[i].len = seq_len[i]; hr[i].rlen_in = MAB_RLEN_OWN; }
+	{ int rc = map_core(ctx, d_base, hr, true); if(rc) { return rc; } }
 	double t0 = RT_WALL_MS();
+	std::vector<std::vector<uint32_t>> words(n_seq);
+	for(uint32_t i = 0; i < n_seq; i++) { if(hr[i].result_words != 0) { post_process(ctx, ctx->h_pool.data(), ctx->h_pool.data() + hr[i].result_ofs, words[i]); } }
+	/* verify the rlen speculation in read order (the reference's -t1 semantics); re-map the reads whose first root test
+	 * would have gone the other way with the true stale value */
+	for(int iter = 0; iter < 8; iter++) {
+		std::vector<uint32_t> redo;
+		uint32_t prev = ctx->rlen_last;
+		for(uint32_t i = 0; i < n_seq; i++) {
+			ReadRec &r = hr[i];
+			if(!(r.dep_flags & 1)) { continue; }					/* no chain was loaded: rlen unchanged */
+			bool used = (r.dep_apos >= r.rlen_used) || (r.dep_flags & 2), actual = (r.dep_apos >= prev) || (r.dep_flags & 2);
+			if(used != actual) { redo.push_back(i); }
+			prev = r.rlen_cur;										/* value left behind by this read (may change after a redo) */
+		}
+		if(redo.empty()) { break; }
+		S.n_retry += (uint32_t)redo.size();
+		/* true stale value for each read to redo, given the current view of its predecessors */
+		std::vector<ReadRec> sub(redo.size());
+		prev = ctx->rlen_last;
+		size_t k = 0;
+		for(uint32_t i = 0; i < n_seq && k < redo.size(); i++) {
+			if(i == redo[k]) { memset(&sub[k], 0, sizeof(ReadRec)); sub[k].seq_ofs = hr[i].seq_ofs; sub[k].len = hr[i].len; sub[k].rlen_in = prev; k++; }
+			if(hr[i].dep_flags & 1) { prev = hr[i].rlen_cur; }
+		}
+		{ int rc = map_core(ctx, d_base, sub, false); if(rc) { return rc; } }
+		for(size_t j = 0; j < redo.size(); j++) {
+			uint32_t i = redo[j];
+			hr[i] = sub[j];
+			words[i].clear();
+			if(sub[j].result_words != 0) { post_process(ctx, ctx->h_pool.data(), ctx->h_pool.data() + sub[j].result_ofs, words[i]); }
+		}
+	}
+	for(uint32_t i = 0; i < n_seq; i++) { if(hr[i].dep_flags & 1) { ctx->rlen_last = hr[i].rlen_cur; } }
 	for(uint32_t i = 0; i < n_seq; i++) {
 		ctx->res_ofs[i] = ctx->res_words.size();
-		if(hr[i].result_words != 0) { post_process(ctx, ctx->h_pool.data(), ctx->h_pool.data() + hr[i].result_ofs, ctx->res_words); }
+		ctx->res_words.insert(ctx->res_words.end(), words[i].begin(), words[i].end());
 	}
 	ctx->res_ofs[n_seq] = ctx->res_words.size();
 	S.ms_post = (float)(RT_WALL_MS() - t0);
@@ -549,4 +587,17 @@ extern "C" int mab_extend_pairs(mab_ctx *ctx, const uint8_t *seq_block, uint64_t
 	RT_FREE(d_seq); RT_FREE(d_ar); RT_FREE(d_p); RT_FREE(d_res); RT_FREE(d_pool); RT_FREE(d_ao);
 	if(rc == MAB_EOVERFLOW) { g_err = "extend_pairs: device workspace overflow"; }
 	return rc;
+}
+
+/* debugging / test entry: runs k_selftest and copies its 64 x 32 words out */
+extern "C" int mab_selftest(mab_ctx *ctx, uint32_t *out)
+{
+	uint32_t *d = nullptr;
+	CK(RT_MALLOC(&d, 4ull * 64 * 32));
+	CK(RT_MEMSET_ASYNC(d, 0, 4ull * 64 * 32, ctx->stream));
+	RT_LAUNCH(k_selftest, 1, 32, 0, ctx->stream, d);
+	CK(RT_STREAM_SYNC(ctx->stream));
+	CK(RT_MEMCPY_D2H(out, d, 4ull * 64 * 32));
+	RT_FREE(d);
+	return MAB_OK;
 }

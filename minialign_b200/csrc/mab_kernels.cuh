@@ -125,6 +125,7 @@ __global__ void k_seed(DevParams P, const uint8_t *base, ReadRec *reads, uint32_
 			if(lane == 0) { r->tot_seeds = tot_seeds; r->tot_resc = tot_resc; r->n_words = n_words; }
 		} else if(lane == 0) {
 			r->n_seed = n_seed; r->seed_n = n_seed; r->n_resc = n_resc; r->presc = 0; r->n_root = 0; r->n_next = 0; r->n_res = 0; r->nbin = 0;
+			r->rlen_cur = r->rlen_in; r->rlen_used = r->rlen_in; r->dep_apos = 0; r->dep_flags = 0;
 			kh_reset((uint64_t *)(ws + r->ws_ofs + ws_layout(r->seed_cap, r->root_cap, r->resc_cap, r->bin_cap).kh), r);
 		}
 	}
@@ -268,6 +269,12 @@ __device__ inline int load_root(const DevParams &P, RCtx &x, Search &st, uint32_
 	uint32_t rsid = x.seed[4ull * lid + 0];
 	const uint32_t *p = x.seed + 4ull * rsid;
 	st.aid = p[1]; st.bid = 0;
+	if(!(r->dep_flags & 1)) {											/* first root of this read: rlen is the previous READ's (see ReadRec) */
+		if(st.rlen == MAB_RLEN_OWN) { st.rlen = ref_seq(P, st.aid).l_seq; }
+		int32_t bs = bs_of(p);
+		uint32_t bpos = (uint32_t)bs + ((uint32_t)(bs >> 31) & st.qlen);
+		r->dep_apos = (uint32_t)as_of(p); r->dep_flags = 1u | (bpos >= st.qlen ? 2u : 0u); r->rlen_used = st.rlen;
+	}
 	load_pos(P, st, p, &st.rev, st.cp);									/* reads rlen of the PREVIOUS chain (3865 before 3873) */
 	st.tp[0] = st.cp[0]; st.tp[1] = st.cp[1];
 	st.iid = iid; st.eid = eid; st.sid = rsid;
@@ -458,7 +465,7 @@ __global__ void k_extend(DevParams P, const uint8_t *base, const uint8_t *ntail,
 		uint32_t n_root = r->n_root, qlen = r->len;
 		const uint8_t *qseq = base + r->seq_ofs;
 		Search st; memset(&st, 0, sizeof(st));
-		st.crem = MAB_CREM; st.min_score = P.min_score; st.qlen = qlen; st.rlen = 0;
+		st.crem = MAB_CREM; st.min_score = P.min_score; st.qlen = qlen; st.rlen = r->rlen_cur;
 		c.err = 0;
 		for(uint32_t k = 0; k < n_root && r->seed_n != 0; k++) {
 			int stop = 0;
@@ -512,6 +519,7 @@ __global__ void k_extend(DevParams P, const uint8_t *base, const uint8_t *ntail,
 			if(fin) { break; }
 		}
 		if(lane == 0) {
+			r->rlen_cur = st.rlen;
 			if(c.err) { r->err |= c.err; }
 			if(r->n_res > 0 || round == last_round || r->err) { finalize_read(x, ctr, pool_cap); }
 		}
@@ -571,6 +579,34 @@ __global__ void k_extend_pairs(DevParams P, const uint8_t *base, const uint8_t *
 		__syncwarp();
 	}
 	if(lane == 0) { atomicAdd(&ctr->n_vectors, (unsigned long long)c.n_vectors); }
+}
+
+
+/* ---------------------------------------------------------------- k_selftest */
+/* evaluates every packed-SIMD / permute / warp primitive the DP relies on, on lane-dependent inputs; tests compare the
+ * device output word for word with the CUDA-on-CPU shim's, which pins the intrinsics' semantics on real hardware */
+__global__ void k_selftest(uint32_t *out)
+{
+	int lane = threadIdx.x & 31;
+	uint32_t x = 0x9e3779b9u * (uint32_t)(lane + 1) ^ 0x7f4a7c15u, y = 0x85ebca6bu * (uint32_t)(lane + 3) ^ 0xc2b2ae35u, z = x * 31u + y;
+	uint32_t xs = x & 0x00ff00ffu, ys = y & 0x00ff00ffu;
+	int f = 0;
+	#define PUT(v) out[32 * (f++) + lane] = (uint32_t)(v)
+	PUT(sext8x2(x)); PUT(unpack8(x & 0xffff)); PUT(pack8(x)); PUT(unpack8h(x & 0xffff)); PUT(pack8h(x)); PUT(h8_to_s16(x));
+	PUT(pack2(-5)); PUT(pack2h(-5)); PUT(clamp8x2(x)); PUT(__vadd2(x, y)); PUT(__vsub2(x, y)); PUT(__vmaxs2(x, y)); PUT(__vmins2(x, y));
+	PUT(__vminu2(x, y)); PUT(__vimax3_s16x2(x, y, z)); PUT(__viaddmax_s16x2(x, y, z)); PUT(__byte_perm(x, y, 0x5432)); PUT(__byte_perm(x, 0, 0x0123));
+	PUT(__shfl_up_sync(MAB_FULL, x, 1)); PUT(__shfl_down_sync(MAB_FULL, x, 1)); PUT(__shfl_sync(MAB_FULL, x, (lane * 7 + 3) & 31));
+	PUT(__ballot_sync(MAB_FULL, (x >> 5) & 1)); PUT(__reduce_add_sync(MAB_FULL, (int)(x & 0xffff) - 30000)); PUT(__reduce_max_sync(MAB_FULL, (int)x));
+	PUT(__popc(x)); PUT(__clz((int)x)); PUT(__ffs((int)x)); PUT(mask_tz(x & 0xff00, y & 0xf0f0));
+	PUT(lo16(x)); PUT(hi16(x)); PUT(xs | ys);
+	{ unsigned long long w = ((unsigned long long)x << 32) | y; unsigned long long r = __shfl_sync(MAB_FULL, w, (lane + 5) & 31); PUT(r); PUT(r >> 32); }
+	{ double d = __dsub_rn(__dmul_rn(__ddiv_rn((double)(int)x, (double)((y & 0xffff) + 1)), 1.0 / 6.0), -4.0 / 6.0); unsigned long long b; memcpy(&b, &d, 8); PUT(b); PUT(b >> 32); }
+	{ float fl = __fmul_rn(__ll2float_rn((long long)(int)x), 0.3f); PUT((uint32_t)(int64_t)__float2ll_rz(fl)); }
+	PUT((uint32_t)(int64_t)__double2ll_rz((double)(x & 0xffff) * 0.9371));
+	{ uint64_t k = pos_key(((uint64_t)x << 32) | y, ((uint64_t)z << 32) | x); PUT(k); PUT(k >> 32); }
+	PUT(crc32c_u64(x, ((uint64_t)y << 32) | z));
+	#undef PUT
+	if(lane == 0) { out[32 * 63] = (uint32_t)f; }
 }
 
 }  // namespace mab

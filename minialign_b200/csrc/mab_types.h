@@ -64,7 +64,16 @@ struct ReadRec {
 	uint32_t kh_mask, kh_cnt, kh_ub, n_words;
 	uint64_t result_ofs;			/* word offset into the result pool, valid when result_words != 0 */
 	uint32_t result_words, err;
+	/* The reference's per-thread buffer keeps `rlen` of the LAST chain it loaded, and mm_search_load_root tests the first
+	 * seed of the next read against that stale value (minialign.c:3865 runs before 3873).  With -t1 this is a sequential
+	 * dependency between consecutive reads; it is reproduced by speculating (rlen_in) and verifying on the host. */
+	uint32_t rlen_in;				/* value of self->rlen when this read starts; MAB_RLEN_OWN = assume the first chain's own reference */
+	uint32_t rlen_cur;				/* running value (carried across rescue rounds) */
+	uint32_t rlen_used;				/* the value the first load_root actually compared against */
+	uint32_t dep_apos, dep_flags;	/* first load_root: raw a-position; bit0 = valid, bit1 = (bpos >= qlen) */
+	uint32_t _pad2;
 };
+#define MAB_RLEN_OWN 0xffffffffu
 
 /* per-read workspace = [seeds 16B x seed_cap][root 8B x root_cap][next 8B x root_cap][resc 16B x resc_cap]
  *                      [kh 16B x MAB_KH_CAP][bin 8B x bin_cap] */

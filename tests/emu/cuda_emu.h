@@ -92,7 +92,11 @@ static inline int __clzll(long long x) { return x ? __builtin_clzll((unsigned lo
 static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline int __ffsll(long long x) { return __builtin_ffsll(x); }
 static inline unsigned __brev(unsigned x) { unsigned r = 0; for(int i = 0; i < 32; i++) { r |= ((x >> i) & 1u) << (31 - i); } return r; }
-static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned s)
+/* full PTX prmt.b32 (default mode): nibble bit 3 replicates the sign of the selected byte */
+static inline unsigned emu_prmt(unsigned a, unsigned b, unsigned s);
+/* the CUDA intrinsic masks the selector with 0x7777 (no sign replication) */
+static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned s) { return emu_prmt(a, b, s & 0x7777u); }
+static inline unsigned emu_prmt(unsigned a, unsigned b, unsigned s)
 {
 	uint64_t v = ((uint64_t)b << 32) | a; unsigned r = 0;
 	for(int i = 0; i < 4; i++) {
