@@ -80,6 +80,7 @@ void mab_release_batch(mab_ctx *ctx);
  * on the context's stream, DP vectors filled, bytes moved each way */
 typedef struct {
 	float ms_total, ms_h2d, ms_seed, ms_sortchain, ms_extend, ms_d2h, ms_post;
+	float ms_extend_r0;			/* the round-0 k_extend launch alone (the dominant kernel), CUDA events on its stream */
 	uint64_t n_vectors;			/* anti-diagonal vectors filled (down + up + replays) */
 	uint64_t n_fill_calls, n_trace;
 	uint64_t h2d_bytes, d2h_bytes;

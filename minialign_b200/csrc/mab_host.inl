@@ -36,6 +36,7 @@ struct mab_ctx {
 	BatchCounters *d_ctr = nullptr;
 	RT_STREAM stream;
 	RT_EVENT ev[8];
+	RT_EVENT rev[24];					/* per-round kernel boundaries: [3r] sortchain start, [3r+1] extend start, [3r+2] extend end */
 	int device_input = 0;
 	uint32_t rlen_last = 0;				/* the reference's self->rlen carried from read to read and batch to batch */
 	/* results of the last batch */
@@ -154,6 +155,7 @@ extern "C" mab_ctx *mab_init(const void *mai_blob, uint64_t size, const mab_para
 	CKP(RT_MALLOC(&ctx->d_ctr, sizeof(BatchCounters)));
 	CKP(RT_STREAM_CREATE(&ctx->stream));
 	for(int i = 0; i < 8; i++) { CKP(RT_EVENT_CREATE(&ctx->ev[i])); }
+	for(int i = 0; i < 24; i++) { CKP(RT_EVENT_CREATE(&ctx->rev[i])); }
 	ctx->n_slots = RT_EXTEND_SLOTS(ctx->n_sm);
 	return ctx;
 }
@@ -383,11 +385,14 @@ static int map_core(mab_ctx *ctx, const uint8_t *d_base, std::vector<ReadRec> &h
 		if(timed) { RT_EVENT_RECORD(ctx->ev[3], ctx->stream); }
 		/* rounds of sort+chain / extend (minialign.c:4444-4448) */
 		for(uint32_t round = 0; round < P.n_occ; round++) {
+			if(timed && round < 8) { RT_EVENT_RECORD(ctx->rev[3 * round], ctx->stream); }
 			RT_LAUNCH(k_sortchain, (n_seq + 63) / 64, 64, 0, ctx->stream, P, ctx->d_reads, n_seq, ctx->d_ws, ctx->d_frames, round);
 			RT_MEMSET_ASYNC(&ctx->d_ctr->work_next, 0, sizeof(unsigned int), ctx->stream);
+			if(timed && round < 8) { RT_EVENT_RECORD(ctx->rev[3 * round + 1], ctx->stream); }
 			RT_LAUNCH(k_extend, ext_ctas, 32 * MAB_WARPS_PER_CTA, 1024 + 1024 * MAB_WARPS_PER_CTA, ctx->stream, P, d_base, (const uint8_t *)ctx->d_ntail, ctx->d_reads, n_seq, ctx->d_ws,
 				ctx->d_arenas, AL.total, blk_cap, ctx->d_pool, pool_words, ctx->d_ctr, round, P.n_occ - 1);
 			S.n_launches += 2;
+			if(timed && round < 8) { RT_EVENT_RECORD(ctx->rev[3 * round + 2], ctx->stream); }
 		}
 		if(timed) { RT_EVENT_RECORD(ctx->ev[4], ctx->stream); }
 		BatchCounters hc;
@@ -476,7 +481,12 @@ extern "C" int mab_map_batch(mab_ctx *ctx, const uint8_t *seq_block, uint64_t bl
 	S.ms_post = (float)(RT_WALL_MS() - t0);
 	S.ms_h2d = RT_EVENT_MS(ctx->ev[0], ctx->ev[1]);
 	S.ms_seed = RT_EVENT_MS(ctx->ev[2], ctx->ev[3]);
-	S.ms_extend = RT_EVENT_MS(ctx->ev[3], ctx->ev[4]);
+	S.ms_sortchain = 0.f; S.ms_extend = 0.f; S.ms_extend_r0 = 0.f;
+	for(uint32_t r = 0; r < ctx->P.n_occ && r < 8; r++) {
+		S.ms_sortchain += RT_EVENT_MS(ctx->rev[3 * r], ctx->rev[3 * r + 1]);
+		float e = RT_EVENT_MS(ctx->rev[3 * r + 1], ctx->rev[3 * r + 2]);
+		S.ms_extend += e; if(r == 0) { S.ms_extend_r0 = e; }
+	}
 	S.ms_d2h = RT_EVENT_MS(ctx->ev[4], ctx->ev[5]);
 	S.ms_total = RT_EVENT_MS(ctx->ev[0], ctx->ev[5]);
 	return MAB_OK;

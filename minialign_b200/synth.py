@@ -140,11 +140,9 @@ def write_fasta(path, records, width: int = 0):
 
 
 def encode_2bit(seq: np.ndarray) -> np.ndarray:
-    """ASCII -> minialign's 1 byte/base codes A,C,G,T=0..3, everything else 4 (minialign.c:214-232)."""
-    tab = np.full(256, 4, dtype=np.uint8)
-    for ch, v in zip(b"ACGTacgt", (0, 1, 2, 3, 0, 1, 2, 3)):
-        tab[ch] = v
-    # minialign maps U/u to T as well
-    tab[ord("U")] = 3
-    tab[ord("u")] = 3
-    return tab[seq]
+    """ASCII -> minialign's 1 byte/base codes: the reader indexes a 16-entry table with the LOW NIBBLE of the character
+    (encaf, minialign.c:214-232): A,a -> 0, C,c -> 1, G,g -> 2, T,t,U,u -> 3, N,n -> 4, everything else -> 0."""
+    enc = np.zeros(16, dtype=np.uint8)
+    for ch, v in ((ord("A"), 0), (ord("C"), 1), (ord("G"), 2), (ord("T"), 3), (ord("U"), 3), (ord("N"), 4)):
+        enc[ch & 0x0F] = v
+    return enc[seq & 0x0F]
