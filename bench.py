@@ -120,7 +120,7 @@ def main():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch-reads", type=int, default=4096)
+    ap.add_argument("--batch-reads", type=int, default=16384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -161,7 +161,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    n_b = min(6, args.warmup + args.steps)
+    n_b = min(3, args.warmup + args.steps)
     t0 = time.time()
     g, idx, blob, batches = build_workload(work + f"/r{rank}", n_b, args.batch_reads, rank, seed=1)
     # weak scaling: every rank maps its own batches (different read seeds per rank)
@@ -204,6 +204,8 @@ def main():
             # the one exchange step of the sharded path: output offsets of this wave (8 B per rank)
             shard.output_offsets(4 * words, device=torch.device("cuda", local))
             m.lib.mab_release_batch(m.h)
+            if os.environ.get("MAB_BENCH_VERBOSE"):
+                log(f"[rank {rank}] step {i} device={mode_device} " + " ".join(f"{k}={v:.2f}" if isinstance(v, float) else f"{k}={v}" for k, v in st.items()))
             agg["bases"] += p[3]; agg["launches"] += st["n_launches"]; agg["h2d"] += st["h2d_bytes"]; agg["d2h"] += st["d2h_bytes"]
             agg["ms_ext"] += st["ms_extend"]; agg["ms_ext_r0"] += st["ms_extend_r0"]; agg["ms_dev"] += st["ms_total"]; agg["vec"] += st["n_vectors"]
         e1.record()

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <algorithm>
+#include <thread>
 
 using namespace mab;
 
@@ -386,7 +387,7 @@ static int map_core(mab_ctx *ctx, const uint8_t *d_base, std::vector<ReadRec> &h
 		/* rounds of sort+chain / extend (minialign.c:4444-4448) */
 		for(uint32_t round = 0; round < P.n_occ; round++) {
 			if(timed && round < 8) { RT_EVENT_RECORD(ctx->rev[3 * round], ctx->stream); }
-			RT_LAUNCH(k_sortchain, (n_seq + 63) / 64, 64, 0, ctx->stream, P, ctx->d_reads, n_seq, ctx->d_ws, ctx->d_frames, round);
+			RT_LAUNCH(k_sortchain, (n_seq + 3) / 4, 128, 0, ctx->stream, P, ctx->d_reads, n_seq, ctx->d_ws, ctx->d_frames, round);
 			RT_MEMSET_ASYNC(&ctx->d_ctr->work_next, 0, sizeof(unsigned int), ctx->stream);
 			if(timed && round < 8) { RT_EVENT_RECORD(ctx->rev[3 * round + 1], ctx->stream); }
 			RT_LAUNCH(k_extend, ext_ctas, 32 * MAB_WARPS_PER_CTA, 1024 + 1024 * MAB_WARPS_PER_CTA, ctx->stream, P, d_base, (const uint8_t *)ctx->d_ntail, ctx->d_reads, n_seq, ctx->d_ws,
@@ -441,7 +442,16 @@ extern "C" int mab_map_batch(mab_ctx *ctx, const uint8_t *seq_block, uint64_t bl
 	{ int rc = map_core(ctx, d_base, hr, true); if(rc) { return rc; } }
 	double t0 = RT_WALL_MS();
 	std::vector<std::vector<uint32_t>> words(n_seq);
-	for(uint32_t i = 0; i < n_seq; i++) { if(hr[i].result_words != 0) { post_process(ctx, ctx->h_pool.data(), ctx->h_pool.data() + hr[i].result_ofs, words[i]); } }
+	{	/* reads are independent here: fan the host post-processing out over the host cores */
+		uint32_t nth = std::max(1u, std::min<uint32_t>(std::min<uint32_t>(std::thread::hardware_concurrency(), 32u), n_seq / 64 + 1));
+		std::vector<std::thread> th;
+		auto work = [&](uint32_t t) {
+			for(uint32_t i = t; i < n_seq; i += nth) { if(hr[i].result_words != 0) { post_process(ctx, ctx->h_pool.data(), ctx->h_pool.data() + hr[i].result_ofs, words[i]); } }
+		};
+		for(uint32_t t = 1; t < nth; t++) { th.emplace_back(work, t); }
+		work(0);
+		for(auto &x : th) { x.join(); }
+	}
 	/* verify the rlen speculation in read order (the reference's -t1 semantics); re-map the reads whose first root test
 	 * would have gone the other way with the true stale value */
 	for(int iter = 0; iter < 8; iter++) {

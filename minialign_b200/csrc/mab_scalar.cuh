@@ -96,6 +96,15 @@ __device__ inline void radix_sort_exact(uint32_t *a, uint32_t n, int esz, uint32
 		uint32_t *end = f + 4;
 		uint32_t *base = a + (uint64_t)esz * beg;
 		if(f[2] == 0xffffffffu) {
+			/* levels on which every key of the range has the same digit move nothing in the reference (one bucket, every
+			 * element already in place) and recurse into the same range: skip them with one scan */
+			{
+				uint64_t k0 = rs_key(base, esz), diff = 0;
+				for(uint32_t i = 1; i < cnt; i++) { diff |= rs_key(base + esz * i, esz) ^ k0; }
+				while(s > 0 && ((diff >> s) & 0xff) == 0) { s = s > 8 ? s - 8 : 0; }
+				f[1] = s;
+				if(((diff >> s) & 0xff) == 0) { lvl--; continue; }		/* s == 0 and uniform: nothing left to order */
+			}
 			/* distribute this range by digit (s) */
 			uint32_t head[256];
 			for(int k = 0; k < 256; k++) { end[k] = 0; }
