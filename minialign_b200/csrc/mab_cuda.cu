@@ -5,6 +5,7 @@
  * There is no CPU fallback: every entry point fails with MAB_ENODEV when the CUDA runtime reports an error.
  */
 #include <cuda_runtime.h>
+#include "mab_types.h"
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
@@ -31,7 +32,7 @@ static inline cudaError_t RT_SET_DEVICE(int d)
 }
 static inline unsigned RT_SM_COUNT(int d) { int n = 0; cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return (unsigned)n; }
 /* persistent extend kernel: 4 CTAs x 4 warps per SM (multiple of the SM count) */
-static inline unsigned RT_EXTEND_SLOTS(unsigned n_sm) { return n_sm * 16; }
+static inline unsigned RT_EXTEND_SLOTS(unsigned n_sm) { return n_sm * 4 * MAB_EXT_CTAS_PER_SM; }
 template <class T> static inline cudaError_t RT_MALLOC(T **p, uint64_t n) { return cudaMalloc((void **)p, n); }
 template <class T> static inline void RT_FREE(T *p) { if(p) { cudaFree((void *)p); } }
 static inline cudaError_t RT_MEMCPY_H2D(void *d, const void *s, uint64_t n) { return cudaMemcpy(d, s, n, cudaMemcpyHostToDevice); }

@@ -102,25 +102,41 @@ __device__ __forceinline__ void build_lut(const DevParams &P, uint32_t *lut, int
 }
 
 /* ---------------------------------------------------------------- one anti-diagonal (gaba.c:1604-1699) */
-template <bool MASKS>
-__device__ __forceinline__ void vec_step(const DpCtx &c, Vec &v, int down, uint32_t newch, uint32_t &mbits, int slot)
+/* loop-invariant operands of a step, hoisted into registers once per fill */
+struct StepK {
+	uint32_t GFH, GFV, ADJH, ADJV, OFSH, OFSV;
+	const uint32_t *lut;
+	bool is0, isL;				/* lane holding cell 0 / cell W-1 */
+};
+__device__ __forceinline__ StepK make_stepk(const DpCtx &c)
 {
 	const DevParams &P = *c.P;
+	StepK k;
+	k.GFH = pack2h(P.gfh); k.GFV = pack2h(P.gfv); k.ADJH = pack2h(P.adjh); k.ADJV = pack2h(P.adjv); k.OFSH = pack2h(P.ofsh); k.OFSV = pack2h(P.ofsv);
+	k.lut = c.lut; k.is0 = c.lane == 0; k.isL = c.lane == c.nl - 1;
+	return k;
+}
+
+/* returns (when MASKS) the traceback nibbles of the two cells at bits 8..11 / 24..27: bit0 = ~h, bit1 = ~v, bit2 = ~e, bit3 = ~f */
+template <bool MASKS>
+__device__ __forceinline__ uint32_t vec_step(const StepK &k, Vec &v, int down, uint32_t newch)
+{
 	if(!down) {			/* _fill_right: bsl dh, df; a new a-base enters at cell 0 */
 		uint32_t uh = __shfl_up_sync(MAB_FULL, v.dh, 1), uf = __shfl_up_sync(MAB_FULL, v.df, 1), ua = __shfl_up_sync(MAB_FULL, v.wa, 1);
-		if(c.lane == 0) { uh = 0; uf = 0; ua = newch << 16; }
+		if(k.is0) { uh = 0; uf = 0; ua = newch << 16; }
 		v.dh = __byte_perm(uh, v.dh, 0x5432); v.df = __byte_perm(uf, v.df, 0x5432); v.wa = __byte_perm(ua, v.wa, 0x5432);
 	} else {			/* _fill_down: bsr dv, de; a new b-base enters at cell W-1 */
 		uint32_t nv = __shfl_down_sync(MAB_FULL, v.dv, 1), ne = __shfl_down_sync(MAB_FULL, v.de, 1), nb = __shfl_down_sync(MAB_FULL, v.wb, 1);
-		if(c.lane == c.nl - 1) { nv = 0; ne = 0; nb = newch; }
+		if(k.isL) { nv = 0; ne = 0; nb = newch; }
 		v.dv = __byte_perm(v.dv, nv, 0x5432); v.de = __byte_perm(v.de, ne, 0x5432); v.wb = __byte_perm(v.wb, nb, 0x5432);
 	}
 	uint32_t idx = v.wa | v.wb;
-	uint32_t t = c.lut[(idx & 0xf) | ((idx >> 12) & 0xf0)];
-	uint32_t dfh = __vadd2(v.dv, pack2h(P.gfh)), dfv = __vsub2(pack2h(P.gfv), v.dh);
+	uint32_t t = k.lut[(idx & 0xf) | ((idx >> 12) & 0xf0)];
+	uint32_t dfh = __vadd2(v.dv, k.GFH), dfv = __vsub2(k.GFV, v.dh);
 	t = __vimax3_s16x2(t, dfv, __vimax3_s16x2(v.de, v.df, dfh));
-	uint32_t te = __viaddmax_s16x2(v.de, pack2h(P.adjh), t);
-	uint32_t tf = __viaddmax_s16x2(v.df, pack2h(P.adjv), t);
+	uint32_t te = __viaddmax_s16x2(v.de, k.ADJH, t);
+	uint32_t tf = __viaddmax_s16x2(v.df, k.ADJV, t);
+	uint32_t bits = 0;
 	if(MASKS) {
 		/* t is the (int8) maximum, so t - x is 0..255 in the high byte: min.u16 against 0x0100 leaves bit 8 set <=> "not equal" */
 		const uint32_t one = 0x01000100u;
@@ -128,19 +144,20 @@ __device__ __forceinline__ void vec_step(const DpCtx &c, Vec &v, int down, uint3
 		uint32_t n_fv = __vminu2(__vsub2(t, dfv), one), n_f = __vminu2(__vsub2(t, v.df), one);
 		uint32_t g_e = __vminu2(__vsub2(te, t), one), g_f = __vminu2(__vsub2(tf, t), one);		/* set <=> te != t */
 		uint32_t NH = n_fh & n_e, NV = n_fv & n_f;								/* ~h, ~v */
-		uint32_t NE = (n_e | ~n_fh) & g_e, NF = (n_f | ~n_fv) & g_f;			/* ~e, ~f */
-		uint32_t bits = ((NH >> 8) & 0x00010001u) | ((NV >> 7) & 0x00020002u) | ((NE >> 6) & 0x00040004u) | ((NF >> 5) & 0x00080008u);
-		mbits |= bits << (4 * slot);
+		uint32_t NE = (n_e | (n_fh ^ one)) & g_e, NF = (n_f | (n_fv ^ one)) & g_f;	/* ~e, ~f */
+		bits = (NF * 2 + NE) * 4 + (NV * 2 + NH);								/* disjoint bits: three IMADs pack the nibble */
 	}
 	uint32_t de = __vadd2(te, v.dh), dh = __vadd2(v.dh, t);
 	uint32_t df = __vsub2(tf, v.dv); t = __vsub2(v.dv, t);
 	v.dv = dh; v.dh = t; v.de = de; v.df = df;
-	uint32_t dH = down ? __vadd2(pack2h(P.ofsv), v.dv) : __vsub2(pack2h(P.ofsh), v.dh);	/* _fill_update_delta */
+	uint32_t dH = down ? __vadd2(k.OFSV, v.dv) : __vsub2(k.OFSH, v.dh);			/* _fill_update_delta */
 	v.delta = __vadd2(v.delta, dH);											/* wraps like int8 */
 	uint32_t d = h8_to_s16(dH);
 	v.drop = clamp8x2(__vsub2(v.drop, d));									/* saturating */
-	int contrib = (c.lane == 0 ? lo16(d) : 0) - (c.lane == c.nl - 1 ? hi16(d) : 0);
+	int contrib = k.is0 ? lo16(d) : 0;
+	if(k.isL) { contrib -= hi16(d); }
 	v.acc += __reduce_add_sync(MAB_FULL, contrib);								/* _dir_update */
+	return bits;
 }
 
 /* load the vector registers from the entry physically before a block (_fill_load_context, gaba.c:1527-1550) */
@@ -310,15 +327,20 @@ __device__ __forceinline__ int32_t create_tail(DpCtx &c, FillWork &w, const Vec 
 }
 
 /* ---------------------------------------------------------------- block loop (gaba.c:1821-2103) */
+/* Bulk blocks (>= 32 bases left on both sides) run 32 steps without bound checks, unrolled by four so the traceback
+ * nibbles of four anti-diagonals land in one 32-bit word per lane (one coalesced 128 B row per four vectors); cap blocks
+ * test the section bounds before every step.  The diff vectors stay in registers from block to block; only the direction
+ * accumulator is re-truncated to int8 at each block boundary like the reference's `blk->acc` store. */
 template <bool MASKS>
-__device__ inline int32_t fill_blocks(DpCtx &c, FillWork &w, Vec &v, uint32_t &xd, int32_t cur)
+__device__ __forceinline__ int32_t fill_blocks(DpCtx &c, FillWork &w, Vec &v, uint32_t &xd, int32_t cur)
 {
 	const DevParams &P = *c.P;
-	int cap = 0;
-	int l = c.lane;
+	const StepK k = make_stepk(c);
+	int cap = 0, first = 1;
+	const int l = c.lane;
+	int xstat_prev = c.blk[cur].xstat;
 	while(1) {
-		MAB_DBG("fill_blocks cur %d xstat %d rem %u %u pridx %u cap %d err %u nblk %u\n", cur, (int)c.blk[cur].xstat, w.rem[0], w.rem[1], w.pridx, cap, c.err, c.nblk);
-		if(c.blk[cur].xstat < 0) { break; }											/* TERM */
+		if(xstat_prev < 0) { break; }												/* TERM */
 		if(!cap && (w.rem[0] < MAB_BLK || w.rem[1] < MAB_BLK || w.pridx < MAB_BLK)) { cap = 1; }
 		int32_t bi = push_blk(c);
 		if(c.err) { break; }
@@ -331,26 +353,46 @@ __device__ inline int32_t fill_blocks(DpCtx &c, FillWork &w, Vec &v, uint32_t &x
 			b->cha[l] = (uint16_t)((v.wa & 0xff) | ((v.wa >> 16) << 8));
 			b->chb[l] = (uint16_t)((v.wb & 0xff) | ((v.wb >> 16) << 8));
 		}
-		vec_load(c, v, &c.blk[bi - 1], xd);
+		if(first) { vec_load(c, v, &c.blk[bi - 1], xd); first = 0; }
+		else { v.delta = 0; v.drop = xd; v.acc = (int32_t)(int8_t)v.acc; v.dir = 0; }
 		uint32_t *mrow = c.masks + 256ull * bi + l;
-		uint32_t mbits = 0;
 		int acnt = 0, bcnt = 0, i = 0;
-		for(; i < MAB_BLK; i++) {
-			v.dir = (v.dir << 1) | (uint32_t)(v.acc < 0);								/* _dir_fetch */
-			int down = (int)(v.dir & 1);
-			if(cap) {																/* _fill_cap_test_idx */
-				int64_t ar = (int64_t)w.rem[0] - (acnt + !down), br = (int64_t)w.rem[1] - (bcnt + down);
-				int64_t pr = ar + br + (int64_t)w.pridx;
-				if((ar | br | pr) < 0) { v.dir >>= 1; break; }
+		if(!cap) {
+			#pragma unroll 1
+			for(int g = 0; g < MAB_BLK / 4; g++) {
+				uint32_t bq[4];
+				#pragma unroll
+				for(int u = 0; u < 4; u++) {
+					v.dir = (v.dir << 1) | (uint32_t)(v.acc < 0);						/* _dir_fetch */
+					int down = (int)(v.dir & 1);
+					uint32_t newch = down ? __shfl_sync(MAB_FULL, bn, bcnt) : __shfl_sync(MAB_FULL, an, acnt);
+					bcnt += down; acnt += 1 - down;
+					bq[u] = vec_step<MASKS>(k, v, down, newch);
+				}
+				if(MASKS) { mrow[32 * g] = (bq[0] >> 8) | (bq[1] >> 4) | bq[2] | (bq[3] << 4); }
 			}
-			uint32_t newch = down ? __shfl_sync(MAB_FULL, bn, bcnt) : __shfl_sync(MAB_FULL, an, acnt);
-			if(down) { bcnt++; } else { acnt++; }
-			vec_step<MASKS>(c, v, down, newch, mbits, i & 3);
-			if(MASKS && (i & 3) == 3) { mrow[32 * (i >> 2)] = mbits; mbits = 0; }
+			i = MAB_BLK;
+		} else {
+			uint32_t mbits = 0;
+			for(; i < MAB_BLK; i++) {
+				v.dir = (v.dir << 1) | (uint32_t)(v.acc < 0);
+				int down = (int)(v.dir & 1);
+				{																/* _fill_cap_test_idx */
+					int64_t ar = (int64_t)w.rem[0] - (acnt + !down), br = (int64_t)w.rem[1] - (bcnt + down);
+					int64_t pr = ar + br + (int64_t)w.pridx;
+					if((ar | br | pr) < 0) { v.dir >>= 1; break; }
+				}
+				uint32_t newch = down ? __shfl_sync(MAB_FULL, bn, bcnt) : __shfl_sync(MAB_FULL, an, acnt);
+				bcnt += down; acnt += 1 - down;
+				uint32_t bits = vec_step<MASKS>(k, v, down, newch);
+				if(MASKS) {
+					mbits |= ((bits >> 8) & 0x000f000fu) << (4 * (i & 3));
+					if((i & 3) == 3) { mrow[32 * (i >> 2)] = mbits; mbits = 0; }
+				}
+			}
+			if(MASKS && (i & 3) != 0) { mrow[32 * (i >> 2)] = mbits; }
 		}
-		if(MASKS && (i & 3) != 0) { mrow[32 * (i >> 2)] = mbits; }
 		c.n_vectors += (uint64_t)i;
-		MAB_DBG(" block bi %d i %d acnt %d bcnt %d dir %08x acc %d\n", bi, i, acnt, bcnt, v.dir, v.acc);
 		w.pridx -= (uint32_t)i;
 		if(i < MAB_BLK && i != 0) { v.dir <<= (MAB_BLK - i); }						/* _dir_adjust_remainder */
 		/* _fill_store_context (gaba.c:1734-1778) */
@@ -373,19 +415,16 @@ __device__ inline int32_t fill_blocks(DpCtx &c, FillWork &w, Vec &v, uint32_t &x
 		if(l < c.nl) {
 			b->dh[l] = (uint16_t)pack8h(v.dh); b->dv[l] = (uint16_t)pack8h(v.dv); b->de[l] = (uint16_t)pack8h(v.de); b->df[l] = (uint16_t)pack8h(v.df);
 		}
-#ifdef MAB_DEBUG_BLK
-		{ int d0 = lo16(__shfl_sync(MAB_FULL, dl, 0)), dW = hi16(__shfl_sync(MAB_FULL, dl, c.nl - 1));
-		if(l == 0 && getenv("ORA_DEBUG")) { fprintf(stderr, "GPU blk acnt %d bcnt %d dir %08x acc %d drop_c %d delta_c %d d0 %d dW %d\n", acnt, bcnt, v.dir, v.acc, dropc, cofs, d0, dW); } }
-#endif
 		if(l == 0) {
 			b->acc = (int8_t)v.acc; b->xstat = (int8_t)xstat; b->acnt = (int8_t)acnt; b->bcnt = (int8_t)bcnt;
 			b->dir_mask = v.dir; b->mm_lo = mlo; b->mm_hi = mhi; b->link = -1;
 			b->arem = w.rem[0] + (uint32_t)acnt; b->brem = w.rem[1] + (uint32_t)bcnt; b->tail = (uint32_t)c.ntail;	/* the tail created next */
 		}
-		__syncwarp();
+		xstat_prev = (int)(int8_t)xstat;
 		cur = bi;
 		if(i != MAB_BLK) { break; }
 	}
+	__syncwarp();
 	return cur;
 }
 
@@ -500,14 +539,15 @@ __device__ inline void leaf_search(DpCtx &c, int32_t ti, Leaf &lf)
 		uint32_t an = 0, bn = 0;
 		if((uint32_t)l < arem) { an = fetch_a(sa, sa.len - arem + l); }
 		if((uint32_t)l < brem) { bn = fetch_b(sb, sb.len - brem + l); }
-		uint32_t mx = 0, dummy = 0;
+		uint32_t mx = 0;
+		const StepK kk = make_stepk(c);
 		int acnt = 0, bcnt = 0;
 		for(int i = 0; i < n; i++) {
 			v.dir = (v.dir << 1) | (uint32_t)(v.acc < 0);
 			int down = (int)(v.dir & 1);
 			uint32_t newch = down ? __shfl_sync(MAB_FULL, bn, bcnt) : __shfl_sync(MAB_FULL, an, acnt);
 			if(down) { bcnt++; } else { acnt++; }
-			vec_step<false>(c, v, down, newch, dummy, 0);
+			vec_step<false>(kk, v, down, newch);
 			uint32_t ulo = __ballot_sync(MAB_FULL, l < c.nl && lo16(v.delta) > lo16(mx));
 			uint32_t uhi = __ballot_sync(MAB_FULL, l < c.nl && hi16(v.delta) > hi16(mx));
 			mx = __vmaxs2(mx, v.delta);
@@ -575,7 +615,7 @@ struct Trace {
 	uint32_t gi[2], ge[2], gf[2];
 	uint64_t npop, plen;
 	uint32_t *path;				/* path words in the result pool */
-	uint32_t cur_word; int64_t cur_idx;
+	uint32_t cur_word; int64_t cur_idx; int32_t cur_bit;
 };
 
 /* stage the 1 KB mask block of entry b into this warp's shared-memory tile (coalesced 128 B rows) */
@@ -599,14 +639,13 @@ __device__ __forceinline__ uint32_t mask_nib(const DpCtx &c, const uint32_t *til
 
 __device__ __forceinline__ void trace_pop(Trace &w, int v, int lane)
 {
-	int64_t bit = (int64_t)w.plen - 1 - (int64_t)w.npop;
-	int64_t wi = bit >> 5;
-	if(wi != w.cur_idx) {
+	/* path bits are produced from the end of the alignment towards its start: fill the current word downwards */
+	if(w.cur_bit < 0) {
 		if(lane == 0) { w.path[w.cur_idx] = w.cur_word; }
-		w.cur_idx = wi; w.cur_word = 0;
+		w.cur_idx--; w.cur_word = 0; w.cur_bit = 31;
 	}
-	w.cur_word |= (uint32_t)v << (bit & 31);
-	w.npop++;
+	w.cur_word |= (uint32_t)v << w.cur_bit;
+	w.cur_bit--; w.npop++;
 }
 
 /* trace_reload_section (gaba.c:2826-2859) */
@@ -626,113 +665,111 @@ __device__ __forceinline__ void trace_reload_section(const DpCtx &c, Trace &w, i
 	w.gidx[i] = gidx; w.sgidx[i] = gidx;
 }
 
-/* trace_core (gaba.c:3111-3232) as an explicit state machine with the reference's bulk / tail modes */
-__device__ inline void trace_core(DpCtx &c, Trace &w, uint32_t *tile)
+/* trace_core (gaba.c:3111-3232): the reference's diag / h-gap / v-gap loops with its bulk and tail modes, as straight
+ * gotos (one shared-memory nibble lookup per popped vector).  The rare block-boundary work sits in one out-of-line
+ * `reload` section that returns to the pop site through `ret`. */
+__device__ __forceinline__ void trace_core(DpCtx &c, Trace &w, uint32_t *tile)
 {
 	const int W = c.W;
 	const uint32_t HEAD_CNT = (uint32_t)(W / MAB_BLK + (W == 16));
 	int32_t b = w.blk, mi = w.mi; uint32_t q = w.q, save = HEAD_CNT;
 	uint32_t dir = c.blk[b].dir_mask >> (MAB_BLK - (mi + 1));
-	int bulk = 0, pos;
-	switch(w.state) {
-		case mab_ts_d:  pos = MP_D_HEAD; break;
-		case mab_ts_v0: pos = MP_V_HEAD; break;
-		case mab_ts_v1: pos = MP_V_TAIL; break;
-		case mab_ts_h0: pos = MP_H_HEAD; break;
-		case mab_ts_h1: pos = MP_H_TAIL; break;
-		default: return;
-	}
+	int bulk = 0, ret = 0;
+	int32_t g0 = w.gidx[0], g1 = w.gidx[1];
+	uint32_t nb;
 	stage_masks(c, b, tile);
-	#define NIB()			mask_nib(c, tile, mi, q)
-	#define TEST_BULK(_ok) { \
-		int32_t _ga = w.gidx[0] - c.blk[b].acnt, _gb = w.gidx[1] - c.blk[b].bcnt; \
-		_ok = !(W > _ga) && !(W > _gb); \
-		if(_ok) { w.gidx[0] = _ga; w.gidx[1] = _gb; } \
-	}
-	#define RELOAD_BLOCK() { \
-		b--; mi = MAB_BLK - 1; dir = c.blk[b].dir_mask; \
-		if(c.blk[b].xstat & MAB_X_HEAD) { \
-			do { b = c.blk[b].link; } while(c.blk[b].xstat & MAB_X_HEAD); \
-			int _cnt = c.blk[b].acnt + c.blk[b].bcnt; \
-			mi = _cnt - 1; dir = c.blk[b].dir_mask >> (MAB_BLK - _cnt); \
-		} \
-	}
-	#define POP(_v) { \
-		if(!bulk) { w.gidx[_v]--; } \
+	nb = mask_nib(c, tile, mi, q);
+	#define POP(_v, _id) { \
+		if(!bulk) { if(_v) { g1--; } else { g0--; } } \
 		trace_pop(w, _v, c.lane); mi--; \
 		q += (dir & 1) - (uint32_t)(_v); dir >>= 1; \
-		if(mi < 0) { \
-			int _term = 0; \
-			if(bulk) { \
-				RELOAD_BLOCK(); \
-				int _ok; TEST_BULK(_ok); \
-				if(!_ok) { \
-					if(q >= (uint32_t)W) { _term = 1; } \
-					else { w.gidx[1] += (int32_t)(q - save); w.gidx[0] += (int32_t)(save - q); save = HEAD_CNT; bulk = 0; } \
-				} \
-			} else { \
-				if(c.blk[b - 1].xstat & MAB_X_HEAD) { \
-					b--; do { b = c.blk[b].link; } while(c.blk[b].xstat & MAB_X_HEAD); \
-					int _cnt = c.blk[b].acnt + c.blk[b].bcnt; \
-					mi = _cnt - 1; dir = c.blk[b].dir_mask >> (MAB_BLK - _cnt); \
-				} else { \
-					RELOAD_BLOCK(); \
-					if(--save >= HEAD_CNT) { int _ok; TEST_BULK(_ok); if(_ok) { save = q; bulk = 1; } } \
-				} \
-			} \
-			if(_term) { goto term; } \
-			stage_masks(c, b, tile); \
-		} \
+		if(mi < 0) { ret = _id; goto reload; } \
+		R##_id: nb = mask_nib(c, tile, mi, q); \
 	}
-	while(1) {
-		uint32_t nb;
-		switch(pos) {
-		case MP_D_HEAD:
-			nb = NIB();
-			if(!(nb & 1)) { pos = MP_H_HEAD; break; }								/* h bit set */
-			if(!bulk && (w.gidx[0] == 0 || w.gidx[1] == 0)) { w.state = mab_ts_d; goto term; }
-			POP(0); pos = MP_D_MID; break;
-		case MP_D_MID:
-			POP(1); pos = MP_D_TAIL; break;
-		case MP_D_TAIL:
-			nb = NIB();
-			if(!(nb & 2)) { pos = MP_V_HEAD; break; }
-			pos = MP_D_HEAD; break;
-		case MP_H_HEAD:
-			nb = NIB();
-			if(nb & 4) {															/* e bit clear: short gap */
-				if(!bulk && w.gidx[0] == 0) { w.state = mab_ts_h0; goto term; }
-				w.gf[0]++; POP(0); pos = MP_D_HEAD; break;
-			}
-			w.gi[0]++; pos = MP_H_BODY; break;
-		case MP_H_BODY:
-			if(!bulk && w.gidx[0] == 0) { w.state = mab_ts_h1; goto term; }
-			w.ge[0]++; POP(0); pos = MP_H_TAIL; break;
-		case MP_H_TAIL:
-			nb = NIB();
-			/* (~h & e) bit clear <=> !(~h set && e set) <=> !((nb & 1) && !(nb & 4)) */
-			pos = !((nb & 1) && !(nb & 4)) ? MP_H_BODY : MP_D_HEAD; break;
-		case MP_V_HEAD:
-			nb = NIB();
-			if(nb & 8) {
-				if(!bulk && w.gidx[1] == 0) { w.state = mab_ts_v0; goto term; }
-				w.gf[1]++; POP(1); pos = MP_D_TAIL; break;
-			}
-			w.gi[1]++; pos = MP_V_BODY; break;
-		case MP_V_BODY:
-			if(!bulk && w.gidx[1] == 0) { w.state = mab_ts_v1; goto term; }
-			w.ge[1]++; POP(1); pos = MP_V_TAIL; break;
-		case MP_V_TAIL:
-			nb = NIB();
-			pos = !((nb & 2) && !(nb & 8)) ? MP_V_BODY : MP_D_TAIL; break;
+	switch(w.state) {
+		case mab_ts_d:  goto L_D_HEAD;
+		case mab_ts_v0: goto L_V_HEAD;
+		case mab_ts_v1: goto L_V_TAIL;
+		case mab_ts_h0: goto L_H_HEAD;
+		case mab_ts_h1: goto L_H_TAIL;
+		default: return;
+	}
+L_D_HEAD:
+	if(!(nb & 1)) { goto L_H_HEAD; }											/* h bit set */
+	if(!bulk && (g0 == 0 || g1 == 0)) { w.state = mab_ts_d; goto term; }
+	POP(0, 1);
+	POP(1, 2);
+L_D_TAIL:
+	if(!(nb & 2)) { goto L_V_HEAD; }
+	goto L_D_HEAD;
+L_H_HEAD:
+	if(nb & 4) {																/* e bit clear: short gap */
+		if(!bulk && g0 == 0) { w.state = mab_ts_h0; goto term; }
+		w.gf[0]++; POP(0, 3);
+		goto L_D_HEAD;
+	}
+	w.gi[0]++;
+L_H_BODY:
+	if(!bulk && g0 == 0) { w.state = mab_ts_h1; goto term; }
+	w.ge[0]++; POP(0, 4);
+L_H_TAIL:
+	if(!((nb & 1) && !(nb & 4))) { goto L_H_BODY; }								/* (~h & e) bit clear */
+	goto L_D_HEAD;
+L_V_HEAD:
+	if(nb & 8) {
+		if(!bulk && g1 == 0) { w.state = mab_ts_v0; goto term; }
+		w.gf[1]++; POP(1, 5);
+		goto L_D_TAIL;
+	}
+	w.gi[1]++;
+L_V_BODY:
+	if(!bulk && g1 == 0) { w.state = mab_ts_v1; goto term; }
+	w.ge[1]++; POP(1, 6);
+L_V_TAIL:
+	if(!((nb & 2) && !(nb & 8))) { goto L_V_BODY; }
+	goto L_D_TAIL;
+
+reload:
+	{
+		/* _trace_test_bulk (3052-3060), _trace_reload_block (3032-3043), _trace_reload_tail (3009-3026) */
+		#define TEST_BULK(_ok) { \
+			int32_t _ga = g0 - c.blk[b].acnt, _gb = g1 - c.blk[b].bcnt; \
+			_ok = !(W > _ga) && !(W > _gb); \
+			if(_ok) { g0 = _ga; g1 = _gb; } \
 		}
+		#define RELOAD_BLOCK() { \
+			b--; mi = MAB_BLK - 1; dir = c.blk[b].dir_mask; \
+			if(c.blk[b].xstat & MAB_X_HEAD) { \
+				do { b = c.blk[b].link; } while(c.blk[b].xstat & MAB_X_HEAD); \
+				int _cnt = c.blk[b].acnt + c.blk[b].bcnt; \
+				mi = _cnt - 1; dir = c.blk[b].dir_mask >> (MAB_BLK - _cnt); \
+			} \
+		}
+		if(bulk) {																/* _trace_bulk_load_n (3070-3082) */
+			RELOAD_BLOCK();
+			int ok; TEST_BULK(ok);
+			if(!ok) {
+				if(q >= (uint32_t)W) { goto term; }
+				g1 += (int32_t)(q - save); g0 += (int32_t)(save - q); save = HEAD_CNT; bulk = 0;
+			}
+		} else {																/* _trace_tail_load_n (3083-3099) */
+			if(c.blk[b - 1].xstat & MAB_X_HEAD) {
+				b--; do { b = c.blk[b].link; } while(c.blk[b].xstat & MAB_X_HEAD);
+				int cnt = c.blk[b].acnt + c.blk[b].bcnt;
+				mi = cnt - 1; dir = c.blk[b].dir_mask >> (MAB_BLK - cnt);
+			} else {
+				RELOAD_BLOCK();
+				if(--save >= HEAD_CNT) { int ok; TEST_BULK(ok); if(ok) { save = q; bulk = 1; } }
+			}
+		}
+		#undef TEST_BULK
+		#undef RELOAD_BLOCK
+		stage_masks(c, b, tile);
+		switch(ret) { case 1: goto R1; case 2: goto R2; case 3: goto R3; case 4: goto R4; case 5: goto R5; default: goto R6; }
 	}
 term:
-	w.blk = b; w.mi = mi; w.q = q & 0xff;
+	w.blk = b; w.mi = mi; w.q = q & 0xff; w.gidx[0] = g0; w.gidx[1] = g1;
 	__syncwarp();
-	#undef NIB
-	#undef TEST_BULK
-	#undef RELOAD_BLOCK
 	#undef POP
 }
 
@@ -756,7 +793,7 @@ __device__ inline uint64_t dp_trace(DpCtx &c, int32_t ti, uint32_t *pool, uint64
 	w.blk = lf.blk; w.mi = (int32_t)lf.p; w.q = lf.q; w.state = mab_ts_d;
 	for(int i = 0; i < 2; i++) { w.gidx[i] = lf.gidx[i]; w.sgidx[i] = lf.sgidx[i]; w.tail[i] = ti; w.ofs[i] = 0; w.id[i] = 0; w.gi[i] = w.ge[i] = w.gf[i] = 0; }
 	w.npop = 0; w.plen = plen; w.path = rec + MAB_ALN_HDR + 8ull * sn;
-	w.cur_idx = (int64_t)(plen >> 5); w.cur_word = 1u << (plen & 31);				/* sentinel (gaba.c:3287) */
+	w.cur_idx = (int64_t)(plen >> 5); w.cur_word = 1u << (plen & 31); w.cur_bit = (int32_t)(plen & 31) - 1;	/* sentinel (gaba.c:3287) */
 	if(c.lane == 0) { w.path[(plen >> 5) + 1] = 0; }
 	uint32_t nseg = 0;
 	uint32_t fuel = sn + 8;

@@ -387,7 +387,7 @@ static int map_core(mab_ctx *ctx, const uint8_t *d_base, std::vector<ReadRec> &h
 		/* rounds of sort+chain / extend (minialign.c:4444-4448) */
 		for(uint32_t round = 0; round < P.n_occ; round++) {
 			if(timed && round < 8) { RT_EVENT_RECORD(ctx->rev[3 * round], ctx->stream); }
-			RT_LAUNCH(k_sortchain, (n_seq + 3) / 4, 128, 0, ctx->stream, P, ctx->d_reads, n_seq, ctx->d_ws, ctx->d_frames, round);
+			RT_LAUNCH(k_sortchain, (n_seq + 3) / 4, 128, 2048 * 4, ctx->stream, P, ctx->d_reads, n_seq, ctx->d_ws, ctx->d_frames, round);
 			RT_MEMSET_ASYNC(&ctx->d_ctr->work_next, 0, sizeof(unsigned int), ctx->stream);
 			if(timed && round < 8) { RT_EVENT_RECORD(ctx->rev[3 * round + 1], ctx->stream); }
 			RT_LAUNCH(k_extend, ext_ctas, 32 * MAB_WARPS_PER_CTA, 1024 + 1024 * MAB_WARPS_PER_CTA, ctx->stream, P, d_base, (const uint8_t *)ctx->d_ntail, ctx->d_reads, n_seq, ctx->d_ws,
@@ -443,7 +443,9 @@ extern "C" int mab_map_batch(mab_ctx *ctx, const uint8_t *seq_block, uint64_t bl
 	double t0 = RT_WALL_MS();
 	std::vector<std::vector<uint32_t>> words(n_seq);
 	{	/* reads are independent here: fan the host post-processing out over the host cores */
-		uint32_t nth = std::max(1u, std::min<uint32_t>(std::min<uint32_t>(std::thread::hardware_concurrency(), 32u), n_seq / 64 + 1));
+		uint32_t hw = std::thread::hardware_concurrency();
+		if(const char *e = getenv("MAB_HOST_THREADS")) { int v = atoi(e); if(v > 0) { hw = (uint32_t)v; } }
+		uint32_t nth = std::max(1u, std::min<uint32_t>(std::min<uint32_t>(hw, 32u), n_seq / 64 + 1));
 		std::vector<std::thread> th;
 		auto work = [&](uint32_t t) {
 			for(uint32_t i = t; i < n_seq; i += nth) { if(hr[i].result_words != 0) { post_process(ctx, ctx->h_pool.data(), ctx->h_pool.data() + hr[i].result_ofs, words[i]); } }
@@ -546,7 +548,7 @@ extern "C" uint64_t mab_seed_chain(mab_ctx *ctx, const uint8_t *seq, uint32_t le
 		RT_MALLOC(&d_ws, L.total + 256);
 		RT_MEMCPY_H2D(d_r, &r, sizeof(r));
 		RT_LAUNCH((k_seed<false>), 1, 32, 512, ctx->stream, P, (const uint8_t *)d_seq, d_r, 1u, d_ws);
-		for(uint32_t i = 0; i <= round && i < P.n_occ; i++) { RT_LAUNCH(k_sortchain, 1, 32, 0, ctx->stream, P, d_r, 1u, d_ws, d_fr, i); }
+		for(uint32_t i = 0; i <= round && i < P.n_occ; i++) { RT_LAUNCH(k_sortchain, 1, 32, 2048, ctx->stream, P, d_r, 1u, d_ws, d_fr, i); }
 		RT_STREAM_SYNC(ctx->stream);
 		RT_MEMCPY_D2H(&r, d_r, sizeof(r));
 		if(r.n_seed) {

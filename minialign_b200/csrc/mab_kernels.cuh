@@ -179,41 +179,55 @@ __global__ void k_sketch_words(DevParams P, const uint8_t *seq, uint32_t len, ui
 /* ---------------------------------------------------------------- k_sortchain */
 __global__ void k_sortchain(DevParams P, ReadRec *reads, uint32_t n_reads, uint8_t *ws, uint32_t *frames, uint32_t round)
 {
-	/* one WARP per read, lane 0 working: the control flow is sequential and data dependent per read, and 32 different
-	 * reads on the lanes of one warp would serialise each other (measured: 74 ms vs the latency of one read) */
+	/* one WARP per read: the sorts are warp-cooperative (radix_sort_exact_warp), the data-dependent sequential parts
+	 * (rescue expansion, chaining) run on lane 0.  (One read per THREAD serialises 32 divergent reads per warp: 74 ms
+	 * measured against the latency of a single read.) */
+	MAB_DYN_SMEM(smem);
+	int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	uint32_t *sm = (uint32_t *)smem + 512 * wib;
 	uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	if(i >= n_reads || (threadIdx.x & 31) != 0) { return; }
+	if(i >= n_reads) { return; }
 	ReadRec *r = &reads[i];
 	if(r->state != 0) { return; }
 	WsLayout L = ws_layout(r->seed_cap, r->root_cap, r->resc_cap, r->bin_cap);
 	uint32_t *seed = (uint32_t *)(ws + r->ws_ofs + L.seed), *root = (uint32_t *)(ws + r->ws_ofs + L.root), *resc = (uint32_t *)(ws + r->ws_ofs + L.resc);
 	uint32_t *fr = frames + (uint64_t)i * 8 * MAB_RS_FRAME;
 	uint32_t n = r->n_seed;
-	r->n_root = 0; r->n_next = 0;
 	if(round > 0) {																/* mm_seed, cnt > 0 (3510-3526) */
-		if(round == 1) { radix_sort_exact(resc, r->n_resc, 4, fr); }
-		for(uint32_t s = 0; s < n; s++) { seed[4ull * s + 3] = 0x7fffffffu; }
-		uint32_t p = r->presc;
-		while(p < r->n_resc && resc[4ull * p + 1] <= P.occ[round]) {
-			const uint32_t *e = resc + 4ull * p;
-			const uint8_t *occ = P.idx + ((uint64_t)e[2] | (uint64_t)e[3] << 32);
-			if(n + e[1] + 2 > r->seed_cap / 2) { r->err |= MAB_ERR_SEED_OVF; break; }
-			for(uint32_t t = 0; t < e[1]; t++) { make_seed(P, seed + 4ull * (n + t), ldg32(occ + 8ull * t), ldg32(occ + 8ull * t + 4), e[0]); }
-			n += e[1]; p++;
+		if(round == 1) { radix_sort_exact_warp(resc, r->n_resc, 4, fr, sm, lane); }
+		for(uint32_t s = lane; s < n; s += 32) { seed[4ull * s + 3] = 0x7fffffffu; }
+		__syncwarp();
+		if(lane == 0) {
+			uint32_t p = r->presc;
+			while(p < r->n_resc && resc[4ull * p + 1] <= P.occ[round]) {
+				const uint32_t *e = resc + 4ull * p;
+				const uint8_t *occ = P.idx + ((uint64_t)e[2] | (uint64_t)e[3] << 32);
+				if(n + e[1] + 2 > r->seed_cap / 2) { r->err |= MAB_ERR_SEED_OVF; break; }
+				for(uint32_t t = 0; t < e[1]; t++) { make_seed(P, seed + 4ull * (n + t), ldg32(occ + 8ull * t), ldg32(occ + 8ull * t + 4), e[0]); }
+				n += e[1]; p++;
+			}
+			r->presc = p;
 		}
-		r->presc = p;
+		n = __shfl_sync(0xffffffffu, n, 0);
 	}
-	r->n_seed = n;
-	if(n == 0) { r->seed_n = 0; return; }
-	uint32_t *s = seed + 4ull * n;													/* sentinel (3531) */
-	s[0] = 0x80000000u; s[1] = 0x7fffffffu; s[2] = 0x80000000u; s[3] = 0x7fffffffu;
-	radix_sort_exact(seed, n + 1, 4, fr);
-	uint32_t seed_n = 0;
-	uint32_t nc = chain_seeds(P, seed, n, root, &seed_n);							/* mm_chain (3702-3721); circular refs unsupported */
-	r->seed_n = seed_n;
+	if(lane == 0) {
+		r->n_root = 0; r->n_next = 0; r->n_seed = n;
+		if(n == 0) { r->seed_n = 0; }
+		else { uint32_t *s = seed + 4ull * n; s[0] = 0x80000000u; s[1] = 0x7fffffffu; s[2] = 0x80000000u; s[3] = 0x7fffffffu; }	/* sentinel (3531) */
+	}
+	__syncwarp();
+	if(n == 0) { return; }
+	radix_sort_exact_warp(seed, n + 1, 4, fr, sm, lane);
+	uint32_t nc = 0;
+	if(lane == 0) {
+		uint32_t seed_n = 0;
+		nc = chain_seeds(P, seed, n, root, &seed_n);							/* mm_chain (3702-3721); circular refs unsupported */
+		r->seed_n = seed_n;
+	}
+	nc = __shfl_sync(0xffffffffu, nc, 0);
 	if(nc == 0) { return; }
-	radix_sort_exact(root, nc, 2, fr);
-	r->n_root = nc;
+	radix_sort_exact_warp(root, nc, 2, fr, sm, lane);
+	if(lane == 0) { r->n_root = nc; }
 }
 
 /* ---------------------------------------------------------------- mm_extend state machine, lane-0 routines */
@@ -439,7 +453,7 @@ __device__ __forceinline__ SecDesc make_sec(const uint8_t *base, uint32_t len, u
 
 /* ---------------------------------------------------------------- k_extend */
 /* shared memory per CTA: 1 KB score LUT + per warp a 1 KB traceback mask tile */
-__global__ void k_extend(DevParams P, const uint8_t *base, const uint8_t *ntail, ReadRec *reads, uint32_t n_reads, uint8_t *ws,
+__global__ void __launch_bounds__(32 * MAB_WARPS_PER_CTA, MAB_EXT_CTAS_PER_SM) k_extend(DevParams P, const uint8_t *base, const uint8_t *ntail, ReadRec *reads, uint32_t n_reads, uint8_t *ws,
 	uint8_t *arenas, uint64_t arena_stride, uint32_t blk_cap, uint32_t *pool, uint64_t pool_cap, BatchCounters *ctr, uint32_t round, uint32_t last_round)
 {
 	MAB_DYN_SMEM(smem);

@@ -147,6 +147,93 @@ __device__ inline void radix_sort_exact(uint32_t *a, uint32_t n, int esz, uint32
 	}
 }
 
+/* Warp-cooperative version of radix_sort_exact: identical result (same permutation cycles, walked by lane 0 in the
+ * reference's order), but the digit histogram, the prefix sum, the uniform-level scan and the insertion sorts of the
+ * (independent) small buckets are spread over the 32 lanes.  `sm` = 512 u32 of shared memory owned by this warp. */
+__device__ inline void radix_sort_exact_warp(uint32_t *a, uint32_t n, int esz, uint32_t *frames, uint32_t *sm, int lane)
+{
+	if(n <= 64) { if(lane == 0) { rs_insertion(a, n, esz); } __syncwarp(); return; }
+	uint32_t *cnt = sm, *head = sm + 256;
+	int lvl = 0;
+	if(lane == 0) { frames[0] = 0; frames[1] = (uint32_t)(esz == 4 ? 56 : 24); frames[2] = 0xffffffffu; frames[3] = n; }
+	__syncwarp();
+	while(lvl >= 0) {
+		uint32_t *f = frames + MAB_RS_FRAME * lvl;
+		uint32_t beg = f[0], s = f[1], cntn = f[3], state = f[2];
+		uint32_t *end = f + 4;
+		uint32_t *base = a + (uint64_t)esz * beg;
+		__syncwarp();
+		if(state == 0xffffffffu) {
+			uint64_t k0 = rs_key(base, esz), diff = 0;
+			for(uint32_t i = 1 + lane; i < cntn; i += 32) { diff |= rs_key(base + esz * i, esz) ^ k0; }
+			uint32_t dlo = __reduce_or_sync(0xffffffffu, (uint32_t)diff), dhi = __reduce_or_sync(0xffffffffu, (uint32_t)(diff >> 32));
+			diff = (uint64_t)dhi << 32 | dlo;
+			while(s > 0 && ((diff >> s) & 0xff) == 0) { s = s > 8 ? s - 8 : 0; }
+			if(((diff >> s) & 0xff) == 0) { lvl--; continue; }
+			for(int k = lane; k < 256; k += 32) { cnt[k] = 0; }
+			__syncwarp();
+			for(uint32_t i = lane; i < cntn; i += 32) { atomicAdd(&cnt[(rs_key(base + esz * i, esz) >> s) & 0xff], 1u); }
+			__syncwarp();
+			/* inclusive prefix sum over 256 counters: 8 per lane + warp scan */
+			uint32_t loc[8], sum = 0;
+			for(int j = 0; j < 8; j++) { sum += cnt[8 * lane + j]; loc[j] = sum; }
+			uint32_t inc = sum;
+			for(int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, inc, d); if(lane >= d) { inc += y; } }
+			uint32_t excl = inc - sum;
+			__syncwarp();
+			for(int j = 0; j < 8; j++) { uint32_t e = excl + loc[j]; end[8 * lane + j] = e; cnt[8 * lane + j] = e; head[8 * lane + j] = e - (loc[j] - (j ? loc[j - 1] : 0)); }
+			__syncwarp();
+			if(lane == 0) {
+				/* the permutation: cycle leaders in bucket order, exactly as the reference walks them */
+				for(int k = 0; k < 256;) {
+					if(head[k] != cnt[k]) {
+						int l = (int)((rs_key(base + esz * head[k], esz) >> s) & 0xff);
+						if(l != k) {
+							uint32_t tmp[4], swp[4];
+							rs_copy(tmp, base + esz * head[k], esz);
+							do {
+								rs_copy(swp, tmp, esz); rs_copy(tmp, base + esz * head[l], esz); rs_copy(base + esz * head[l], swp, esz); head[l]++;
+								l = (int)((rs_key(tmp, esz) >> s) & 0xff);
+							} while(l != k);
+							rs_copy(base + esz * head[k], tmp, esz); head[k]++;
+						} else { head[k]++; }
+					} else { k++; }
+				}
+				f[1] = s; f[2] = 0;
+			}
+			__syncwarp();
+			if(s == 0) { lvl--; continue; }
+			/* small buckets are independent: insertion-sort them in parallel, one bucket per lane at a time */
+			for(int k = lane; k < 256; k += 32) {
+				uint32_t b0 = k == 0 ? 0 : end[k - 1], sz = end[k] - b0;
+				if(sz > 1 && sz <= 64) { rs_insertion(base + esz * b0, sz, esz); }
+			}
+			__syncwarp();
+		}
+		/* descend into the large buckets in order */
+		uint32_t ns = s > 8 ? s - 8 : 0;
+		uint32_t kcur = f[2];
+		int descended = 0;
+		__syncwarp();
+		while(kcur < 256) {
+			uint32_t k = kcur++;
+			uint32_t b0 = k == 0 ? 0 : end[k - 1], sz = end[k] - b0;
+			if(sz > 64) {
+				if(lane == 0) {
+					f[2] = kcur;
+					uint32_t *g = frames + MAB_RS_FRAME * (lvl + 1);
+					g[0] = beg + b0; g[1] = ns; g[2] = 0xffffffffu; g[3] = sz;
+				}
+				lvl++; descended = 1;
+				break;
+			}
+		}
+		__syncwarp();
+		if(!descended) { lvl--; }
+	}
+	__syncwarp();
+}
+
 /* ---------------------------------------------------------------- seeds and chaining (minialign.c:3340-3625) */
 __device__ __forceinline__ uint32_t u_of(uint32_t x, uint32_t y) { return ((x << 1) - y) + MAB_OFS0; }
 __device__ __forceinline__ uint32_t v_of(uint32_t x, uint32_t y) { return ((y << 1) - x) + MAB_OFS0; }

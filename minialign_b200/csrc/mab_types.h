@@ -12,6 +12,9 @@ namespace mab {
 #define MAB_KH_CAP		1024u		/* slots of the per-read dedup hash (reference starts at 256 and doubles) */
 #define MAB_MAX_TAILS	24
 #define MAB_WARPS_PER_CTA 4
+#ifndef MAB_EXT_CTAS_PER_SM
+#define MAB_EXT_CTAS_PER_SM 6		/* resident CTAs of the persistent extend kernel per SM (register budget = 65536 / (128 x this)) */
+#endif
 
 /* GABA status bits (gaba.h:45-51) and block status (gaba.c:670-680) */
 #define MAB_UPDATE_A	0x000fu
