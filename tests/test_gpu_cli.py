@@ -1,0 +1,46 @@
+"""Drop-in check at the command line: `minialign-b200 -xpacbio ref.mai reads.fa` must print the reference's SAM byte for byte
+(every line except @PG)."""
+import os
+import subprocess
+
+import pytest
+
+from conftest import GOLD, ROOT
+import refh
+
+pytestmark = pytest.mark.gpu
+CLI = os.path.join(ROOT, "minialign_b200", "minialign-b200")
+
+
+def run_cli(args):
+    if not os.path.exists(CLI):
+        subprocess.check_call(["make", "-s", "-f", "minialign_b200/csrc/host/Makefile"], cwd=ROOT)
+    p = subprocess.run([CLI, *args], capture_output=True)
+    assert p.returncode == 0, p.stderr.decode()[-500:]
+    return [l for l in p.stdout.decode().split("\n") if not l.startswith("@PG")]
+
+
+@pytest.mark.parametrize("golden,extra", [("golden_pacbio.sam", []), ("golden_tags.sam", ["-TAS,XS,NM,MD,NH,IH"])])
+def test_cli_matches_golden_sam(golden, extra):
+    got = run_cli(["-xpacbio", *extra, os.path.join(GOLD, "small.mai"), os.path.join(GOLD, "reads.fa")])
+    exp = [l for l in open(os.path.join(GOLD, golden)).read().split("\n") if not l.startswith("@PG")]
+    assert got == exp
+
+
+@pytest.mark.skipif(not os.path.exists(refh.BIN), reason="oracle/_ref/minialign not built")
+@pytest.mark.parametrize("preset", ["pacbio", "ont.1dsq"])
+def test_cli_matches_live_reference_on_20kb_reads(tmp_path, preset):
+    """BASELINE config 0 in small: E.coli-like reference, PBSIM-like 20 kb reads, reference run with -t1 on the box's CPU."""
+    from minialign_b200 import synth
+    g = synth.make_genome(1_000_000, 2, seed=21)
+    reads = synth.make_reads(g, 6_000_000, seed=22) + synth.make_hard_reads(g, seed=23)
+    fa, rd, idx = str(tmp_path / "g.fa"), str(tmp_path / "r.fa"), str(tmp_path / "g.mai")
+    synth.write_fasta(fa, g, 80); synth.write_fasta(rd, reads)
+    subprocess.check_call([refh.BIN, "-x" + preset, "-d", idx, fa], stderr=subprocess.DEVNULL)
+    ref = subprocess.run([refh.BIN, "-x" + preset, "-t1", "-TAS,XS,NM,MD,SA", idx, rd], capture_output=True)
+    assert ref.returncode == 0
+    exp = [l for l in ref.stdout.decode().split("\n") if not l.startswith("@PG")]
+    got = run_cli(["-x" + preset, "-TAS,XS,NM,MD,SA", "-n", "97", idx, rd])          # odd batch size: state must carry across batches
+    assert len(got) == len(exp)
+    bad = [i for i, (a, b) in enumerate(zip(got, exp)) if a != b]
+    assert not bad, (len(bad), got[bad[0]][:200], exp[bad[0]][:200])
