@@ -63,10 +63,22 @@ struct DpCtx {
 	uint64_t n_vectors;
 };
 
+/* Band registers of one warp (lane l holds cells 2l and 2l+1 as the two 16-bit halves of each register).
+ * Representation (chosen so that one step needs no packed subtraction, which sm_100 has no instruction for):
+ *   A = -dh, V = dv, E = de, F = df    exact H8 values (int8 in the high byte, low byte 0)
+ *   every candidate of the max (score, dfh, dfv, de, df) and T = max, TE, TF carry +1 ulp in the low byte, so that
+ *   ~x (= -x - 1 ulp) of an exact value added to a T-space value is exact again:  de' = TE + ~A, dv' = ~A + T,
+ *   df' = TF + ~V, A' = T + ~V.  The ulp never reaches the high byte, so int8 wrap-around and signed order are unchanged.
+ *   ndrop = -drop as sign-extended s16 (saturating, gaba.c:1650), delta = H8 (wrapping), md = s16.
+ *   wa / wb = base codes of the two cells, pre-scaled by 4 (a << 2, b << 4) so their OR is a byte offset into the LUT. */
 struct Vec {
-	uint32_t dh, dv, de, df, delta, drop, md, wa, wb;
+	uint32_t A, V, E, F, delta, ndrop, md, wa, wb;
 	int32_t acc; uint32_t dir;
 };
+__device__ __forceinline__ uint32_t vneg2(uint32_t x) { return __vadd2(~x, 0x00010001u); }
+/* window registers <-> the packed {cell 2l, cell 2l+1} byte pairs kept in block / tail records */
+__device__ __forceinline__ uint32_t win_load(uint32_t c16) { return ((c16 & 0xffu) | ((c16 >> 8) << 16)) << 2; }
+__device__ __forceinline__ uint32_t win_store(uint32_t w) { return ((w >> 2) & 0xffu) | (((w >> 18) & 0xffu) << 8); }
 
 /* reader work (gaba_reader_work_s, gaba.c:400-423), warp-uniform */
 struct FillWork {
@@ -96,77 +108,126 @@ __device__ __forceinline__ uint32_t fetch_b(const SecDesc &s, uint32_t i)
 __device__ __forceinline__ void build_lut(const DevParams &P, uint32_t *lut, int tid, int nthreads)
 {
 	for(int i = tid; i < 256; i += nthreads) {
-		uint32_t lo = (uint32_t)(uint8_t)P.sb[i & 15] << 8, hi = (uint32_t)(uint8_t)P.sb[i >> 4] << 8;
+		uint32_t lo = ((uint32_t)(uint8_t)P.sb[i & 15] << 8) | 1u, hi = ((uint32_t)(uint8_t)P.sb[i >> 4] << 8) | 1u;	/* T-space: +1 ulp */
 		lut[i] = lo | (hi << 16);
 	}
 }
 
 /* ---------------------------------------------------------------- one anti-diagonal (gaba.c:1604-1699) */
-/* loop-invariant operands of a step, hoisted into registers once per fill */
+/* per-lane operands of a step (everything else is a kernel-parameter constant) */
 struct StepK {
-	uint32_t GFH, GFV, ADJH, ADJV, OFSH, OFSV;
-	const uint32_t *lut;
-	bool is0, isL;				/* lane holding cell 0 / cell W-1 */
+	uint32_t selR, selD;		/* PRMT selectors of the two band shifts: the edge lane pulls in a zero byte instead of its neighbour */
+	uint32_t insA, insB;		/* bit-select masks that drop the new base into cell 0 (lane 0, low half) / cell W-1 (last lane, high half) */
+	uint32_t accw;				/* DP4A weights: lane 0 contributes +delta[0], the last lane -delta[W-1] to the direction accumulator */
+	const uint8_t *lut;
 };
 __device__ __forceinline__ StepK make_stepk(const DpCtx &c)
 {
-	const DevParams &P = *c.P;
 	StepK k;
-	k.GFH = pack2h(P.gfh); k.GFV = pack2h(P.gfv); k.ADJH = pack2h(P.adjh); k.ADJV = pack2h(P.adjv); k.OFSH = pack2h(P.ofsh); k.OFSV = pack2h(P.ofsv);
-	k.lut = c.lut; k.is0 = c.lane == 0; k.isL = c.lane == c.nl - 1;
+	bool is0 = c.lane == 0, isL = c.lane == c.nl - 1;
+	k.lut = (const uint8_t *)c.lut;
+	k.selR = is0 ? 0x5444u : 0x5432u; k.selD = isL ? 0x0032u : 0x5432u;
+	k.insA = is0 ? 0x0000ffffu : 0u; k.insB = isL ? 0xffff0000u : 0u;
+	k.accw = is0 ? 0x00000100u : (isL ? 0xff000000u : 0u);
+#ifndef MAB_EMU
+	/* keep the per-lane words in registers: without the barrier the compiler re-derives them from the lane id every step */
+	asm volatile("" : "+r"(k.selR), "+r"(k.selD), "+r"(k.insA), "+r"(k.insB), "+r"(k.accw));
+#endif
 	return k;
 }
-
-/* returns (when MASKS) the traceback nibbles of the two cells at bits 8..11 / 24..27: bit0 = ~h, bit1 = ~v, bit2 = ~e, bit3 = ~f */
-template <bool MASKS>
-__device__ __forceinline__ uint32_t vec_step(const StepK &k, Vec &v, int down, uint32_t newch)
+__device__ __forceinline__ int dp4a_ss(uint32_t a, uint32_t b, int c)
 {
-	if(!down) {			/* _fill_right: bsl dh, df; a new a-base enters at cell 0 */
-		uint32_t uh = __shfl_up_sync(MAB_FULL, v.dh, 1), uf = __shfl_up_sync(MAB_FULL, v.df, 1), ua = __shfl_up_sync(MAB_FULL, v.wa, 1);
-		if(k.is0) { uh = 0; uf = 0; ua = newch << 16; }
-		v.dh = __byte_perm(uh, v.dh, 0x5432); v.df = __byte_perm(uf, v.df, 0x5432); v.wa = __byte_perm(ua, v.wa, 0x5432);
-	} else {			/* _fill_down: bsr dv, de; a new b-base enters at cell W-1 */
-		uint32_t nv = __shfl_down_sync(MAB_FULL, v.dv, 1), ne = __shfl_down_sync(MAB_FULL, v.de, 1), nb = __shfl_down_sync(MAB_FULL, v.wb, 1);
-		if(k.isL) { nv = 0; ne = 0; nb = newch; }
-		v.dv = __byte_perm(v.dv, nv, 0x5432); v.de = __byte_perm(v.de, ne, 0x5432); v.wb = __byte_perm(v.wb, nb, 0x5432);
-	}
-	uint32_t idx = v.wa | v.wb;
-	uint32_t t = k.lut[(idx & 0xf) | ((idx >> 12) & 0xf0)];
-	uint32_t dfh = __vadd2(v.dv, k.GFH), dfv = __vsub2(k.GFV, v.dh);
-	t = __vimax3_s16x2(t, dfv, __vimax3_s16x2(v.de, v.df, dfh));
-	uint32_t te = __viaddmax_s16x2(v.de, k.ADJH, t);
-	uint32_t tf = __viaddmax_s16x2(v.df, k.ADJV, t);
+#ifdef MAB_EMU
+	for(int i = 0; i < 4; i++) { c += (int)(int8_t)(a >> (8 * i)) * (int)(int8_t)(b >> (8 * i)); }
+	return c;
+#else
+	return __dp4a((int)a, (int)b, c);
+#endif
+}
+
+/* the two band shifts (gaba.c:1673-1699); na = new a-base code in the low half, nb = new b-base code in the HIGH half */
+__device__ __forceinline__ void shift_right(const StepK &k, Vec &v, uint32_t na)		/* _fill_right: bsl dh, df; a new a-base enters at cell 0 */
+{
+	uint32_t ua = __shfl_up_sync(MAB_FULL, v.A, 1), uf = __shfl_up_sync(MAB_FULL, v.F, 1), uw = __shfl_up_sync(MAB_FULL, v.wa, 1);
+	v.A = prmt(ua, v.A, k.selR); v.F = prmt(uf, v.F, k.selR);
+	uint32_t w = __byte_perm(uw, v.wa, 0x5432);
+	v.wa = (w & ~k.insA) | (na & k.insA);
+}
+__device__ __forceinline__ void shift_down(const StepK &k, Vec &v, uint32_t nb)			/* _fill_down: bsr dv, de; a new b-base enters at cell W-1 */
+{
+	uint32_t nv = __shfl_down_sync(MAB_FULL, v.V, 1), ne = __shfl_down_sync(MAB_FULL, v.E, 1), nw = __shfl_down_sync(MAB_FULL, v.wb, 1);
+	v.V = prmt(v.V, nv, k.selD); v.E = prmt(v.E, ne, k.selD);
+	uint32_t w = __byte_perm(v.wb, nw, 0x5432);
+	v.wb = (w & ~k.insB) | (nb & k.insB);
+}
+
+/* The cell update of one anti-diagonal after the shift (gaba.c:1604-1655).  DOWN / MASKS / ONE are compile-time: ONE is the
+ * bit (per 16-bit half) the four traceback flags are normalised to, so that an unrolled group of four vectors lands in one
+ * word without shifts.  Returns (when MASKS) the nibble {bit0 = ~h, bit1 = ~v, bit2 = ~e, bit3 = ~f} of the two cells at
+ * bit log2(ONE) of each half. */
+template <bool DOWN, bool MASKS, uint32_t ONE>
+__device__ __forceinline__ uint32_t vec_core(const DevParams &P, const StepK &k, Vec &v)
+{
+	const uint32_t EPS = 0x00010001u;
+	uint32_t x = v.wa | v.wb;
+	uint32_t S = *(const uint32_t *)(k.lut + ((x | (x >> 12)) & 0x3fcu));
+	uint32_t dfh = __vadd2(v.V, P.K_GFH1), dfv = __vadd2(v.A, P.K_GFV1);
+	uint32_t T = __vimax3_s16x2(S, dfh, dfv);
+	T = __viaddmax_s16x2(v.E, EPS, T);
+	T = __viaddmax_s16x2(v.F, EPS, T);
+	uint32_t TE = __viaddmax_s16x2(v.E, P.K_ADJH1, T), TF = __viaddmax_s16x2(v.F, P.K_ADJV1, T);
 	uint32_t bits = 0;
 	if(MASKS) {
-		/* t is the (int8) maximum, so t - x is 0..255 in the high byte: min.u16 against 0x0100 leaves bit 8 set <=> "not equal" */
-		const uint32_t one = 0x01000100u;
-		uint32_t n_fh = __vminu2(__vsub2(t, dfh), one), n_e = __vminu2(__vsub2(t, v.de), one);
-		uint32_t n_fv = __vminu2(__vsub2(t, dfv), one), n_f = __vminu2(__vsub2(t, v.df), one);
-		uint32_t g_e = __vminu2(__vsub2(te, t), one), g_f = __vminu2(__vsub2(tf, t), one);		/* set <=> te != t */
-		uint32_t NH = n_fh & n_e, NV = n_fv & n_f;								/* ~h, ~v */
-		uint32_t NE = (n_e | (n_fh ^ one)) & g_e, NF = (n_f | (n_fv ^ one)) & g_f;	/* ~e, ~f */
-		bits = (NF * 2 + NE) * 4 + (NV * 2 + NH);								/* disjoint bits: three IMADs pack the nibble */
+		/* T is the maximum, so T - x is 0..255 in the high byte and "min.u16 against ONE" leaves ONE set <=> not equal */
+		uint32_t n_e = __viaddmin_u16x2(T, ~v.E, ONE), n_f = __viaddmin_u16x2(T, ~v.F, ONE);
+		uint32_t n_fh = __vminu2(T ^ dfh, ONE), n_fv = __vminu2(T ^ dfv, ONE);
+		uint32_t g_e = __vminu2(TE ^ T, ONE), g_f = __vminu2(TF ^ T, ONE);				/* set <=> te != t */
+		uint32_t NH = n_fh & n_e, NV = n_fv & n_f;										/* ~h, ~v */
+		uint32_t NE = (n_e | ~n_fh) & g_e, NF = (n_f | ~n_fv) & g_f;						/* ~e, ~f */
+		bits = (NF * 2 + NE) * 4 + (NV * 2 + NH);										/* disjoint bits: three IMADs pack the nibble */
 	}
-	uint32_t de = __vadd2(te, v.dh), dh = __vadd2(v.dh, t);
-	uint32_t df = __vsub2(tf, v.dv); t = __vsub2(v.dv, t);
-	v.dv = dh; v.dh = t; v.de = de; v.df = df;
-	uint32_t dH = down ? __vadd2(k.OFSV, v.dv) : __vsub2(k.OFSH, v.dh);			/* _fill_update_delta */
-	v.delta = __vadd2(v.delta, dH);											/* wraps like int8 */
-	uint32_t d = h8_to_s16(dH);
-	v.drop = clamp8x2(__vsub2(v.drop, d));									/* saturating */
-	int contrib = k.is0 ? lo16(d) : 0;
-	if(k.isL) { contrib -= hi16(d); }
-	v.acc += __reduce_add_sync(MAB_FULL, contrib);								/* _dir_update */
+	uint32_t Pp = ~v.A, N = ~v.V;
+	v.E = __vadd2(TE, Pp); v.F = __vadd2(TF, N);
+	v.V = __vadd2(Pp, T); v.A = __vadd2(T, N);
+	uint32_t dH = __vadd2(P.K_OFS, DOWN ? v.V : v.A);										/* _fill_update_delta (ofsh == ofsv) */
+	v.delta = __vadd2(v.delta, dH);														/* wraps like int8 */
+	v.ndrop = __vmaxs2(__viaddmin_s16x2(v.ndrop, h8_to_s16(dH), 0x00800080u), 0xff81ff81u);	/* -(drop subs delta), saturating */
+	v.acc += __reduce_add_sync(MAB_FULL, dp4a_ss(dH, k.accw, 0));							/* _dir_update */
 	return bits;
+}
+/* One unchecked step of a bulk block: direction from the accumulator (_dir_fetch), next base of that side, shift, update.
+ * The direction word and the two base counters live in ordinary (per-lane, identical) registers inside the block and are
+ * made warp-uniform again by one broadcast at the block end: the per-step uniform-datapath bookkeeping would cost more. */
+struct BulkCnt { uint32_t dir, acnt, bcnt; };
+template <bool MASKS, uint32_t ONE>
+__device__ __forceinline__ uint32_t bulk_step(const DevParams &P, const StepK &k, Vec &v, uint32_t an, uint32_t bn, BulkCnt &n)
+{
+	if(v.acc < 0) {																		/* warp-uniform */
+		n.dir = n.dir * 2 + 1; shift_down(k, v, __shfl_sync(MAB_FULL, bn, n.bcnt)); n.bcnt++;
+		return vec_core<true, MASKS, ONE>(P, k, v);
+	}
+	n.dir = n.dir * 2; shift_right(k, v, __shfl_sync(MAB_FULL, an, n.acnt)); n.acnt++;
+	return vec_core<false, MASKS, ONE>(P, k, v);
+}
+template <bool MASKS, uint32_t ONE>
+__device__ __forceinline__ uint32_t vec_step(const DevParams &P, const StepK &k, Vec &v, bool down, uint32_t newch)
+{
+	if(down) { shift_down(k, v, newch); return vec_core<true, MASKS, ONE>(P, k, v); }
+	shift_right(k, v, newch); return vec_core<false, MASKS, ONE>(P, k, v);
+}
+template <bool MASKS>
+__device__ __forceinline__ uint32_t vec_step_rt(const DevParams &P, const StepK &k, Vec &v, int down, uint32_t newch)
+{
+	return vec_step<MASKS, 0x01000100u>(P, k, v, down != 0, newch);
 }
 
 /* load the vector registers from the entry physically before a block (_fill_load_context, gaba.c:1527-1550) */
 __device__ __forceinline__ void vec_load(const DpCtx &c, Vec &v, const BlkEntry *prev, uint32_t xd)
 {
 	int l = c.lane;
-	v.dh = unpack8h(prev->dh[l]); v.dv = unpack8h(prev->dv[l]); v.de = unpack8h(prev->de[l]); v.df = unpack8h(prev->df[l]);
-	v.delta = 0; v.drop = xd;
-	v.acc = prev->acc; v.dir = 0;
+	v.A = vneg2(unpack8h(prev->dh[l])); v.V = unpack8h(prev->dv[l]); v.E = unpack8h(prev->de[l]); v.F = unpack8h(prev->df[l]);
+	v.delta = 0; v.ndrop = vneg2(xd);
+	v.acc = __reduce_add_sync(MAB_FULL, l == 0 ? (int)prev->acc : 0); v.dir = 0;		/* warp-uniform by construction */
 }
 
 /* ---------------------------------------------------------------- tails, sections */
@@ -228,8 +289,7 @@ __device__ __forceinline__ int32_t load_vectors(DpCtx &c, int32_t tail, Vec &v, 
 {
 	const TailRec *t = &c.tails[tail];
 	int l = c.lane, ls = l < c.nl ? l : 0;
-	v.wa = (uint32_t)(t->cha[ls] & 0xff) | ((uint32_t)(t->cha[ls] >> 8) << 16);
-	v.wb = (uint32_t)(t->chb[ls] & 0xff) | ((uint32_t)(t->chb[ls] >> 8) << 16);
+	v.wa = win_load(t->cha[ls]); v.wb = win_load(t->chb[ls]);
 	xd = unpack8(t->xd[ls]);
 	v.md = (uint32_t)(uint16_t)t->md[2 * ls] | ((uint32_t)(uint16_t)t->md[2 * ls + 1] << 16);
 	int32_t prev = t->last_blk;
@@ -251,12 +311,12 @@ __device__ __forceinline__ void window_consume(const DpCtx &c, Vec &v, const Fil
 	for(uint32_t k = 0; k < n; k++) {
 		uint32_t pos = s.len - w.rem[side] + k;
 		if(side == 0) {
-			uint32_t ch = fetch_a(s, pos);
+			uint32_t ch = fetch_a(s, pos) << 2;
 			uint32_t ua = __shfl_up_sync(MAB_FULL, v.wa, 1);
 			if(c.lane == 0) { ua = ch << 16; }
 			v.wa = __byte_perm(ua, v.wa, 0x5432);
 		} else {
-			uint32_t ch = fetch_b(s, pos);
+			uint32_t ch = fetch_b(s, pos) << 2;
 			uint32_t nb = __shfl_down_sync(MAB_FULL, v.wb, 1);
 			if(c.lane == c.nl - 1) { nb = ch; }
 			v.wb = __byte_perm(v.wb, nb, 0x5432);
@@ -301,8 +361,7 @@ __device__ __forceinline__ int32_t create_tail(DpCtx &c, FillWork &w, const Vec 
 	int mx = l < c.nl ? (m0 > m1 ? m0 : m1) : -32768;
 	int mdrop = __reduce_max_sync(MAB_FULL, mx);
 	if(l < c.nl) {
-		t->cha[l] = (uint16_t)((v.wa & 0xff) | ((v.wa >> 16) << 8));
-		t->chb[l] = (uint16_t)((v.wb & 0xff) | ((v.wb >> 16) << 8));
+		t->cha[l] = (uint16_t)win_store(v.wa); t->chb[l] = (uint16_t)win_store(v.wb);
 		t->xd[l] = (uint16_t)pack8(xd);
 		t->md[2 * l] = (int16_t)lo16(v.md); t->md[2 * l + 1] = (int16_t)hi16(v.md);
 	}
@@ -345,46 +404,42 @@ __device__ __forceinline__ int32_t fill_blocks(DpCtx &c, FillWork &w, Vec &v, ui
 		int32_t bi = push_blk(c);
 		if(c.err) { break; }
 		BlkEntry *b = &c.blk[bi];
-		/* prefetch up to 32 bases of each side, one per lane (fill_fetch_core, gaba.c:1125-1144) */
+		/* prefetch up to 32 bases of each side, one per lane (fill_fetch_core, gaba.c:1125-1144), pre-scaled like the windows */
 		uint32_t an = 0, bn = 0;
-		if((uint32_t)l < w.rem[0]) { an = fetch_a(w.sec[0], w.sec[0].len - w.rem[0] + l); }
-		if((uint32_t)l < w.rem[1]) { bn = fetch_b(w.sec[1], w.sec[1].len - w.rem[1] + l); }
-		if(l < c.nl) {
-			b->cha[l] = (uint16_t)((v.wa & 0xff) | ((v.wa >> 16) << 8));
-			b->chb[l] = (uint16_t)((v.wb & 0xff) | ((v.wb >> 16) << 8));
-		}
+		if((uint32_t)l < w.rem[0]) { an = fetch_a(w.sec[0], w.sec[0].len - w.rem[0] + l) << 2; }
+		if((uint32_t)l < w.rem[1]) { bn = fetch_b(w.sec[1], w.sec[1].len - w.rem[1] + l) << 18; }		/* enters a high half */
+		if(l < c.nl) { b->cha[l] = (uint16_t)win_store(v.wa); b->chb[l] = (uint16_t)win_store(v.wb); }
 		if(first) { vec_load(c, v, &c.blk[bi - 1], xd); first = 0; }
-		else { v.delta = 0; v.drop = xd; v.acc = (int32_t)(int8_t)v.acc; v.dir = 0; }
+		else { v.delta = 0; v.acc = (int32_t)(int8_t)v.acc; v.dir = 0; }				/* ndrop carries over: xd == drop of the previous block */
 		uint32_t *mrow = c.masks + 256ull * bi + l;
 		int acnt = 0, bcnt = 0, i = 0;
 		if(!cap) {
+			BulkCnt n; n.dir = 0; n.acnt = 0; n.bcnt = 0;
+#ifndef MAB_EMU
+			asm volatile("" : "+r"(n.dir), "+r"(n.acnt), "+r"(n.bcnt));					/* plain registers, see bulk_step */
+#endif
 			#pragma unroll 1
 			for(int g = 0; g < MAB_BLK / 4; g++) {
-				uint32_t bq[4];
-				#pragma unroll
-				for(int u = 0; u < 4; u++) {
-					v.dir = (v.dir << 1) | (uint32_t)(v.acc < 0);						/* _dir_fetch */
-					int down = (int)(v.dir & 1);
-					uint32_t newch = down ? __shfl_sync(MAB_FULL, bn, bcnt) : __shfl_sync(MAB_FULL, an, acnt);
-					bcnt += down; acnt += 1 - down;
-					bq[u] = vec_step<MASKS>(k, v, down, newch);
-				}
-				if(MASKS) { mrow[32 * g] = (bq[0] >> 8) | (bq[1] >> 4) | bq[2] | (bq[3] << 4); }
+				uint32_t b0 = bulk_step<MASKS, 0x00010001u>(P, k, v, an, bn, n), b1 = bulk_step<MASKS, 0x00100010u>(P, k, v, an, bn, n);
+				uint32_t b2 = bulk_step<MASKS, 0x01000100u>(P, k, v, an, bn, n), b3 = bulk_step<MASKS, 0x01000100u>(P, k, v, an, bn, n);
+				if(MASKS) { mrow[32 * g] = (b0 | b1 | b2) + b3 * 16; }					/* nibble u of each half = vector 4g + u */
 			}
+			v.dir = __shfl_sync(MAB_FULL, n.dir, 0);
+			bcnt = __popc(v.dir); acnt = MAB_BLK - bcnt;
 			i = MAB_BLK;
 		} else {
 			uint32_t mbits = 0;
 			for(; i < MAB_BLK; i++) {
-				v.dir = (v.dir << 1) | (uint32_t)(v.acc < 0);
-				int down = (int)(v.dir & 1);
+				int down = v.acc < 0;
 				{																/* _fill_cap_test_idx */
 					int64_t ar = (int64_t)w.rem[0] - (acnt + !down), br = (int64_t)w.rem[1] - (bcnt + down);
 					int64_t pr = ar + br + (int64_t)w.pridx;
-					if((ar | br | pr) < 0) { v.dir >>= 1; break; }
+					if((ar | br | pr) < 0) { break; }							/* direction not consumed (the reference winds it back) */
 				}
+				v.dir = (v.dir << 1) | (uint32_t)down;
 				uint32_t newch = down ? __shfl_sync(MAB_FULL, bn, bcnt) : __shfl_sync(MAB_FULL, an, acnt);
 				bcnt += down; acnt += 1 - down;
-				uint32_t bits = vec_step<MASKS>(k, v, down, newch);
+				uint32_t bits = vec_step_rt<MASKS>(P, k, v, down, newch);
 				if(MASKS) {
 					mbits |= ((bits >> 8) & 0x000f000fu) << (4 * (i & 3));
 					if((i & 3) == 3) { mrow[32 * (i >> 2)] = mbits; mbits = 0; }
@@ -398,22 +453,23 @@ __device__ __forceinline__ int32_t fill_blocks(DpCtx &c, FillWork &w, Vec &v, ui
 		/* _fill_store_context (gaba.c:1734-1778) */
 		int ctr = c.W / 4;															/* lane holding cell W/2 (low half) */
 		uint32_t dl = h8_to_s16(v.delta);										/* delta as sign-extended int8 */
-		int dropc = lo16(__shfl_sync(MAB_FULL, v.drop, ctr)), cofs = lo16(__shfl_sync(MAB_FULL, dl, ctr));
+		uint32_t drop = vneg2(v.ndrop);
+		int dropc = lo16(__shfl_sync(MAB_FULL, drop, ctr)), cofs = lo16(__shfl_sync(MAB_FULL, dl, ctr));
 		int xstat = (P.tx - dropc) & MAB_X_TERM;
-		uint32_t sum = sext8x2(__vadd2(v.drop, dl));
+		uint32_t sum = sext8x2(__vadd2(drop, dl));
 		uint32_t mlo = __ballot_sync(MAB_FULL, l < c.nl && lo16(sum) > lo16(xd));
 		uint32_t mhi = __ballot_sync(MAB_FULL, l < c.nl && hi16(sum) > hi16(xd));
 		/* middle delta with the overflow / underflow rescue terms */
 		uint32_t md = __vadd2(v.md, dl);
-		uint32_t ov = sext8x2(~sum & (v.drop & dl));
+		uint32_t ov = sext8x2(~sum & (drop & dl));
 		md = __vadd2(md, ov & 0x01000100u);
-		uint32_t uv = sext8x2(clamp8x2(__vsub2(dl, 0x00400040u)) | v.drop);
+		uint32_t uv = sext8x2(clamp8x2(__vsub2(dl, 0x00400040u)) | drop);
 		md = __vadd2(md, uv & 0x01000100u);
 		md = __vsub2(md, pack2(cofs + 0x0100));
-		v.md = md; xd = v.drop;
+		v.md = md; xd = drop;
 		w.ofsd += cofs; w.rem[0] -= (uint32_t)acnt; w.rem[1] -= (uint32_t)bcnt;
 		if(l < c.nl) {
-			b->dh[l] = (uint16_t)pack8h(v.dh); b->dv[l] = (uint16_t)pack8h(v.dv); b->de[l] = (uint16_t)pack8h(v.de); b->df[l] = (uint16_t)pack8h(v.df);
+			b->dh[l] = (uint16_t)pack8h(vneg2(v.A)); b->dv[l] = (uint16_t)pack8h(v.V); b->de[l] = (uint16_t)pack8h(v.E); b->df[l] = (uint16_t)pack8h(v.F);
 		}
 		if(l == 0) {
 			b->acc = (int8_t)v.acc; b->xstat = (int8_t)xstat; b->acnt = (int8_t)acnt; b->bcnt = (int8_t)bcnt;
@@ -532,13 +588,12 @@ __device__ inline void leaf_search(DpCtx &c, int32_t ti, Leaf &lf)
 		SecDesc sa = bt->sec[0], sb = bt->sec[1];
 		uint32_t arem = blk->arem, brem = blk->brem;
 		Vec v;
-		v.wa = (uint32_t)(blk->cha[ls] & 0xff) | ((uint32_t)(blk->cha[ls] >> 8) << 16);
-		v.wb = (uint32_t)(blk->chb[ls] & 0xff) | ((uint32_t)(blk->chb[ls] >> 8) << 16);
+		v.wa = win_load(blk->cha[ls]); v.wb = win_load(blk->chb[ls]);
 		v.md = 0;
 		vec_load(c, v, &c.blk[b - 1], 0);
 		uint32_t an = 0, bn = 0;
-		if((uint32_t)l < arem) { an = fetch_a(sa, sa.len - arem + l); }
-		if((uint32_t)l < brem) { bn = fetch_b(sb, sb.len - brem + l); }
+		if((uint32_t)l < arem) { an = fetch_a(sa, sa.len - arem + l) << 2; }
+		if((uint32_t)l < brem) { bn = fetch_b(sb, sb.len - brem + l) << 18; }
 		uint32_t mx = 0;
 		const StepK kk = make_stepk(c);
 		int acnt = 0, bcnt = 0;
@@ -547,7 +602,7 @@ __device__ inline void leaf_search(DpCtx &c, int32_t ti, Leaf &lf)
 			int down = (int)(v.dir & 1);
 			uint32_t newch = down ? __shfl_sync(MAB_FULL, bn, bcnt) : __shfl_sync(MAB_FULL, an, acnt);
 			if(down) { bcnt++; } else { acnt++; }
-			vec_step<false>(kk, v, down, newch);
+			vec_step_rt<false>(*c.P, kk, v, down, newch);
 			uint32_t ulo = __ballot_sync(MAB_FULL, l < c.nl && lo16(v.delta) > lo16(mx));
 			uint32_t uhi = __ballot_sync(MAB_FULL, l < c.nl && hi16(v.delta) > hi16(mx));
 			mx = __vmaxs2(mx, v.delta);

@@ -86,6 +86,11 @@ void init_gaba_consts(DevParams &P, const mab_params_t *p)
 	for(int i = 0; i < 16; i++) { P.sb[i] = (int8_t)(p->score_matrix[i] + 2 * ofs); }
 	P.adjh = P.adjv = p->gi; P.ofsh = P.ofsv = -ofs; P.gfh = ofs - p->gfb; P.gfv = ofs - p->gfa;
 	P.tx = (int8_t)(p->xdrop - 128);
+	{
+		auto h8 = [](int v) { uint32_t x = ((uint32_t)(uint8_t)(int8_t)v) << 8; return x | (x << 16); };
+		const uint32_t ulp = 0x00010001u;
+		P.K_GFH1 = h8(P.gfh) + ulp; P.K_GFV1 = h8(P.gfv) + ulp; P.K_ADJH1 = h8(P.adjh) + ulp; P.K_ADJV1 = h8(P.adjv) + ulp; P.K_OFS = h8(P.ofsh);
+	}
 	P.gi = p->gi; P.ge = p->ge; P.gfa = p->gfa; P.gfb = p->gfb;
 	long long diag = 0, off = 0;
 	for(int i = 0; i < 16; i++) { if((i & 3) == (i >> 2)) { diag += p->score_matrix[i]; } else { off += p->score_matrix[i]; } }
@@ -390,7 +395,7 @@ static int map_core(mab_ctx *ctx, const uint8_t *d_base, std::vector<ReadRec> &h
 			RT_LAUNCH(k_sortchain, (n_seq + 3) / 4, 128, 2048 * 4, ctx->stream, P, ctx->d_reads, n_seq, ctx->d_ws, ctx->d_frames, round);
 			RT_MEMSET_ASYNC(&ctx->d_ctr->work_next, 0, sizeof(unsigned int), ctx->stream);
 			if(timed && round < 8) { RT_EVENT_RECORD(ctx->rev[3 * round + 1], ctx->stream); }
-			RT_LAUNCH(k_extend, ext_ctas, 32 * MAB_WARPS_PER_CTA, 1024 + 1024 * MAB_WARPS_PER_CTA, ctx->stream, P, d_base, (const uint8_t *)ctx->d_ntail, ctx->d_reads, n_seq, ctx->d_ws,
+			RT_LAUNCH(k_extend, ext_ctas, 32 * MAB_WARPS_PER_CTA, 1024 + 2048 * MAB_WARPS_PER_CTA, ctx->stream, P, d_base, (const uint8_t *)ctx->d_ntail, ctx->d_reads, n_seq, ctx->d_ws,
 				ctx->d_arenas, AL.total, blk_cap, ctx->d_pool, pool_words, ctx->d_ctr, round, P.n_occ - 1);
 			S.n_launches += 2;
 			if(timed && round < 8) { RT_EVENT_RECORD(ctx->rev[3 * round + 2], ctx->stream); }
@@ -580,7 +585,7 @@ extern "C" int mab_extend_pairs(mab_ctx *ctx, const uint8_t *seq_block, uint64_t
 	CK(RT_MEMCPY_H2D(d_seq, seq_block, block_size)); CK(RT_MEMCPY_H2D(d_p, pairs, sizeof(PairIn) * (uint64_t)n));
 	BatchCounters zero; memset(&zero, 0, sizeof(zero));
 	CK(RT_MEMCPY_H2D(ctx->d_ctr, &zero, sizeof(zero)));
-	RT_LAUNCH(k_extend_pairs, ctas, 32 * MAB_WARPS_PER_CTA, 1024 + 1024 * MAB_WARPS_PER_CTA, ctx->stream, P, (const uint8_t *)d_seq, (const uint8_t *)ctx->d_ntail, (const PairIn *)d_p, n, d_res, d_ao,
+	RT_LAUNCH(k_extend_pairs, ctas, 32 * MAB_WARPS_PER_CTA, 1024 + 2048 * MAB_WARPS_PER_CTA, ctx->stream, P, (const uint8_t *)d_seq, (const uint8_t *)ctx->d_ntail, (const PairIn *)d_p, n, d_res, d_ao,
 		d_ar, AL.total, blk_cap, d_pool, pool_words, ctx->d_ctr);
 	CK(RT_STREAM_SYNC(ctx->stream));
 	BatchCounters hc; CK(RT_MEMCPY_D2H(&hc, ctx->d_ctr, sizeof(hc)));

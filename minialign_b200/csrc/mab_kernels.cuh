@@ -192,9 +192,9 @@ __global__ void k_sortchain(DevParams P, ReadRec *reads, uint32_t n_reads, uint8
 	WsLayout L = ws_layout(r->seed_cap, r->root_cap, r->resc_cap, r->bin_cap);
 	uint32_t *seed = (uint32_t *)(ws + r->ws_ofs + L.seed), *root = (uint32_t *)(ws + r->ws_ofs + L.root), *resc = (uint32_t *)(ws + r->ws_ofs + L.resc);
 	uint32_t *fr = frames + (uint64_t)i * 8 * MAB_RS_FRAME;
-	uint32_t n = r->n_seed;
+	uint32_t n = r->n_seed, sort_err = 0;
 	if(round > 0) {																/* mm_seed, cnt > 0 (3510-3526) */
-		if(round == 1) { radix_sort_exact_warp(resc, r->n_resc, 4, fr, sm, lane); }
+		if(round == 1) { radix_sort_exact_warp(resc, r->n_resc, 4, fr, sm, lane, &sort_err); }
 		for(uint32_t s = lane; s < n; s += 32) { seed[4ull * s + 3] = 0x7fffffffu; }
 		__syncwarp();
 		if(lane == 0) {
@@ -217,7 +217,7 @@ __global__ void k_sortchain(DevParams P, ReadRec *reads, uint32_t n_reads, uint8
 	}
 	__syncwarp();
 	if(n == 0) { return; }
-	radix_sort_exact_warp(seed, n + 1, 4, fr, sm, lane);
+	radix_sort_exact_warp(seed, n + 1, 4, fr, sm, lane, &sort_err);
 	uint32_t nc = 0;
 	if(lane == 0) {
 		uint32_t seed_n = 0;
@@ -226,8 +226,9 @@ __global__ void k_sortchain(DevParams P, ReadRec *reads, uint32_t n_reads, uint8
 	}
 	nc = __shfl_sync(0xffffffffu, nc, 0);
 	if(nc == 0) { return; }
-	radix_sort_exact_warp(root, nc, 2, fr, sm, lane);
+	radix_sort_exact_warp(root, nc, 2, fr, sm, lane, &sort_err);
 	if(lane == 0) { r->n_root = nc; }
+	if(__any_sync(0xffffffffu, sort_err != 0) && lane == 0) { r->err |= MAB_ERR_SEED_OVF; }
 }
 
 /* ---------------------------------------------------------------- mm_extend state machine, lane-0 routines */
@@ -299,7 +300,10 @@ __device__ inline int load_root(const DevParams &P, RCtx &x, Search &st, uint32_
 	return 0;
 }
 
-__device__ inline uint32_t load_next(const DevParams &P, RCtx &x, Search &st, uint32_t *frames)							/* 3887-3944 */
+/* mm_search_load_next (3887-3944) in two lane-0 halves around the sort of the candidate list, which runs warp-cooperatively
+ * (and keeps the single-thread radix sort, whose control flow defeats the compiler's convergence analysis for the whole
+ * kernel, out of k_extend).  collect returns the number of candidates to sort (0 = no next seed). */
+__device__ inline uint32_t load_next_collect(const DevParams &P, RCtx &x, Search &st)
 {
 	ReadRec *r = x.r;
 	if(st.srem == 0) { return 0; }
@@ -324,13 +328,17 @@ __device__ inline uint32_t load_next(const DevParams &P, RCtx &x, Search &st, ui
 	}
 	st.sid = (uint32_t)sid;
 	r->n_next = (uint32_t)ncnt;
-	if(ncnt == 0) { st.pacc = 0; st.srem = 0; return 0; }
-	radix_sort_exact(n, (uint32_t)ncnt, 2, frames);
+	if(ncnt == 0) { st.pacc = 0; st.srem = 0; }
+	return (uint32_t)ncnt;
+}
+__device__ inline void load_next_pick(const DevParams &P, RCtx &x, Search &st)
+{
+	ReadRec *r = x.r;
+	const uint32_t *n = x.next;
 	r->n_next--;
 	uint32_t nsid = n[2ull * r->n_next + 1];
-	st.pacc = (uint32_t)(ofs - n[2ull * r->n_next]);
-	load_pos(P, st, s + 4ull * nsid, &st.rev, st.cp);
-	return st.srem;
+	st.pacc = (uint32_t)(2ull * P.tglen - n[2ull * r->n_next]);
+	load_pos(P, st, x.seed + 4ull * nsid, &st.rev, st.cp);
 }
 
 __device__ inline int test_dup(RCtx &x, Search &st, const PosPair &cp)													/* 3952-3981 */
@@ -452,17 +460,19 @@ __device__ __forceinline__ SecDesc make_sec(const uint8_t *base, uint32_t len, u
 }
 
 /* ---------------------------------------------------------------- k_extend */
-/* shared memory per CTA: 1 KB score LUT + per warp a 1 KB traceback mask tile */
+/* shared memory per CTA: 1 KB score LUT + per warp a 2 KB tile (traceback nibbles / sort scratch) */
 __global__ void __launch_bounds__(32 * MAB_WARPS_PER_CTA, MAB_EXT_CTAS_PER_SM) k_extend(DevParams P, const uint8_t *base, const uint8_t *ntail, ReadRec *reads, uint32_t n_reads, uint8_t *ws,
 	uint8_t *arenas, uint64_t arena_stride, uint32_t blk_cap, uint32_t *pool, uint64_t pool_cap, BatchCounters *ctr, uint32_t round, uint32_t last_round)
 {
 	MAB_DYN_SMEM(smem);
 	uint32_t *lut = (uint32_t *)smem;
-	int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-	uint32_t *tile = (uint32_t *)smem + 256 + 256 * wib;
+	/* warp-uniform indices go through a lane-0 broadcast: the compiler then knows that every pointer derived from them (arena,
+	 * tile) and every branch on data loaded through them is warp-uniform, and drops the divergence guards around the shuffles */
+	int lane = threadIdx.x & 31, wib = __shfl_sync(MAB_FULL, (int)(threadIdx.x >> 5), 0);
+	uint32_t *tile = (uint32_t *)smem + 256 + 512 * wib;
 	build_lut(P, lut, threadIdx.x, blockDim.x);
 	__syncthreads();
-	uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	uint32_t gw = __shfl_sync(MAB_FULL, (blockIdx.x * blockDim.x + threadIdx.x) >> 5, 0);
 	uint8_t *arena = arenas + arena_stride * gw;
 	DpCtx c; dp_ctx_init(c, &P, arena, blk_cap, lut, lane);
 	uint32_t *frames = (uint32_t *)(arena + arena_layout(blk_cap).frames);
@@ -525,7 +535,13 @@ __global__ void __launch_bounds__(32 * MAB_WARPS_PER_CTA, MAB_EXT_CTAS_PER_SM) k
 				}
 				if(c.err) { break; }
 				if(brk) { break; }
-				if(adv && lane == 0) { load_next(P, x, st, frames); }
+				if(adv) {
+					uint32_t ncnt = 0;
+					if(lane == 0) { ncnt = load_next_collect(P, x, st); }
+					ncnt = __shfl_sync(MAB_FULL, ncnt, 0);
+					if(ncnt > 1) { radix_sort_exact_warp(x.next, ncnt, 2, frames, tile, lane, &c.err); }	/* the trace tile is idle here */
+					if(ncnt != 0 && lane == 0) { load_next_pick(P, x, st); }
+				}
 				__syncwarp();
 			}
 			if(c.err) { break; }
@@ -556,11 +572,11 @@ __global__ void k_extend_pairs(DevParams P, const uint8_t *base, const uint8_t *
 {
 	MAB_DYN_SMEM(smem);
 	uint32_t *lut = (uint32_t *)smem;
-	int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-	uint32_t *tile = (uint32_t *)smem + 256 + 256 * wib;
+	int lane = threadIdx.x & 31, wib = __shfl_sync(MAB_FULL, (int)(threadIdx.x >> 5), 0);
+	uint32_t *tile = (uint32_t *)smem + 256 + 512 * wib;
 	build_lut(P, lut, threadIdx.x, blockDim.x);
 	__syncthreads();
-	uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+	uint32_t gw = __shfl_sync(MAB_FULL, (blockIdx.x * blockDim.x + threadIdx.x) >> 5, 0), nw = (gridDim.x * blockDim.x) >> 5;
 	DpCtx c; dp_ctx_init(c, &P, arenas + arena_stride * gw, blk_cap, lut, lane);
 	SecDesc tsec = make_sec(ntail, 96, 0xfffffffeu, 0);
 	for(uint32_t i = gw; i < n; i += nw) {
@@ -621,6 +637,9 @@ __global__ void k_selftest(uint32_t *out)
 	PUT((uint32_t)(int64_t)__double2ll_rz((double)(x & 0xffff) * 0.9371));
 	{ uint64_t k = pos_key(((uint64_t)x << 32) | y, ((uint64_t)z << 32) | x); PUT(k); PUT(k >> 32); }
 	PUT(crc32c_u64(x, ((uint64_t)y << 32) | z));
+	PUT(__viaddmin_u16x2(x, y, 0x01000100u)); PUT(__viaddmin_s16x2(x, y, 0x00800080u)); PUT(dp4a_ss(x, y, (int)z)); PUT(dp4a_ss(x, 0xff000000u, 0));
+	PUT(prmt(x, y, 0x5444)); PUT(prmt(x, y, 0x0032)); PUT(vneg2(x)); PUT(win_store(win_load(x & 0xffff)));
+	PUT(__match_any_sync(MAB_FULL, (x >> 7) & 3)); PUT(__ldg(&out[32 * 0 + ((lane + 1) & 31)]) * 0 + h8_to_s16(x));
 	#undef PUT
 	if(lane == 0) { out[32 * 63] = (uint32_t)f; }
 }

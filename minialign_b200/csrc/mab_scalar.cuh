@@ -11,9 +11,12 @@ namespace mab {
 
 #define MAB_OFS0 0x40000000u
 
-__device__ __forceinline__ uint64_t ldg64(const uint8_t *p) { return *(const uint64_t *)p; }
-__device__ __forceinline__ uint32_t ldg32(const uint8_t *p) { return *(const uint32_t *)p; }
-__device__ __forceinline__ uint16_t ldg16(const uint8_t *p) { return *(const uint16_t *)p; }
+/* index image loads: explicit ld.global.nc.  Besides the read-only path this matters for code generation: a load through the
+ * generic pointer stored in DevParams counts as thread-varying for the compiler's uniformity analysis, a global load from a
+ * warp-uniform address does not, and everything derived from it (section lengths -> loop bounds) stays warp-uniform. */
+__device__ __forceinline__ uint64_t ldg64(const uint8_t *p) { return __ldg((const unsigned long long *)p); }
+__device__ __forceinline__ uint32_t ldg32(const uint8_t *p) { return __ldg((const uint32_t *)p); }
+__device__ __forceinline__ uint16_t ldg16(const uint8_t *p) { return __ldg((const uint16_t *)p); }
 
 /* reference sequence descriptor (mm_idx_seq_t, minialign.c:2464-2470) */
 struct RefSeq { const uint8_t *seq; uint32_t l_seq; uint32_t circular; };
@@ -66,9 +69,9 @@ __device__ __forceinline__ const uint8_t *idx_get(const DevParams &P, uint64_t m
  * (8 levels x 257 u32).  esz = element size in u32 words: 4 (key = words 1:0) or 2 (key = word 0). */
 __device__ __forceinline__ uint64_t rs_key(const uint32_t *e, int esz) { return esz == 4 ? ((uint64_t)e[1] << 32 | e[0]) : (uint64_t)e[0]; }
 
-__device__ inline void rs_copy(uint32_t *d, const uint32_t *s, int esz) { for(int i = 0; i < esz; i++) { d[i] = s[i]; } }
+__device__ __forceinline__ void rs_copy(uint32_t *d, const uint32_t *s, int esz) { for(int i = 0; i < esz; i++) { d[i] = s[i]; } }
 
-__device__ inline void rs_insertion(uint32_t *a, uint32_t n, int esz)
+__device__ __forceinline__ void rs_insertion(uint32_t *a, uint32_t n, int esz)
 {
 	uint32_t tmp[4];
 	for(uint32_t i = 1; i < n; i++) {
@@ -82,98 +85,46 @@ __device__ inline void rs_insertion(uint32_t *a, uint32_t n, int esz)
 	}
 }
 
-/* frames: per level {beg, s, k, end[256]} as u32; at most 8 levels for a 64-bit key */
-#define MAB_RS_FRAME 260
-__device__ inline void radix_sort_exact(uint32_t *a, uint32_t n, int esz, uint32_t *frames)
-{
-	if(n <= 64) { rs_insertion(a, n, esz); return; }
-	int lvl = 0;
-	uint32_t *f = frames;
-	f[0] = 0; f[1] = (uint32_t)(esz == 4 ? 56 : 24); f[2] = 0xffffffffu; f[3] = n;		/* beg, s, k (unset), n */
-	while(lvl >= 0) {
-		f = frames + MAB_RS_FRAME * lvl;
-		uint32_t beg = f[0], s = f[1], cnt = f[3];
-		uint32_t *end = f + 4;
-		uint32_t *base = a + (uint64_t)esz * beg;
-		if(f[2] == 0xffffffffu) {
-			/* levels on which every key of the range has the same digit move nothing in the reference (one bucket, every
-			 * element already in place) and recurse into the same range: skip them with one scan */
-			{
-				uint64_t k0 = rs_key(base, esz), diff = 0;
-				for(uint32_t i = 1; i < cnt; i++) { diff |= rs_key(base + esz * i, esz) ^ k0; }
-				while(s > 0 && ((diff >> s) & 0xff) == 0) { s = s > 8 ? s - 8 : 0; }
-				f[1] = s;
-				if(((diff >> s) & 0xff) == 0) { lvl--; continue; }		/* s == 0 and uniform: nothing left to order */
-			}
-			/* distribute this range by digit (s) */
-			uint32_t head[256];
-			for(int k = 0; k < 256; k++) { end[k] = 0; }
-			for(uint32_t i = 0; i < cnt; i++) { end[(rs_key(base + esz * i, esz) >> s) & 0xff]++; }
-			head[0] = 0;
-			for(int k = 1; k < 256; k++) { end[k] += end[k - 1]; head[k] = end[k - 1]; }
-			for(int k = 0; k < 256;) {
-				if(head[k] != end[k]) {
-					int l = (int)((rs_key(base + esz * head[k], esz) >> s) & 0xff);
-					if(l != k) {
-						uint32_t tmp[4], swp[4];
-						rs_copy(tmp, base + esz * head[k], esz);
-						do {
-							rs_copy(swp, tmp, esz); rs_copy(tmp, base + esz * head[l], esz); rs_copy(base + esz * head[l], swp, esz); head[l]++;
-							l = (int)((rs_key(tmp, esz) >> s) & 0xff);
-						} while(l != k);
-						rs_copy(base + esz * head[k], tmp, esz); head[k]++;
-					} else { head[k]++; }
-				} else { k++; }
-			}
-			if(s == 0) { lvl--; continue; }
-			f[2] = 0;
-		}
-		/* visit child buckets in order */
-		uint32_t ns = s > 8 ? s - 8 : 0;
-		int descended = 0;
-		while(f[2] < 256) {
-			uint32_t k = f[2]++;
-			uint32_t b0 = k == 0 ? 0 : end[k - 1], sz = end[k] - b0;
-			if(sz > 64) {
-				uint32_t *g = frames + MAB_RS_FRAME * (lvl + 1);
-				g[0] = beg + b0; g[1] = ns; g[2] = 0xffffffffu; g[3] = sz;
-				lvl++; descended = 1;
-				break;
-			} else if(sz > 1) {
-				rs_insertion(base + esz * b0, sz, esz);
-			}
-		}
-		if(!descended) { lvl--; }
-	}
-}
-
-/* Warp-cooperative version of radix_sort_exact: identical result (same permutation cycles, walked by lane 0 in the
- * reference's order), but the digit histogram, the prefix sum, the uniform-level scan and the insertion sorts of the
- * (independent) small buckets are spread over the 32 lanes.  `sm` = 512 u32 of shared memory owned by this warp. */
-__device__ inline void radix_sort_exact_warp(uint32_t *a, uint32_t n, int esz, uint32_t *frames, uint32_t *sm, int lane)
+/* Warp-cooperative exact sort.  The reference's sort is unstable and the order it leaves equal keys in is observable
+ * downstream (chaining walks the array in order), so the permutation cycles of every distribution pass are followed by
+ * lane 0 in exactly the reference's order; the digit histogram, the prefix sum, the scan that skips levels on which all
+ * keys of a range share the digit (such a pass moves nothing in the reference and recurses into the same range) and the
+ * insertion sorts of the (independent) small buckets are spread over the 32 lanes.  Buckets larger than 64 go on an explicit
+ * stack of {beg, cnt | shift/8 << 29} pairs; sub-ranges are disjoint, so the order they are processed in does not matter.
+ * `sm` = 512 u32 of shared memory owned by this warp, `stack` = MAB_RS_STACK pairs of (global) scratch owned by this warp.
+ * Structured control flow only: this is inlined into k_extend, whose shuffles rely on provable warp convergence. */
+#define MAB_RS_FRAME 260						/* scratch u32 per "frame"; callers allocate 8 frames per warp */
+#define MAB_RS_STACK (8 * MAB_RS_FRAME / 2)
+__device__ __forceinline__ void radix_sort_exact_warp(uint32_t *a, uint32_t n, int esz, uint32_t *stack, uint32_t *sm, int lane, uint32_t *err)
 {
 	if(n <= 64) { if(lane == 0) { rs_insertion(a, n, esz); } __syncwarp(); return; }
 	uint32_t *cnt = sm, *head = sm + 256;
-	int lvl = 0;
-	if(lane == 0) { frames[0] = 0; frames[1] = (uint32_t)(esz == 4 ? 56 : 24); frames[2] = 0xffffffffu; frames[3] = n; }
+	uint32_t sp = 1;
+	if(lane == 0) { stack[0] = 0; stack[1] = n | ((esz == 4 ? 7u : 3u) << 29); }
 	__syncwarp();
-	while(lvl >= 0) {
-		uint32_t *f = frames + MAB_RS_FRAME * lvl;
-		uint32_t beg = f[0], s = f[1], cntn = f[3], state = f[2];
-		uint32_t *end = f + 4;
+	while(sp > 0) {
+		sp--;
+		uint32_t beg = stack[2 * sp], w1 = stack[2 * sp + 1];
+		uint32_t cntn = w1 & 0x1fffffffu, s = (w1 >> 29) * 8;
 		uint32_t *base = a + (uint64_t)esz * beg;
 		__syncwarp();
-		if(state == 0xffffffffu) {
-			uint64_t k0 = rs_key(base, esz), diff = 0;
-			for(uint32_t i = 1 + lane; i < cntn; i += 32) { diff |= rs_key(base + esz * i, esz) ^ k0; }
-			uint32_t dlo = __reduce_or_sync(0xffffffffu, (uint32_t)diff), dhi = __reduce_or_sync(0xffffffffu, (uint32_t)(diff >> 32));
-			diff = (uint64_t)dhi << 32 | dlo;
-			while(s > 0 && ((diff >> s) & 0xff) == 0) { s = s > 8 ? s - 8 : 0; }
-			if(((diff >> s) & 0xff) == 0) { lvl--; continue; }
+		uint64_t k0 = rs_key(base, esz), diff = 0;
+		for(uint32_t i = 1 + lane; i < cntn; i += 32) { diff |= rs_key(base + esz * i, esz) ^ k0; }
+		uint32_t dlo = __reduce_or_sync(0xffffffffu, (uint32_t)diff), dhi = __reduce_or_sync(0xffffffffu, (uint32_t)(diff >> 32));
+		diff = (uint64_t)dhi << 32 | dlo;
+		while(s > 0 && ((diff >> s) & 0xff) == 0) { s -= 8; }
+		if(((diff >> s) & 0xff) != 0) {				/* else: s == 0 and uniform, nothing left to order */
 			for(int k = lane; k < 256; k += 32) { cnt[k] = 0; }
 			__syncwarp();
-			for(uint32_t i = lane; i < cntn; i += 32) { atomicAdd(&cnt[(rs_key(base + esz * i, esz) >> s) & 0xff], 1u); }
-			__syncwarp();
+			/* digit histogram: lanes holding the same digit elect a leader that adds their count (no shared-memory atomics: the
+			 * compiler's atomic aggregation code defeats the convergence analysis of the whole kernel) */
+			for(uint32_t i0 = 0; i0 < cntn; i0 += 32) {
+				uint32_t i = i0 + lane;
+				uint32_t d = i < cntn ? (uint32_t)((rs_key(base + esz * i, esz) >> s) & 0xff) : 0x100u + (uint32_t)lane;
+				uint32_t m = __match_any_sync(0xffffffffu, d);
+				if(d < 0x100u && lane == __ffs((int)m) - 1) { cnt[d] += (uint32_t)__popc(m); }
+				__syncwarp();
+			}
 			/* inclusive prefix sum over 256 counters: 8 per lane + warp scan */
 			uint32_t loc[8], sum = 0;
 			for(int j = 0; j < 8; j++) { sum += cnt[8 * lane + j]; loc[j] = sum; }
@@ -181,10 +132,10 @@ __device__ inline void radix_sort_exact_warp(uint32_t *a, uint32_t n, int esz, u
 			for(int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, inc, d); if(lane >= d) { inc += y; } }
 			uint32_t excl = inc - sum;
 			__syncwarp();
-			for(int j = 0; j < 8; j++) { uint32_t e = excl + loc[j]; end[8 * lane + j] = e; cnt[8 * lane + j] = e; head[8 * lane + j] = e - (loc[j] - (j ? loc[j - 1] : 0)); }
+			for(int j = 0; j < 8; j++) { uint32_t e = excl + loc[j]; cnt[8 * lane + j] = e; head[8 * lane + j] = e - (loc[j] - (j ? loc[j - 1] : 0)); }
 			__syncwarp();
 			if(lane == 0) {
-				/* the permutation: cycle leaders in bucket order, exactly as the reference walks them */
+				/* the permutation: cycle leaders in bucket order, exactly as the reference walks them (ksort.h:97-118) */
 				for(int k = 0; k < 256;) {
 					if(head[k] != cnt[k]) {
 						int l = (int)((rs_key(base + esz * head[k], esz) >> s) & 0xff);
@@ -199,39 +150,26 @@ __device__ inline void radix_sort_exact_warp(uint32_t *a, uint32_t n, int esz, u
 						} else { head[k]++; }
 					} else { k++; }
 				}
-				f[1] = s; f[2] = 0;
 			}
 			__syncwarp();
-			if(s == 0) { lvl--; continue; }
-			/* small buckets are independent: insertion-sort them in parallel, one bucket per lane at a time */
-			for(int k = lane; k < 256; k += 32) {
-				uint32_t b0 = k == 0 ? 0 : end[k - 1], sz = end[k] - b0;
-				if(sz > 1 && sz <= 64) { rs_insertion(base + esz * b0, sz, esz); }
-			}
-			__syncwarp();
-		}
-		/* descend into the large buckets in order */
-		uint32_t ns = s > 8 ? s - 8 : 0;
-		uint32_t kcur = f[2];
-		int descended = 0;
-		__syncwarp();
-		while(kcur < 256) {
-			uint32_t k = kcur++;
-			uint32_t b0 = k == 0 ? 0 : end[k - 1], sz = end[k] - b0;
-			if(sz > 64) {
-				if(lane == 0) {
-					f[2] = kcur;
-					uint32_t *g = frames + MAB_RS_FRAME * (lvl + 1);
-					g[0] = beg + b0; g[1] = ns; g[2] = 0xffffffffu; g[3] = sz;
+			if(s > 0) {
+				uint32_t ns = s - 8;
+				for(int j = 0; j < 8; j++) {
+					int k = 32 * j + lane;
+					uint32_t b0 = k == 0 ? 0 : cnt[k - 1], sz = cnt[k] - b0;
+					if(sz > 1 && sz <= 64) { rs_insertion(base + esz * b0, sz, esz); }		/* independent small buckets, one per lane */
+					uint32_t m = __ballot_sync(0xffffffffu, sz > 64);
+					if(sz > 64) {
+						uint32_t pos = sp + (uint32_t)__popc(m & ((1u << lane) - 1));
+						if(pos < MAB_RS_STACK) { stack[2 * pos] = beg + b0; stack[2 * pos + 1] = sz | ((ns >> 3) << 29); }
+					}
+					sp += (uint32_t)__popc(m);
+					if(sp > MAB_RS_STACK) { sp = MAB_RS_STACK; *err |= 1u; }				/* warp-uniform */
 				}
-				lvl++; descended = 1;
-				break;
 			}
 		}
 		__syncwarp();
-		if(!descended) { lvl--; }
 	}
-	__syncwarp();
 }
 
 /* ---------------------------------------------------------------- seeds and chaining (minialign.c:3340-3625) */

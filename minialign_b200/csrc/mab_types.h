@@ -51,6 +51,9 @@ struct DevParams {
 	double mcoef, imx, xmx;
 	int8_t sb[16];
 	int32_t adjh, adjv, ofsh, ofsv, gfh, gfv, tx;
+	/* the same constants as packed H8 pairs (value in the high byte of both 16-bit halves; "+1" = plus one ulp, see mab_dp.cuh)
+	 * ready to be used as constant-bank operands: K_OFS = ofsh = ofsv */
+	uint32_t K_GFH1, K_GFV1, K_ADJH1, K_ADJV1, K_OFS;
 	int32_t gi, ge, gfa, gfb;
 	RootTpl root[3];				/* W = 64, 32, 16 */
 };

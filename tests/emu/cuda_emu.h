@@ -75,6 +75,7 @@ template <class T> static inline T __shfl_up_sync(unsigned, T v, unsigned d, int
 template <class T> static inline T __shfl_down_sync(unsigned, T v, unsigned d, int = 32) { uint64_t x = 0; memcpy(&x, &v, sizeof(T)); unsigned l = emu::g_cur->lane; const uint64_t *a = emu::warp_gather(x); T r; memcpy(&r, &a[l + d < 32 ? l + d : l], sizeof(T)); return r; }
 template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m, int = 32) { uint64_t x = 0; memcpy(&x, &v, sizeof(T)); unsigned l = emu::g_cur->lane; const uint64_t *a = emu::warp_gather(x); T r; memcpy(&r, &a[(l ^ m) & 31], sizeof(T)); return r; }
 static inline unsigned __ballot_sync(unsigned, int p) { const uint64_t *a = emu::warp_gather(p != 0); unsigned r = 0; for(int i = 0; i < 32; i++) { r |= (unsigned)(a[i] & 1) << i; } return r & ((emu::g_cur->warp->nlive >= 32) ? 0xffffffffu : 0xffffffffu); }
+static inline unsigned __match_any_sync(unsigned, unsigned v) { const uint64_t *a = emu::warp_gather(v); unsigned r = 0; for(int i = 0; i < 32; i++) { r |= (unsigned)((uint32_t)a[i] == v) << i; } return r; }
 static inline int __any_sync(unsigned m, int p) { return __ballot_sync(m, p) != 0; }
 static inline int __all_sync(unsigned m, int p) { return __ballot_sync(m, !p) == 0; }
 static inline int __reduce_add_sync(unsigned, int v) { const uint64_t *a = emu::warp_gather((uint64_t)(uint32_t)v); uint32_t s = 0; for(int i = 0; i < 32; i++) { s += (uint32_t)a[i]; } return (int)s; }
@@ -119,6 +120,8 @@ static inline unsigned __vimax3_s16x2(unsigned a, unsigned b, unsigned c) { retu
 static inline unsigned __vimin3_s16x2(unsigned a, unsigned b, unsigned c) { return __vmins2(__vmins2(a, b), c); }
 static inline unsigned __viaddmax_s16x2(unsigned a, unsigned b, unsigned c) { return __vmaxs2(__vadd2(a, b), c); }
 static inline unsigned __viaddmin_s16x2(unsigned a, unsigned b, unsigned c) { return __vmins2(__vadd2(a, b), c); }
+static inline unsigned __viaddmin_u16x2(unsigned a, unsigned b, unsigned c) { return __vminu2(__vadd2(a, b), c); }
+static inline unsigned __vimin3_u16x2(unsigned a, unsigned b, unsigned c) { return __vminu2(__vminu2(a, b), c); }
 static inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned s) { s &= 31; return s ? (hi << s) | (lo >> (32 - s)) : hi; }
 static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned s) { s &= 31; return s ? (lo >> s) | (hi << (32 - s)) : lo; }
 static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
