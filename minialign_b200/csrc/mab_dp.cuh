@@ -54,7 +54,8 @@ __device__ __forceinline__ uint32_t clamp8x2(uint32_t x) { return __vmaxs2(__vmi
 struct DpCtx {
 	const DevParams *P;
 	BlkEntry *blk; uint32_t blk_cap;
-	uint32_t *masks;				/* 256 u32 per entry (only written by traced fills) */
+	uint32_t *masks;				/* 512 u32 (2 KB) per entry, only written by traced fills: row j (128 B) holds vectors 2j and 2j+1,
+									 * lane l's word = bytes {2j: cell 2l, cell 2l+1, 2j+1: cell 2l, cell 2l+1}, one flag nibble per byte */
 	TailRec *tails;
 	const uint32_t *lut;			/* 256-entry packed score LUT in shared memory */
 	uint32_t nblk, ntail;
@@ -161,14 +162,12 @@ __device__ __forceinline__ void shift_down(const StepK &k, Vec &v, uint32_t nb)	
 	v.wb = (w & ~k.insB) | (nb & k.insB);
 }
 
-/* The cell update of one anti-diagonal after the shift (gaba.c:1604-1655).  DOWN / MASKS / ONE are compile-time: ONE is the
- * bit (per 16-bit half) the four traceback flags are normalised to, so that an unrolled group of four vectors lands in one
- * word without shifts.  Returns (when MASKS) the nibble {bit0 = ~h, bit1 = ~v, bit2 = ~e, bit3 = ~f} of the two cells at
- * bit log2(ONE) of each half. */
-template <bool DOWN, bool MASKS, uint32_t ONE>
+/* The cell update of one anti-diagonal after the shift (gaba.c:1604-1655).  Returns (when MASKS) the traceback nibble
+ * {bit0 = ~h, bit1 = ~v, bit2 = ~e, bit3 = ~f} of the two cells in the low bits of each 16-bit half. */
+template <bool DOWN, bool MASKS>
 __device__ __forceinline__ uint32_t vec_core(const DevParams &P, const StepK &k, Vec &v)
 {
-	const uint32_t EPS = 0x00010001u;
+	const uint32_t EPS = 0x00010001u, ONE = 0x00010001u;
 	uint32_t x = v.wa | v.wb;
 	uint32_t S = *(const uint32_t *)(k.lut + ((x | (x >> 12)) & 0x3fcu));
 	uint32_t dfh = __vadd2(v.V, P.K_GFH1), dfv = __vadd2(v.A, P.K_GFV1);
@@ -199,26 +198,26 @@ __device__ __forceinline__ uint32_t vec_core(const DevParams &P, const StepK &k,
  * The direction word and the two base counters live in ordinary (per-lane, identical) registers inside the block and are
  * made warp-uniform again by one broadcast at the block end: the per-step uniform-datapath bookkeeping would cost more. */
 struct BulkCnt { uint32_t dir, acnt, bcnt; };
-template <bool MASKS, uint32_t ONE>
+template <bool MASKS>
 __device__ __forceinline__ uint32_t bulk_step(const DevParams &P, const StepK &k, Vec &v, uint32_t an, uint32_t bn, BulkCnt &n)
 {
 	if(v.acc < 0) {																		/* warp-uniform */
 		n.dir = n.dir * 2 + 1; shift_down(k, v, __shfl_sync(MAB_FULL, bn, n.bcnt)); n.bcnt++;
-		return vec_core<true, MASKS, ONE>(P, k, v);
+		return vec_core<true, MASKS>(P, k, v);
 	}
 	n.dir = n.dir * 2; shift_right(k, v, __shfl_sync(MAB_FULL, an, n.acnt)); n.acnt++;
-	return vec_core<false, MASKS, ONE>(P, k, v);
+	return vec_core<false, MASKS>(P, k, v);
 }
-template <bool MASKS, uint32_t ONE>
+template <bool MASKS>
 __device__ __forceinline__ uint32_t vec_step(const DevParams &P, const StepK &k, Vec &v, bool down, uint32_t newch)
 {
-	if(down) { shift_down(k, v, newch); return vec_core<true, MASKS, ONE>(P, k, v); }
-	shift_right(k, v, newch); return vec_core<false, MASKS, ONE>(P, k, v);
+	if(down) { shift_down(k, v, newch); return vec_core<true, MASKS>(P, k, v); }
+	shift_right(k, v, newch); return vec_core<false, MASKS>(P, k, v);
 }
 template <bool MASKS>
 __device__ __forceinline__ uint32_t vec_step_rt(const DevParams &P, const StepK &k, Vec &v, int down, uint32_t newch)
 {
-	return vec_step<MASKS, 0x01000100u>(P, k, v, down != 0, newch);
+	return vec_step<MASKS>(P, k, v, down != 0, newch);
 }
 
 /* load the vector registers from the entry physically before a block (_fill_load_context, gaba.c:1527-1550) */
@@ -411,7 +410,7 @@ __device__ __forceinline__ int32_t fill_blocks(DpCtx &c, FillWork &w, Vec &v, ui
 		if(l < c.nl) { b->cha[l] = (uint16_t)win_store(v.wa); b->chb[l] = (uint16_t)win_store(v.wb); }
 		if(first) { vec_load(c, v, &c.blk[bi - 1], xd); first = 0; }
 		else { v.delta = 0; v.acc = (int32_t)(int8_t)v.acc; v.dir = 0; }				/* ndrop carries over: xd == drop of the previous block */
-		uint32_t *mrow = c.masks + 256ull * bi + l;
+		uint32_t *mrow = c.masks + 512ull * bi + l;
 		int acnt = 0, bcnt = 0, i = 0;
 		if(!cap) {
 			BulkCnt n; n.dir = 0; n.acnt = 0; n.bcnt = 0;
@@ -420,15 +419,15 @@ __device__ __forceinline__ int32_t fill_blocks(DpCtx &c, FillWork &w, Vec &v, ui
 #endif
 			#pragma unroll 1
 			for(int g = 0; g < MAB_BLK / 4; g++) {
-				uint32_t b0 = bulk_step<MASKS, 0x00010001u>(P, k, v, an, bn, n), b1 = bulk_step<MASKS, 0x00100010u>(P, k, v, an, bn, n);
-				uint32_t b2 = bulk_step<MASKS, 0x01000100u>(P, k, v, an, bn, n), b3 = bulk_step<MASKS, 0x01000100u>(P, k, v, an, bn, n);
-				if(MASKS) { mrow[32 * g] = (b0 | b1 | b2) + b3 * 16; }					/* nibble u of each half = vector 4g + u */
+				uint32_t b0 = bulk_step<MASKS>(P, k, v, an, bn, n), b1 = bulk_step<MASKS>(P, k, v, an, bn, n);
+				if(MASKS) { mrow[64 * g] = __byte_perm(b0, b1, 0x6420); }				/* one coalesced 128 B row per two vectors */
+				uint32_t b2 = bulk_step<MASKS>(P, k, v, an, bn, n), b3 = bulk_step<MASKS>(P, k, v, an, bn, n);
+				if(MASKS) { mrow[64 * g + 32] = __byte_perm(b2, b3, 0x6420); }
 			}
 			v.dir = __shfl_sync(MAB_FULL, n.dir, 0);
 			bcnt = __popc(v.dir); acnt = MAB_BLK - bcnt;
 			i = MAB_BLK;
 		} else {
-			uint32_t mbits = 0;
 			for(; i < MAB_BLK; i++) {
 				int down = v.acc < 0;
 				{																/* _fill_cap_test_idx */
@@ -440,12 +439,8 @@ __device__ __forceinline__ int32_t fill_blocks(DpCtx &c, FillWork &w, Vec &v, ui
 				uint32_t newch = down ? __shfl_sync(MAB_FULL, bn, bcnt) : __shfl_sync(MAB_FULL, an, acnt);
 				bcnt += down; acnt += 1 - down;
 				uint32_t bits = vec_step_rt<MASKS>(P, k, v, down, newch);
-				if(MASKS) {
-					mbits |= ((bits >> 8) & 0x000f000fu) << (4 * (i & 3));
-					if((i & 3) == 3) { mrow[32 * (i >> 2)] = mbits; mbits = 0; }
-				}
+				if(MASKS) { ((uint16_t *)(mrow + 32 * (i >> 1)))[i & 1] = (uint16_t)__byte_perm(bits, 0, 0x4420); }
 			}
-			if(MASKS && (i & 3) != 0) { mrow[32 * (i >> 2)] = mbits; }
 		}
 		c.n_vectors += (uint64_t)i;
 		w.pridx -= (uint32_t)i;
@@ -668,39 +663,30 @@ struct Trace {
 	int32_t gidx[2], sgidx[2]; uint32_t ofs[2], id[2];
 	int32_t tail[2];
 	uint32_t gi[2], ge[2], gf[2];
-	uint64_t npop, plen;
+	/* Path bits are produced from the end of the alignment towards its start.  pidx = bits still to be produced; the 64-bit
+	 * accumulator holds the nacc produced-but-unstored bits [pidx, 32 (widx + 1)), newest at bit 0; every path word above widx
+	 * is already in memory.  Whole words are stored at block boundaries only (<= 32 pops apart). */
+	uint32_t pidx, nacc; int32_t widx;
+	uint64_t pacc;
 	uint32_t *path;				/* path words in the result pool */
-	uint32_t cur_word; int64_t cur_idx; int32_t cur_bit;
 };
 
-/* stage the 1 KB mask block of entry b into this warp's shared-memory tile (coalesced 128 B rows) */
-__device__ __forceinline__ void stage_masks(const DpCtx &c, int32_t b, uint32_t *tile)
+/* Stage the 2 KB mask block of entry b into this warp's shared-memory tile as one flag nibble per byte, tile8[vector][cell]
+ * (64 B per vector), so that the walk below needs one byte load per popped vector.  Global reads are coalesced 128 B rows.
+ * For W = 16 the cells 16..31 read as "all flags clear" like the zero-extended 16-bit mask words of the reference. */
+__device__ __forceinline__ void stage_masks(const DpCtx &c, int32_t b, uint8_t *tile8)
 {
-	const uint32_t *src = c.masks + 256ull * b;
+	const uint32_t *src = c.masks + 512ull * b + c.lane;
+	uint16_t *dst = (uint16_t *)tile8 + c.lane;
+	const bool pad = c.W == 16 && c.lane >= 8;
 	__syncwarp();				/* every lane is done reading the previous tile (lanes are not lock-stepped on sm_70+) */
-	for(int g = 0; g < 8; g++) { tile[32 * g + c.lane] = src[32 * g + c.lane]; }
-	__syncwarp();
-}
-
-/* nibble of (vector mi, cell q): bit0 = ~h, bit1 = ~v, bit2 = ~e, bit3 = ~f.  q is taken modulo the mask word width like
- * the reference's `mask->x.all >> q` on x86 (gaba.c:2952-2973) */
-__device__ __forceinline__ uint32_t mask_nib(const DpCtx &c, const uint32_t *tile, int32_t mi, uint32_t q)
-{
-	uint32_t qq;
-	if(c.W == 64) { qq = q & 63; } else if(c.W == 32) { qq = q & 31; } else { qq = q & 31; if(qq >= 16) { return 0xfu; } }
-	uint32_t wd = tile[32 * (mi >> 2) + (qq >> 1)];
-	return (wd >> (16 * (qq & 1) + 4 * (mi & 3))) & 0xfu;
-}
-
-__device__ __forceinline__ void trace_pop(Trace &w, int v, int lane)
-{
-	/* path bits are produced from the end of the alignment towards its start: fill the current word downwards */
-	if(w.cur_bit < 0) {
-		if(lane == 0) { w.path[w.cur_idx] = w.cur_word; }
-		w.cur_idx--; w.cur_word = 0; w.cur_bit = 31;
+	#pragma unroll 4
+	for(int j = 0; j < 16; j++) {
+		uint32_t wd = src[32 * j];
+		if(pad) { wd = 0x0f0f0f0fu; }
+		dst[64 * j] = (uint16_t)wd; dst[64 * j + 32] = (uint16_t)(wd >> 16);
 	}
-	w.cur_word |= (uint32_t)v << w.cur_bit;
-	w.cur_bit--; w.npop++;
+	__syncwarp();
 }
 
 /* trace_reload_section (gaba.c:2826-2859) */
@@ -721,25 +707,37 @@ __device__ __forceinline__ void trace_reload_section(const DpCtx &c, Trace &w, i
 }
 
 /* trace_core (gaba.c:3111-3232): the reference's diag / h-gap / v-gap loops with its bulk and tail modes, as straight
- * gotos (one shared-memory nibble lookup per popped vector).  The rare block-boundary work sits in one out-of-line
- * `reload` section that returns to the pop site through `ret`. */
-__device__ __forceinline__ void trace_core(DpCtx &c, Trace &w, uint32_t *tile)
+ * gotos.  Per popped vector: one byte load gives the cell's flag nibble (bit0 = ~h, bit1 = ~v, bit2 = ~e, bit3 = ~f; q is
+ * taken modulo the mask word width like the reference's `mask->x.all >> q` on x86, gaba.c:2952-2973) and the path bit is
+ * shifted into a 64-bit accumulator (the reference's `path_array << 1 | isV`, gaba.c:2978-2991); whole path words are stored
+ * at block boundaries.  The rare block-boundary work sits in one out-of-line `reload` section that returns to the pop site
+ * through `ret`.  In bulk mode the section counters were advanced by whole blocks beforehand (dec = 0) and stay >= W, so the
+ * "counter exhausted" tests need no mode check. */
+__device__ __forceinline__ void trace_core(DpCtx &c, Trace &w, uint8_t *tile8)
 {
 	const int W = c.W;
 	const uint32_t HEAD_CNT = (uint32_t)(W / MAB_BLK + (W == 16));
+	const uint32_t qmask = W == 64 ? 63u : 31u;
 	int32_t b = w.blk, mi = w.mi; uint32_t q = w.q, save = HEAD_CNT;
 	uint32_t dir = c.blk[b].dir_mask >> (MAB_BLK - (mi + 1));
 	int bulk = 0, ret = 0;
-	int32_t g0 = w.gidx[0], g1 = w.gidx[1];
+	int32_t g0 = w.gidx[0], g1 = w.gidx[1], dec = 1;
+	uint64_t pacc = w.pacc; uint32_t nacc = w.nacc; int32_t widx = w.widx;
 	uint32_t nb;
-	stage_masks(c, b, tile);
-	nb = mask_nib(c, tile, mi, q);
+	/* at most two whole words are pending: nacc < 32 after a flush, <= 32 pops per block */
+	#define FLUSH_PATH() { \
+		if(nacc >= 32) { nacc -= 32; if(c.lane == 0) { w.path[widx] = (uint32_t)(pacc >> nacc); } widx--; } \
+		if(nacc >= 32) { nacc -= 32; if(c.lane == 0) { w.path[widx] = (uint32_t)(pacc >> nacc); } widx--; } \
+	}
+	stage_masks(c, b, tile8);
+	#define NIB() ( (uint32_t)tile8[(mi << 6) + (int32_t)(q & qmask)] )
+	nb = NIB();
 	#define POP(_v, _id) { \
-		if(!bulk) { if(_v) { g1--; } else { g0--; } } \
-		trace_pop(w, _v, c.lane); mi--; \
-		q += (dir & 1) - (uint32_t)(_v); dir >>= 1; \
+		if(_v) { g1 -= dec; } else { g0 -= dec; } \
+		pacc = (pacc << 1) | (uint64_t)(_v); nacc++; \
+		q += (dir & 1) - (uint32_t)(_v); dir >>= 1; mi--; \
 		if(mi < 0) { ret = _id; goto reload; } \
-		R##_id: nb = mask_nib(c, tile, mi, q); \
+		R##_id: nb = NIB(); \
 	}
 	switch(w.state) {
 		case mab_ts_d:  goto L_D_HEAD;
@@ -751,7 +749,7 @@ __device__ __forceinline__ void trace_core(DpCtx &c, Trace &w, uint32_t *tile)
 	}
 L_D_HEAD:
 	if(!(nb & 1)) { goto L_H_HEAD; }											/* h bit set */
-	if(!bulk && (g0 == 0 || g1 == 0)) { w.state = mab_ts_d; goto term; }
+	if(g0 == 0 || g1 == 0) { w.state = mab_ts_d; goto term; }
 	POP(0, 1);
 	POP(1, 2);
 L_D_TAIL:
@@ -759,26 +757,26 @@ L_D_TAIL:
 	goto L_D_HEAD;
 L_H_HEAD:
 	if(nb & 4) {																/* e bit clear: short gap */
-		if(!bulk && g0 == 0) { w.state = mab_ts_h0; goto term; }
+		if(g0 == 0) { w.state = mab_ts_h0; goto term; }
 		w.gf[0]++; POP(0, 3);
 		goto L_D_HEAD;
 	}
 	w.gi[0]++;
 L_H_BODY:
-	if(!bulk && g0 == 0) { w.state = mab_ts_h1; goto term; }
+	if(g0 == 0) { w.state = mab_ts_h1; goto term; }
 	w.ge[0]++; POP(0, 4);
 L_H_TAIL:
 	if(!((nb & 1) && !(nb & 4))) { goto L_H_BODY; }								/* (~h & e) bit clear */
 	goto L_D_HEAD;
 L_V_HEAD:
 	if(nb & 8) {
-		if(!bulk && g1 == 0) { w.state = mab_ts_v0; goto term; }
+		if(g1 == 0) { w.state = mab_ts_v0; goto term; }
 		w.gf[1]++; POP(1, 5);
 		goto L_D_TAIL;
 	}
 	w.gi[1]++;
 L_V_BODY:
-	if(!bulk && g1 == 0) { w.state = mab_ts_v1; goto term; }
+	if(g1 == 0) { w.state = mab_ts_v1; goto term; }
 	w.ge[1]++; POP(1, 6);
 L_V_TAIL:
 	if(!((nb & 2) && !(nb & 8))) { goto L_V_BODY; }
@@ -805,7 +803,7 @@ reload:
 			int ok; TEST_BULK(ok);
 			if(!ok) {
 				if(q >= (uint32_t)W) { goto term; }
-				g1 += (int32_t)(q - save); g0 += (int32_t)(save - q); save = HEAD_CNT; bulk = 0;
+				g1 += (int32_t)(q - save); g0 += (int32_t)(save - q); save = HEAD_CNT; bulk = 0; dec = 1;
 			}
 		} else {																/* _trace_tail_load_n (3083-3099) */
 			if(c.blk[b - 1].xstat & MAB_X_HEAD) {
@@ -814,23 +812,28 @@ reload:
 				mi = cnt - 1; dir = c.blk[b].dir_mask >> (MAB_BLK - cnt);
 			} else {
 				RELOAD_BLOCK();
-				if(--save >= HEAD_CNT) { int ok; TEST_BULK(ok); if(ok) { save = q; bulk = 1; } }
+				if(--save >= HEAD_CNT) { int ok; TEST_BULK(ok); if(ok) { save = q; bulk = 1; dec = 0; } }
 			}
 		}
 		#undef TEST_BULK
 		#undef RELOAD_BLOCK
-		stage_masks(c, b, tile);
+		FLUSH_PATH();
+		stage_masks(c, b, tile8);
 		switch(ret) { case 1: goto R1; case 2: goto R2; case 3: goto R3; case 4: goto R4; case 5: goto R5; default: goto R6; }
 	}
 term:
+	FLUSH_PATH();
 	w.blk = b; w.mi = mi; w.q = q & 0xff; w.gidx[0] = g0; w.gidx[1] = g1;
+	w.pacc = pacc; w.nacc = nacc; w.widx = widx; w.pidx = (uint32_t)(widx + 1) * 32u - nacc;
 	__syncwarp();
 	#undef POP
+	#undef NIB
+	#undef FLUSH_PATH
 }
 
 /* gaba_dp_trace (gaba.c:3244-3393).  Allocates the alignment record from the result pool (lane 0 bumps the pointer),
  * returns its word offset or UINT64_MAX when the path left the band / the pool is full (err set in that case). */
-__device__ inline uint64_t dp_trace(DpCtx &c, int32_t ti, uint32_t *pool, uint64_t pool_cap, BatchCounters *ctr, uint32_t *tile)
+__device__ inline uint64_t dp_trace(DpCtx &c, int32_t ti, uint32_t *pool, uint64_t pool_cap, BatchCounters *ctr, uint32_t *tile32)
 {
 	const DevParams &P = *c.P;
 	const TailRec *t = &c.tails[ti];
@@ -847,21 +850,27 @@ __device__ inline uint64_t dp_trace(DpCtx &c, int32_t ti, uint32_t *pool, uint64
 	Trace w;
 	w.blk = lf.blk; w.mi = (int32_t)lf.p; w.q = lf.q; w.state = mab_ts_d;
 	for(int i = 0; i < 2; i++) { w.gidx[i] = lf.gidx[i]; w.sgidx[i] = lf.sgidx[i]; w.tail[i] = ti; w.ofs[i] = 0; w.id[i] = 0; w.gi[i] = w.ge[i] = w.gf[i] = 0; }
-	w.npop = 0; w.plen = plen; w.path = rec + MAB_ALN_HDR + 8ull * sn;
-	w.cur_idx = (int64_t)(plen >> 5); w.cur_word = 1u << (plen & 31); w.cur_bit = (int32_t)(plen & 31) - 1;	/* sentinel (gaba.c:3287) */
-	if(c.lane == 0) { w.path[(plen >> 5) + 1] = 0; }
+	if(plen >= 0x80000000ull) { c.err |= MAB_ERR_DP_OVF; return 0xffffffffffffffffull; }	/* 2^31 path bits: not a read */
+	w.pidx = (uint32_t)plen; w.path = rec + MAB_ALN_HDR + 8ull * sn;
+	w.pacc = 1; w.widx = (int32_t)(plen >> 5); w.nacc = 32u - ((uint32_t)plen & 31u);	/* sentinel bit at plen (gaba.c:3287), zeros above it */
+	if(c.lane == 0) {
+		w.path[(plen >> 5) + 1] = 0;
+		if(plen == 0) { w.path[0] = 1u; }												/* nothing will be popped */
+	}
 	uint32_t nseg = 0;
 	uint32_t fuel = sn + 8;
-	while(w.npop < plen) {
+	/* the remaining-bits counter comes out of the walk, whose data-dependent branches the compiler cannot prove warp-uniform:
+	 * re-broadcast it so that this loop (and with it everything after the trace) counts as convergent code */
+	while(__shfl_sync(MAB_FULL, w.pidx, 0) != 0) {
 		if(fuel-- == 0) { c.err |= MAB_ERR_DP_OVF; return 0xffffffffffffffffull; }		/* more segments than sections: cannot happen */
 		if(w.gidx[0] < (int32_t)((w.state & MAB_TS_H) != 0)) { trace_reload_section(c, w, 0); }
 		if(w.gidx[1] < (int32_t)((w.state & MAB_TS_V) != 0)) { trace_reload_section(c, w, 1); }
-		trace_core(c, w, tile);
+		trace_core(c, w, (uint8_t *)tile32);
 		if(w.q >= (uint32_t)c.W) { return 0xffffffffffffffffull; }					/* out of band: abort (gaba.c:3324-3328) */
 		/* trace_push_segment (gaba.c:2865-2895): slots fill from the back */
 		if(c.lane == 0 && nseg < sn) {
 			uint32_t *s = rec + MAB_ALN_HDR + 8ull * (sn - 1 - nseg);
-			uint64_t ppos = plen - w.npop;
+			uint64_t ppos = w.pidx;
 			s[0] = w.id[0]; s[1] = w.id[1];
 			s[2] = w.ofs[0] + (uint32_t)w.gidx[0]; s[3] = w.ofs[1] + (uint32_t)w.gidx[1];
 			s[4] = (uint32_t)(w.sgidx[0] - w.gidx[0]); s[5] = (uint32_t)(w.sgidx[1] - w.gidx[1]);
@@ -871,7 +880,6 @@ __device__ inline uint64_t dp_trace(DpCtx &c, int32_t ti, uint32_t *pool, uint64
 		w.sgidx[0] = w.gidx[0]; w.sgidx[1] = w.gidx[1];
 	}
 	if(c.lane == 0) {
-		w.path[w.cur_idx] = w.cur_word;
 		/* identity (gaba.c:3334-3355): only the a-side counters enter the sum (_mm_mul_epi32 multiplies the low lane) */
 		uint32_t gc0 = w.ge[0] + w.gf[0], gc1 = w.ge[1] + w.gf[1];
 		int32_t g0 = (int32_t)((uint32_t)P.gi * w.gi[0] + (uint32_t)P.ge * w.ge[0] + (uint32_t)P.gfa * w.gf[0]);

@@ -431,7 +431,7 @@ __device__ inline void finalize_read(RCtx &x, BatchCounters *ctr, uint64_t pool_
 	r->result_ofs = ofs; r->result_words = (uint32_t)words;
 }
 
-/* per-warp DP arena: [SlotHdr pad 64 B][TailRec x MAB_MAX_TAILS][BlkEntry x blk_cap][masks 1 KB x blk_cap][frames] */
+/* per-warp DP arena: [SlotHdr pad 64 B][TailRec x MAB_MAX_TAILS][BlkEntry x blk_cap][masks 2 KB x blk_cap][frames] */
 struct ArenaLayout { uint64_t tails, blk, masks, frames, total; };
 static inline __host__ __device__ ArenaLayout arena_layout(uint32_t blk_cap)
 {
@@ -441,7 +441,7 @@ static inline __host__ __device__ ArenaLayout arena_layout(uint32_t blk_cap)
 	a.blk = (a.blk + 127) & ~127ull;
 	a.masks = a.blk + sizeof(BlkEntry) * (uint64_t)blk_cap;
 	a.masks = (a.masks + 127) & ~127ull;
-	a.frames = a.masks + 1024ull * blk_cap;
+	a.frames = a.masks + 2048ull * blk_cap;
 	a.total = (a.frames + 4ull * 8 * MAB_RS_FRAME + 255) & ~255ull;
 	return a;
 }
