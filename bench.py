@@ -196,8 +196,10 @@ def main():
 
         def one(m, i, timed):
             p = packed[i % n_b]
+            tw = time.perf_counter()
             m.map_packed(dev_blocks[i % n_b].data_ptr() if mode_device else p[0].data_ptr(), p[0].numel(), p[1], p[2])
             st = m.stats()
+            st["py_call_ms"] = 1e3 * (time.perf_counter() - tw)
             words = sum(int(m.lib.mab_result(m.h, j, None)) for j in range(0, len(p[2]), max(1, len(p[2]) // 64)))
             m.lib.mab_release_batch(m.h)
             if timed:
@@ -209,21 +211,32 @@ def main():
                     agg["out_words"] += words
 
         def drive(first, count, timed):
+            errs = []
+
             def worker(t):
-                torch.cuda.set_device(local)
-                for i in range(first + t, first + count, len(ms)):
-                    one(ms[t], i, timed)
+                try:
+                    torch.cuda.set_device(local)
+                    for i in range(first + t, first + count, len(ms)):
+                        one(ms[t], i, timed)
+                except Exception as e:       # a failed batch must fail the run, not shorten it
+                    errs.append(e)
             th = [threading.Thread(target=worker, args=(t,)) for t in range(len(ms))]
             [x.start() for x in th]
             [x.join() for x in th]
+            if errs:
+                raise errs[0]
 
         drive(0, max(warmup, len(ms)), False)
         sampler = ClockSampler(local); sampler.start()
+        # device-side timing: the events sit on torch's (idle) stream; the first is recorded after a full device sync, the second
+        # after the next one, so the interval covers everything the contexts ran on their own streams in between
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
-        t = time.perf_counter()
+        ev0.record()
         drive(warmup, steps, True)
         torch.cuda.synchronize()
-        secs = time.perf_counter() - t
+        ev1.record(); ev1.synchronize()
+        secs = ev0.elapsed_time(ev1) / 1e3
         # the one exchange step of the sharded path: output offsets of this wave (8 B per rank)
         shard.output_offsets(4 * agg["out_words"], device=torch.device("cuda", local))
         barrier()

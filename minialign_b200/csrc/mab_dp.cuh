@@ -706,6 +706,19 @@ __device__ __forceinline__ void trace_reload_section(const DpCtx &c, Trace &w, i
 	w.gidx[i] = gidx; w.sgidx[i] = gidx;
 }
 
+/* one byte of this warp's tile, addressed in the shared window (a generic-pointer load makes the compiler rebuild the
+ * shared base from SR_CgaCtaId on every pop) */
+__device__ __forceinline__ uint32_t tile_ld8(const uint8_t *tile8, uint32_t tile_s, int32_t idx)
+{
+#ifdef MAB_EMU
+	(void)tile_s; return (uint32_t)tile8[idx];
+#else
+	(void)tile8; uint32_t v;
+	asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(tile_s + (uint32_t)idx) : "memory");
+	return v;
+#endif
+}
+
 /* trace_core (gaba.c:3111-3232): the reference's diag / h-gap / v-gap loops with its bulk and tail modes, as straight
  * gotos.  Per popped vector: one byte load gives the cell's flag nibble (bit0 = ~h, bit1 = ~v, bit2 = ~e, bit3 = ~f; q is
  * taken modulo the mask word width like the reference's `mask->x.all >> q` on x86, gaba.c:2952-2973) and the path bit is
@@ -729,8 +742,13 @@ __device__ __forceinline__ void trace_core(DpCtx &c, Trace &w, uint8_t *tile8)
 		if(nacc >= 32) { nacc -= 32; if(c.lane == 0) { w.path[widx] = (uint32_t)(pacc >> nacc); } widx--; } \
 		if(nacc >= 32) { nacc -= 32; if(c.lane == 0) { w.path[widx] = (uint32_t)(pacc >> nacc); } widx--; } \
 	}
+#ifdef MAB_EMU
+	const uint32_t tile_s = 0;
+#else
+	const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile8);
+#endif
 	stage_masks(c, b, tile8);
-	#define NIB() ( (uint32_t)tile8[(mi << 6) + (int32_t)(q & qmask)] )
+	#define NIB() tile_ld8(tile8, tile_s, (mi << 6) + (int32_t)(q & qmask))
 	nb = NIB();
 	#define POP(_v, _id) { \
 		if(_v) { g1 -= dec; } else { g0 -= dec; } \

@@ -32,6 +32,7 @@ struct mab_ctx {
 	ReadRec *d_reads = nullptr; uint64_t reads_cap = 0;
 	uint8_t *d_ws = nullptr; uint64_t ws_cap = 0;
 	uint32_t *d_frames = nullptr; uint64_t frames_cap = 0;
+	uint32_t *d_recs = nullptr; uint64_t recs_cap = 0;		/* minimizer records of k_seed_scan: 16 B per base position of the read block */
 	uint8_t *d_arenas = nullptr; uint64_t arenas_cap = 0;
 	uint32_t *d_pool = nullptr; uint64_t pool_cap = 0;
 	BatchCounters *d_ctr = nullptr;
@@ -170,7 +171,7 @@ extern "C" void mab_destroy(mab_ctx *ctx)
 {
 	if(ctx == nullptr) { return; }
 	RT_FREE(ctx->d_idx); RT_FREE(ctx->d_ntail); RT_FREE(ctx->d_ctr); RT_FREE(ctx->d_seq); RT_FREE(ctx->d_reads); RT_FREE(ctx->d_ws);
-	RT_FREE(ctx->d_frames); RT_FREE(ctx->d_arenas); RT_FREE(ctx->d_pool);
+	RT_FREE(ctx->d_frames); RT_FREE(ctx->d_recs); RT_FREE(ctx->d_arenas); RT_FREE(ctx->d_pool);
 	delete ctx;
 }
 
@@ -359,15 +360,23 @@ static int map_core(mab_ctx *ctx, const uint8_t *d_base, std::vector<ReadRec> &h
 	if(timed) { RT_EVENT_RECORD(ctx->ev[1], ctx->stream); }
 	/* count pass, workspace sizing */
 	uint32_t seed_ctas = std::max<uint32_t>(1, std::min<uint32_t>((n_seq + MAB_WARPS_PER_CTA - 1) / MAB_WARPS_PER_CTA, ctx->n_sm * 8));
-	RT_LAUNCH((k_seed<true>), seed_ctas, 32 * MAB_WARPS_PER_CTA, 512 * MAB_WARPS_PER_CTA, ctx->stream, P, d_base, ctx->d_reads, n_seq, (uint8_t *)nullptr);
+	{
+		uint64_t span = 0;
+		for(uint32_t i = 0; i < n_seq; i++) { span = std::max<uint64_t>(span, hr[i].seq_ofs + hr[i].len); }
+		int rc = grow(&ctx->d_recs, &ctx->recs_cap, 16ull * span + 256); if(rc) { return rc; }
+	}
+	RT_LAUNCH(k_seed_scan, seed_ctas, 32 * MAB_WARPS_PER_CTA, 512 * MAB_WARPS_PER_CTA, ctx->stream, P, d_base, ctx->d_reads, n_seq, ctx->d_recs);
 	S.n_launches++;
 	CK(RT_MEMCPY_D2H_ASYNC(hr.data(), ctx->d_reads, sizeof(ReadRec) * (uint64_t)n_seq, ctx->stream));
-	CK(RT_STREAM_SYNC(ctx->stream));
+	{ double tw = RT_WALL_MS(); CK(RT_STREAM_SYNC(ctx->stream)); S.ms_wall_wait += (float)(RT_WALL_MS() - tw); }
+	double t_sizing = RT_WALL_MS();
 	S.d2h_bytes += sizeof(ReadRec) * (uint64_t)n_seq;
 	uint64_t ws_total = 0;
+	uint32_t sc_cap = 64;					/* seeds k_sortchain stages in shared memory: every read up to MAB_SC_MAX seeds (48 KB per warp) */
 	for(uint32_t i = 0; i < n_seq; i++) {
 		ReadRec &r = hr[i];
 		if(r.state != 0) { continue; }
+		sc_cap = std::max(sc_cap, std::min<uint32_t>(r.tot_seeds + 2, MAB_SC_MAX));
 		r.seed_cap = 2 * (r.tot_seeds + 1) + 8; r.root_cap = r.tot_seeds + 8; r.resc_cap = r.tot_resc + 4; r.bin_cap = 2 * r.tot_seeds + 128;
 		r.ws_ofs = ws_total;
 		ws_total += ws_layout(r.seed_cap, r.root_cap, r.resc_cap, r.bin_cap).total;
@@ -379,6 +388,7 @@ static int map_core(mab_ctx *ctx, const uint8_t *d_base, std::vector<ReadRec> &h
 	uint32_t ext_ctas = std::max<uint32_t>(1, std::min<uint32_t>(ctx->n_slots / MAB_WARPS_PER_CTA, (n_seq + MAB_WARPS_PER_CTA - 1) / MAB_WARPS_PER_CTA));
 	{ int rc = grow(&ctx->d_arenas, &ctx->arenas_cap, AL.total * (uint64_t)ext_ctas * MAB_WARPS_PER_CTA); if(rc) { return rc; } }
 	uint64_t pool_need = tot_len / 4 + 64ull * n_seq + (1u << 16);				/* ~2 bits per base and alignment, x4 head room */
+	S.ms_wall_sizing += (float)(RT_WALL_MS() - t_sizing);
 	for(int attempt = 0; attempt < 3; attempt++) {
 		{ int rc = grow(&ctx->d_pool, &ctx->pool_cap, 4 * pool_need); if(rc) { return rc; } }
 		uint64_t pool_words = ctx->pool_cap / 4;
@@ -386,13 +396,13 @@ static int map_core(mab_ctx *ctx, const uint8_t *d_base, std::vector<ReadRec> &h
 		BatchCounters zero; memset(&zero, 0, sizeof(zero));
 		CK(RT_MEMCPY_H2D_ASYNC(ctx->d_ctr, &zero, sizeof(zero), ctx->stream));
 		if(timed) { RT_EVENT_RECORD(ctx->ev[2], ctx->stream); }
-		RT_LAUNCH((k_seed<false>), seed_ctas, 32 * MAB_WARPS_PER_CTA, 512 * MAB_WARPS_PER_CTA, ctx->stream, P, d_base, ctx->d_reads, n_seq, ctx->d_ws);
+		RT_LAUNCH(k_seed_expand, seed_ctas, 32 * MAB_WARPS_PER_CTA, 0, ctx->stream, P, ctx->d_reads, n_seq, ctx->d_ws, (const uint32_t *)ctx->d_recs);
 		S.n_launches++;
 		if(timed) { RT_EVENT_RECORD(ctx->ev[3], ctx->stream); }
 		/* rounds of sort+chain / extend (minialign.c:4444-4448) */
 		for(uint32_t round = 0; round < P.n_occ; round++) {
 			if(timed && round < 8) { RT_EVENT_RECORD(ctx->rev[3 * round], ctx->stream); }
-			RT_LAUNCH(k_sortchain, (n_seq + 3) / 4, 128, 2048 * 4, ctx->stream, P, ctx->d_reads, n_seq, ctx->d_ws, ctx->d_frames, round);
+			RT_LAUNCH(k_sortchain, n_seq, 32, 16 * sc_cap + 2048, ctx->stream, P, ctx->d_reads, n_seq, ctx->d_ws, ctx->d_frames, round, sc_cap);
 			RT_MEMSET_ASYNC(&ctx->d_ctr->work_next, 0, sizeof(unsigned int), ctx->stream);
 			if(timed && round < 8) { RT_EVENT_RECORD(ctx->rev[3 * round + 1], ctx->stream); }
 			RT_LAUNCH(k_extend, ext_ctas, 32 * MAB_WARPS_PER_CTA, 1024 + 2048 * MAB_WARPS_PER_CTA, ctx->stream, P, d_base, (const uint8_t *)ctx->d_ntail, ctx->d_reads, n_seq, ctx->d_ws,
@@ -404,7 +414,7 @@ static int map_core(mab_ctx *ctx, const uint8_t *d_base, std::vector<ReadRec> &h
 		BatchCounters hc;
 		CK(RT_MEMCPY_D2H_ASYNC(&hc, ctx->d_ctr, sizeof(hc), ctx->stream));
 		CK(RT_MEMCPY_D2H_ASYNC(hr.data(), ctx->d_reads, sizeof(ReadRec) * (uint64_t)n_seq, ctx->stream));
-		CK(RT_STREAM_SYNC(ctx->stream));
+		{ double tw = RT_WALL_MS(); CK(RT_STREAM_SYNC(ctx->stream)); S.ms_wall_wait += (float)(RT_WALL_MS() - tw); }
 		uint32_t err = 0;
 		for(uint32_t i = 0; i < n_seq; i++) { err |= hr[i].err; }
 		S.n_vectors += hc.n_vectors; S.n_fill_calls += hc.n_fill; S.n_trace += hc.n_trace;
@@ -419,7 +429,7 @@ static int map_core(mab_ctx *ctx, const uint8_t *d_base, std::vector<ReadRec> &h
 		ctx->h_pool.resize((size_t)top + 4);
 		if(top) { CK(RT_MEMCPY_D2H_ASYNC(ctx->h_pool.data(), ctx->d_pool, 4 * top, ctx->stream)); }
 		if(timed) { RT_EVENT_RECORD(ctx->ev[5], ctx->stream); }
-		CK(RT_STREAM_SYNC(ctx->stream));
+		{ double tw = RT_WALL_MS(); CK(RT_STREAM_SYNC(ctx->stream)); S.ms_wall_wait += (float)(RT_WALL_MS() - tw); }
 		S.d2h_bytes += 4 * top + sizeof(ReadRec) * (uint64_t)n_seq + sizeof(hc);
 		break;
 	}
@@ -430,6 +440,7 @@ extern "C" int mab_map_batch(mab_ctx *ctx, const uint8_t *seq_block, uint64_t bl
 {
 	mab_stats_t &S = ctx->stats;
 	memset(&S, 0, sizeof(S));
+	const double t_call = RT_WALL_MS();
 	ctx->res_words.clear(); ctx->res_ofs.assign((size_t)n_seq + 1, 0);
 	if(n_seq == 0) { return MAB_OK; }
 	CK(RT_SET_DEVICE(ctx->device));
@@ -506,6 +517,7 @@ extern "C" int mab_map_batch(mab_ctx *ctx, const uint8_t *seq_block, uint64_t bl
 	}
 	S.ms_d2h = RT_EVENT_MS(ctx->ev[4], ctx->ev[5]);
 	S.ms_total = RT_EVENT_MS(ctx->ev[0], ctx->ev[5]);
+	S.ms_wall = (float)(RT_WALL_MS() - t_call);
 	return MAB_OK;
 }
 
@@ -543,7 +555,9 @@ extern "C" uint64_t mab_seed_chain(mab_ctx *ctx, const uint8_t *seq, uint32_t le
 	RT_MEMCPY_H2D(d_seq, seq, len);
 	ReadRec r; memset(&r, 0, sizeof(r)); r.len = len;
 	RT_MEMCPY_H2D(d_r, &r, sizeof(r));
-	RT_LAUNCH((k_seed<true>), 1, 32, 512, ctx->stream, P, (const uint8_t *)d_seq, d_r, 1u, (uint8_t *)nullptr);
+	uint32_t *d_rec = nullptr;
+	if(!RT_OK(RT_MALLOC(&d_rec, 16ull * len + 256))) { RT_FREE(d_seq); RT_FREE(d_r); RT_FREE(d_fr); return 0; }
+	RT_LAUNCH(k_seed_scan, 1, 32, 512, ctx->stream, P, (const uint8_t *)d_seq, d_r, 1u, d_rec);
 	RT_STREAM_SYNC(ctx->stream);
 	RT_MEMCPY_D2H(&r, d_r, sizeof(r));
 	uint64_t ns = 0;
@@ -552,8 +566,8 @@ extern "C" uint64_t mab_seed_chain(mab_ctx *ctx, const uint8_t *seq, uint32_t le
 		WsLayout L = ws_layout(r.seed_cap, r.root_cap, r.resc_cap, r.bin_cap);
 		RT_MALLOC(&d_ws, L.total + 256);
 		RT_MEMCPY_H2D(d_r, &r, sizeof(r));
-		RT_LAUNCH((k_seed<false>), 1, 32, 512, ctx->stream, P, (const uint8_t *)d_seq, d_r, 1u, d_ws);
-		for(uint32_t i = 0; i <= round && i < P.n_occ; i++) { RT_LAUNCH(k_sortchain, 1, 32, 2048, ctx->stream, P, d_r, 1u, d_ws, d_fr, i); }
+		RT_LAUNCH(k_seed_expand, 1, 32, 0, ctx->stream, P, d_r, 1u, d_ws, (const uint32_t *)d_rec);
+		{ uint32_t sc_cap = std::max<uint32_t>(64u, std::min<uint32_t>(r.tot_seeds + 2, MAB_SC_MAX)); for(uint32_t i = 0; i <= round && i < P.n_occ; i++) { RT_LAUNCH(k_sortchain, 1, 32, 16 * sc_cap + 2048, ctx->stream, P, d_r, 1u, d_ws, d_fr, i, sc_cap); } }
 		RT_STREAM_SYNC(ctx->stream);
 		RT_MEMCPY_D2H(&r, d_r, sizeof(r));
 		if(r.n_seed) {
@@ -563,7 +577,7 @@ extern "C" uint64_t mab_seed_chain(mab_ctx *ctx, const uint8_t *seq, uint32_t le
 		}
 		RT_FREE(d_ws);
 	}
-	RT_FREE(d_seq); RT_FREE(d_r); RT_FREE(d_fr);
+	RT_FREE(d_seq); RT_FREE(d_r); RT_FREE(d_fr); RT_FREE(d_rec);
 	return ns;
 }
 

@@ -29,10 +29,14 @@ __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t x, int lane, uint32_
 	return s - x;
 }
 
-/* ---------------------------------------------------------------- k_seed */
-/* shared memory per warp: 64-entry ring of encoded minimizer candidates (u64) */
-template <bool COUNT>
-__global__ void k_seed(DevParams P, const uint8_t *base, ReadRec *reads, uint32_t n_reads, uint8_t *ws)
+/* ---------------------------------------------------------------- k_seed_scan / k_seed_expand */
+/* k_seed_scan: the sketch + probe pass.  Every minimizer with 0 < n <= occ[n_occ - 1] occurrences leaves a 16 B record
+ * {qs, n, byte offset of its occurrence array in the index image (lo, hi)} in emission order at recs[4 * (seq_ofs + j)]
+ * (a read emits at most one minimizer per base, so its slice of the block-sized record array cannot overflow), and the
+ * per-read totals size the workspaces.  k_seed_expand then only replays the records (mm_collect_seed / mm_expand,
+ * minialign.c:3420-3493): no second sketch, no second probe.
+ * shared memory per warp: 64-entry ring of encoded minimizer candidates (u64) */
+__global__ void k_seed_scan(DevParams P, const uint8_t *base, ReadRec *reads, uint32_t n_reads, uint32_t *recs)
 {
 	MAB_DYN_SMEM(smem);
 	int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -44,14 +48,13 @@ __global__ void k_seed(DevParams P, const uint8_t *base, ReadRec *reads, uint32_
 		ReadRec *r = &reads[rid];
 		uint32_t len = r->len;
 		if(len < P.k || (double)len * P.mcoef < (double)P.min_score) {			/* minialign.c:4434 */
-			if(lane == 0) { r->state = 1; r->tot_seeds = 0; r->tot_resc = 0; r->n_seed = 0; r->n_resc = 0; r->result_words = 0; }
+			if(lane == 0) { r->state = 1; r->tot_seeds = 0; r->tot_resc = 0; r->n_seed = 0; r->n_resc = 0; r->result_words = 0; r->n_rec = 0; }
 			continue;
 		}
 		const uint8_t *seq = base + r->seq_ofs;
+		uint32_t *rec = recs + 4ull * r->seq_ofs;
 		uint32_t npos = len - (uint32_t)kk;
-		uint32_t *seeds = nullptr, *resc = nullptr;
-		if(!COUNT) { WsLayout L = ws_layout(r->seed_cap, r->root_cap, r->resc_cap, r->bin_cap); seeds = (uint32_t *)(ws + r->ws_ofs + L.seed); resc = (uint32_t *)(ws + r->ws_ofs + L.resc); }
-		uint32_t n_seed = 0, n_resc = 0, tot_seeds = 0, tot_resc = 0, n_words = 0;
+		uint32_t tot_seeds = 0, tot_resc = 0, n_words = 0, n_rec = 0;
 		uint64_t vcarry = 0;				/* u: previous window minimum */
 		uint32_t idx_carry = (uint32_t)w;	/* decoder state: previous emitted in-block index (v = w), number of block starts */
 		uint32_t nblk_carry = 0;
@@ -101,32 +104,55 @@ __global__ void k_seed(DevParams P, const uint8_t *base, ReadRec *reads, uint32_
 				qs = (uint32_t)((bpos + (k & (0 - fr))) ^ (0 - fr));
 				if(n > max_occ) { n = 0; occ = nullptr; }
 			}
-			uint32_t is_resc = n > resc_occ, n_exp = is_resc ? 0 : n;
-			if(COUNT) {
-				tot_seeds += n; tot_resc += is_resc;
-			} else {
-				uint32_t tot_e, tot_r;
-				uint32_t eo = warp_excl_scan(n_exp, lane, &tot_e), ro = warp_excl_scan(is_resc, lane, &tot_r);
-				if(n_seed + tot_e + 2 > r->seed_cap || n_resc + tot_r > r->resc_cap) { if(lane == 0) { r->err |= MAB_ERR_SEED_OVF; } break; }
-				for(uint32_t i = 0; i < n_exp; i++) {								/* mm_expand (3420-3446) */
-					make_seed(P, seeds + 4ull * (n_seed + eo + i), ldg32(occ + 8ull * i), ldg32(occ + 8ull * i + 4), qs);
-				}
-				if(is_resc) {
-					uint32_t *s = resc + 4ull * (n_resc + ro);
-					uint64_t ofs = (uint64_t)(occ - P.idx);
-					s[0] = qs; s[1] = n; s[2] = (uint32_t)ofs; s[3] = (uint32_t)(ofs >> 32);
-				}
-				n_seed += tot_e; n_resc += tot_r;
+			uint32_t hit = __ballot_sync(MAB_FULL, n != 0);
+			if(n != 0) {
+				uint32_t *s = rec + 4ull * (n_rec + (uint32_t)__popc(hit & ((1u << lane) - 1)));
+				uint64_t ofs = (uint64_t)(occ - P.idx);
+				s[0] = qs; s[1] = n; s[2] = (uint32_t)ofs; s[3] = (uint32_t)(ofs >> 32);
+				tot_seeds += n; tot_resc += n > resc_occ;
 			}
+			n_rec += (uint32_t)__popc(hit);
 			__syncwarp();
 		}
-		if(COUNT) {
-			tot_seeds = __reduce_add_sync(MAB_FULL, tot_seeds); tot_resc = __reduce_add_sync(MAB_FULL, tot_resc);
-			if(lane == 0) { r->tot_seeds = tot_seeds; r->tot_resc = tot_resc; r->n_words = n_words; }
-		} else if(lane == 0) {
+		tot_seeds = __reduce_add_sync(MAB_FULL, tot_seeds); tot_resc = __reduce_add_sync(MAB_FULL, tot_resc);
+		if(lane == 0) { r->tot_seeds = tot_seeds; r->tot_resc = tot_resc; r->n_words = n_words; r->n_rec = n_rec; }
+	}
+}
+
+__global__ void k_seed_expand(DevParams P, ReadRec *reads, uint32_t n_reads, uint8_t *ws, const uint32_t *recs)
+{
+	int lane = threadIdx.x & 31;
+	uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+	uint32_t const resc_occ = P.occ[0];
+	for(uint32_t rid = gw; rid < n_reads; rid += nw) {
+		ReadRec *r = &reads[rid];
+		if(r->state != 0) { continue; }
+		WsLayout L = ws_layout(r->seed_cap, r->root_cap, r->resc_cap, r->bin_cap);
+		uint32_t *seeds = (uint32_t *)(ws + r->ws_ofs + L.seed), *resc = (uint32_t *)(ws + r->ws_ofs + L.resc);
+		const uint32_t *rec = recs + 4ull * r->seq_ofs;
+		uint32_t n_rec = r->n_rec, n_seed = 0, n_resc = 0;
+		for(uint32_t c0 = 0; c0 < n_rec; c0 += 32) {
+			uint32_t j = c0 + lane;
+			uint32_t qs = 0, n = 0; uint64_t ofs = 0;
+			if(j < n_rec) { uint4 e = ((const uint4 *)rec)[j]; qs = e.x; n = e.y; ofs = (uint64_t)e.z | (uint64_t)e.w << 32; }
+			uint32_t is_resc = n > resc_occ, n_exp = is_resc ? 0 : n;
+			uint32_t tot_e, tot_r;
+			uint32_t eo = warp_excl_scan(n_exp, lane, &tot_e), ro = warp_excl_scan(is_resc, lane, &tot_r);
+			if(n_seed + tot_e + 2 > r->seed_cap || n_resc + tot_r > r->resc_cap) { if(lane == 0) { r->err |= MAB_ERR_SEED_OVF; } break; }
+			const uint8_t *occ = P.idx + ofs;
+			for(uint32_t i = 0; i < n_exp; i++) {								/* mm_expand (3420-3446) */
+				make_seed(P, seeds + 4ull * (n_seed + eo + i), ldg32(occ + 8ull * i), ldg32(occ + 8ull * i + 4), qs);
+			}
+			if(is_resc) {
+				uint32_t *s = resc + 4ull * (n_resc + ro);
+				s[0] = qs; s[1] = n; s[2] = (uint32_t)ofs; s[3] = (uint32_t)(ofs >> 32);
+			}
+			n_seed += tot_e; n_resc += tot_r;
+		}
+		if(lane == 0) {
 			r->n_seed = n_seed; r->seed_n = n_seed; r->n_resc = n_resc; r->presc = 0; r->n_root = 0; r->n_next = 0; r->n_res = 0; r->nbin = 0;
 			r->rlen_cur = r->rlen_in; r->rlen_used = r->rlen_in; r->dep_apos = 0; r->dep_flags = 0;
-			kh_reset((uint64_t *)(ws + r->ws_ofs + ws_layout(r->seed_cap, r->root_cap, r->resc_cap, r->bin_cap).kh), r);
+			kh_reset((uint64_t *)(ws + r->ws_ofs + L.kh), r);
 		}
 	}
 }
@@ -177,14 +203,17 @@ __global__ void k_sketch_words(DevParams P, const uint8_t *seq, uint32_t len, ui
 }
 
 /* ---------------------------------------------------------------- k_sortchain */
-__global__ void k_sortchain(DevParams P, ReadRec *reads, uint32_t n_reads, uint8_t *ws, uint32_t *frames, uint32_t round)
+__global__ void k_sortchain(DevParams P, ReadRec *reads, uint32_t n_reads, uint8_t *ws, uint32_t *frames, uint32_t round, uint32_t sc_cap)
 {
-	/* one WARP per read: the sorts are warp-cooperative (radix_sort_exact_warp), the data-dependent sequential parts
-	 * (rescue expansion, chaining) run on lane 0.  (One read per THREAD serialises 32 divergent reads per warp: 74 ms
-	 * measured against the latency of a single read.) */
+	/* One WARP per read: the sorts are warp-cooperative (radix_sort_exact_warp), the data-dependent sequential parts (the
+	 * permutation cycles of the sort, rescue expansion, chaining) run on lane 0.  Those are chains of dependent loads, so
+	 * the read's seed array (16 B x (n + 1), sentinel included) is staged in shared memory for the duration when it fits
+	 * `sc_cap` seeds: ~30-cycle instead of ~600-cycle steps.  Leaves (appended behind the sentinel, touched once each) and
+	 * the small root / rescue arrays stay in global memory.  Shared memory per warp: 16 B x sc_cap + 2 KB sort scratch. */
 	MAB_DYN_SMEM(smem);
 	int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-	uint32_t *sm = (uint32_t *)smem + 512 * wib;
+	uint32_t per_warp = 4u * sc_cap + 512u;
+	uint32_t *sm = (uint32_t *)smem + (uint64_t)per_warp * wib, *sseed = sm + 512;
 	uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if(i >= n_reads) { return; }
 	ReadRec *r = &reads[i];
@@ -193,9 +222,15 @@ __global__ void k_sortchain(DevParams P, ReadRec *reads, uint32_t n_reads, uint8
 	uint32_t *seed = (uint32_t *)(ws + r->ws_ofs + L.seed), *root = (uint32_t *)(ws + r->ws_ofs + L.root), *resc = (uint32_t *)(ws + r->ws_ofs + L.resc);
 	uint32_t *fr = frames + (uint64_t)i * 8 * MAB_RS_FRAME;
 	uint32_t n = r->n_seed, sort_err = 0;
+	const bool staged = r->tot_seeds + 2 <= sc_cap;							/* tot_seeds bounds n over all rescue rounds */
+	uint32_t *sd = staged ? sseed : seed;
+	if(staged) {
+		for(uint32_t t = lane; t < n; t += 32) { ((uint4 *)sseed)[t] = ((const uint4 *)seed)[t]; }
+		__syncwarp();
+	}
 	if(round > 0) {																/* mm_seed, cnt > 0 (3510-3526) */
 		if(round == 1) { radix_sort_exact_warp(resc, r->n_resc, 4, fr, sm, lane, &sort_err); }
-		for(uint32_t s = lane; s < n; s += 32) { seed[4ull * s + 3] = 0x7fffffffu; }
+		for(uint32_t s = lane; s < n; s += 32) { sd[4ull * s + 3] = 0x7fffffffu; }
 		__syncwarp();
 		if(lane == 0) {
 			uint32_t p = r->presc;
@@ -203,7 +238,7 @@ __global__ void k_sortchain(DevParams P, ReadRec *reads, uint32_t n_reads, uint8
 				const uint32_t *e = resc + 4ull * p;
 				const uint8_t *occ = P.idx + ((uint64_t)e[2] | (uint64_t)e[3] << 32);
 				if(n + e[1] + 2 > r->seed_cap / 2) { r->err |= MAB_ERR_SEED_OVF; break; }
-				for(uint32_t t = 0; t < e[1]; t++) { make_seed(P, seed + 4ull * (n + t), ldg32(occ + 8ull * t), ldg32(occ + 8ull * t + 4), e[0]); }
+				for(uint32_t t = 0; t < e[1]; t++) { make_seed(P, sd + 4ull * (n + t), ldg32(occ + 8ull * t), ldg32(occ + 8ull * t + 4), e[0]); }
 				n += e[1]; p++;
 			}
 			r->presc = p;
@@ -213,21 +248,26 @@ __global__ void k_sortchain(DevParams P, ReadRec *reads, uint32_t n_reads, uint8
 	if(lane == 0) {
 		r->n_root = 0; r->n_next = 0; r->n_seed = n;
 		if(n == 0) { r->seed_n = 0; }
-		else { uint32_t *s = seed + 4ull * n; s[0] = 0x80000000u; s[1] = 0x7fffffffu; s[2] = 0x80000000u; s[3] = 0x7fffffffu; }	/* sentinel (3531) */
+		else { uint32_t *s = sd + 4ull * n; s[0] = 0x80000000u; s[1] = 0x7fffffffu; s[2] = 0x80000000u; s[3] = 0x7fffffffu; }	/* sentinel (3531) */
 	}
 	__syncwarp();
 	if(n == 0) { return; }
-	radix_sort_exact_warp(seed, n + 1, 4, fr, sm, lane, &sort_err);
+	radix_sort_exact_warp(sd, n + 1, 4, fr, sm, lane, &sort_err);
 	uint32_t nc = 0;
 	if(lane == 0) {
 		uint32_t seed_n = 0;
-		nc = chain_seeds(P, seed, n, root, &seed_n);							/* mm_chain (3702-3721); circular refs unsupported */
+		nc = chain_seeds(P, sd, seed, n, root, &seed_n);							/* mm_chain (3702-3721); circular refs unsupported */
 		r->seed_n = seed_n;
 	}
 	nc = __shfl_sync(0xffffffffu, nc, 0);
-	if(nc == 0) { return; }
-	radix_sort_exact_warp(root, nc, 2, fr, sm, lane, &sort_err);
-	if(lane == 0) { r->n_root = nc; }
+	if(staged) {
+		__syncwarp();
+		for(uint32_t t = lane; t < n + 1; t += 32) { ((uint4 *)seed)[t] = ((const uint4 *)sseed)[t]; }
+	}
+	if(nc != 0) {
+		radix_sort_exact_warp(root, nc, 2, fr, sm, lane, &sort_err);
+		if(lane == 0) { r->n_root = nc; }
+	}
 	if(__any_sync(0xffffffffu, sort_err != 0) && lane == 0) { r->err |= MAB_ERR_SEED_OVF; }
 }
 

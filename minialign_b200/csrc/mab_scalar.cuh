@@ -213,14 +213,17 @@ __device__ __forceinline__ int32_t pdiff_wv(const V4 &w, const V4 &f)
 	return (int32_t)(((uint32_t)w.l0 - (uint32_t)f.l0) + ((uint32_t)w.l2 - (uint32_t)f.l2));
 }
 
-/* mm_chain_seeds (minialign.c:3547-3625).  s = seed array ({upos, rid, vpos, lid} x n_seed, sentinel at n_seed, leaves
- * appended behind it), c = root array ({plen, lid}).  Returns #chains, *seed_n = seeds + sentinel + leaves. */
-__device__ inline uint32_t chain_seeds(const DevParams &P, uint32_t *s, uint32_t n_seed, uint32_t *c, uint32_t *seed_n)
+/* mm_chain_seeds (minialign.c:3547-3625).  s = seed array ({upos, rid, vpos, lid} x n_seed, sentinel at n_seed), lf = the
+ * array the leaves are appended to behind the sentinel (index n_seed + 1 onwards; the same array as s in the reference --
+ * k_sortchain keeps the seeds in shared memory and the rarely touched leaves in global memory), c = root array
+ * ({plen, lid}).  Returns #chains, *seed_n = seeds + sentinel + leaves. */
+__device__ inline uint32_t chain_seeds(const DevParams &P, uint32_t *s, uint32_t *lfb, uint32_t n_seed, uint32_t *c, uint32_t *seed_n)
 {
 	uint32_t ncid = 0, nlid = n_seed + 1, nlsid = 0, tsid = n_seed;
 	while(nlsid < tsid) {
 		uint32_t lid = nlid++;
-		uint32_t *lf = s + 4ull * lid;							/* leaf: {rsid, rid, lsid, cid} */
+		uint32_t *lf = lfb + 4ull * lid;						/* leaf: {rsid, rid, lsid, cid} */
+		uint32_t lf_lsid = nlsid;
 		lf[0] = nlsid; lf[2] = nlsid; lf[1] = s[4ull * nlsid + 1]; lf[3] = 0xffffffffu;
 		uint32_t plen = s[4ull * nlsid] + s[4ull * nlsid + 2], scnt = 1;
 		uint64_t nrsid = nlsid; nlsid = 0xffffffffu;
@@ -243,11 +246,11 @@ __device__ inline uint32_t chain_seeds(const DevParams &P, uint32_t *s, uint32_t
 			s[4ull * (uint32_t)nrsid + 3] = lid; scnt++;
 			if((uint64_t)nlsid <= nrsid) { nlsid = 0xffffffffu; }
 		}
-		if(nrsid == lf[2]) { continue; }
+		if(nrsid == lf_lsid) { continue; }
 		uint32_t cid = 0xffffffffu;
 		if(s[4ull * nrsid + 3] < lid) {
-			nrsid = s[4ull * s[4ull * nrsid + 3] + 0];
-			cid = s[4ull * s[4ull * nrsid + 3] + 3];
+			nrsid = lfb[4ull * s[4ull * nrsid + 3] + 0];
+			cid = lfb[4ull * s[4ull * nrsid + 3] + 3];
 		}
 		if(cid == 0xffffffffu) { cid = ncid++; c[2ull * cid] = MAB_OFS0; c[2ull * cid + 1] = lid; }
 		lf[3] = cid; lf[0] = (uint32_t)nrsid;

@@ -11,6 +11,7 @@ namespace mab {
 #define MAB_BLK			32
 #define MAB_KH_CAP		1024u		/* slots of the per-read dedup hash (reference starts at 256 and doubles) */
 #define MAB_MAX_TAILS	24
+#define MAB_SC_MAX		2944u		/* seeds per read k_sortchain stages in shared memory (16 B each + 2 KB scratch = 48 KB) */
 #define MAB_WARPS_PER_CTA 4
 #ifndef MAB_EXT_CTAS_PER_SM
 #define MAB_EXT_CTAS_PER_SM 6		/* resident CTAs of the persistent extend kernel per SM (register budget = 65536 / (128 x this)) */
@@ -77,7 +78,7 @@ struct ReadRec {
 	uint32_t rlen_cur;				/* running value (carried across rescue rounds) */
 	uint32_t rlen_used;				/* the value the first load_root actually compared against */
 	uint32_t dep_apos, dep_flags;	/* first load_root: raw a-position; bit0 = valid, bit1 = (bpos >= qlen) */
-	uint32_t _pad2;
+	uint32_t n_rec;					/* minimizer records left by k_seed_scan for k_seed_expand */
 };
 #define MAB_RLEN_OWN 0xffffffffu
 
