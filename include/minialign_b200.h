@@ -110,6 +110,11 @@ typedef struct {
 int mab_extend_pairs(mab_ctx *ctx, const uint8_t *seq_block, uint64_t block_size, const mab_pair_t *pairs, uint32_t n,
 	uint32_t *res /* 16 x n */, uint32_t *aln_out, uint64_t aln_cap, uint64_t *aln_ofs /* n + 1 */);
 
+/* integer roofline of the DP step: runs the bulk block loop of the fill (the product's own step code) on register-resident
+ * synthetic state with k_extend's launch shape, n_blocks x 32 anti-diagonals per warp; *vectors_per_s = achieved ceiling
+ * (bench.py reports k_extend against it) */
+int mab_fill_peak(mab_ctx *ctx, int masks, uint32_t n_blocks, double *vectors_per_s);
+
 /* runs every packed-SIMD / permute / warp primitive the DP uses on fixed inputs; out = 64 x 32 words (test hook) */
 int mab_selftest(mab_ctx *ctx, uint32_t *out);
 

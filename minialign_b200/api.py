@@ -80,6 +80,8 @@ def load_library(lib_path: str | None = None):
     L.mab_seed_chain.argtypes = [C.c_void_p, u8p, C.c_uint32, C.c_uint32, u32p, C.c_uint64, u64p, u32p, C.c_uint64, u64p]
     L.mab_extend_pairs.restype = C.c_int
     L.mab_extend_pairs.argtypes = [C.c_void_p, u8p, C.c_uint64, C.POINTER(MabPair), C.c_uint32, u32p, u32p, C.c_uint64, u64p]
+    L.mab_fill_peak.restype = C.c_int
+    L.mab_fill_peak.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.POINTER(C.c_double)]
     L.mab_selftest.restype = C.c_int
     L.mab_selftest.argtypes = [C.c_void_p, u32p]
     return L
@@ -139,6 +141,14 @@ class Mapper:
         s = MabStats()
         self.lib.mab_last_stats(self.h, C.byref(s))
         return {k: getattr(s, k) for k, _ in MabStats._fields_}
+
+    def fill_peak(self, masks: bool = True, n_blocks: int = 2000) -> float:
+        """Vectors/s ceiling of the DP step's instruction mix (k_fill_peak); see include/minialign_b200.h."""
+        v = C.c_double(0.0)
+        rc = self.lib.mab_fill_peak(self.h, 1 if masks else 0, n_blocks, C.byref(v))
+        if rc != 0:
+            raise RuntimeError("mab_fill_peak failed: " + self.lib.mab_last_error().decode())
+        return v.value
 
     def selftest(self) -> np.ndarray:
         out = np.zeros(64 * 32, dtype=np.uint32)

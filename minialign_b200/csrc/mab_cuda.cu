@@ -46,6 +46,7 @@ static inline cudaError_t RT_EVENT_CREATE(RT_EVENT *e) { return cudaEventCreate(
 static inline void RT_EVENT_RECORD(RT_EVENT e, RT_STREAM s) { cudaEventRecord(e, s); }
 static inline float RT_EVENT_MS(RT_EVENT a, RT_EVENT b) { float ms = 0.f; if(cudaEventElapsedTime(&ms, a, b) != cudaSuccess) { ms = 0.f; cudaGetLastError(); } return ms; }
 static inline double RT_WALL_MS() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+#define RT_FUNC_MAX_SMEM(kernel, bytes) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))
 #define RT_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 
 #include "mab_host.inl"

@@ -76,6 +76,21 @@ struct Vec {
 	uint32_t A, V, E, F, delta, ndrop, md, wa, wb;
 	int32_t acc; uint32_t dir;
 };
+/* Pipe balance.  On sm_100 the ALU pipe (LOP3 / PRMT / SHF / VIADD / VIMNMX ...) and the FMA pipe (IMAD ...) each accept one warp
+ * instruction every two cycles per scheduler; the DP step is almost pure ALU work and saturates that pipe at ~0.5 IPC while the
+ * FMA pipe idles (k_fill_peak: ~106 cycles per anti-diagonal for ~50 ALU instructions).  The helpers below express a few
+ * operations as integer multiply-adds so that they issue on the FMA pipe; their constant operands come from kernel parameters
+ * because the assembler folds a literal multiplier back into the ALU form. */
+__device__ __forceinline__ uint32_t not_fma(uint32_t x, uint32_t m1)					/* ~x = x * -1 + -1 */
+{
+#if defined(MAB_EMU) || defined(MAB_NO_FMA_NOT)
+	(void)m1; return ~x;
+#else
+	uint32_t d;
+	asm("mad.lo.u32 %0, %1, %2, %2;" : "=r"(d) : "r"(x), "r"(m1));
+	return d;
+#endif
+}
 __device__ __forceinline__ uint32_t vneg2(uint32_t x) { return __vadd2(~x, 0x00010001u); }
 /* window registers <-> the packed {cell 2l, cell 2l+1} byte pairs kept in block / tail records */
 __device__ __forceinline__ uint32_t win_load(uint32_t c16) { return ((c16 & 0xffu) | ((c16 >> 8) << 16)) << 2; }
@@ -178,14 +193,14 @@ __device__ __forceinline__ uint32_t vec_core(const DevParams &P, const StepK &k,
 	uint32_t bits = 0;
 	if(MASKS) {
 		/* T is the maximum, so T - x is 0..255 in the high byte and "min.u16 against ONE" leaves ONE set <=> not equal */
-		uint32_t n_e = __viaddmin_u16x2(T, ~v.E, ONE), n_f = __viaddmin_u16x2(T, ~v.F, ONE);
+		uint32_t n_e = __viaddmin_u16x2(T, not_fma(v.E, P.K_M1), ONE), n_f = __viaddmin_u16x2(T, not_fma(v.F, P.K_M1), ONE);
 		uint32_t n_fh = __vminu2(T ^ dfh, ONE), n_fv = __vminu2(T ^ dfv, ONE);
 		uint32_t g_e = __vminu2(TE ^ T, ONE), g_f = __vminu2(TF ^ T, ONE);				/* set <=> te != t */
 		uint32_t NH = n_fh & n_e, NV = n_fv & n_f;										/* ~h, ~v */
 		uint32_t NE = (n_e | ~n_fh) & g_e, NF = (n_f | ~n_fv) & g_f;						/* ~e, ~f */
 		bits = (NF * 2 + NE) * 4 + (NV * 2 + NH);										/* disjoint bits: three IMADs pack the nibble */
 	}
-	uint32_t Pp = ~v.A, N = ~v.V;
+	uint32_t Pp = not_fma(v.A, P.K_M1), N = not_fma(v.V, P.K_M1);
 	v.E = __vadd2(TE, Pp); v.F = __vadd2(TF, N);
 	v.V = __vadd2(Pp, T); v.A = __vadd2(T, N);
 	uint32_t dH = __vadd2(P.K_OFS, DOWN ? v.V : v.A);										/* _fill_update_delta (ofsh == ofsv) */

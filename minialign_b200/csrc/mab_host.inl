@@ -91,6 +91,7 @@ void init_gaba_consts(DevParams &P, const mab_params_t *p)
 		auto h8 = [](int v) { uint32_t x = ((uint32_t)(uint8_t)(int8_t)v) << 8; return x | (x << 16); };
 		const uint32_t ulp = 0x00010001u;
 		P.K_GFH1 = h8(P.gfh) + ulp; P.K_GFV1 = h8(P.gfv) + ulp; P.K_ADJH1 = h8(P.adjh) + ulp; P.K_ADJV1 = h8(P.adjv) + ulp; P.K_OFS = h8(P.ofsh);
+		P.K_M1 = 0xffffffffu;
 	}
 	P.gi = p->gi; P.ge = p->ge; P.gfa = p->gfa; P.gfb = p->gfb;
 	long long diag = 0, off = 0;
@@ -372,11 +373,27 @@ static int map_core(mab_ctx *ctx, const uint8_t *d_base, std::vector<ReadRec> &h
 	double t_sizing = RT_WALL_MS();
 	S.d2h_bytes += sizeof(ReadRec) * (uint64_t)n_seq;
 	uint64_t ws_total = 0;
-	uint32_t sc_cap = 64;					/* seeds k_sortchain stages in shared memory: every read up to MAB_SC_MAX seeds (48 KB per warp) */
+	/* k_sortchain size classes: the ordinary reads (up to the 90th percentile of the seed bound) run with a small shared-memory
+	 * footprint, the seed-rich rest in a second launch with up to MAB_SC_MAX seeds staged */
+	uint32_t sc_cap1 = 64, sc_cap2 = 64, sc_max_bound = 0;
+	{
+		std::vector<uint32_t> bnd;
+		for(uint32_t i = 0; i < n_seq; i++) { if(hr[i].state == 0) { bnd.push_back(hr[i].tot_seeds + 2); } }
+		if(!bnd.empty()) {
+			size_t k90 = (bnd.size() * 9) / 10; if(k90 >= bnd.size()) { k90 = bnd.size() - 1; }
+			std::nth_element(bnd.begin(), bnd.begin() + k90, bnd.end());
+			sc_cap1 = std::max<uint32_t>(64u, std::min<uint32_t>((bnd[k90] + 63u) & ~63u, MAB_SC_SMALL));
+			sc_max_bound = *std::max_element(bnd.begin(), bnd.end());
+			sc_cap2 = std::max<uint32_t>(sc_cap1, std::min<uint32_t>((sc_max_bound + 63u) & ~63u, MAB_SC_MAX));
+		}
+		if(const char *e = getenv("MAB_SC_CAP")) {									/* test hook: tiny caps push reads through the unstaged (global memory) path */
+			uint32_t v = (uint32_t)atoi(e);
+			if(v >= 64) { sc_cap1 = std::min(sc_cap1, v); sc_cap2 = std::min(std::max(sc_cap2, sc_cap1), std::max(v, sc_cap1)); }
+		}
+	}
 	for(uint32_t i = 0; i < n_seq; i++) {
 		ReadRec &r = hr[i];
 		if(r.state != 0) { continue; }
-		sc_cap = std::max(sc_cap, std::min<uint32_t>(r.tot_seeds + 2, MAB_SC_MAX));
 		r.seed_cap = 2 * (r.tot_seeds + 1) + 8; r.root_cap = r.tot_seeds + 8; r.resc_cap = r.tot_resc + 4; r.bin_cap = 2 * r.tot_seeds + 128;
 		r.ws_ofs = ws_total;
 		ws_total += ws_layout(r.seed_cap, r.root_cap, r.resc_cap, r.bin_cap).total;
@@ -402,7 +419,12 @@ static int map_core(mab_ctx *ctx, const uint8_t *d_base, std::vector<ReadRec> &h
 		/* rounds of sort+chain / extend (minialign.c:4444-4448) */
 		for(uint32_t round = 0; round < P.n_occ; round++) {
 			if(timed && round < 8) { RT_EVENT_RECORD(ctx->rev[3 * round], ctx->stream); }
-			RT_LAUNCH(k_sortchain, n_seq, 32, 16 * sc_cap + 2048, ctx->stream, P, ctx->d_reads, n_seq, ctx->d_ws, ctx->d_frames, round, sc_cap);
+			RT_LAUNCH(k_sortchain, n_seq, 32, 16 * sc_cap1 + 2048, ctx->stream, P, ctx->d_reads, n_seq, ctx->d_ws, ctx->d_frames, round, sc_cap1, 0u, sc_cap1);
+				if(sc_max_bound > sc_cap1) {										/* the seed-rich class (staged up to sc_cap2 seeds, global memory beyond) */
+					RT_FUNC_MAX_SMEM(k_sortchain, 16 * MAB_SC_MAX + 2048);
+					RT_LAUNCH(k_sortchain, n_seq, 32, 16 * sc_cap2 + 2048, ctx->stream, P, ctx->d_reads, n_seq, ctx->d_ws, ctx->d_frames, round, sc_cap2, sc_cap1, 0xffffffffu);
+					S.n_launches++;
+				}
 			RT_MEMSET_ASYNC(&ctx->d_ctr->work_next, 0, sizeof(unsigned int), ctx->stream);
 			if(timed && round < 8) { RT_EVENT_RECORD(ctx->rev[3 * round + 1], ctx->stream); }
 			RT_LAUNCH(k_extend, ext_ctas, 32 * MAB_WARPS_PER_CTA, 1024 + 2048 * MAB_WARPS_PER_CTA, ctx->stream, P, d_base, (const uint8_t *)ctx->d_ntail, ctx->d_reads, n_seq, ctx->d_ws,
@@ -567,7 +589,7 @@ extern "C" uint64_t mab_seed_chain(mab_ctx *ctx, const uint8_t *seq, uint32_t le
 		RT_MALLOC(&d_ws, L.total + 256);
 		RT_MEMCPY_H2D(d_r, &r, sizeof(r));
 		RT_LAUNCH(k_seed_expand, 1, 32, 0, ctx->stream, P, d_r, 1u, d_ws, (const uint32_t *)d_rec);
-		{ uint32_t sc_cap = std::max<uint32_t>(64u, std::min<uint32_t>(r.tot_seeds + 2, MAB_SC_MAX)); for(uint32_t i = 0; i <= round && i < P.n_occ; i++) { RT_LAUNCH(k_sortchain, 1, 32, 16 * sc_cap + 2048, ctx->stream, P, d_r, 1u, d_ws, d_fr, i, sc_cap); } }
+		{ uint32_t sc_cap = std::max<uint32_t>(64u, std::min<uint32_t>(r.tot_seeds + 2, MAB_SC_SMALL)); for(uint32_t i = 0; i <= round && i < P.n_occ; i++) { RT_LAUNCH(k_sortchain, 1, 32, 16 * sc_cap + 2048, ctx->stream, P, d_r, 1u, d_ws, d_fr, i, sc_cap, 0u, 0xffffffffu); } }
 		RT_STREAM_SYNC(ctx->stream);
 		RT_MEMCPY_D2H(&r, d_r, sizeof(r));
 		if(r.n_seed) {
@@ -628,6 +650,25 @@ extern "C" int mab_extend_pairs(mab_ctx *ctx, const uint8_t *seq_block, uint64_t
 	RT_FREE(d_seq); RT_FREE(d_ar); RT_FREE(d_p); RT_FREE(d_res); RT_FREE(d_pool); RT_FREE(d_ao);
 	if(rc == MAB_EOVERFLOW) { g_err = "extend_pairs: device workspace overflow"; }
 	return rc;
+}
+
+extern "C" int mab_fill_peak(mab_ctx *ctx, int masks, uint32_t n_blocks, double *vectors_per_s)
+{
+	CK(RT_SET_DEVICE(ctx->device));
+	uint32_t ctas = std::max<uint32_t>(1, ctx->n_slots / MAB_WARPS_PER_CTA), warps = ctas * MAB_WARPS_PER_CTA;
+	uint32_t *d_ring = nullptr, *d_sink = nullptr;
+	CK(RT_MALLOC(&d_ring, 4ull * 512 * 4 * warps)); CK(RT_MALLOC(&d_sink, 4ull * warps));
+	for(int rep = 0; rep < 2; rep++) {												/* first launch warms up */
+		RT_EVENT_RECORD(ctx->ev[6], ctx->stream);
+		if(masks) { RT_LAUNCH((k_fill_peak<true>), ctas, 32 * MAB_WARPS_PER_CTA, 1024, ctx->stream, ctx->P, d_ring, n_blocks, d_sink); }
+		else { RT_LAUNCH((k_fill_peak<false>), ctas, 32 * MAB_WARPS_PER_CTA, 1024, ctx->stream, ctx->P, d_ring, n_blocks, d_sink); }
+		RT_EVENT_RECORD(ctx->ev[7], ctx->stream);
+		CK(RT_STREAM_SYNC(ctx->stream));
+	}
+	float ms = RT_EVENT_MS(ctx->ev[6], ctx->ev[7]);
+	RT_FREE(d_ring); RT_FREE(d_sink);
+	*vectors_per_s = ms > 0.f ? (double)warps * n_blocks * MAB_BLK / (ms * 1e-3) : 0.0;
+	return MAB_OK;
 }
 
 /* debugging / test entry: runs k_selftest and copies its 64 x 32 words out */

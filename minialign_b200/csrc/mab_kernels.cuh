@@ -203,33 +203,24 @@ __global__ void k_sketch_words(DevParams P, const uint8_t *seq, uint32_t len, ui
 }
 
 /* ---------------------------------------------------------------- k_sortchain */
-__global__ void k_sortchain(DevParams P, ReadRec *reads, uint32_t n_reads, uint8_t *ws, uint32_t *frames, uint32_t round, uint32_t sc_cap)
+/* One WARP per read: the sorts are warp-cooperative (radix_sort_exact_warp), the data-dependent sequential parts (the
+ * permutation cycles of the sort, rescue expansion, chaining) run on lane 0.  Those are chains of dependent loads, so the
+ * read's seed array (16 B x (n + 1), sentinel included) is staged in shared memory for the duration (STAGED = true: ~30-cycle
+ * instead of ~600-cycle steps, and the compiler knows the address space).  Leaves (appended behind the sentinel, touched once
+ * each) and the small root / rescue arrays stay in global memory.  Shared memory per warp: 16 B x sc_cap + 2 KB sort scratch. */
+template <bool STAGED>
+__device__ __forceinline__ void sortchain_read(const DevParams &P, ReadRec *r, uint8_t *ws, uint32_t *fr, uint32_t round, uint32_t *sm, uint32_t *sseed, int lane)
 {
-	/* One WARP per read: the sorts are warp-cooperative (radix_sort_exact_warp), the data-dependent sequential parts (the
-	 * permutation cycles of the sort, rescue expansion, chaining) run on lane 0.  Those are chains of dependent loads, so
-	 * the read's seed array (16 B x (n + 1), sentinel included) is staged in shared memory for the duration when it fits
-	 * `sc_cap` seeds: ~30-cycle instead of ~600-cycle steps.  Leaves (appended behind the sentinel, touched once each) and
-	 * the small root / rescue arrays stay in global memory.  Shared memory per warp: 16 B x sc_cap + 2 KB sort scratch. */
-	MAB_DYN_SMEM(smem);
-	int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-	uint32_t per_warp = 4u * sc_cap + 512u;
-	uint32_t *sm = (uint32_t *)smem + (uint64_t)per_warp * wib, *sseed = sm + 512;
-	uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	if(i >= n_reads) { return; }
-	ReadRec *r = &reads[i];
-	if(r->state != 0) { return; }
 	WsLayout L = ws_layout(r->seed_cap, r->root_cap, r->resc_cap, r->bin_cap);
 	uint32_t *seed = (uint32_t *)(ws + r->ws_ofs + L.seed), *root = (uint32_t *)(ws + r->ws_ofs + L.root), *resc = (uint32_t *)(ws + r->ws_ofs + L.resc);
-	uint32_t *fr = frames + (uint64_t)i * 8 * MAB_RS_FRAME;
 	uint32_t n = r->n_seed, sort_err = 0;
-	const bool staged = r->tot_seeds + 2 <= sc_cap;							/* tot_seeds bounds n over all rescue rounds */
-	uint32_t *sd = staged ? sseed : seed;
-	if(staged) {
+	uint32_t *sd = STAGED ? sseed : seed;
+	if(STAGED) {
 		for(uint32_t t = lane; t < n; t += 32) { ((uint4 *)sseed)[t] = ((const uint4 *)seed)[t]; }
 		__syncwarp();
 	}
 	if(round > 0) {																/* mm_seed, cnt > 0 (3510-3526) */
-		if(round == 1) { radix_sort_exact_warp(resc, r->n_resc, 4, fr, sm, lane, &sort_err); }
+		if(round == 1) { radix_sort_exact_warp<4>(resc, r->n_resc, fr, sm, lane, &sort_err); }
 		for(uint32_t s = lane; s < n; s += 32) { sd[4ull * s + 3] = 0x7fffffffu; }
 		__syncwarp();
 		if(lane == 0) {
@@ -252,7 +243,7 @@ __global__ void k_sortchain(DevParams P, ReadRec *reads, uint32_t n_reads, uint8
 	}
 	__syncwarp();
 	if(n == 0) { return; }
-	radix_sort_exact_warp(sd, n + 1, 4, fr, sm, lane, &sort_err);
+	radix_sort_exact_warp<4>(sd, n + 1, fr, sm, lane, &sort_err);
 	uint32_t nc = 0;
 	if(lane == 0) {
 		uint32_t seed_n = 0;
@@ -260,15 +251,35 @@ __global__ void k_sortchain(DevParams P, ReadRec *reads, uint32_t n_reads, uint8
 		r->seed_n = seed_n;
 	}
 	nc = __shfl_sync(0xffffffffu, nc, 0);
-	if(staged) {
+	if(STAGED) {
 		__syncwarp();
 		for(uint32_t t = lane; t < n + 1; t += 32) { ((uint4 *)seed)[t] = ((const uint4 *)sseed)[t]; }
 	}
 	if(nc != 0) {
-		radix_sort_exact_warp(root, nc, 2, fr, sm, lane, &sort_err);
+		radix_sort_exact_warp<2>(root, nc, fr, sm, lane, &sort_err);
 		if(lane == 0) { r->n_root = nc; }
 	}
 	if(__any_sync(0xffffffffu, sort_err != 0) && lane == 0) { r->err |= MAB_ERR_SEED_OVF; }
+}
+
+/* Handles the reads whose seed bound (tot_seeds + 2, over all rescue rounds) lies in (lo_cap, hi_cap]: the host launches it
+ * once per size class so that the many ordinary reads run with a small shared-memory footprint (high occupancy) and the few
+ * seed-rich ones with a large one.  hi_cap = UINT32_MAX in the last class; reads above sc_cap work in global memory. */
+__global__ void k_sortchain(DevParams P, ReadRec *reads, uint32_t n_reads, uint8_t *ws, uint32_t *frames, uint32_t round, uint32_t sc_cap, uint32_t lo_cap, uint32_t hi_cap)
+{
+	MAB_DYN_SMEM(smem);
+	int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	uint32_t per_warp = 4u * sc_cap + 512u;
+	uint32_t *sm = (uint32_t *)smem + (uint64_t)per_warp * wib, *sseed = sm + 512;
+	uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if(i >= n_reads) { return; }
+	ReadRec *r = &reads[i];
+	if(r->state != 0) { return; }
+	uint32_t bound = r->tot_seeds + 2;
+	if(bound <= lo_cap || bound > hi_cap) { return; }
+	uint32_t *fr = frames + (uint64_t)i * 8 * MAB_RS_FRAME;
+	if(bound <= sc_cap) { sortchain_read<true>(P, r, ws, fr, round, sm, sseed, lane); }
+	else { sortchain_read<false>(P, r, ws, fr, round, sm, sseed, lane); }
 }
 
 /* ---------------------------------------------------------------- mm_extend state machine, lane-0 routines */
@@ -579,7 +590,7 @@ __global__ void __launch_bounds__(32 * MAB_WARPS_PER_CTA, MAB_EXT_CTAS_PER_SM) k
 					uint32_t ncnt = 0;
 					if(lane == 0) { ncnt = load_next_collect(P, x, st); }
 					ncnt = __shfl_sync(MAB_FULL, ncnt, 0);
-					if(ncnt > 1) { radix_sort_exact_warp(x.next, ncnt, 2, frames, tile, lane, &c.err); }	/* the trace tile is idle here */
+					if(ncnt > 1) { radix_sort_exact_warp<2>(x.next, ncnt, frames, tile, lane, &c.err); }	/* the trace tile is idle here */
 					if(ncnt != 0 && lane == 0) { load_next_pick(P, x, st); }
 				}
 				__syncwarp();
@@ -653,6 +664,54 @@ __global__ void k_extend_pairs(DevParams P, const uint8_t *base, const uint8_t *
 	if(lane == 0) { atomicAdd(&ctr->n_vectors, (unsigned long long)c.n_vectors); }
 }
 
+
+/* ---------------------------------------------------------------- k_fill_peak (integer roofline of the DP step) */
+/* The bulk block loop of fill_blocks<MASKS> (the very same bulk_step code) on register-resident synthetic band state, with the
+ * same launch shape as k_extend: no sequence fetches, no block bookkeeping, no search / trace, mask rows written to a small
+ * per-warp ring that stays in L2.  Its vectors/s is the ceiling the instruction mix of the DP step allows on this GPU; bench.py
+ * reports k_extend's vectors/s against it (SURVEY.md section 8d asks for exactly this denominator). */
+template <bool MASKS>
+__global__ void __launch_bounds__(32 * MAB_WARPS_PER_CTA, MAB_EXT_CTAS_PER_SM) k_fill_peak(DevParams P, uint32_t *ring, uint32_t n_blocks, uint32_t *sink)
+{
+	MAB_DYN_SMEM(smem);
+	uint32_t *lut = (uint32_t *)smem;
+	int lane = threadIdx.x & 31;
+	build_lut(P, lut, threadIdx.x, blockDim.x);
+	__syncthreads();
+	uint32_t gw = __shfl_sync(MAB_FULL, (blockIdx.x * blockDim.x + threadIdx.x) >> 5, 0);
+	DpCtx c; c.P = &P; c.lut = lut; c.lane = lane; c.W = 64; c.nl = 32; c.widx = 0;
+	const StepK k = make_stepk(c);
+	const RootTpl &R = P.root[0];
+	Vec v;
+	v.A = vneg2(unpack8h((uint32_t)(uint8_t)R.dh[2 * lane] | ((uint32_t)(uint8_t)R.dh[2 * lane + 1] << 8)));
+	v.V = unpack8h((uint32_t)(uint8_t)R.dv[2 * lane] | ((uint32_t)(uint8_t)R.dv[2 * lane + 1] << 8));
+	v.E = unpack8h((uint32_t)(uint8_t)R.de[2 * lane] | ((uint32_t)(uint8_t)R.de[2 * lane + 1] << 8));
+	v.F = unpack8h((uint32_t)(uint8_t)R.df[2 * lane] | ((uint32_t)(uint8_t)R.df[2 * lane + 1] << 8));
+	v.delta = 0; v.ndrop = 0; v.md = 0; v.wa = 0; v.wb = 0; v.dir = 0;
+	v.acc = __reduce_add_sync(MAB_FULL, 0);
+	uint32_t x = 0x9e3779b9u * (gw * 32 + lane + 1);
+	uint32_t *mrow = ring + 512ull * 4 * gw + lane;
+	uint32_t acc = 0;
+	for(uint32_t b = 0; b < n_blocks; b++) {
+		x = x * 1664525u + 1013904223u;
+		uint32_t an = ((x >> 8) & 3u) << 2, bn = ((x >> 16) & 3u) << 20;			/* random bases, pre-scaled like fill_blocks */
+		BulkCnt n; n.dir = 0; n.acnt = 0; n.bcnt = 0;
+#ifndef MAB_EMU
+		asm volatile("" : "+r"(n.dir), "+r"(n.acnt), "+r"(n.bcnt));
+#endif
+		uint32_t *m = mrow + 512 * (b & 3);
+		#pragma unroll 1
+		for(int g = 0; g < MAB_BLK / 4; g++) {
+			uint32_t b0 = bulk_step<MASKS>(P, k, v, an, bn, n), b1 = bulk_step<MASKS>(P, k, v, an, bn, n);
+			if(MASKS) { m[64 * g] = __byte_perm(b0, b1, 0x6420); }
+			uint32_t b2 = bulk_step<MASKS>(P, k, v, an, bn, n), b3 = bulk_step<MASKS>(P, k, v, an, bn, n);
+			if(MASKS) { m[64 * g + 32] = __byte_perm(b2, b3, 0x6420); }
+		}
+		acc += __shfl_sync(MAB_FULL, n.dir, 0) + v.delta;
+		v.delta = 0; v.acc = (int32_t)(int8_t)v.acc;
+	}
+	if(lane == 0) { sink[gw] = acc + v.A + v.V + v.E + v.F + v.ndrop; }
+}
 
 /* ---------------------------------------------------------------- k_selftest */
 /* evaluates every packed-SIMD / permute / warp primitive the DP relies on, on lane-dependent inputs; tests compare the

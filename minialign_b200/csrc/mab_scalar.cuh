@@ -67,20 +67,25 @@ __device__ __forceinline__ const uint8_t *idx_get(const DevParams &P, uint64_t m
  * the order it leaves equal keys in is observable downstream (chaining walks the array in order), so the permutation
  * cycles are followed in exactly the reference's order.  Iterative, with an explicit frame stack in `frames`
  * (8 levels x 257 u32).  esz = element size in u32 words: 4 (key = words 1:0) or 2 (key = word 0). */
-__device__ __forceinline__ uint64_t rs_key(const uint32_t *e, int esz) { return esz == 4 ? ((uint64_t)e[1] << 32 | e[0]) : (uint64_t)e[0]; }
-
-__device__ __forceinline__ void rs_copy(uint32_t *d, const uint32_t *s, int esz) { for(int i = 0; i < esz; i++) { d[i] = s[i]; } }
-
-__device__ __forceinline__ void rs_insertion(uint32_t *a, uint32_t n, int esz)
+/* ESZ = element size in u32 words: 4 (seeds / rescue entries, key = words 1:0) or 2 (roots / next, key = word 0) */
+template <int ESZ> __device__ __forceinline__ uint64_t rs_key(const uint32_t *e) { return ESZ == 4 ? ((uint64_t)e[1] << 32 | e[0]) : (uint64_t)e[0]; }
+template <int ESZ> __device__ __forceinline__ void rs_copy(uint32_t *d, const uint32_t *s)
 {
-	uint32_t tmp[4];
+	if(ESZ == 4) { *(uint4 *)d = *(const uint4 *)s; } else { *(uint2 *)d = *(const uint2 *)s; }
+}
+
+/* insertion sort of the reference (ksort.h:82-95): stable, used below 65 elements */
+template <int ESZ>
+__device__ __forceinline__ void rs_insertion(uint32_t *a, uint32_t n)
+{
 	for(uint32_t i = 1; i < n; i++) {
-		if(rs_key(a + esz * i, esz) < rs_key(a + esz * (i - 1), esz)) {
-			rs_copy(tmp, a + esz * i, esz);
-			uint64_t tk = rs_key(tmp, esz);
+		if(rs_key<ESZ>(a + ESZ * i) < rs_key<ESZ>(a + ESZ * (i - 1))) {
+			uint32_t tmp[4] __attribute__((aligned(16)));
+			rs_copy<ESZ>(tmp, a + ESZ * i);
+			uint64_t tk = rs_key<ESZ>(tmp);
 			uint32_t j;
-			for(j = i; j > 0 && tk < rs_key(a + esz * (j - 1), esz); j--) { rs_copy(a + esz * j, a + esz * (j - 1), esz); }
-			rs_copy(a + esz * j, tmp, esz);
+			for(j = i; j > 0 && tk < rs_key<ESZ>(a + ESZ * (j - 1)); j--) { rs_copy<ESZ>(a + ESZ * j, a + ESZ * (j - 1)); }
+			rs_copy<ESZ>(a + ESZ * j, tmp);
 		}
 	}
 }
@@ -95,9 +100,11 @@ __device__ __forceinline__ void rs_insertion(uint32_t *a, uint32_t n, int esz)
  * Structured control flow only: this is inlined into k_extend, whose shuffles rely on provable warp convergence. */
 #define MAB_RS_FRAME 260						/* scratch u32 per "frame"; callers allocate 8 frames per warp */
 #define MAB_RS_STACK (8 * MAB_RS_FRAME / 2)
-__device__ __forceinline__ void radix_sort_exact_warp(uint32_t *a, uint32_t n, int esz, uint32_t *stack, uint32_t *sm, int lane, uint32_t *err)
+template <int ESZ>
+__device__ __forceinline__ void radix_sort_exact_warp(uint32_t *a, uint32_t n, uint32_t *stack, uint32_t *sm, int lane, uint32_t *err)
 {
-	if(n <= 64) { if(lane == 0) { rs_insertion(a, n, esz); } __syncwarp(); return; }
+	constexpr int esz = ESZ;
+	if(n <= 64) { if(lane == 0) { rs_insertion<ESZ>(a, n); } __syncwarp(); return; }
 	uint32_t *cnt = sm, *head = sm + 256;
 	uint32_t sp = 1;
 	if(lane == 0) { stack[0] = 0; stack[1] = n | ((esz == 4 ? 7u : 3u) << 29); }
@@ -108,8 +115,8 @@ __device__ __forceinline__ void radix_sort_exact_warp(uint32_t *a, uint32_t n, i
 		uint32_t cntn = w1 & 0x1fffffffu, s = (w1 >> 29) * 8;
 		uint32_t *base = a + (uint64_t)esz * beg;
 		__syncwarp();
-		uint64_t k0 = rs_key(base, esz), diff = 0;
-		for(uint32_t i = 1 + lane; i < cntn; i += 32) { diff |= rs_key(base + esz * i, esz) ^ k0; }
+		uint64_t k0 = rs_key<ESZ>(base), diff = 0;
+		for(uint32_t i = 1 + lane; i < cntn; i += 32) { diff |= rs_key<ESZ>(base + esz * i) ^ k0; }
 		uint32_t dlo = __reduce_or_sync(0xffffffffu, (uint32_t)diff), dhi = __reduce_or_sync(0xffffffffu, (uint32_t)(diff >> 32));
 		diff = (uint64_t)dhi << 32 | dlo;
 		while(s > 0 && ((diff >> s) & 0xff) == 0) { s -= 8; }
@@ -120,7 +127,7 @@ __device__ __forceinline__ void radix_sort_exact_warp(uint32_t *a, uint32_t n, i
 			 * compiler's atomic aggregation code defeats the convergence analysis of the whole kernel) */
 			for(uint32_t i0 = 0; i0 < cntn; i0 += 32) {
 				uint32_t i = i0 + lane;
-				uint32_t d = i < cntn ? (uint32_t)((rs_key(base + esz * i, esz) >> s) & 0xff) : 0x100u + (uint32_t)lane;
+				uint32_t d = i < cntn ? (uint32_t)((rs_key<ESZ>(base + esz * i) >> s) & 0xff) : 0x100u + (uint32_t)lane;
 				uint32_t m = __match_any_sync(0xffffffffu, d);
 				if(d < 0x100u && lane == __ffs((int)m) - 1) { cnt[d] += (uint32_t)__popc(m); }
 				__syncwarp();
@@ -138,15 +145,15 @@ __device__ __forceinline__ void radix_sort_exact_warp(uint32_t *a, uint32_t n, i
 				/* the permutation: cycle leaders in bucket order, exactly as the reference walks them (ksort.h:97-118) */
 				for(int k = 0; k < 256;) {
 					if(head[k] != cnt[k]) {
-						int l = (int)((rs_key(base + esz * head[k], esz) >> s) & 0xff);
+						int l = (int)((rs_key<ESZ>(base + esz * head[k]) >> s) & 0xff);
 						if(l != k) {
-							uint32_t tmp[4], swp[4];
-							rs_copy(tmp, base + esz * head[k], esz);
+							uint32_t tmp[4] __attribute__((aligned(16))), swp[4] __attribute__((aligned(16)));
+							rs_copy<ESZ>(tmp, base + esz * head[k]);
 							do {
-								rs_copy(swp, tmp, esz); rs_copy(tmp, base + esz * head[l], esz); rs_copy(base + esz * head[l], swp, esz); head[l]++;
-								l = (int)((rs_key(tmp, esz) >> s) & 0xff);
+								rs_copy<ESZ>(swp, tmp); rs_copy<ESZ>(tmp, base + esz * head[l]); rs_copy<ESZ>(base + esz * head[l], swp); head[l]++;
+								l = (int)((rs_key<ESZ>(tmp) >> s) & 0xff);
 							} while(l != k);
-							rs_copy(base + esz * head[k], tmp, esz); head[k]++;
+							rs_copy<ESZ>(base + esz * head[k], tmp); head[k]++;
 						} else { head[k]++; }
 					} else { k++; }
 				}
@@ -157,7 +164,7 @@ __device__ __forceinline__ void radix_sort_exact_warp(uint32_t *a, uint32_t n, i
 				for(int j = 0; j < 8; j++) {
 					int k = 32 * j + lane;
 					uint32_t b0 = k == 0 ? 0 : cnt[k - 1], sz = cnt[k] - b0;
-					if(sz > 1 && sz <= 64) { rs_insertion(base + esz * b0, sz, esz); }		/* independent small buckets, one per lane */
+					if(sz > 1 && sz <= 64) { rs_insertion<ESZ>(base + esz * b0, sz); }		/* independent small buckets, one per lane */
 					uint32_t m = __ballot_sync(0xffffffffu, sz > 64);
 					if(sz > 64) {
 						uint32_t pos = sp + (uint32_t)__popc(m & ((1u << lane) - 1));

@@ -11,7 +11,8 @@ namespace mab {
 #define MAB_BLK			32
 #define MAB_KH_CAP		1024u		/* slots of the per-read dedup hash (reference starts at 256 and doubles) */
 #define MAB_MAX_TAILS	24
-#define MAB_SC_MAX		2944u		/* seeds per read k_sortchain stages in shared memory (16 B each + 2 KB scratch = 48 KB) */
+#define MAB_SC_SMALL		2944u		/* largest shared-memory staging of the ordinary size class of k_sortchain (16 B per seed + 2 KB = 48 KB) */
+#define MAB_SC_MAX		6016u		/* ... and of the seed-rich class (96 KB, opt-in dynamic shared memory) */
 #define MAB_WARPS_PER_CTA 4
 #ifndef MAB_EXT_CTAS_PER_SM
 #define MAB_EXT_CTAS_PER_SM 6		/* resident CTAs of the persistent extend kernel per SM (register budget = 65536 / (128 x this)) */
@@ -55,6 +56,7 @@ struct DevParams {
 	/* the same constants as packed H8 pairs (value in the high byte of both 16-bit halves; "+1" = plus one ulp, see mab_dp.cuh)
 	 * ready to be used as constant-bank operands: K_OFS = ofsh = ofsv */
 	uint32_t K_GFH1, K_GFV1, K_ADJH1, K_ADJV1, K_OFS;
+	uint32_t K_M1;					/* 0xffffffff as a run-time value (a multiplier operand the assembler must not fold, see mab_dp.cuh) */
 	int32_t gi, ge, gfa, gfb;
 	RootTpl root[3];				/* W = 64, 32, 16 */
 };

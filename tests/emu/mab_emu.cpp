@@ -26,6 +26,7 @@ static inline int RT_EVENT_CREATE(RT_EVENT *e) { *e = 0; return 0; }
 static inline void RT_EVENT_RECORD(RT_EVENT, RT_STREAM) {}
 static inline float RT_EVENT_MS(RT_EVENT, RT_EVENT) { return 0.f; }
 static inline double RT_WALL_MS() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+#define RT_FUNC_MAX_SMEM(kernel, bytes) do {} while(0)
 #define RT_LAUNCH(kernel, grid, block, smem, stream, ...) emu::launch(dim3(grid), dim3(block), (smem), [&] { kernel(__VA_ARGS__); })
 
 #include "../../minialign_b200/csrc/mab_host.inl"

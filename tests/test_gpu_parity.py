@@ -85,6 +85,23 @@ def test_map_batch_golden(gpu, gold):
         assert np.array_equal(e, g)
 
 
+def test_map_batch_golden_unstaged_sortchain(gold, monkeypatch):
+    """Same golden batch with the shared-memory staging of k_sortchain capped at 64 seeds: nearly every read takes the
+    global-memory path of the exact sort / chaining, results must not change."""
+    monkeypatch.setenv("MAB_SC_CAP", "64")
+    m = api.Mapper(gold["blob"], "pacbio")
+    got = m.map_batch(gold["enc"])
+    m.close()
+    for e, g in zip(gold["align"], got):
+        assert np.array_equal(e, g)
+
+
+def test_fill_peak_reports_a_ceiling(gpu):
+    """The integer-roofline microbenchmark runs and the masked step is not faster than the unmasked one."""
+    pm, pu = gpu.fill_peak(True, 500), gpu.fill_peak(False, 500)
+    assert 0 < pm <= pu * 1.05
+
+
 def test_map_batch_edge_cases(gold):
     m = api.Mapper(gold["blob"], "pacbio")
     assert m.map_batch([]) == []
