@@ -124,6 +124,7 @@ static inline unsigned __viaddmax_s16x2(unsigned a, unsigned b, unsigned c) { re
 static inline unsigned __viaddmin_s16x2(unsigned a, unsigned b, unsigned c) { return __vmins2(__vadd2(a, b), c); }
 static inline unsigned __viaddmin_u16x2(unsigned a, unsigned b, unsigned c) { return __vminu2(__vadd2(a, b), c); }
 static inline unsigned __vimin3_u16x2(unsigned a, unsigned b, unsigned c) { return __vminu2(__vminu2(a, b), c); }
+static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 static inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned s) { s &= 31; return s ? (hi << s) | (lo >> (32 - s)) : hi; }
 static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned s) { s &= 31; return s ? (lo >> s) | (hi << (32 - s)) : lo; }
 static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
