@@ -30,6 +30,8 @@ import numpy as np
 
 GENOME_BP = 4_640_000
 BYTES_PER_BASE = 160.0          # algorithmic HBM bytes per read base
+TRAFFIC_PER_BASE = 292.0        # dram__bytes_read.sum + dram__bytes_write.sum of k_extend per read base, ncu --set full capture
+                                # in profiles/r01_ncu_k_extend_full.json (49.3 GB for the 169 Mbase launch)
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "minialign")
 
 
@@ -135,7 +137,7 @@ def main():
         if rank != 0:
             return
         n_b = 1
-        g, idx, blob, batches = build_workload(work, n_b, min(args.batch_reads, 1024))
+        g, idx, blob, batches = build_workload(work, n_b, min(args.batch_reads, 4096))    # bounded sample per step: ~84 Mbases
         from minialign_b200 import synth
         fa = os.path.join(work, "ref_step.fa")
         synth.write_fasta(fa, batches[0])
@@ -283,7 +285,8 @@ def main():
         "data": "synthetic", "config": config, "clocks": clocks,
         "e2e": {"value": bases_e2e / 1e6 / secs_e2e, "unit": "Mbases/s", "h2d_bytes_per_step": agg_e2e["h2d"] // args.steps, "d2h_bytes_per_step": agg_e2e["d2h"] // args.steps},
         "gpu_launches": agg_dev["launches"],
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": TRAFFIC_PER_BASE * agg_solo["bases"] / n_solo,
+                     "traffic_source": "profiles/r01_ncu_k_extend_full.json: 292 B per read base (mask stream widened to 1 B per cell, DESIGN.md section 5)",
                      "kernel": "k_extend (round 0)", "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                      "note": "algorithmic bytes = 160 B/read base (SURVEY 8d); the kernel is integer-issue bound, not HBM bound: see DESIGN.md section 5",
                      "ms_per_launch": 1e3 * k_s, "gcups": 64.0 * agg_solo["vec"] / max(1e-9, agg_solo["ms_ext"] / 1e3) / 1e9,
