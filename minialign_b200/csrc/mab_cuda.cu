@@ -34,6 +34,8 @@ static inline unsigned RT_SM_COUNT(int d) { int n = 0; cudaDeviceGetAttribute(&n
 /* persistent extend kernel: 4 CTAs x 4 warps per SM (multiple of the SM count) */
 static inline unsigned RT_EXTEND_SLOTS(unsigned n_sm) { return n_sm * 4 * MAB_EXT_CTAS_PER_SM; }
 template <class T> static inline cudaError_t RT_MALLOC(T **p, uint64_t n) { return cudaMalloc((void **)p, n); }
+template <class T> static inline cudaError_t RT_HOST_ALLOC(T **p, uint64_t n) { return cudaHostAlloc((void **)p, n, cudaHostAllocDefault); }
+template <class T> static inline void RT_HOST_FREE(T *p) { if(p) { cudaFreeHost((void *)p); } }
 template <class T> static inline void RT_FREE(T *p) { if(p) { cudaFree((void *)p); } }
 static inline cudaError_t RT_MEMCPY_H2D(void *d, const void *s, uint64_t n) { return cudaMemcpy(d, s, n, cudaMemcpyHostToDevice); }
 static inline cudaError_t RT_MEMCPY_D2H(void *d, const void *s, uint64_t n) { return cudaMemcpy(d, s, n, cudaMemcpyDeviceToHost); }

@@ -42,8 +42,10 @@ struct mab_ctx {
 	int device_input = 0;
 	uint32_t rlen_last = 0;				/* the reference's self->rlen carried from read to read and batch to batch */
 	/* results of the last batch */
-	std::vector<uint32_t> res_words; std::vector<uint64_t> res_ofs;
-	std::vector<uint32_t> h_pool; std::vector<ReadRec> h_reads;
+	uint32_t *res_words = nullptr; uint64_t res_cap = 0;	/* flat results of the last batch (uninitialised storage, filled in parallel) */
+	std::vector<uint64_t> res_ofs;
+	uint32_t *h_pool = nullptr; uint64_t h_pool_cap = 0;	/* pinned host copy of the device result pool */
+	std::vector<ReadRec> h_reads;
 	mab_stats_t stats;
 };
 
@@ -173,6 +175,7 @@ extern "C" void mab_destroy(mab_ctx *ctx)
 	if(ctx == nullptr) { return; }
 	RT_FREE(ctx->d_idx); RT_FREE(ctx->d_ntail); RT_FREE(ctx->d_ctr); RT_FREE(ctx->d_seq); RT_FREE(ctx->d_reads); RT_FREE(ctx->d_ws);
 	RT_FREE(ctx->d_frames); RT_FREE(ctx->d_recs); RT_FREE(ctx->d_arenas); RT_FREE(ctx->d_pool);
+	RT_HOST_FREE(ctx->h_pool); delete[] ctx->res_words;
 	delete ctx;
 }
 
@@ -257,8 +260,13 @@ inline int32_t SC(uint32_t x) { return (int32_t)0x40000000 - (int32_t)x; }
 inline uint32_t clip_mapq(double x) { uint32_t v = (uint32_t)x; return std::min(v, 60u * 16); }
 }  // namespace
 
-/* sort, prune, supplementary/secondary split, MAPQ, pack into the flat layout */
-static void post_process(mab_ctx *ctx, const uint32_t *pool, const uint32_t *rec, std::vector<uint32_t> &out)
+/* One alignment of a read's result in output order: where its record sits in the pool, its rank and MAPQ. */
+struct PlanItem { const uint32_t *a; uint32_t rank, mapq; };
+struct ReadPlan { size_t first; uint32_t count, n_uniq; uint64_t words; };
+
+/* sort, prune, supplementary/secondary split, MAPQ (minialign.c:4175-4396): decides the output of one read without copying
+ * anything; appends its items to `items` and returns the plan (words = size of the flat record post_emit will write) */
+static ReadPlan post_plan(mab_ctx *ctx, const uint32_t *pool, const uint32_t *rec, std::vector<PlanItem> &items)
 {
 	uint32_t n_res = rec[0];
 	std::vector<HRes> bins(n_res);
@@ -320,35 +328,44 @@ static void post_process(mab_ctx *ctx, const uint32_t *pool, const uint32_t *rec
 	for(uint64_t i = n_uniq; i < n_res; i++) {
 		mapq[res[2 * i + 1]] = clip_mapq(-10.0 * 16 * log10(1.0 - tpe * (double)(res[2 * i] - lsc + 1) / (double)tsc));
 	}
-	/* mm_pack_reg (4364-4396) into the flat layout */
-	size_t base = out.size();
-	out.push_back(0); out.push_back(0);
-	uint32_t cnt = 0, uniq = 0;
+	/* mm_pack_reg (4364-4396): output order */
+	ReadPlan pl; pl.first = items.size(); pl.count = 0; pl.n_uniq = 0; pl.words = 2;
 	for(uint64_t i = 0; i < n_res; i++) {
 		const HRes &h = bins[res[2 * i + 1]];
 		for(uint32_t j = 0; j < h.n_aln; j++) {
 			const uint32_t *a = aln_at(h, j);
-			uint32_t slen = a[7], npw = a[9], sn = a[10];
-			for(int t = 0; t < 10; t++) { out.push_back(a[t]); }
-			out.push_back((uint32_t)i); out.push_back(mapq[res[2 * i + 1]]);
-			out.push_back(0); out.push_back(0); out.push_back(0); out.push_back(0);
-			const uint32_t *seg = a + MAB_ALN_HDR + 8ull * (sn - slen);
-			out.insert(out.end(), seg, seg + 8ull * slen);
-			const uint32_t *path = a + MAB_ALN_HDR + 8ull * sn;
-			out.insert(out.end(), path, path + npw);
-			cnt++;
+			PlanItem it; it.a = a; it.rank = (uint32_t)i; it.mapq = mapq[res[2 * i + 1]];
+			items.push_back(it);
+			pl.words += 16 + 8ull * a[7] + a[9];
+			pl.count++;
 		}
-		if(i == n_uniq - 1) { uniq = cnt; }
+		if(i == n_uniq - 1) { pl.n_uniq = pl.count; }
 	}
-	out[base] = cnt; out[base + 1] = uniq;
+	return pl;
+}
+
+/* writes the flat record of one read (layout in include/minialign_b200.h) */
+static void post_emit(const ReadPlan &pl, const PlanItem *items, uint32_t *out)
+{
+	out[0] = pl.count; out[1] = pl.n_uniq;
+	uint32_t *w = out + 2;
+	for(uint32_t k = 0; k < pl.count; k++) {
+		const uint32_t *a = items[k].a;
+		uint32_t slen = a[7], npw = a[9], sn = a[10];
+		memcpy(w, a, 40);
+		w[10] = items[k].rank; w[11] = items[k].mapq; w[12] = w[13] = w[14] = w[15] = 0;
+		memcpy(w + 16, a + MAB_ALN_HDR + 8ull * (sn - slen), 32ull * slen);
+		memcpy(w + 16 + 8ull * slen, a + MAB_ALN_HDR + 8ull * sn, 4ull * npw);
+		w += 16 + 8ull * slen + npw;
+	}
 }
 
 /* ---------------------------------------------------------------- batch driver */
 static uint32_t dp_blk_cap(uint32_t maxlen) { return (uint32_t)((4ull * ((uint64_t)maxlen + 512)) / 32 + 64); }
 
 /* one pass of the device pipeline over `hr` (seq_ofs / len / rlen_in filled in); on return hr holds the device-side
- * records and ctx->h_pool the result pool */
-static int map_core(mab_ctx *ctx, const uint8_t *d_base, std::vector<ReadRec> &hr, bool timed)
+ * records and ctx->h_pool (or *alt_pool) the result pool */
+static int map_core(mab_ctx *ctx, const uint8_t *d_base, std::vector<ReadRec> &hr, bool timed, std::vector<uint32_t> *alt_pool = nullptr)
 {
 	const DevParams &P = ctx->P;
 	mab_stats_t &S = ctx->stats;
@@ -448,8 +465,18 @@ static int map_core(mab_ctx *ctx, const uint8_t *d_base, std::vector<ReadRec> &h
 		}
 		if(err) { g_err = "device workspace overflow (error bits " + std::to_string(err) + ")"; return MAB_EOVERFLOW; }
 		uint64_t top = hc.pool_top;
-		ctx->h_pool.resize((size_t)top + 4);
-		if(top) { CK(RT_MEMCPY_D2H_ASYNC(ctx->h_pool.data(), ctx->d_pool, 4 * top, ctx->stream)); }
+		uint32_t *dst;
+		if(alt_pool) { alt_pool->resize((size_t)top + 4); dst = alt_pool->data(); }			/* re-mapped reads (rare): pageable side buffer */
+		else {
+			if(4 * (top + 4) > ctx->h_pool_cap) {
+				RT_HOST_FREE(ctx->h_pool); ctx->h_pool = nullptr; ctx->h_pool_cap = 0;
+				uint64_t nb = 4 * (top + 4) + (top + 4);									/* 25 % head room */
+				if(!RT_OK(RT_HOST_ALLOC(&ctx->h_pool, nb))) { g_err = std::string("pinned host allocation failed: ") + RT_ERRSTR(); return MAB_ENOMEM; }
+				ctx->h_pool_cap = nb;
+			}
+			dst = ctx->h_pool;
+		}
+		if(top) { CK(RT_MEMCPY_D2H_ASYNC(dst, ctx->d_pool, 4 * top, ctx->stream)); }
 		if(timed) { RT_EVENT_RECORD(ctx->ev[5], ctx->stream); }
 		{ double tw = RT_WALL_MS(); CK(RT_STREAM_SYNC(ctx->stream)); S.ms_wall_wait += (float)(RT_WALL_MS() - tw); }
 		S.d2h_bytes += 4 * top + sizeof(ReadRec) * (uint64_t)n_seq + sizeof(hc);
@@ -463,7 +490,7 @@ extern "C" int mab_map_batch(mab_ctx *ctx, const uint8_t *seq_block, uint64_t bl
 	mab_stats_t &S = ctx->stats;
 	memset(&S, 0, sizeof(S));
 	const double t_call = RT_WALL_MS();
-	ctx->res_words.clear(); ctx->res_ofs.assign((size_t)n_seq + 1, 0);
+	ctx->res_ofs.assign((size_t)n_seq + 1, 0);
 	if(n_seq == 0) { return MAB_OK; }
 	CK(RT_SET_DEVICE(ctx->device));
 	RT_EVENT_RECORD(ctx->ev[0], ctx->stream);
@@ -479,21 +506,11 @@ extern "C" int mab_map_batch(mab_ctx *ctx, const uint8_t *seq_block, uint64_t bl
 	for(uint32_t i = 0; i < n_seq; i++) { memset(&hr[i], 0, sizeof(ReadRec)); hr[i].seq_ofs = seq_ofs[i]; hr[i].len = seq_len[i]; hr[i].rlen_in = MAB_RLEN_OWN; }
 	{ int rc = map_core(ctx, d_base, hr, true); if(rc) { return rc; } }
 	double t0 = RT_WALL_MS();
-	std::vector<std::vector<uint32_t>> words(n_seq);
-	{	/* reads are independent here: fan the host post-processing out over the host cores */
-		uint32_t hw = std::thread::hardware_concurrency();
-		if(const char *e = getenv("MAB_HOST_THREADS")) { int v = atoi(e); if(v > 0) { hw = (uint32_t)v; } }
-		uint32_t nth = std::max(1u, std::min<uint32_t>(std::min<uint32_t>(hw, 32u), n_seq / 64 + 1));
-		std::vector<std::thread> th;
-		auto work = [&](uint32_t t) {
-			for(uint32_t i = t; i < n_seq; i += nth) { if(hr[i].result_words != 0) { post_process(ctx, ctx->h_pool.data(), ctx->h_pool.data() + hr[i].result_ofs, words[i]); } }
-		};
-		for(uint32_t t = 1; t < nth; t++) { th.emplace_back(work, t); }
-		work(0);
-		for(auto &x : th) { x.join(); }
-	}
-	/* verify the rlen speculation in read order (the reference's -t1 semantics); re-map the reads whose first root test
-	 * would have gone the other way with the true stale value */
+	/* verify the rlen speculation in read order (the reference's -t1 semantics); re-map the reads whose first root test would
+	 * have gone the other way with the true stale value.  Their results land in side pools; src[i] = pool read i refers to. */
+	std::vector<const uint32_t *> src(n_seq, ctx->h_pool);
+	std::vector<std::vector<uint32_t>> side;
+	side.reserve(8);
 	for(int iter = 0; iter < 8; iter++) {
 		std::vector<uint32_t> redo;
 		uint32_t prev = ctx->rlen_last;
@@ -514,20 +531,39 @@ extern "C" int mab_map_batch(mab_ctx *ctx, const uint8_t *seq_block, uint64_t bl
 			if(i == redo[k]) { memset(&sub[k], 0, sizeof(ReadRec)); sub[k].seq_ofs = hr[i].seq_ofs; sub[k].len = hr[i].len; sub[k].rlen_in = prev; k++; }
 			if(hr[i].dep_flags & 1) { prev = hr[i].rlen_cur; }
 		}
-		{ int rc = map_core(ctx, d_base, sub, false); if(rc) { return rc; } }
-		for(size_t j = 0; j < redo.size(); j++) {
-			uint32_t i = redo[j];
-			hr[i] = sub[j];
-			words[i].clear();
-			if(sub[j].result_words != 0) { post_process(ctx, ctx->h_pool.data(), ctx->h_pool.data() + sub[j].result_ofs, words[i]); }
-		}
+		side.emplace_back();
+		{ int rc = map_core(ctx, d_base, sub, false, &side.back()); if(rc) { return rc; } }
+		for(size_t j = 0; j < redo.size(); j++) { hr[redo[j]] = sub[j]; src[redo[j]] = side.back().data(); }
 	}
 	for(uint32_t i = 0; i < n_seq; i++) { if(hr[i].dep_flags & 1) { ctx->rlen_last = hr[i].rlen_cur; } }
-	for(uint32_t i = 0; i < n_seq; i++) {
-		ctx->res_ofs[i] = ctx->res_words.size();
-		ctx->res_words.insert(ctx->res_words.end(), words[i].begin(), words[i].end());
-	}
-	ctx->res_ofs[n_seq] = ctx->res_words.size();
+	/* host post-processing, fanned out over the host cores: plan every read (no copying), prefix-sum the sizes, then write the
+	 * flat records straight into their final place */
+	uint32_t hw = std::thread::hardware_concurrency();
+	if(const char *e = getenv("MAB_HOST_THREADS")) { int v = atoi(e); if(v > 0) { hw = (uint32_t)v; } }
+	uint32_t nth = std::max(1u, std::min<uint32_t>(std::min<uint32_t>(hw, 32u), n_seq / 64 + 1));
+	std::vector<std::vector<PlanItem>> items(nth);
+	std::vector<ReadPlan> plan(n_seq);
+	auto run_par = [&](auto &&fn) {
+		std::vector<std::thread> th;
+		for(uint32_t t = 1; t < nth; t++) { th.emplace_back(fn, t); }
+		fn(0u);
+		for(auto &x : th) { x.join(); }
+	};
+	run_par([&](uint32_t t) {
+		for(uint32_t i = t; i < n_seq; i += nth) {
+			if(hr[i].result_words != 0) { plan[i] = post_plan(ctx, src[i], src[i] + hr[i].result_ofs, items[t]); }
+			else { plan[i].first = 0; plan[i].count = 0; plan[i].n_uniq = 0; plan[i].words = 0; }
+		}
+	});
+	uint64_t total = 0;
+	for(uint32_t i = 0; i < n_seq; i++) { ctx->res_ofs[i] = total; total += plan[i].words; }
+	ctx->res_ofs[n_seq] = total;
+	if(total > ctx->res_cap) { delete[] ctx->res_words; ctx->res_cap = total + total / 4 + 1024; ctx->res_words = new uint32_t[ctx->res_cap]; }
+	run_par([&](uint32_t t) {
+		for(uint32_t i = t; i < n_seq; i += nth) {
+			if(plan[i].words != 0) { post_emit(plan[i], items[t].data() + plan[i].first, ctx->res_words + ctx->res_ofs[i]); }
+		}
+	});
 	S.ms_post = (float)(RT_WALL_MS() - t0);
 	S.ms_h2d = RT_EVENT_MS(ctx->ev[0], ctx->ev[1]);
 	S.ms_seed = RT_EVENT_MS(ctx->ev[2], ctx->ev[3]);
@@ -547,10 +583,10 @@ extern "C" uint64_t mab_result(const mab_ctx *ctx, uint32_t i, const uint32_t **
 {
 	if((size_t)i + 1 >= ctx->res_ofs.size()) { return 0; }
 	uint64_t n = ctx->res_ofs[i + 1] - ctx->res_ofs[i];
-	if(words) { *words = n ? ctx->res_words.data() + ctx->res_ofs[i] : nullptr; }
+	if(words) { *words = n ? ctx->res_words + ctx->res_ofs[i] : nullptr; }
 	return n;
 }
-extern "C" void mab_release_batch(mab_ctx *ctx) { ctx->res_words.clear(); ctx->res_ofs.clear(); }
+extern "C" void mab_release_batch(mab_ctx *ctx) { ctx->res_ofs.clear(); }
 
 /* ---------------------------------------------------------------- stage-level entry points */
 extern "C" uint64_t mab_sketch(mab_ctx *ctx, const uint8_t *seq, uint32_t len, uint64_t *out, uint64_t cap)
