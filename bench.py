@@ -156,6 +156,14 @@ def main():
                           "e2e": {"value": v, "unit": "Mbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
+    # native libraries (NCCL's version banner, ...) write to fd 1: keep the real stdout for the one JSON line, send the rest to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+
     import torch
     import torch.distributed as dist
     from minialign_b200 import api, shard
@@ -303,7 +311,7 @@ def main():
                 line["cpu_baseline"] = cpu_baseline(idx, batches, work)
             except Exception as e:   # the reference binary is test infrastructure: report its absence, never fake it
                 line["cpu_baseline"] = {"value": None, "unit": "Mbases/s", "cores": host_threads(), "kind": "reference", "sample": f"unavailable: {e}"}
-        print(json.dumps(line))
+        emit(line)
     [m.close() for m in ms]
     if world > 1:
         dist.destroy_process_group()

@@ -44,3 +44,23 @@ def test_cli_matches_live_reference_on_20kb_reads(tmp_path, preset):
     assert len(got) == len(exp)
     bad = [i for i, (a, b) in enumerate(zip(got, exp)) if a != b]
     assert not bad, (len(bad), got[bad[0]][:200], exp[bad[0]][:200])
+
+
+@pytest.mark.skipif(not os.path.exists(refh.BIN), reason="oracle/_ref/minialign not built")
+def test_cli_matches_live_reference_multi_contig_repeats(tmp_path):
+    """BASELINE config 2 in small (sacCer3-like: 17 contigs) with heavier planted repeat families, so that the rescue rounds
+    (occ thresholds), secondary / supplementary records and the seed-rich sort class are exercised; reference run with -t1."""
+    from minialign_b200 import synth
+    g = synth.make_genome(6_000_000, 17, seed=31, repeats=((30, 4000), (120, 1200), (400, 300)))
+    reads = synth.make_reads(g, 8_000_000, seed=32) + synth.make_hard_reads(g, seed=33)
+    fa, rd, idx = str(tmp_path / "g.fa"), str(tmp_path / "r.fa"), str(tmp_path / "g.mai")
+    synth.write_fasta(fa, g, 80); synth.write_fasta(rd, reads)
+    subprocess.check_call([refh.BIN, "-xpacbio", "-d", idx, fa], stderr=subprocess.DEVNULL)
+    ref = subprocess.run([refh.BIN, "-xpacbio", "-t1", "-TAS,XS,NM,MD,NH,IH", idx, rd], capture_output=True)
+    assert ref.returncode == 0
+    exp = [l for l in ref.stdout.decode().split("\n") if not l.startswith("@PG")]
+    got = run_cli(["-xpacbio", "-TAS,XS,NM,MD,NH,IH", idx, rd])
+    assert len(got) == len(exp)
+    bad = [i for i, (a, b) in enumerate(zip(got, exp)) if a != b]
+    assert not bad, (len(bad), got[bad[0]][:200], exp[bad[0]][:200])
+    assert sum(1 for l in exp if l and not l.startswith("@") and int(l.split("\t")[1]) & 0x900) > 0     # secondary / supplementary present
