@@ -383,29 +383,30 @@ static int map_core(mab_ctx *ctx, const uint8_t *d_base, std::vector<ReadRec> &h
 		for(uint32_t i = 0; i < n_seq; i++) { span = std::max<uint64_t>(span, hr[i].seq_ofs + hr[i].len); }
 		int rc = grow(&ctx->d_recs, &ctx->recs_cap, 16ull * span + 256); if(rc) { return rc; }
 	}
-	RT_LAUNCH(k_seed_scan, seed_ctas, 32 * MAB_WARPS_PER_CTA, 512 * MAB_WARPS_PER_CTA, ctx->stream, P, d_base, ctx->d_reads, n_seq, ctx->d_recs);
+	RT_LAUNCH(k_seed_scan, seed_ctas, 32 * MAB_WARPS_PER_CTA, 2560 * MAB_WARPS_PER_CTA, ctx->stream, P, d_base, ctx->d_reads, n_seq, ctx->d_recs);
 	S.n_launches++;
 	CK(RT_MEMCPY_D2H_ASYNC(hr.data(), ctx->d_reads, sizeof(ReadRec) * (uint64_t)n_seq, ctx->stream));
 	{ double tw = RT_WALL_MS(); CK(RT_STREAM_SYNC(ctx->stream)); S.ms_wall_wait += (float)(RT_WALL_MS() - tw); }
 	double t_sizing = RT_WALL_MS();
 	S.d2h_bytes += sizeof(ReadRec) * (uint64_t)n_seq;
 	uint64_t ws_total = 0;
-	/* k_sortchain size classes: the ordinary reads (up to the 90th percentile of the seed bound) run with a small shared-memory
-	 * footprint, the seed-rich rest in a second launch with up to MAB_SC_MAX seeds staged */
-	uint32_t sc_cap1 = 64, sc_cap2 = 64, sc_max_bound = 0;
-	{
+	/* k_sortchain size classes, per round kind (round 0 stages a read's own seeds, later rounds all of them): the ordinary
+	 * reads (up to the 90th percentile of the seed bound) run with a small shared-memory footprint, the seed-rich rest in a
+	 * second launch with up to MAB_SC_MAX seeds staged */
+	struct ScCaps { uint32_t cap1, cap2, max_bound; } sc[2] = { { 64, 64, 0 }, { 64, 64, 0 } };
+	for(int kind = 0; kind < 2; kind++) {
 		std::vector<uint32_t> bnd;
-		for(uint32_t i = 0; i < n_seq; i++) { if(hr[i].state == 0) { bnd.push_back(hr[i].tot_seeds + 2); } }
+		for(uint32_t i = 0; i < n_seq; i++) { if(hr[i].state == 0) { bnd.push_back((kind == 0 ? hr[i].tot_seeds0 : hr[i].tot_seeds) + 2); } }
 		if(!bnd.empty()) {
 			size_t k90 = (bnd.size() * 9) / 10; if(k90 >= bnd.size()) { k90 = bnd.size() - 1; }
 			std::nth_element(bnd.begin(), bnd.begin() + k90, bnd.end());
-			sc_cap1 = std::max<uint32_t>(64u, std::min<uint32_t>((bnd[k90] + 63u) & ~63u, MAB_SC_SMALL));
-			sc_max_bound = *std::max_element(bnd.begin(), bnd.end());
-			sc_cap2 = std::max<uint32_t>(sc_cap1, std::min<uint32_t>((sc_max_bound + 63u) & ~63u, MAB_SC_MAX));
+			sc[kind].cap1 = std::max<uint32_t>(64u, std::min<uint32_t>((bnd[k90] + 63u) & ~63u, MAB_SC_SMALL));
+			sc[kind].max_bound = *std::max_element(bnd.begin(), bnd.end());
+			sc[kind].cap2 = std::max<uint32_t>(sc[kind].cap1, std::min<uint32_t>((sc[kind].max_bound + 63u) & ~63u, MAB_SC_MAX));
 		}
 		if(const char *e = getenv("MAB_SC_CAP")) {									/* test hook: tiny caps push reads through the unstaged (global memory) path */
 			uint32_t v = (uint32_t)atoi(e);
-			if(v >= 64) { sc_cap1 = std::min(sc_cap1, v); sc_cap2 = std::min(std::max(sc_cap2, sc_cap1), std::max(v, sc_cap1)); }
+			if(v >= 64) { sc[kind].cap1 = std::min(sc[kind].cap1, v); sc[kind].cap2 = std::min(sc[kind].cap2, std::max(v, sc[kind].cap1)); }
 		}
 	}
 	for(uint32_t i = 0; i < n_seq; i++) {
@@ -436,12 +437,13 @@ static int map_core(mab_ctx *ctx, const uint8_t *d_base, std::vector<ReadRec> &h
 		/* rounds of sort+chain / extend (minialign.c:4444-4448) */
 		for(uint32_t round = 0; round < P.n_occ; round++) {
 			if(timed && round < 8) { RT_EVENT_RECORD(ctx->rev[3 * round], ctx->stream); }
-			RT_LAUNCH(k_sortchain, n_seq, 32, 16 * sc_cap1 + 2048, ctx->stream, P, ctx->d_reads, n_seq, ctx->d_ws, ctx->d_frames, round, sc_cap1, 0u, sc_cap1);
-				if(sc_max_bound > sc_cap1) {										/* the seed-rich class (staged up to sc_cap2 seeds, global memory beyond) */
-					RT_FUNC_MAX_SMEM(k_sortchain, 16 * MAB_SC_MAX + 2048);
-					RT_LAUNCH(k_sortchain, n_seq, 32, 16 * sc_cap2 + 2048, ctx->stream, P, ctx->d_reads, n_seq, ctx->d_ws, ctx->d_frames, round, sc_cap2, sc_cap1, 0xffffffffu);
-					S.n_launches++;
-				}
+			const ScCaps &C = sc[round == 0 ? 0 : 1];
+			RT_LAUNCH(k_sortchain, n_seq, 32, 16 * C.cap1 + 2048, ctx->stream, P, ctx->d_reads, n_seq, ctx->d_ws, ctx->d_frames, round, C.cap1, 0u, C.cap1);
+			if(C.max_bound > C.cap1) {												/* the seed-rich class (staged up to cap2 seeds, global memory beyond) */
+				RT_FUNC_MAX_SMEM(k_sortchain, 16 * MAB_SC_MAX + 2048);
+				RT_LAUNCH(k_sortchain, n_seq, 32, 16 * C.cap2 + 2048, ctx->stream, P, ctx->d_reads, n_seq, ctx->d_ws, ctx->d_frames, round, C.cap2, C.cap1, 0xffffffffu);
+				S.n_launches++;
+			}
 			RT_MEMSET_ASYNC(&ctx->d_ctr->work_next, 0, sizeof(unsigned int), ctx->stream);
 			if(timed && round < 8) { RT_EVENT_RECORD(ctx->rev[3 * round + 1], ctx->stream); }
 			RT_LAUNCH(k_extend, ext_ctas, 32 * MAB_WARPS_PER_CTA, 1024 + 2048 * MAB_WARPS_PER_CTA, ctx->stream, P, d_base, (const uint8_t *)ctx->d_ntail, ctx->d_reads, n_seq, ctx->d_ws,
@@ -615,7 +617,7 @@ extern "C" uint64_t mab_seed_chain(mab_ctx *ctx, const uint8_t *seq, uint32_t le
 	RT_MEMCPY_H2D(d_r, &r, sizeof(r));
 	uint32_t *d_rec = nullptr;
 	if(!RT_OK(RT_MALLOC(&d_rec, 16ull * len + 256))) { RT_FREE(d_seq); RT_FREE(d_r); RT_FREE(d_fr); return 0; }
-	RT_LAUNCH(k_seed_scan, 1, 32, 512, ctx->stream, P, (const uint8_t *)d_seq, d_r, 1u, d_rec);
+	RT_LAUNCH(k_seed_scan, 1, 32, 2560, ctx->stream, P, (const uint8_t *)d_seq, d_r, 1u, d_rec);
 	RT_STREAM_SYNC(ctx->stream);
 	RT_MEMCPY_D2H(&r, d_r, sizeof(r));
 	uint64_t ns = 0;

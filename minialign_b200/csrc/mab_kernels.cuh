@@ -35,12 +35,12 @@ __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t x, int lane, uint32_
  * (a read emits at most one minimizer per base, so its slice of the block-sized record array cannot overflow), and the
  * per-read totals size the workspaces.  k_seed_expand then only replays the records (mm_collect_seed / mm_expand,
  * minialign.c:3420-3493): no second sketch, no second probe.
- * shared memory per warp: 64-entry ring of encoded minimizer candidates (u64) */
+ * shared memory per warp: five 64-entry rings of encoded minimizer candidates (u64): 2560 B */
 __global__ void k_seed_scan(DevParams P, const uint8_t *base, ReadRec *reads, uint32_t n_reads, uint32_t *recs)
 {
 	MAB_DYN_SMEM(smem);
 	int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-	uint64_t *ring = (uint64_t *)smem + 64 * wib;
+	uint64_t *ring = (uint64_t *)smem + 320 * wib;
 	uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
 	uint64_t const k = P.k, w = P.w, kk = k - 1, shift1 = 2 * kk, mask = (1ull << (2 * k)) - 1;
 	uint32_t const max_occ = P.occ[P.n_occ - 1], resc_occ = P.occ[0];
@@ -48,20 +48,51 @@ __global__ void k_seed_scan(DevParams P, const uint8_t *base, ReadRec *reads, ui
 		ReadRec *r = &reads[rid];
 		uint32_t len = r->len;
 		if(len < P.k || (double)len * P.mcoef < (double)P.min_score) {			/* minialign.c:4434 */
-			if(lane == 0) { r->state = 1; r->tot_seeds = 0; r->tot_resc = 0; r->n_seed = 0; r->n_resc = 0; r->result_words = 0; r->n_rec = 0; }
+			if(lane == 0) { r->state = 1; r->tot_seeds = 0; r->tot_seeds0 = 0; r->tot_resc = 0; r->n_seed = 0; r->n_resc = 0; r->result_words = 0; r->n_rec = 0; }
 			continue;
 		}
 		const uint8_t *seq = base + r->seq_ofs;
 		uint32_t *rec = recs + 4ull * r->seq_ofs;
 		uint32_t npos = len - (uint32_t)kk;
-		uint32_t tot_seeds = 0, tot_resc = 0, n_words = 0, n_rec = 0;
+		uint32_t tot_seeds = 0, tot_seeds0 = 0, tot_resc = 0, n_words = 0, n_rec = 0;
 		uint64_t vcarry = 0;				/* u: previous window minimum */
 		uint32_t idx_carry = (uint32_t)w;	/* decoder state: previous emitted in-block index (v = w), number of block starts */
 		uint32_t nblk_carry = 0;
+		/* Bit-plane k-mer construction (k <= 16, no N in reach): the two low bits of 64 consecutive base codes sit in ballot
+		 * words; lane j cuts its k bits out with a funnel shift, reverses and spreads them to the even / odd bit positions, and
+		 * gets the reverse-complement k-mer by complementing, bit-reversing and swapping the bits of each pair back.  Chunks that
+		 * see an N (code 4 leaks into the neighbouring base, minialign.c:2383-2398) take the literal per-base loop below.
+		 * The window minimum over w positions is min(m_p[j], m_p[j - (w - p)]) with p the largest power of two <= w and m_p built
+		 * by doubling; the shifted reads go through per-level 64-entry rings so that they reach into the previous chunk. */
+		uint32_t cur = seq[lane], p0c = __ballot_sync(MAB_FULL, cur & 1), p1c = __ballot_sync(MAB_FULL, cur & 2), nc = __ballot_sync(MAB_FULL, cur >= 4), nprev = 0;
+		const bool fastk = k <= 16;
+		uint32_t c0w = 0;					/* c0 mod w */
+		const uint32_t lane_r = (uint32_t)lane % (uint32_t)w;
+		int plog = 0; while((2u << plog) <= (uint32_t)w) { plog++; }		/* p = 1 << plog */
+		const uint32_t pw = 1u << plog, tailofs = (uint32_t)w - pw;
+		for(int t = lane; t < 64 * 5; t += 32) { ring[t] = 0xffffffffffffffffull; }
+		__syncwarp();
 		for(uint32_t c0 = 0; c0 < npos; c0 += 32) {
 			uint32_t j = c0 + lane;
+			uint32_t nxt = seq[c0 + 32 + lane];								/* inside the read or its 64 B margin */
+			uint32_t p0n = __ballot_sync(MAB_FULL, nxt & 1), p1n = __ballot_sync(MAB_FULL, nxt & 2), nn = __ballot_sync(MAB_FULL, nxt >= 4);
 			uint64_t enc = 0xffffffffffffffffull;
-			if(j < npos) {
+			uint32_t jm = c0w + lane_r; if(jm >= (uint32_t)w) { jm -= (uint32_t)w; } if(jm >= (uint32_t)w) { jm -= (uint32_t)w; }	/* j mod w */
+			if(fastk && ((nprev >> 31) | nc | (nn & 0xffffu)) == 0) {
+				if(j < npos) {
+					uint32_t km1 = (1u << k) - 1;
+					uint32_t x0 = __funnelshift_r(p0c, p0n, lane) & km1, x1 = __funnelshift_r(p1c, p1n, lane) & km1;		/* bit t = base j + t */
+					uint32_t r0 = __brev(x0) >> (32 - (uint32_t)k), r1 = __brev(x1) >> (32 - (uint32_t)k);					/* bit i = base j + k - 1 - i */
+					r0 = (r0 | (r0 << 8)) & 0x00ff00ffu; r0 = (r0 | (r0 << 4)) & 0x0f0f0f0fu; r0 = (r0 | (r0 << 2)) & 0x33333333u; r0 = (r0 | (r0 << 1)) & 0x55555555u;
+					r1 = (r1 | (r1 << 8)) & 0x00ff00ffu; r1 = (r1 | (r1 << 4)) & 0x0f0f0f0fu; r1 = (r1 | (r1 << 2)) & 0x33333333u; r1 = (r1 | (r1 << 1)) & 0x55555555u;
+					uint32_t m32 = (uint32_t)mask;
+					uint32_t k0 = r0 | (r1 << 1);
+					uint32_t z = __brev(~k0 & m32) >> (32 - 2 * (uint32_t)k);
+					uint32_t k1 = ((z >> 1) & 0x55555555u) | ((z & 0x55555555u) << 1);
+					uint32_t km = k0 < k1 ? k0 : k1, mm = k0 < k1 ? 0u : 0x80u;
+					enc = (uint64_t)km << 8 | (uint64_t)(jm | mm);				/* k <= 16: the CRC term of hash64 is 0 */
+				}
+			} else if(j < npos) {
 				/* k-mer seq[j .. j+kk]; N (code 4) leaks one bit into the neighbouring base exactly like the rolling update */
 				uint64_t k0 = 0, k1 = 0;
 				for(uint64_t t = 0; t < k; t++) { uint64_t c = seq[j + t]; k0 |= c << (2 * (kk - t)); k1 |= ((3ull ^ c) << shift1) >> (2 * (kk - t)); }
@@ -69,15 +100,28 @@ __global__ void k_seed_scan(DevParams P, const uint8_t *base, ReadRec *reads, ui
 				if(j > 0) { k1 |= ((3ull ^ (uint64_t)seq[j - 1]) << shift1) >> (2 * k); }
 				uint64_t km = k0 < k1 ? k0 : k1, kx = k0 < k1 ? k1 : k0, mm = k0 < k1 ? 0 : 0x80;
 				uint64_t h = ((uint64_t)crc32c_u64((uint32_t)kx, kx) ^ km) & mask;
-				enc = h << 8 | (uint64_t)(j % (uint32_t)w) | mm;
+				enc = h << 8 | (uint64_t)jm | mm;
 			}
-			ring[j & 63] = enc;
-			__syncwarp();
-			uint64_t v = 0xffffffffffffffffull;
-			if(j < npos) {
-				uint32_t lo = j + 1 >= (uint32_t)w ? j + 1 - (uint32_t)w : 0;
-				for(uint32_t t = lo; t <= j; t++) { uint64_t e = ring[t & 63]; v = e < v ? e : v; }
+			nprev = nc; p0c = p0n; p1c = p1n; nc = nn;
+			c0w += 32 % (uint32_t)w; if(c0w >= (uint32_t)w) { c0w -= (uint32_t)w; }
+			/* windowed minimum */
+			uint64_t m = enc;
+			for(int lv = 0; lv < plog; lv++) {
+				uint64_t *rg = ring + 64 * lv;
+				rg[j & 63] = m;
+				__syncwarp();
+				uint64_t o = rg[(j - (1u << lv)) & 63];
+				m = o < m ? o : m;
 			}
+			uint64_t v = m;
+			if(tailofs) {
+				uint64_t *rg = ring + 64 * 4;
+				rg[j & 63] = m;
+				__syncwarp();
+				uint64_t o = rg[(j - tailofs) & 63];
+				v = o < m ? o : m;
+			}
+			if(j >= npos) { v = 0xffffffffffffffffull; }
 			uint64_t u = __shfl_up_sync(MAB_FULL, v, 1);
 			if(lane == 0) { u = vcarry; }
 			vcarry = __shfl_sync(MAB_FULL, v, 31);
@@ -109,13 +153,13 @@ __global__ void k_seed_scan(DevParams P, const uint8_t *base, ReadRec *reads, ui
 				uint32_t *s = rec + 4ull * (n_rec + (uint32_t)__popc(hit & ((1u << lane) - 1)));
 				uint64_t ofs = (uint64_t)(occ - P.idx);
 				s[0] = qs; s[1] = n; s[2] = (uint32_t)ofs; s[3] = (uint32_t)(ofs >> 32);
-				tot_seeds += n; tot_resc += n > resc_occ;
+				tot_seeds += n; tot_seeds0 += n > resc_occ ? 0 : n; tot_resc += n > resc_occ;
 			}
 			n_rec += (uint32_t)__popc(hit);
 			__syncwarp();
 		}
-		tot_seeds = __reduce_add_sync(MAB_FULL, tot_seeds); tot_resc = __reduce_add_sync(MAB_FULL, tot_resc);
-		if(lane == 0) { r->tot_seeds = tot_seeds; r->tot_resc = tot_resc; r->n_words = n_words; r->n_rec = n_rec; }
+		tot_seeds = __reduce_add_sync(MAB_FULL, tot_seeds); tot_seeds0 = __reduce_add_sync(MAB_FULL, tot_seeds0); tot_resc = __reduce_add_sync(MAB_FULL, tot_resc);
+		if(lane == 0) { r->tot_seeds = tot_seeds; r->tot_seeds0 = tot_seeds0; r->tot_resc = tot_resc; r->n_words = n_words; r->n_rec = n_rec; }
 	}
 }
 
@@ -262,7 +306,8 @@ __device__ __forceinline__ void sortchain_read(const DevParams &P, ReadRec *r, u
 	if(__any_sync(0xffffffffu, sort_err != 0) && lane == 0) { r->err |= MAB_ERR_SEED_OVF; }
 }
 
-/* Handles the reads whose seed bound (tot_seeds + 2, over all rescue rounds) lies in (lo_cap, hi_cap]: the host launches it
+/* Handles the reads whose seed bound (round 0: its own seeds; later rounds: all seeds incl. rescued ones; + sentinel) lies in
+ * (lo_cap, hi_cap]: the host launches it
  * once per size class so that the many ordinary reads run with a small shared-memory footprint (high occupancy) and the few
  * seed-rich ones with a large one.  hi_cap = UINT32_MAX in the last class; reads above sc_cap work in global memory. */
 __global__ void k_sortchain(DevParams P, ReadRec *reads, uint32_t n_reads, uint8_t *ws, uint32_t *frames, uint32_t round, uint32_t sc_cap, uint32_t lo_cap, uint32_t hi_cap)
@@ -275,7 +320,7 @@ __global__ void k_sortchain(DevParams P, ReadRec *reads, uint32_t n_reads, uint8
 	if(i >= n_reads) { return; }
 	ReadRec *r = &reads[i];
 	if(r->state != 0) { return; }
-	uint32_t bound = r->tot_seeds + 2;
+	uint32_t bound = (round == 0 ? r->tot_seeds0 : r->tot_seeds) + 2;
 	if(bound <= lo_cap || bound > hi_cap) { return; }
 	uint32_t *fr = frames + (uint64_t)i * 8 * MAB_RS_FRAME;
 	if(bound <= sc_cap) { sortchain_read<true>(P, r, ws, fr, round, sm, sseed, lane); }

@@ -81,6 +81,7 @@ struct ReadRec {
 	uint32_t rlen_used;				/* the value the first load_root actually compared against */
 	uint32_t dep_apos, dep_flags;	/* first load_root: raw a-position; bit0 = valid, bit1 = (bpos >= qlen) */
 	uint32_t n_rec;					/* minimizer records left by k_seed_scan for k_seed_expand */
+	uint32_t tot_seeds0, _pad3;		/* seeds of round 0 alone (occurrence count <= occ[0]): what k_sortchain has to stage in round 0 */
 };
 #define MAB_RLEN_OWN 0xffffffffu
 
