@@ -167,6 +167,10 @@ extern "C" mab_ctx *mab_init(const void *mai_blob, uint64_t size, const mab_para
 	for(int i = 0; i < 8; i++) { CKP(RT_EVENT_CREATE(&ctx->ev[i])); }
 	for(int i = 0; i < 24; i++) { CKP(RT_EVENT_CREATE(&ctx->rev[i])); }
 	ctx->n_slots = RT_EXTEND_SLOTS(ctx->n_sm);
+	if(const char *e = getenv("MAB_EXT_CTAS")) {										/* resident k_extend CTAs per SM actually launched (<= MAB_EXT_CTAS_PER_SM) */
+		int v = atoi(e);
+		if(v >= 1 && v <= MAB_EXT_CTAS_PER_SM) { ctx->n_slots = ctx->n_sm * MAB_WARPS_PER_CTA * (uint32_t)v; }
+	}
 	return ctx;
 }
 
@@ -421,6 +425,13 @@ static int map_core(mab_ctx *ctx, const uint8_t *d_base, std::vector<ReadRec> &h
 	uint32_t blk_cap = dp_blk_cap(maxlen);
 	ArenaLayout AL = arena_layout(blk_cap);
 	uint32_t ext_ctas = std::max<uint32_t>(1, std::min<uint32_t>(ctx->n_slots / MAB_WARPS_PER_CTA, (n_seq + MAB_WARPS_PER_CTA - 1) / MAB_WARPS_PER_CTA));
+	{	/* the DP arenas are sized by the longest read of the batch (312 B per base per resident warp): with very long reads fewer
+		 * warps stay resident rather than asking for more than MAB_ARENA_BUDGET bytes of HBM per context */
+		uint64_t budget = 40ull << 30;
+		if(const char *e = getenv("MAB_ARENA_BUDGET_MB")) { long v = atol(e); if(v > 0) { budget = (uint64_t)v << 20; } }
+		uint64_t fit = budget / (AL.total * MAB_WARPS_PER_CTA);
+		if(fit < ext_ctas) { ext_ctas = (uint32_t)std::max<uint64_t>(1, fit); }
+	}
 	{ int rc = grow(&ctx->d_arenas, &ctx->arenas_cap, AL.total * (uint64_t)ext_ctas * MAB_WARPS_PER_CTA); if(rc) { return rc; } }
 	uint64_t pool_need = tot_len / 4 + 64ull * n_seq + (1u << 16);				/* ~2 bits per base and alignment, x4 head room */
 	S.ms_wall_sizing += (float)(RT_WALL_MS() - t_sizing);

@@ -96,6 +96,34 @@ def test_map_batch_golden_unstaged_sortchain(gold, monkeypatch):
         assert np.array_equal(e, g)
 
 
+def test_long_reads_under_a_small_arena_budget(tmp_path, monkeypatch):
+    """Reads far longer than the benchmark's (~60-150 kb) with the DP-arena budget squeezed so that only a few warps stay
+    resident: exact against the oracle."""
+    import subprocess
+    import refh
+    from minialign_b200 import mai
+    if not os.path.exists(refh.BIN):
+        pytest.skip("oracle/_ref/minialign not built (needed to build the index)")
+    monkeypatch.setenv("MAB_ARENA_BUDGET_MB", "512")
+    g = synth.make_genome(1_500_000, 2, seed=41)
+    fa, idx = str(tmp_path / "g.fa"), str(tmp_path / "g.mai")
+    synth.write_fasta(fa, g, 80)
+    subprocess.check_call([refh.BIN, "-xpacbio", "-d", idx, fa], stderr=subprocess.DEVNULL)
+    blob = mai.load_mai(idx)
+    hdr = mai.parse_header(blob)
+    reads = synth.make_reads(g, 1_200_000, seed=5, len_mean=100000, len_sd=30000, len_max=160000)
+    enc = [synth.encode_2bit(r) for _, r in reads]
+    assert max(e.size for e in enc) > 64000
+    m = api.Mapper(blob, "pacbio")
+    got = m.map_batch(enc)
+    m.close()
+    o = ora.Oracle(dict(ora.PACBIO, occ=hdr["occ"][:3]), blob)
+    for s, x in zip(enc, got):
+        assert np.array_equal(o.align(s), x)
+    o.close()
+    assert sum(len(x) > 0 for x in got) >= len(enc) // 2
+
+
 def test_fill_peak_reports_a_ceiling(gpu):
     """The integer-roofline microbenchmark runs and the masked step is not faster than the unmasked one."""
     pm, pu = gpu.fill_peak(True, 500), gpu.fill_peak(False, 500)
