@@ -3,12 +3,15 @@
  *
  *   minialign-b200 [-x preset] [-t N] [-T tag,tag] [-a -b -p -q -r -Y -s -m -W -G ...] ref.mai reads.fa[.gz] [...] > out.sam
  *
- * Loads a prebuilt .mai index ("PG00" framed zlib stream, minialign.c:1135-1502, 3136-3167), parses FASTA/FASTQ into the
- * reference's 1 byte/base codes (minialign.c:214-232), maps batches through the C ABI (libminialign_b200.so, CUDA, no CPU
- * fallback) and prints SAM with mab_sam.cpp.  Index construction (-d / FASTA references) stays with the reference binary.
+ *   minialign-b200 [-x preset] [-k -w -f -B] -d out.mai ref.fa                                      (index construction)
+ *
+ * Loads a prebuilt .mai index ("PG00" framed zlib stream, minialign.c:1135-1502, 3136-3167) or builds the index from a FASTA
+ * reference on the host (mab_index.cpp), parses FASTA/FASTQ into the reference's 1 byte/base codes (minialign.c:214-232),
+ * maps batches through the C ABI (libminialign_b200.so, CUDA, no CPU fallback) and prints SAM with mab_sam.cpp.
  */
 #include "../../../include/minialign_b200.h"
 #include "mab_sam.h"
+#include "mab_index.h"
 #include <zlib.h>
 #include <chrono>
 #include <cstdio>
@@ -91,6 +94,7 @@ struct SeqReader {
 
 struct Opts {
 	mab_params_t p; uint32_t tags = 0; int device = 0; uint32_t batch_reads = 16384; uint64_t batch_bases = 400ull << 20;
+	MabIdxParams ip; bool w_set = false; std::string dump;
 	std::vector<std::string> pos;
 };
 
@@ -147,7 +151,15 @@ static bool apply_opt(Opts &o, char c, const char *arg)
 		case 'G': o.p.glen = atoi(arg); return true;
 		case 'T': o.tags |= mab_sam_parse_tags(arg); return true;
 		case 't': return true;									/* host worker threads: the mapping runs on the GPU */
-		case 'k': case 'w': case 'f': case 'B': return true;	/* index-time parameters: taken from the .mai */
+		case 'k': o.ip.k = (uint32_t)atoi(arg); return true;	/* index-time parameters: used when the index is built here, a .mai carries its own */
+		case 'w': o.ip.w = (uint32_t)atoi(arg); o.w_set = true; return true;
+		case 'B': o.ip.b = (uint32_t)atoi(arg); return true;
+		case 'f': {												/* minialign.c:6012-6020: descending frequency thresholds */
+			o.ip.n_frq = 0;
+			for(const char *q = arg; *q && o.ip.n_frq < 7;) { o.ip.frq[o.ip.n_frq++] = (float)atof(q); const char *cm = strchr(q, ','); if(!cm) { break; } q = cm + 1; }
+			return o.ip.n_frq > 0;
+		}
+		case 'd': o.dump = arg; return true;
 		case 'g': o.device = atoi(arg); return true;
 		case 'n': o.batch_reads = (uint32_t)atoi(arg); return true;
 		default: return false;
@@ -166,15 +178,27 @@ int main(int argc, char **argv)
 		const char *a = argv[i];
 		if(a[0] == '-' && a[1] != '\0') {
 			if(a[1] == 'v') { fprintf(stderr, "[M::main] Version: 0.6.0-devel, Build: B200 (sm_100a)\n"); return 0; }
-			if(a[1] == 'd') { fprintf(stderr, "[E::main] index construction (-d) is not part of the GPU mapping path: build the .mai with the reference `minialign -d`.\n"); return 1; }
 			const char *arg = a[2] ? a + 2 : (i + 1 < argc ? argv[++i] : "");
 			if(!apply_opt(o, a[1], arg)) { fprintf(stderr, "[E::main] unknown or unsupported option `-%c'.\n", a[1]); return 1; }
 		} else { o.pos.push_back(a); }
 	}
-	if(o.pos.size() < 2) { fprintf(stderr, "usage: minialign-b200 [-x preset] [-T tags] <ref.mai> <reads.fa> [...] > out.sam\n"); return 1; }
-	if(o.pos[0].size() < 4 || o.pos[0].substr(o.pos[0].size() - 4) != ".mai") { fprintf(stderr, "[E::main_align] the reference must be a prebuilt .mai index (build it with `minialign -d`).\n"); return 1; }
+	if(!o.w_set) { o.ip.w = (uint32_t)(int)(2.0 / 3.0 * o.ip.k + .499); }							/* default window size when -w is absent (minialign.c:6111) */
+	if(o.pos.size() < (o.dump.empty() ? 2u : 1u)) { fprintf(stderr, "usage: minialign-b200 [-x preset] [-T tags] <ref.fa|ref.mai> <reads.fa> [...] > out.sam\n       minialign-b200 [-x preset] -d <out.mai> <ref.fa>\n"); return 1; }
 	std::vector<uint8_t> blob;
-	if(!load_mai(o.pos[0].c_str(), blob)) { fprintf(stderr, "[E::main_align] failed to load index block from `%s'. Please check file path and version, or rebuild the index.\n", o.pos[0].c_str()); return 1; }
+	if(!load_mai(o.pos[0].c_str(), blob)) {															/* not an index: a FASTA reference, build it here */
+		SeqReader rr(o.pos[0].c_str());
+		if(!rr.fp) { fprintf(stderr, "[E::main_align] failed to open index file `%s'. Please check file path and it exists.\n", o.pos[0].c_str()); return 1; }
+		std::vector<MabIdxSeq> refs; Rec r;
+		while(rr.next(r)) { if(r.seq.empty()) { continue; } MabIdxSeq q; q.name = r.name; q.seq = std::move(r.seq); refs.push_back(std::move(q)); }
+		std::string err;
+		if(!mab_build_index(refs, o.ip, blob, err)) { fprintf(stderr, "[E::main_index] failed to build index from `%s': %s\n", o.pos[0].c_str(), err.c_str()); return 1; }
+		fprintf(stderr, "[M::main_index::%.3f] built index for %zu target sequence(s).\n", now() - t0, refs.size());
+	}
+	if(!o.dump.empty()) {
+		if(!mab_write_mai(o.dump.c_str(), blob)) { fprintf(stderr, "[E::main_index] failed to write index to `%s'.\n", o.dump.c_str()); return 1; }
+		fprintf(stderr, "[M::main] Command: %s\n[M::main] Real time: %.3f sec\n", cmdline.c_str(), now() - t0);
+		return 0;
+	}
 	mab_ctx *ctx = mab_init(blob.data(), blob.size(), &o.p, o.device);
 	if(!ctx) { fprintf(stderr, "[E::main_align] failed to instanciate alignment context: %s\n", mab_last_error()); return 1; }
 	uint32_t n_ref = mab_n_ref(ctx);

@@ -36,7 +36,7 @@ def load_mai(path: str) -> np.ndarray:
 
 
 def parse_header(blob: np.ndarray) -> dict:
-    b = blob.tobytes()[:64]
+    b = blob[:64].tobytes()
     bkt, mask = struct.unpack_from("<QQ", b, 0)
     bb, w, k, n_occ = struct.unpack_from("<BBBB", b, 16)
     occ = list(struct.unpack_from("<7I", b, 20))

@@ -64,3 +64,6 @@ def test_cli_matches_live_reference_multi_contig_repeats(tmp_path):
     bad = [i for i, (a, b) in enumerate(zip(got, exp)) if a != b]
     assert not bad, (len(bad), got[bad[0]][:200], exp[bad[0]][:200])
     assert sum(1 for l in exp if l and not l.startswith("@") and int(l.split("\t")[1]) & 0x900) > 0     # secondary / supplementary present
+    # the same with the FASTA reference on the command line: the index is built by mab_index.cpp instead of the reference
+    got_fa = run_cli(["-xpacbio", "-TAS,XS,NM,MD,NH,IH", fa, rd])
+    assert got_fa == exp
