@@ -32,6 +32,7 @@ struct mab_ctx {
 	ReadRec *d_reads = nullptr; uint64_t reads_cap = 0;
 	uint8_t *d_ws = nullptr; uint64_t ws_cap = 0;
 	uint32_t *d_frames = nullptr; uint64_t frames_cap = 0;
+	uint32_t *d_order = nullptr; uint64_t order_cap = 0;	/* work order of k_extend: read indices by descending length */
 	uint32_t *d_recs = nullptr; uint64_t recs_cap = 0;		/* minimizer records of k_seed_scan: 16 B per base position of the read block */
 	uint8_t *d_arenas = nullptr; uint64_t arenas_cap = 0;
 	uint32_t *d_pool = nullptr; uint64_t pool_cap = 0;
@@ -178,7 +179,7 @@ extern "C" void mab_destroy(mab_ctx *ctx)
 {
 	if(ctx == nullptr) { return; }
 	RT_FREE(ctx->d_idx); RT_FREE(ctx->d_ntail); RT_FREE(ctx->d_ctr); RT_FREE(ctx->d_seq); RT_FREE(ctx->d_reads); RT_FREE(ctx->d_ws);
-	RT_FREE(ctx->d_frames); RT_FREE(ctx->d_recs); RT_FREE(ctx->d_arenas); RT_FREE(ctx->d_pool);
+	RT_FREE(ctx->d_frames); RT_FREE(ctx->d_order); RT_FREE(ctx->d_recs); RT_FREE(ctx->d_arenas); RT_FREE(ctx->d_pool);
 	RT_HOST_FREE(ctx->h_pool); delete[] ctx->res_words;
 	delete ctx;
 }
@@ -422,6 +423,13 @@ static int map_core(mab_ctx *ctx, const uint8_t *d_base, std::vector<ReadRec> &h
 	}
 	{ int rc = grow(&ctx->d_ws, &ctx->ws_cap, ws_total + 256); if(rc) { return rc; } }
 	{ int rc = grow(&ctx->d_frames, &ctx->frames_cap, 4ull * 8 * MAB_RS_FRAME * n_seq); if(rc) { return rc; } }
+	{	/* longest-processing-time-first work order for the persistent extend kernel (shortens its tail) */
+		int rc = grow(&ctx->d_order, &ctx->order_cap, 4ull * n_seq); if(rc) { return rc; }
+		std::vector<uint32_t> order(n_seq);
+		for(uint32_t i = 0; i < n_seq; i++) { order[i] = i; }
+		std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return hr[a].len > hr[b].len; });
+		CK(RT_MEMCPY_H2D_ASYNC(ctx->d_order, order.data(), 4ull * n_seq, ctx->stream));		/* pageable source: staged before the call returns */
+	}
 	uint32_t blk_cap = dp_blk_cap(maxlen);
 	ArenaLayout AL = arena_layout(blk_cap);
 	uint32_t ext_ctas = std::max<uint32_t>(1, std::min<uint32_t>(ctx->n_slots / MAB_WARPS_PER_CTA, (n_seq + MAB_WARPS_PER_CTA - 1) / MAB_WARPS_PER_CTA));
@@ -457,7 +465,7 @@ static int map_core(mab_ctx *ctx, const uint8_t *d_base, std::vector<ReadRec> &h
 			}
 			RT_MEMSET_ASYNC(&ctx->d_ctr->work_next, 0, sizeof(unsigned int), ctx->stream);
 			if(timed && round < 8) { RT_EVENT_RECORD(ctx->rev[3 * round + 1], ctx->stream); }
-			RT_LAUNCH(k_extend, ext_ctas, 32 * MAB_WARPS_PER_CTA, 1024 + 2048 * MAB_WARPS_PER_CTA, ctx->stream, P, d_base, (const uint8_t *)ctx->d_ntail, ctx->d_reads, n_seq, ctx->d_ws,
+			RT_LAUNCH(k_extend, ext_ctas, 32 * MAB_WARPS_PER_CTA, 1024 + 2048 * MAB_WARPS_PER_CTA, ctx->stream, P, d_base, (const uint8_t *)ctx->d_ntail, ctx->d_reads, (const uint32_t *)ctx->d_order, n_seq, ctx->d_ws,
 				ctx->d_arenas, AL.total, blk_cap, ctx->d_pool, pool_words, ctx->d_ctr, round, P.n_occ - 1);
 			S.n_launches += 2;
 			if(timed && round < 8) { RT_EVENT_RECORD(ctx->rev[3 * round + 2], ctx->stream); }

@@ -6,7 +6,8 @@
  *                   (u,v) seeds (mm_collect_seed / mm_expand, 3420-3493).  COUNT=true only sizes the workspaces.
  *   k_sortchain     one thread per read: rescue-round seeding (mm_seed, 3500-3541), the reference's exact radix sort,
  *                   array chaining (mm_chain, 3702-3721).
- *   k_extend        persistent warps, one read at a time: the mm_extend state machine (4118-4173) on lane 0, the GABA
+ *   k_extend        persistent warps, one read at a time (longest reads first: `order`, so that the reads still running when the
+ *                   work list is empty are the short ones): the mm_extend state machine (4118-4173) on lane 0, the GABA
  *                   fill / search / trace (mab_dp.cuh) on all 32 lanes.
  *   k_extend_pairs  stage-level test entry: one warp per explicit sequence pair.
  */
@@ -557,7 +558,7 @@ __device__ __forceinline__ SecDesc make_sec(const uint8_t *base, uint32_t len, u
 
 /* ---------------------------------------------------------------- k_extend */
 /* shared memory per CTA: 1 KB score LUT + per warp a 2 KB tile (traceback nibbles / sort scratch) */
-__global__ void __launch_bounds__(32 * MAB_WARPS_PER_CTA, MAB_EXT_CTAS_PER_SM) k_extend(DevParams P, const uint8_t *base, const uint8_t *ntail, ReadRec *reads, uint32_t n_reads, uint8_t *ws,
+__global__ void __launch_bounds__(32 * MAB_WARPS_PER_CTA, MAB_EXT_CTAS_PER_SM) k_extend(DevParams P, const uint8_t *base, const uint8_t *ntail, ReadRec *reads, const uint32_t *order, uint32_t n_reads, uint8_t *ws,
 	uint8_t *arenas, uint64_t arena_stride, uint32_t blk_cap, uint32_t *pool, uint64_t pool_cap, BatchCounters *ctr, uint32_t round, uint32_t last_round)
 {
 	MAB_DYN_SMEM(smem);
@@ -576,7 +577,7 @@ __global__ void __launch_bounds__(32 * MAB_WARPS_PER_CTA, MAB_EXT_CTAS_PER_SM) k
 	uint64_t n_fill = 0, n_trace = 0;
 	while(1) {
 		uint32_t rid = 0;
-		if(lane == 0) { rid = atomicAdd(&ctr->work_next, 1u); }
+		if(lane == 0) { rid = atomicAdd(&ctr->work_next, 1u); rid = rid < n_reads ? order[rid] : n_reads; }
 		rid = __shfl_sync(MAB_FULL, rid, 0);
 		if(rid >= n_reads) { break; }
 		ReadRec *r = &reads[rid];
