@@ -46,6 +46,8 @@ struct mab_ctx {
 	uint32_t *res_words = nullptr; uint64_t res_cap = 0;	/* flat results of the last batch (uninitialised storage, filled in parallel) */
 	std::vector<uint64_t> res_ofs;
 	uint32_t *h_pool = nullptr; uint64_t h_pool_cap = 0;	/* pinned host copy of the device result pool */
+	uint8_t *pin = nullptr; uint64_t pin_cap = 0;			/* pinned bounce buffer: [ReadRec x n][order u32 x n][BatchCounters x 2] (every async copy has a
+															 * pinned host side: a pageable one blocks inside the runtime and stalls the other contexts' submissions) */
 	std::vector<ReadRec> h_reads;
 	mab_stats_t stats;
 };
@@ -180,7 +182,7 @@ extern "C" void mab_destroy(mab_ctx *ctx)
 	if(ctx == nullptr) { return; }
 	RT_FREE(ctx->d_idx); RT_FREE(ctx->d_ntail); RT_FREE(ctx->d_ctr); RT_FREE(ctx->d_seq); RT_FREE(ctx->d_reads); RT_FREE(ctx->d_ws);
 	RT_FREE(ctx->d_frames); RT_FREE(ctx->d_order); RT_FREE(ctx->d_recs); RT_FREE(ctx->d_arenas); RT_FREE(ctx->d_pool);
-	RT_HOST_FREE(ctx->h_pool); delete[] ctx->res_words;
+	RT_HOST_FREE(ctx->h_pool); RT_HOST_FREE(ctx->pin); delete[] ctx->res_words;
 	delete ctx;
 }
 
@@ -378,7 +380,20 @@ static int map_core(mab_ctx *ctx, const uint8_t *d_base, std::vector<ReadRec> &h
 	uint32_t maxlen = 0; uint64_t tot_len = 0;
 	for(uint32_t i = 0; i < n_seq; i++) { maxlen = std::max(maxlen, hr[i].len); tot_len += hr[i].len; }
 	{ int rc = grow(&ctx->d_reads, &ctx->reads_cap, sizeof(ReadRec) * (uint64_t)n_seq); if(rc) { return rc; } }
-	CK(RT_MEMCPY_H2D_ASYNC(ctx->d_reads, hr.data(), sizeof(ReadRec) * (uint64_t)n_seq, ctx->stream));
+	const uint64_t rr_bytes = sizeof(ReadRec) * (uint64_t)n_seq;
+	{
+		uint64_t need = rr_bytes + 4ull * n_seq + 2 * sizeof(BatchCounters) + 256;
+		if(need > ctx->pin_cap) {
+			RT_HOST_FREE(ctx->pin); ctx->pin = nullptr; ctx->pin_cap = 0;
+			if(!RT_OK(RT_HOST_ALLOC(&ctx->pin, need + need / 4))) { g_err = std::string("pinned host allocation failed: ") + RT_ERRSTR(); return MAB_ENOMEM; }
+			ctx->pin_cap = need + need / 4;
+		}
+	}
+	ReadRec *pin_rr = (ReadRec *)ctx->pin;
+	uint32_t *pin_order = (uint32_t *)(ctx->pin + rr_bytes);
+	BatchCounters *pin_ctr = (BatchCounters *)(ctx->pin + ((rr_bytes + 4ull * n_seq + 127) & ~127ull));
+	memcpy(pin_rr, hr.data(), rr_bytes);
+	CK(RT_MEMCPY_H2D_ASYNC(ctx->d_reads, pin_rr, rr_bytes, ctx->stream));
 	S.h2d_bytes += sizeof(ReadRec) * (uint64_t)n_seq;
 	if(timed) { RT_EVENT_RECORD(ctx->ev[1], ctx->stream); }
 	/* count pass, workspace sizing */
@@ -390,8 +405,9 @@ static int map_core(mab_ctx *ctx, const uint8_t *d_base, std::vector<ReadRec> &h
 	}
 	RT_LAUNCH(k_seed_scan, seed_ctas, 32 * MAB_WARPS_PER_CTA, 2560 * MAB_WARPS_PER_CTA, ctx->stream, P, d_base, ctx->d_reads, n_seq, ctx->d_recs);
 	S.n_launches++;
-	CK(RT_MEMCPY_D2H_ASYNC(hr.data(), ctx->d_reads, sizeof(ReadRec) * (uint64_t)n_seq, ctx->stream));
+	CK(RT_MEMCPY_D2H_ASYNC(pin_rr, ctx->d_reads, rr_bytes, ctx->stream));
 	{ double tw = RT_WALL_MS(); CK(RT_STREAM_SYNC(ctx->stream)); S.ms_wall_wait += (float)(RT_WALL_MS() - tw); }
+	memcpy(hr.data(), pin_rr, rr_bytes);
 	double t_sizing = RT_WALL_MS();
 	S.d2h_bytes += sizeof(ReadRec) * (uint64_t)n_seq;
 	uint64_t ws_total = 0;
@@ -425,10 +441,9 @@ static int map_core(mab_ctx *ctx, const uint8_t *d_base, std::vector<ReadRec> &h
 	{ int rc = grow(&ctx->d_frames, &ctx->frames_cap, 4ull * 8 * MAB_RS_FRAME * n_seq); if(rc) { return rc; } }
 	{	/* longest-processing-time-first work order for the persistent extend kernel (shortens its tail) */
 		int rc = grow(&ctx->d_order, &ctx->order_cap, 4ull * n_seq); if(rc) { return rc; }
-		std::vector<uint32_t> order(n_seq);
-		for(uint32_t i = 0; i < n_seq; i++) { order[i] = i; }
-		std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return hr[a].len > hr[b].len; });
-		CK(RT_MEMCPY_H2D_ASYNC(ctx->d_order, order.data(), 4ull * n_seq, ctx->stream));		/* pageable source: staged before the call returns */
+		for(uint32_t i = 0; i < n_seq; i++) { pin_order[i] = i; }
+		std::stable_sort(pin_order, pin_order + n_seq, [&](uint32_t a, uint32_t b) { return hr[a].len > hr[b].len; });
+		CK(RT_MEMCPY_H2D_ASYNC(ctx->d_order, pin_order, 4ull * n_seq, ctx->stream));
 	}
 	uint32_t blk_cap = dp_blk_cap(maxlen);
 	ArenaLayout AL = arena_layout(blk_cap);
@@ -446,9 +461,10 @@ static int map_core(mab_ctx *ctx, const uint8_t *d_base, std::vector<ReadRec> &h
 	for(int attempt = 0; attempt < 3; attempt++) {
 		{ int rc = grow(&ctx->d_pool, &ctx->pool_cap, 4 * pool_need); if(rc) { return rc; } }
 		uint64_t pool_words = ctx->pool_cap / 4;
-		CK(RT_MEMCPY_H2D_ASYNC(ctx->d_reads, hr.data(), sizeof(ReadRec) * (uint64_t)n_seq, ctx->stream));
-		BatchCounters zero; memset(&zero, 0, sizeof(zero));
-		CK(RT_MEMCPY_H2D_ASYNC(ctx->d_ctr, &zero, sizeof(zero), ctx->stream));
+		memcpy(pin_rr, hr.data(), rr_bytes);
+		CK(RT_MEMCPY_H2D_ASYNC(ctx->d_reads, pin_rr, rr_bytes, ctx->stream));
+		memset(&pin_ctr[0], 0, sizeof(BatchCounters));
+		CK(RT_MEMCPY_H2D_ASYNC(ctx->d_ctr, &pin_ctr[0], sizeof(BatchCounters), ctx->stream));
 		if(timed) { RT_EVENT_RECORD(ctx->ev[2], ctx->stream); }
 		RT_LAUNCH(k_seed_expand, seed_ctas, 32 * MAB_WARPS_PER_CTA, 0, ctx->stream, P, ctx->d_reads, n_seq, ctx->d_ws, (const uint32_t *)ctx->d_recs);
 		S.n_launches++;
@@ -471,10 +487,11 @@ static int map_core(mab_ctx *ctx, const uint8_t *d_base, std::vector<ReadRec> &h
 			if(timed && round < 8) { RT_EVENT_RECORD(ctx->rev[3 * round + 2], ctx->stream); }
 		}
 		if(timed) { RT_EVENT_RECORD(ctx->ev[4], ctx->stream); }
-		BatchCounters hc;
-		CK(RT_MEMCPY_D2H_ASYNC(&hc, ctx->d_ctr, sizeof(hc), ctx->stream));
-		CK(RT_MEMCPY_D2H_ASYNC(hr.data(), ctx->d_reads, sizeof(ReadRec) * (uint64_t)n_seq, ctx->stream));
+		CK(RT_MEMCPY_D2H_ASYNC(&pin_ctr[1], ctx->d_ctr, sizeof(BatchCounters), ctx->stream));
+		CK(RT_MEMCPY_D2H_ASYNC(pin_rr, ctx->d_reads, rr_bytes, ctx->stream));
 		{ double tw = RT_WALL_MS(); CK(RT_STREAM_SYNC(ctx->stream)); S.ms_wall_wait += (float)(RT_WALL_MS() - tw); }
+		BatchCounters hc = pin_ctr[1];
+		memcpy(hr.data(), pin_rr, rr_bytes);
 		uint32_t err = 0;
 		for(uint32_t i = 0; i < n_seq; i++) { err |= hr[i].err; }
 		S.n_vectors += hc.n_vectors; S.n_fill_calls += hc.n_fill; S.n_trace += hc.n_trace;
