@@ -16,7 +16,7 @@ typedef cudaEvent_t RT_EVENT;
 static thread_local cudaError_t g_rt_last = cudaSuccess;
 static inline bool RT_OK(cudaError_t e) { g_rt_last = e; return e == cudaSuccess; }
 static inline const char *RT_ERRSTR() { return cudaGetErrorString(g_rt_last); }
-static inline cudaError_t RT_SET_DEVICE(int d)
+static inline cudaError_t RT_SET_DEVICE(int d)				/* mab_init: pick the device and insist on sm_100 */
 {
 	int n = 0;
 	cudaError_t e = cudaGetDeviceCount(&n);
@@ -24,12 +24,13 @@ static inline cudaError_t RT_SET_DEVICE(int d)
 	if(d < 0 || d >= n) { return cudaErrorInvalidDevice; }
 	e = cudaSetDevice(d);
 	if(e != cudaSuccess) { return e; }
-	cudaDeviceProp p;
-	e = cudaGetDeviceProperties(&p, d);
+	int major = 0;
+	e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d);
 	if(e != cudaSuccess) { return e; }
-	if(p.major < 10) { return cudaErrorInvalidDevice; }		/* sm_100a code only */
+	if(major < 10) { return cudaErrorInvalidDevice; }		/* sm_100a code only */
 	return cudaSuccess;
 }
+static inline cudaError_t RT_USE_DEVICE(int d) { return cudaSetDevice(d); }		/* per call: cheap, no property queries (they take driver locks) */
 static inline unsigned RT_SM_COUNT(int d) { int n = 0; cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return (unsigned)n; }
 /* persistent extend kernel: 4 CTAs x 4 warps per SM (multiple of the SM count) */
 static inline unsigned RT_EXTEND_SLOTS(unsigned n_sm) { return n_sm * 4 * MAB_EXT_CTAS_PER_SM; }

@@ -377,6 +377,7 @@ static int map_core(mab_ctx *ctx, const uint8_t *d_base, std::vector<ReadRec> &h
 	const DevParams &P = ctx->P;
 	mab_stats_t &S = ctx->stats;
 	uint32_t n_seq = (uint32_t)hr.size();
+	double t_sub = RT_WALL_MS();
 	uint32_t maxlen = 0; uint64_t tot_len = 0;
 	for(uint32_t i = 0; i < n_seq; i++) { maxlen = std::max(maxlen, hr[i].len); tot_len += hr[i].len; }
 	{ int rc = grow(&ctx->d_reads, &ctx->reads_cap, sizeof(ReadRec) * (uint64_t)n_seq); if(rc) { return rc; } }
@@ -406,6 +407,7 @@ static int map_core(mab_ctx *ctx, const uint8_t *d_base, std::vector<ReadRec> &h
 	RT_LAUNCH(k_seed_scan, seed_ctas, 32 * MAB_WARPS_PER_CTA, 2560 * MAB_WARPS_PER_CTA, ctx->stream, P, d_base, ctx->d_reads, n_seq, ctx->d_recs);
 	S.n_launches++;
 	CK(RT_MEMCPY_D2H_ASYNC(pin_rr, ctx->d_reads, rr_bytes, ctx->stream));
+	S.ms_wall_submit += (float)(RT_WALL_MS() - t_sub);
 	{ double tw = RT_WALL_MS(); CK(RT_STREAM_SYNC(ctx->stream)); S.ms_wall_wait += (float)(RT_WALL_MS() - tw); }
 	memcpy(hr.data(), pin_rr, rr_bytes);
 	double t_sizing = RT_WALL_MS();
@@ -459,6 +461,7 @@ static int map_core(mab_ctx *ctx, const uint8_t *d_base, std::vector<ReadRec> &h
 	uint64_t pool_need = tot_len / 4 + 64ull * n_seq + (1u << 16);				/* ~2 bits per base and alignment, x4 head room */
 	S.ms_wall_sizing += (float)(RT_WALL_MS() - t_sizing);
 	for(int attempt = 0; attempt < 3; attempt++) {
+		t_sub = RT_WALL_MS();
 		{ int rc = grow(&ctx->d_pool, &ctx->pool_cap, 4 * pool_need); if(rc) { return rc; } }
 		uint64_t pool_words = ctx->pool_cap / 4;
 		memcpy(pin_rr, hr.data(), rr_bytes);
@@ -489,6 +492,7 @@ static int map_core(mab_ctx *ctx, const uint8_t *d_base, std::vector<ReadRec> &h
 		if(timed) { RT_EVENT_RECORD(ctx->ev[4], ctx->stream); }
 		CK(RT_MEMCPY_D2H_ASYNC(&pin_ctr[1], ctx->d_ctr, sizeof(BatchCounters), ctx->stream));
 		CK(RT_MEMCPY_D2H_ASYNC(pin_rr, ctx->d_reads, rr_bytes, ctx->stream));
+		S.ms_wall_submit += (float)(RT_WALL_MS() - t_sub);
 		{ double tw = RT_WALL_MS(); CK(RT_STREAM_SYNC(ctx->stream)); S.ms_wall_wait += (float)(RT_WALL_MS() - tw); }
 		BatchCounters hc = pin_ctr[1];
 		memcpy(hr.data(), pin_rr, rr_bytes);
@@ -530,7 +534,7 @@ extern "C" int mab_map_batch(mab_ctx *ctx, const uint8_t *seq_block, uint64_t bl
 	const double t_call = RT_WALL_MS();
 	ctx->res_ofs.assign((size_t)n_seq + 1, 0);
 	if(n_seq == 0) { return MAB_OK; }
-	CK(RT_SET_DEVICE(ctx->device));
+	CK(RT_USE_DEVICE(ctx->device));
 	RT_EVENT_RECORD(ctx->ev[0], ctx->stream);
 	const uint8_t *d_base;
 	if(ctx->device_input) { d_base = seq_block; }
@@ -728,7 +732,7 @@ extern "C" int mab_extend_pairs(mab_ctx *ctx, const uint8_t *seq_block, uint64_t
 
 extern "C" int mab_fill_peak(mab_ctx *ctx, int masks, uint32_t n_blocks, double *vectors_per_s)
 {
-	CK(RT_SET_DEVICE(ctx->device));
+	CK(RT_USE_DEVICE(ctx->device));
 	uint32_t ctas = std::max<uint32_t>(1, ctx->n_slots / MAB_WARPS_PER_CTA), warps = ctas * MAB_WARPS_PER_CTA;
 	uint32_t *d_ring = nullptr, *d_sink = nullptr;
 	CK(RT_MALLOC(&d_ring, 4ull * 512 * 4 * warps)); CK(RT_MALLOC(&d_sink, 4ull * warps));

@@ -11,6 +11,7 @@ typedef int RT_EVENT;
 static inline bool RT_OK(int x) { return x == 0; }
 static inline const char *RT_ERRSTR() { return "emu"; }
 static inline int RT_SET_DEVICE(int) { return 0; }
+static inline int RT_USE_DEVICE(int) { return 0; }
 static inline unsigned RT_SM_COUNT(int) { return 2; }
 static inline unsigned RT_EXTEND_SLOTS(unsigned n_sm) { return n_sm * 4; }
 template <class T> static inline int RT_MALLOC(T **p, uint64_t n) { *p = (T *)aligned_alloc(256, (n + 255) / 256 * 256); memset(*p, 0xab, n); return *p ? 0 : 1; }
