@@ -13,7 +13,14 @@
 #include "mab_sam.h"
 #include "mab_index.h"
 #include <zlib.h>
+#include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -23,25 +30,45 @@
 static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 /* ---- .mai loader ---- */
+/* The container is a sequence of independently deflated frames (<= 1 MiB raw each): read them all, inflate them on all host
+ * cores (the reference does the same with its worker threads), concatenate. */
 static bool load_mai(const char *path, std::vector<uint8_t> &blob)
 {
 	FILE *fp = fopen(path, "rb");
 	if(!fp) { return false; }
-	std::vector<uint8_t> raw, cbuf, obuf(1 << 21);
+	std::vector<std::vector<uint8_t>> frames;
 	while(true) {
 		char magic[4]; uint32_t len;
 		if(fread(magic, 1, 4, fp) != 4 || memcmp(magic, "PG00", 4) != 0) { break; }
 		if(fread(&len, 4, 1, fp) != 1 || len == 0xffffffffu || len == 0) { break; }
-		cbuf.resize(len);
-		if(fread(cbuf.data(), 1, len, fp) != len) { fclose(fp); return false; }
-		z_stream zs; memset(&zs, 0, sizeof(zs));
-		zs.next_in = cbuf.data(); zs.avail_in = len; zs.next_out = obuf.data(); zs.avail_out = (uInt)obuf.size();
-		if(inflateInit2(&zs, 15) != Z_OK) { fclose(fp); return false; }
-		int rc = inflate(&zs, Z_FINISH); inflateEnd(&zs);
-		if(rc != Z_STREAM_END) { fclose(fp); return false; }
-		raw.insert(raw.end(), obuf.data(), obuf.data() + (obuf.size() - zs.avail_out));
+		frames.emplace_back(len);
+		if(fread(frames.back().data(), 1, len, fp) != len) { fclose(fp); return false; }
 	}
 	fclose(fp);
+	if(frames.empty()) { return false; }
+	std::vector<std::vector<uint8_t>> raws(frames.size());
+	std::atomic<size_t> next(0); std::atomic<bool> ok(true);
+	auto work = [&]() {
+		std::vector<uint8_t> obuf(1 << 21);
+		for(size_t i; (i = next.fetch_add(1)) < frames.size();) {
+			z_stream zs; memset(&zs, 0, sizeof(zs));
+			zs.next_in = frames[i].data(); zs.avail_in = (uInt)frames[i].size(); zs.next_out = obuf.data(); zs.avail_out = (uInt)obuf.size();
+			if(inflateInit2(&zs, 15) != Z_OK) { ok = false; return; }
+			int rc = inflate(&zs, Z_FINISH); inflateEnd(&zs);
+			if(rc != Z_STREAM_END) { ok = false; return; }
+			raws[i].assign(obuf.data(), obuf.data() + (obuf.size() - zs.avail_out));
+		}
+	};
+	unsigned nth = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+	std::vector<std::thread> th;
+	for(unsigned t = 1; t < nth; t++) { th.emplace_back(work); }
+	work();
+	for(auto &x : th) { x.join(); }
+	if(!ok) { return false; }
+	std::vector<uint8_t> raw;
+	size_t tot = 0; for(auto &r : raws) { tot += r.size(); }
+	raw.reserve(tot);
+	for(auto &r : raws) { raw.insert(raw.end(), r.begin(), r.end()); }
 	if(raw.size() < 12) { return false; }
 	uint32_t magic; uint64_t size; memcpy(&magic, raw.data(), 4); memcpy(&size, raw.data() + 4, 8);
 	if(magic != 0x0849414du || raw.size() < 12 + size) { return false; }
@@ -50,42 +77,64 @@ static bool load_mai(const char *path, std::vector<uint8_t> &blob)
 }
 
 /* ---- FASTA / FASTQ reader (gz transparent) ---- */
+/* Chunked: 4 MiB reads, memchr for the line ends, whole lines encoded through a 256-entry table (the low-nibble table encaf,
+ * minialign.c:214-232) straight into the record. */
 struct Rec { std::string name, qual; std::vector<uint8_t> seq; };
 struct SeqReader {
-	gzFile fp; std::string line; bool have = false, eof = false;
-	uint8_t enc[16];
-	explicit SeqReader(const char *path) {
+	gzFile fp; std::vector<char> buf; size_t pos = 0, end = 0; bool eof = false;
+	std::string line; bool have = false;
+	uint8_t enc[256];
+	explicit SeqReader(const char *path) : buf(4 << 20) {
 		fp = strcmp(path, "-") == 0 ? gzdopen(0, "rb") : gzopen(path, "rb");
-		memset(enc, 0, sizeof(enc));
-		enc['A' & 15] = 0; enc['C' & 15] = 1; enc['G' & 15] = 2; enc['T' & 15] = 3; enc['U' & 15] = 3; enc['N' & 15] = 4;	/* encaf: low nibble table */
+		if(fp) { gzbuffer(fp, 1 << 20); }
+		uint8_t e16[16]; memset(e16, 0, sizeof(e16));
+		e16['A' & 15] = 0; e16['C' & 15] = 1; e16['G' & 15] = 2; e16['T' & 15] = 3; e16['U' & 15] = 3; e16['N' & 15] = 4;
+		for(int i = 0; i < 256; i++) { enc[i] = e16[i & 15]; }
 	}
 	~SeqReader() { if(fp) { gzclose(fp); } }
-	bool getline() {
-		if(have) { have = false; return true; }
-		line.clear();
-		char buf[65536];
-		while(true) {
-			if(!gzgets(fp, buf, sizeof(buf))) { eof = true; return !line.empty(); }
-			size_t l = strlen(buf); line.append(buf, l);
-			if(l && buf[l - 1] == '\n') { break; }
-		}
-		while(!line.empty() && (line.back() == '\n' || line.back() == '\r')) { line.pop_back(); }
+	bool fill() {
+		if(eof) { return false; }
+		if(pos < end) { memmove(buf.data(), buf.data() + pos, end - pos); }
+		end -= pos; pos = 0;
+		if(end == buf.size()) { buf.resize(buf.size() * 2); }
+		int n = gzread(fp, buf.data() + end, (unsigned)(buf.size() - end));
+		if(n <= 0) { eof = true; return false; }
+		end += (size_t)n;
 		return true;
 	}
+	/* next line without its terminator as [*b, *b + *n); false at end of input */
+	bool getline(const char **b, size_t *n) {
+		if(have) { have = false; *b = line.data(); *n = line.size(); return true; }
+		while(true) {
+			const char *nl = pos < end ? (const char *)memchr(buf.data() + pos, '\n', end - pos) : nullptr;
+			if(nl) {
+				*b = buf.data() + pos; *n = (size_t)(nl - *b); pos = (size_t)(nl - buf.data()) + 1;
+				if(*n && (*b)[*n - 1] == '\r') { (*n)--; }
+				return true;
+			}
+			if(!fill()) {
+				if(pos < end) { *b = buf.data() + pos; *n = end - pos; pos = end; return true; }
+				return false;
+			}
+		}
+	}
+	void unget(const char *b, size_t n) { line.assign(b, n); have = true; }
 	bool next(Rec &r) {
 		r.name.clear(); r.qual.clear(); r.seq.clear();
-		while(getline()) {
-			if(line.empty()) { continue; }
-			if(line[0] != '>' && line[0] != '@') { continue; }
-			bool fq = line[0] == '@';
-			size_t e = 1; while(e < line.size() && line[e] != ' ' && line[e] != '\t') { e++; }
-			r.name = line.substr(1, e - 1);
-			while(getline()) {
-				if(!fq && !line.empty() && line[0] == '>') { have = true; break; }
-				if(fq && !line.empty() && line[0] == '+') { break; }
-				for(char c : line) { r.seq.push_back(enc[(uint8_t)c & 15]); }
+		const char *b; size_t n;
+		while(getline(&b, &n)) {
+			if(n == 0 || (b[0] != '>' && b[0] != '@')) { continue; }
+			bool fq = b[0] == '@';
+			size_t e = 1; while(e < n && b[e] != ' ' && b[e] != '\t') { e++; }
+			r.name.assign(b + 1, e - 1);
+			r.seq.reserve(32768);
+			while(getline(&b, &n)) {
+				if(!fq && n && b[0] == '>') { unget(b, n); break; }
+				if(fq && n && b[0] == '+') { break; }
+				size_t o = r.seq.size(); r.seq.resize(o + n);
+				for(size_t i = 0; i < n; i++) { r.seq[o + i] = enc[(uint8_t)b[i]]; }
 			}
-			if(fq) { while(r.qual.size() < r.seq.size() && getline()) { r.qual += line; } }
+			if(fq) { while(r.qual.size() < r.seq.size() && getline(&b, &n)) { r.qual.append(b, n); } }
 			return true;
 		}
 		return false;
@@ -199,41 +248,106 @@ int main(int argc, char **argv)
 		fprintf(stderr, "[M::main] Command: %s\n[M::main] Real time: %.3f sec\n", cmdline.c_str(), now() - t0);
 		return 0;
 	}
+	/* Pipeline: a reader thread parses and packs the next batches (reads already sit 1 byte/base with 64 B margins, the layout of
+	 * bseq_t, minialign.c:2109-2146) while this thread maps the current one; the SAM text of a batch is formatted by all host
+	 * cores, one slice of reads each, and written in input order.  One context, batches in input order: the reference's
+	 * per-thread state (rlen) carries over exactly as with -t1. */
+	struct Batch { std::vector<Rec> recs; std::vector<uint8_t> block; std::vector<uint64_t> ofs; std::vector<uint32_t> len; uint64_t bases = 0; size_t file = 0; bool last_of_file = false; bool open_failed = false; };
+	std::mutex mu; std::condition_variable cv;
+	std::deque<std::unique_ptr<Batch>> queue; bool done = false, stop = false;
+	std::thread reader([&]() {
+		for(size_t qi = 1; qi < o.pos.size(); qi++) {
+			SeqReader rd(o.pos[qi].c_str());
+			if(!rd.fp) { auto bt = std::make_unique<Batch>(); bt->file = qi; bt->open_failed = true; std::unique_lock<std::mutex> lk(mu); queue.push_back(std::move(bt)); cv.notify_all(); break; }
+			bool more = true;
+			while(more) {
+				auto bt = std::make_unique<Batch>(); bt->file = qi;
+				Rec r;
+				while(bt->recs.size() < o.batch_reads && bt->bases < o.batch_bases && (more = rd.next(r))) { if(r.seq.empty()) { continue; } bt->bases += r.seq.size(); bt->recs.push_back(std::move(r)); }
+				bt->last_of_file = !more;
+				if(!bt->recs.empty()) {
+					bt->block.assign(64 + bt->bases + 64ull * bt->recs.size() + 64, 0);
+					bt->ofs.resize(bt->recs.size()); bt->len.resize(bt->recs.size());
+					uint64_t p = 64;
+					for(size_t i = 0; i < bt->recs.size(); i++) {
+						bt->ofs[i] = p; bt->len[i] = (uint32_t)bt->recs[i].seq.size();
+						memcpy(bt->block.data() + p, bt->recs[i].seq.data(), bt->len[i]); p += bt->len[i] + 64;
+						std::vector<uint8_t>().swap(bt->recs[i].seq);
+					}
+				}
+				std::unique_lock<std::mutex> lk(mu);
+				cv.wait(lk, [&]() { return queue.size() < 2 || stop; });
+				if(stop) { return; }
+				queue.push_back(std::move(bt)); cv.notify_all();
+			}
+		}
+		std::unique_lock<std::mutex> lk(mu); done = true; cv.notify_all();
+	});
+	double t_idx = now() - t0;
 	mab_ctx *ctx = mab_init(blob.data(), blob.size(), &o.p, o.device);
-	if(!ctx) { fprintf(stderr, "[E::main_align] failed to instanciate alignment context: %s\n", mab_last_error()); return 1; }
+	if(!ctx) {
+		fprintf(stderr, "[E::main_align] failed to instanciate alignment context: %s\n", mab_last_error());
+		{ std::unique_lock<std::mutex> lk(mu); stop = true; cv.notify_all(); }
+		reader.join();
+		return 1;
+	}
 	uint32_t n_ref = mab_n_ref(ctx);
 	std::vector<MabSamRef> refs(n_ref);
 	for(uint32_t i = 0; i < n_ref; i++) { mab_ref_info(ctx, i, &refs[i].name, &refs[i].l_name, &refs[i].l_seq, &refs[i].seq); }
-	fprintf(stderr, "[M::main_align::%.3f] loaded/built index for %u target sequence(s).\n", now() - t0, n_ref);
+	fprintf(stderr, "[M::main_align::%.3f] loaded/built index for %u target sequence(s) (index file %.3f s, device context %.3f s).\n", now() - t0, n_ref, t_idx, now() - t0 - t_idx);
 	double tmap = now(); uint64_t tot_bases = 0, tot_reads = 0;
 	std::string out; out.reserve(64 << 20);
 	mab_sam_header(out, refs.data(), n_ref, "0.6.0-devel", cmdline.c_str());
-	for(size_t qi = 1; qi < o.pos.size(); qi++) {
-		SeqReader rd(o.pos[qi].c_str());
-		if(!rd.fp) { fprintf(stderr, "[E::main_align] failed to open sequence file `%s'. Please check file path and format.\n", o.pos[qi].c_str()); return 1; }
-		bool more = true;
-		while(more) {
-			std::vector<Rec> recs; uint64_t bases = 0;
-			Rec r;
-			while(recs.size() < o.batch_reads && bases < o.batch_bases && (more = rd.next(r))) { if(r.seq.empty()) { continue; } bases += r.seq.size(); recs.push_back(std::move(r)); }
-			if(recs.empty()) { break; }
-			std::vector<uint8_t> block(64 + bases + 64ull * recs.size() + 64, 0);
-			std::vector<uint64_t> ofs(recs.size()); std::vector<uint32_t> len(recs.size());
-			uint64_t p = 64;
-			for(size_t i = 0; i < recs.size(); i++) { ofs[i] = p; len[i] = (uint32_t)recs[i].seq.size(); memcpy(block.data() + p, recs[i].seq.data(), len[i]); p += len[i] + 64; }
-			int rc = mab_map_batch(ctx, block.data(), block.size(), ofs.data(), len.data(), (uint32_t)recs.size());
-			if(rc != MAB_OK) { fprintf(stderr, "[E::main_align] failed to map sequence file `%s': %s\n", o.pos[qi].c_str(), mab_last_error()); return 1; }
-			for(size_t i = 0; i < recs.size(); i++) {
-				const uint32_t *w = nullptr; uint64_t n = mab_result(ctx, (uint32_t)i, &w);
-				MabSamRead q = { recs[i].name.c_str(), (uint32_t)recs[i].name.size(), block.data() + ofs[i], len[i], recs[i].qual.empty() ? nullptr : recs[i].qual.c_str() };
-				mab_sam_record(out, refs.data(), &q, w, n, o.tags);
-				if(out.size() > (48u << 20)) { fwrite(out.data(), 1, out.size(), stdout); out.clear(); }
-			}
-			mab_release_batch(ctx);
-			tot_bases += bases; tot_reads += recs.size();
+	unsigned nfmt = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+	std::vector<std::string> parts(nfmt);										/* per-slice SAM text, reused from batch to batch */
+	int rc_main = 0;
+	double t_wait = 0, t_map = 0, t_fmt = 0, t_wr = 0;
+	while(true) {
+		std::unique_ptr<Batch> bt;
+		double tq = now();
+		{
+			std::unique_lock<std::mutex> lk(mu);
+			cv.wait(lk, [&]() { return !queue.empty() || done; });
+			if(queue.empty()) { break; }
+			bt = std::move(queue.front()); queue.pop_front(); cv.notify_all();
 		}
-		fprintf(stderr, "[M::main_align::%.3f] finished mapping `%s' onto `%s'.\n", now() - t0, o.pos[qi].c_str(), o.pos[0].c_str());
+		t_wait += now() - tq;
+		if(rc_main) { continue; }												/* drain the queue after an error */
+		if(bt->open_failed) { fprintf(stderr, "[E::main_align] failed to open sequence file `%s'. Please check file path and format.\n", o.pos[bt->file].c_str()); rc_main = 1; continue; }
+		if(!bt->recs.empty()) {
+			double tm0 = now();
+			int rc = mab_map_batch(ctx, bt->block.data(), bt->block.size(), bt->ofs.data(), bt->len.data(), (uint32_t)bt->recs.size());
+			t_map += now() - tm0; tm0 = now();
+			if(rc != MAB_OK) { fprintf(stderr, "[E::main_align] failed to map sequence file `%s': %s\n", o.pos[bt->file].c_str(), mab_last_error()); rc_main = 1; continue; }
+			size_t n = bt->recs.size(), nsl = std::min<size_t>(nfmt, (n + 63) / 64);
+			for(auto &pz : parts) { pz.clear(); }
+			auto fmt = [&](size_t t) {
+				std::string &dst = parts[t];
+				size_t lo = n * t / nsl, hi = n * (t + 1) / nsl, est = 0;
+				for(size_t i = lo; i < hi; i++) { est += bt->len[i] + bt->len[i] / 3 + 512; }
+				if(dst.capacity() < est) { dst.reserve(est + est / 8); }
+				for(size_t i = lo; i < hi; i++) {
+					const uint32_t *w = nullptr; uint64_t nw = mab_result(ctx, (uint32_t)i, &w);
+					MabSamRead q = { bt->recs[i].name.c_str(), (uint32_t)bt->recs[i].name.size(), bt->block.data() + bt->ofs[i], bt->len[i], bt->recs[i].qual.empty() ? nullptr : bt->recs[i].qual.c_str() };
+					mab_sam_record(dst, refs.data(), &q, w, nw, o.tags);
+				}
+			};
+			std::vector<std::thread> th;
+			for(size_t t = 1; t < nsl; t++) { th.emplace_back(fmt, t); }
+			fmt(0);
+			for(auto &x : th) { x.join(); }
+			mab_release_batch(ctx);
+			t_fmt += now() - tm0; tm0 = now();
+			if(!out.empty()) { fwrite(out.data(), 1, out.size(), stdout); out.clear(); }
+			for(size_t t = 0; t < nsl; t++) { fwrite(parts[t].data(), 1, parts[t].size(), stdout); }
+			t_wr += now() - tm0;
+			tot_bases += bt->bases; tot_reads += n;
+		}
+		if(bt->last_of_file) { fprintf(stderr, "[M::main_align::%.3f] finished mapping `%s' onto `%s'.\n", now() - t0, o.pos[bt->file].c_str(), o.pos[0].c_str()); }
 	}
+	reader.join();
+	if(rc_main) { mab_destroy(ctx); return rc_main; }
+	fprintf(stderr, "[M::main_align] host pipeline: waited for the reader %.3f s, mapping %.3f s, SAM formatting %.3f s, writing %.3f s\n", t_wait, t_map, t_fmt, t_wr);
 	fwrite(out.data(), 1, out.size(), stdout);
 	double tm = now() - tmap;
 	fprintf(stderr, "[M::main] mapped %llu reads / %.1f Mbases in %.3f sec (%.1f Mbases/s)\n", (unsigned long long)tot_reads, tot_bases / 1e6, tm, tot_bases / 1e6 / tm);

@@ -86,8 +86,13 @@ void put_core(std::string &o, const MabSamRef *r, const MabSamRead *q, const uin
 	put_cigar_rv(o, pb, ppos, (uint64_t)alen + blen);
 	if(tl) { put_num(o, tl); o.push_back((flag & 0x900) ? 'H' : 'S'); }
 	o.append("\t*\t0\t0\t");
-	if(bid & 1) { for(uint32_t i = qs; i < qe; i++) { o.push_back(DEC_F[q->seq[i] & 15]); } }
-	else { const uint8_t *b = q->seq + (q->l_seq - qe); for(uint32_t i = qe - qs; i > 0; i--) { o.push_back(DEC_R[b[i - 1] & 15]); } }
+	{	/* sequence, decoded in bulk (forward: decaf, reverse strand: reversed + complemented, decar) */
+		size_t o0 = o.size(), n = qe - qs;
+		o.resize(o0 + n);
+		char *d = &o[o0];
+		if(bid & 1) { const uint8_t *b = q->seq + qs; for(size_t i = 0; i < n; i++) { d[i] = DEC_F[b[i] & 15]; } }
+		else { const uint8_t *b = q->seq + (q->l_seq - qe); for(size_t i = 0; i < n; i++) { d[i] = DEC_R[b[n - 1 - i] & 15]; } }
+	}
 	o.push_back('\t');
 	if(q->qual && q->qual[0] != '\0') {
 		if(bid & 1) { o.append(q->qual + qs, qe - qs); }
@@ -148,7 +153,7 @@ extern "C" void mab_sam_record(std::string &o, const MabSamRef *refs, const MabS
 {
 	if(n_words == 0) {										/* mm_print_sam_unmapped (5126-5141) */
 		o.append(q->name, q->l_name); o.append("\t4\t*\t0\t0\t*\t*\t0\t0\t");
-		for(uint32_t i = 0; i < q->l_seq; i++) { o.push_back(DEC_F[q->seq[i] & 15]); }
+		{ size_t o0 = o.size(); o.resize(o0 + q->l_seq); char *d = &o[o0]; for(uint32_t i = 0; i < q->l_seq; i++) { d[i] = DEC_F[q->seq[i] & 15]; } }
 		o.push_back('\t');
 		if(q->qual && q->qual[0] != '\0') { o.append(q->qual, q->l_seq); } else { o.push_back('*'); }
 		o.push_back('\n');
