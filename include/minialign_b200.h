@@ -76,6 +76,14 @@ int mab_map_batch(mab_ctx *ctx, const uint8_t *seq_block, uint64_t block_size,
 uint64_t mab_result(const mab_ctx *ctx, uint32_t i, const uint32_t **words);
 void mab_release_batch(mab_ctx *ctx);
 
+/* Detach the results of the last batch from the context: the returned object owns them (like the batch's lmm arena in the
+ * reference, freed by the drain, minialign.c:4615-4623), stays valid across further mab_map_batch calls and may be read from
+ * another thread, so that printing batch i overlaps mapping batch i + 1.  mab_results_get has the semantics of mab_result. */
+typedef struct mab_results mab_results;
+mab_results *mab_detach_batch(mab_ctx *ctx);
+uint64_t mab_results_get(const mab_results *r, uint32_t i, const uint32_t **words);
+void mab_results_free(mab_results *r);
+
 /* device-side statistics of the last batch (for bench.py / roofline): kernel milliseconds measured with CUDA events
  * on the context's stream, DP vectors filled, bytes moved each way */
 typedef struct {

@@ -72,6 +72,11 @@ def load_library(lib_path: str | None = None):
     L.mab_result.restype = C.c_uint64
     L.mab_result.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(u32p)]
     L.mab_release_batch.argtypes = [C.c_void_p]
+    L.mab_detach_batch.restype = C.c_void_p
+    L.mab_detach_batch.argtypes = [C.c_void_p]
+    L.mab_results_get.restype = C.c_uint64
+    L.mab_results_get.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(u32p)]
+    L.mab_results_free.argtypes = [C.c_void_p]
     L.mab_last_stats.argtypes = [C.c_void_p, C.POINTER(MabStats)]
     L.mab_set_device_input.argtypes = [C.c_void_p, C.c_int]
     L.mab_sketch.restype = C.c_uint64

@@ -299,9 +299,48 @@ int main(int argc, char **argv)
 	std::string out; out.reserve(64 << 20);
 	mab_sam_header(out, refs.data(), n_ref, "0.6.0-devel", cmdline.c_str());
 	unsigned nfmt = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
-	std::vector<std::string> parts(nfmt);										/* per-slice SAM text, reused from batch to batch */
+	/* writer stage: takes (batch, detached results) in input order, formats the SAM text on all cores, writes it */
+	struct Done { std::unique_ptr<Batch> bt; mab_results *res; };
+	std::mutex wmu; std::condition_variable wcv; std::deque<Done> wq; bool wdone = false;
+	double t_fmt = 0, t_wr = 0;
+	std::thread writer([&]() {
+		std::vector<std::string> parts(nfmt);									/* per-slice SAM text, reused from batch to batch */
+		if(!out.empty()) { fwrite(out.data(), 1, out.size(), stdout); out.clear(); }		/* the header */
+		while(true) {
+			Done d;
+			{
+				std::unique_lock<std::mutex> lk(wmu);
+				wcv.wait(lk, [&]() { return !wq.empty() || wdone; });
+				if(wq.empty()) { break; }
+				d = std::move(wq.front()); wq.pop_front(); wcv.notify_all();
+			}
+			Batch *bt = d.bt.get();
+			double tm0 = now();
+			size_t n = bt->recs.size(), nsl = std::min<size_t>(nfmt, (n + 63) / 64);
+			for(auto &pz : parts) { pz.clear(); }
+			auto fmt = [&](size_t t) {
+				std::string &dst = parts[t];
+				size_t lo = n * t / nsl, hi = n * (t + 1) / nsl, est = 0;
+				for(size_t i = lo; i < hi; i++) { est += bt->len[i] + bt->len[i] / 3 + 512; }
+				if(dst.capacity() < est) { dst.reserve(est + est / 8); }
+				for(size_t i = lo; i < hi; i++) {
+					const uint32_t *w = nullptr; uint64_t nw = mab_results_get(d.res, (uint32_t)i, &w);
+					MabSamRead q = { bt->recs[i].name.c_str(), (uint32_t)bt->recs[i].name.size(), bt->block.data() + bt->ofs[i], bt->len[i], bt->recs[i].qual.empty() ? nullptr : bt->recs[i].qual.c_str() };
+					mab_sam_record(dst, refs.data(), &q, w, nw, o.tags);
+				}
+			};
+			std::vector<std::thread> th;
+			for(size_t t = 1; t < nsl; t++) { th.emplace_back(fmt, t); }
+			if(nsl) { fmt(0); }
+			for(auto &x : th) { x.join(); }
+			mab_results_free(d.res);
+			t_fmt += now() - tm0; tm0 = now();
+			for(size_t t = 0; t < nsl; t++) { fwrite(parts[t].data(), 1, parts[t].size(), stdout); }
+			t_wr += now() - tm0;
+		}
+	});
 	int rc_main = 0;
-	double t_wait = 0, t_map = 0, t_fmt = 0, t_wr = 0;
+	double t_wait = 0, t_map = 0, t_wwait = 0;
 	while(true) {
 		std::unique_ptr<Batch> bt;
 		double tq = now();
@@ -314,40 +353,27 @@ int main(int argc, char **argv)
 		t_wait += now() - tq;
 		if(rc_main) { continue; }												/* drain the queue after an error */
 		if(bt->open_failed) { fprintf(stderr, "[E::main_align] failed to open sequence file `%s'. Please check file path and format.\n", o.pos[bt->file].c_str()); rc_main = 1; continue; }
+		bool last = bt->last_of_file; size_t file = bt->file;
 		if(!bt->recs.empty()) {
 			double tm0 = now();
 			int rc = mab_map_batch(ctx, bt->block.data(), bt->block.size(), bt->ofs.data(), bt->len.data(), (uint32_t)bt->recs.size());
-			t_map += now() - tm0; tm0 = now();
+			t_map += now() - tm0;
 			if(rc != MAB_OK) { fprintf(stderr, "[E::main_align] failed to map sequence file `%s': %s\n", o.pos[bt->file].c_str(), mab_last_error()); rc_main = 1; continue; }
-			size_t n = bt->recs.size(), nsl = std::min<size_t>(nfmt, (n + 63) / 64);
-			for(auto &pz : parts) { pz.clear(); }
-			auto fmt = [&](size_t t) {
-				std::string &dst = parts[t];
-				size_t lo = n * t / nsl, hi = n * (t + 1) / nsl, est = 0;
-				for(size_t i = lo; i < hi; i++) { est += bt->len[i] + bt->len[i] / 3 + 512; }
-				if(dst.capacity() < est) { dst.reserve(est + est / 8); }
-				for(size_t i = lo; i < hi; i++) {
-					const uint32_t *w = nullptr; uint64_t nw = mab_result(ctx, (uint32_t)i, &w);
-					MabSamRead q = { bt->recs[i].name.c_str(), (uint32_t)bt->recs[i].name.size(), bt->block.data() + bt->ofs[i], bt->len[i], bt->recs[i].qual.empty() ? nullptr : bt->recs[i].qual.c_str() };
-					mab_sam_record(dst, refs.data(), &q, w, nw, o.tags);
-				}
-			};
-			std::vector<std::thread> th;
-			for(size_t t = 1; t < nsl; t++) { th.emplace_back(fmt, t); }
-			fmt(0);
-			for(auto &x : th) { x.join(); }
-			mab_release_batch(ctx);
-			t_fmt += now() - tm0; tm0 = now();
-			if(!out.empty()) { fwrite(out.data(), 1, out.size(), stdout); out.clear(); }
-			for(size_t t = 0; t < nsl; t++) { fwrite(parts[t].data(), 1, parts[t].size(), stdout); }
-			t_wr += now() - tm0;
-			tot_bases += bt->bases; tot_reads += n;
+			tot_bases += bt->bases; tot_reads += bt->recs.size();
+			Done d; d.res = mab_detach_batch(ctx); d.bt = std::move(bt);
+			tm0 = now();
+			std::unique_lock<std::mutex> lk(wmu);
+			wcv.wait(lk, [&]() { return wq.size() < 2; });
+			wq.push_back(std::move(d)); wcv.notify_all();
+			t_wwait += now() - tm0;
 		}
-		if(bt->last_of_file) { fprintf(stderr, "[M::main_align::%.3f] finished mapping `%s' onto `%s'.\n", now() - t0, o.pos[bt->file].c_str(), o.pos[0].c_str()); }
+		if(last) { fprintf(stderr, "[M::main_align::%.3f] finished mapping `%s' onto `%s'.\n", now() - t0, o.pos[file].c_str(), o.pos[0].c_str()); }
 	}
+	{ std::unique_lock<std::mutex> lk(wmu); wdone = true; wcv.notify_all(); }
+	writer.join();
 	reader.join();
 	if(rc_main) { mab_destroy(ctx); return rc_main; }
-	fprintf(stderr, "[M::main_align] host pipeline: waited for the reader %.3f s, mapping %.3f s, SAM formatting %.3f s, writing %.3f s\n", t_wait, t_map, t_fmt, t_wr);
+	fprintf(stderr, "[M::main_align] host pipeline: mapper waited for the reader %.3f s and for the writer %.3f s, mapping %.3f s; writer: SAM formatting %.3f s, writing %.3f s\n", t_wait, t_wwait, t_map, t_fmt, t_wr);
 	fwrite(out.data(), 1, out.size(), stdout);
 	double tm = now() - tmap;
 	fprintf(stderr, "[M::main] mapped %llu reads / %.1f Mbases in %.3f sec (%.1f Mbases/s)\n", (unsigned long long)tot_reads, tot_bases / 1e6, tm, tot_bases / 1e6 / tm);

@@ -630,6 +630,23 @@ extern "C" uint64_t mab_result(const mab_ctx *ctx, uint32_t i, const uint32_t **
 }
 extern "C" void mab_release_batch(mab_ctx *ctx) { ctx->res_ofs.clear(); }
 
+struct mab_results { uint32_t *words; std::vector<uint64_t> ofs; };
+extern "C" mab_results *mab_detach_batch(mab_ctx *ctx)
+{
+	mab_results *r = new mab_results();
+	r->words = ctx->res_words; r->ofs.swap(ctx->res_ofs);
+	ctx->res_words = nullptr; ctx->res_cap = 0; ctx->res_ofs.clear();
+	return r;
+}
+extern "C" uint64_t mab_results_get(const mab_results *r, uint32_t i, const uint32_t **words)
+{
+	if((size_t)i + 1 >= r->ofs.size()) { return 0; }
+	uint64_t n = r->ofs[i + 1] - r->ofs[i];
+	if(words) { *words = n ? r->words + r->ofs[i] : nullptr; }
+	return n;
+}
+extern "C" void mab_results_free(mab_results *r) { if(r) { delete[] r->words; delete r; } }
+
 /* ---------------------------------------------------------------- stage-level entry points */
 extern "C" uint64_t mab_sketch(mab_ctx *ctx, const uint8_t *seq, uint32_t len, uint64_t *out, uint64_t cap)
 {
