@@ -8,8 +8,9 @@
  *                               (+ gaba_init / gaba_dp_init,                gaba_wrap.h:245-295, gaba.c:3848-3928)
  *   mab_map_batch               pt_worker_t mm_align_worker: for each read  minialign.c:4589-4601
  *                               of a bseq_t batch call mm_align_seq          minialign.c:4427-4474
- *   mab_result_* / release      mm_reg_t / mm_aln_t / gaba_alignment_t views minialign.c:3260-3267, gaba.h:193-219
- *                               that mm_align_drain_intl hands the printer   minialign.c:4607-4626
+ *   mab_result / release,       mm_reg_t / mm_aln_t / gaba_alignment_t views minialign.c:3260-3267, gaba.h:193-219
+ *   mab_detach_batch /          that mm_align_drain_intl hands the printer   minialign.c:4607-4626
+ *   mab_results_get / _free     (detached = owned by the caller like the batch's lmm arena, 4615-4623)
  *   mab_sketch                  mm_sketch                                   minialign.c:2410-2435
  *   mab_seed_chain              mm_seed + mm_chain                          minialign.c:3500-3541, 3702-3721
  *   mab_extend_pair             the body of the mm_extend loop:             minialign.c:4134-4154
