@@ -43,6 +43,16 @@ PACBIO = dict(k=15, w=10, b=14, n_occ=3, occ=[0, 0, 0], wlen=7000, glen=7000, mi
 ONT = dict(PACBIO, gi=6, ge=2, gfa=4, gfb=4, score_matrix=[2 if i % 5 == 0 else -6 for i in range(16)])
 
 
+def custom(a, b, gi, ge, gfa, gfb, xdrop):
+    """A non-preset scoring scheme (-a -b -p -q -r -Y, minialign.c:5950-6000) and the command line that selects it."""
+    prm = dict(PACBIO, gi=gi, ge=ge, gfa=gfa, gfb=gfb, xdrop=xdrop, score_matrix=[a if i % 5 == 0 else -b for i in range(16)])
+    return prm, ("-xpacbio", f"-a{a}", f"-b{b}", f"-p{gi}", f"-q{ge}", f"-r{gfa},{gfb}", f"-Y{xdrop}")
+
+
+CUSTOM = [custom(1, 2, 2, 1, 2, 2, 30), custom(3, 5, 5, 3, 4, 5, 70), custom(4, 6, 6, 2, 4, 4, 90), custom(1, 1, 1, 1, 2, 2, 20)]
+API_KEYS = ("wlen", "glen", "min_score", "min_ratio", "gi", "ge", "gfa", "gfb", "xdrop", "score_matrix")
+
+
 def _u8(a):
     return a.ctypes.data_as(C.POINTER(C.c_uint8))
 

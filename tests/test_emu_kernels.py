@@ -48,6 +48,26 @@ def test_emu_extend_pairs(gold, key, preset):
     m.close()
 
 
+@pytest.mark.parametrize("ci", [0, 1])
+def test_emu_extend_pairs_custom_scoring(gold, ci):
+    """Non-preset scoring schemes (the oracle is pinned to the reference for the same schemes in test_oracle_vs_ref.py)."""
+    from minialign_b200 import synth
+    prm = ora.CUSTOM[ci][0]
+    m = api.Mapper(gold["blob"], {k: prm[k] for k in ora.API_KEYS}, lib_path=build_emu())
+    o = ora.Oracle(prm)
+    rng = np.random.default_rng(7 + ci)
+    pairs = []
+    while len(pairs) < 40:
+        a = rng.integers(0, 4, size=int(rng.choice([9, 64, 65, 130, 500])) + int(rng.integers(0, 20))).astype(np.uint8)
+        b = synth.encode_2bit(synth._mutate(np.frombuffer(b"ACGT", dtype=np.uint8)[a], float(rng.choice([1.0, 0.9, 0.8, 0.6])), rng))
+        if b.size >= 2:
+            pairs.append((a, b, int(rng.integers(0, min(a.size, 30))), int(rng.integers(0, min(b.size, 30))), 0, int(rng.integers(0, 3)), 0))
+    for p, (r2, a2) in zip(pairs, m.extend_pairs(pairs)):
+        r1, a1 = o.extend(*p)
+        assert np.array_equal(r1, r2) and np.array_equal(a1, a2)
+    m.close()
+
+
 def test_emu_map_batch_matches_reference_golden(emu, gold):
     """End to end through mab_map_batch: seed -> sort/chain -> extend -> host post-processing, in file order (state carry)."""
     idx = [i for i, s in enumerate(gold["enc"]) if s.size <= 6000][:48]

@@ -47,6 +47,27 @@ def test_cli_matches_live_reference_on_20kb_reads(tmp_path, preset):
 
 
 @pytest.mark.skipif(not os.path.exists(refh.BIN), reason="oracle/_ref/minialign not built")
+@pytest.mark.parametrize("opts", [["-a1", "-b2", "-p2", "-q1", "-r2,2", "-Y30", "-s40", "-m0.2"],
+                                  ["-a3", "-b5", "-p5", "-q3", "-r4,5", "-Y70", "-s200", "-m0.5", "-W3000", "-G2000"]])
+def test_cli_matches_live_reference_custom_scoring(tmp_path, opts):
+    """Non-preset scoring / filtering options (minialign.c:5950-6030): score matrix, gap model, X-drop, min score / ratio,
+    chaining windows; reference run with -t1."""
+    from minialign_b200 import synth
+    g = synth.make_genome(800_000, 3, seed=41, repeats=((20, 3000), (60, 800)))
+    reads = synth.make_reads(g, 3_000_000, seed=42) + synth.make_hard_reads(g, seed=43)
+    fa, rd, idx = str(tmp_path / "g.fa"), str(tmp_path / "r.fa"), str(tmp_path / "g.mai")
+    synth.write_fasta(fa, g, 80); synth.write_fasta(rd, reads)
+    subprocess.check_call([refh.BIN, "-xpacbio", "-d", idx, fa], stderr=subprocess.DEVNULL)
+    ref = subprocess.run([refh.BIN, "-xpacbio", *opts, "-t1", "-TAS,XS,NM,MD,SA", idx, rd], capture_output=True)
+    assert ref.returncode == 0
+    exp = [l for l in ref.stdout.decode().split("\n") if not l.startswith("@PG")]
+    got = run_cli(["-xpacbio", *opts, "-TAS,XS,NM,MD,SA", idx, rd])
+    assert len(got) == len(exp) and sum(1 for l in exp if l and not l.startswith("@")) > 50
+    bad = [i for i, (a, b) in enumerate(zip(got, exp)) if a != b]
+    assert not bad, (len(bad), got[bad[0]][:200], exp[bad[0]][:200])
+
+
+@pytest.mark.skipif(not os.path.exists(refh.BIN), reason="oracle/_ref/minialign not built")
 def test_cli_matches_live_reference_multi_contig_repeats(tmp_path):
     """BASELINE config 2 in small (sacCer3-like: 17 contigs) with heavier planted repeat families, so that the rescue rounds
     (occ thresholds), secondary / supplementary records and the seed-rich sort class are exercised; reference run with -t1."""

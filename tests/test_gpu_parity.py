@@ -52,9 +52,9 @@ def test_extend_pairs_golden(gold, key, preset):
         assert np.array_equal(r, r2) and np.array_equal(a, a2)
 
 
-@pytest.mark.parametrize("preset,prm", [("pacbio", ora.PACBIO), ("ont.1dsq", ora.ONT)])
+@pytest.mark.parametrize("preset,prm", [("pacbio", ora.PACBIO), ("ont.1dsq", ora.ONT)] + [(None, p) for p, _ in ora.CUSTOM])
 def test_extend_pairs_fuzz_vs_oracle(gold, preset, prm):
-    m = api.Mapper(gold["blob"], preset)
+    m = api.Mapper(gold["blob"], preset or {k: prm[k] for k in ora.API_KEYS})
     o = ora.Oracle(prm)
     rng = np.random.default_rng(99)
     pairs = []

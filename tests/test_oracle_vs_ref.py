@@ -9,12 +9,12 @@ from minialign_b200 import synth
 pytestmark = pytest.mark.skipif(not refh.available(), reason="oracle/_ref/libref_harness.so not built (needs /root/reference)")
 
 
-@pytest.mark.parametrize("preset,prm", [("pacbio", ora.PACBIO), ("ont.1dsq", ora.ONT)])
-def test_extend_fuzz(gold, preset, prm):
-    h = refh.RefHarness(gold["mai"], args=("-x" + preset,))
+@pytest.mark.parametrize("args,prm,n", [(("-xpacbio",), ora.PACBIO, 300), (("-xont.1dsq",), ora.ONT, 300)] + [(a, p, 120) for p, a in ora.CUSTOM])
+def test_extend_fuzz(gold, args, prm, n):
+    h = refh.RefHarness(gold["mai"], args=args)
     o = ora.Oracle(prm)
     rng = np.random.default_rng(1234)
-    for it in range(300):
+    for it in range(n):
         L = max(2, int(rng.choice([3, 9, 33, 64, 65, 100, 400, 1200])) + int(rng.integers(0, 20)))
         a = rng.integers(0, 4, size=L).astype(np.uint8)
         b = synth.encode_2bit(synth._mutate(np.frombuffer(b"ACGT", dtype=np.uint8)[a], float(rng.choice([1.0, 0.9, 0.8, 0.6])), rng))
