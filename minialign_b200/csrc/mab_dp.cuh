@@ -687,7 +687,7 @@ struct Trace {
 };
 
 /* Stage the 2 KB mask block of entry b into this warp's shared-memory tile as one flag nibble per byte, tile8[vector][cell]
- * (64 B per vector), so that the walk below needs one byte load per popped vector.  Global reads are coalesced 128 B rows.
+ * (64 B per vector at a pitch of MAB_TROW), so that the walk below needs one byte load per popped vector.  Global reads are coalesced 128 B rows.
  * For W = 16 the cells 16..31 read as "all flags clear" like the zero-extended 16-bit mask words of the reference. */
 __device__ __forceinline__ void stage_masks(const DpCtx &c, int32_t b, uint8_t *tile8)
 {
@@ -699,7 +699,7 @@ __device__ __forceinline__ void stage_masks(const DpCtx &c, int32_t b, uint8_t *
 	for(int j = 0; j < 16; j++) {
 		uint32_t wd = src[32 * j];
 		if(pad) { wd = 0x0f0f0f0fu; }
-		dst[64 * j] = (uint16_t)wd; dst[64 * j + 32] = (uint16_t)(wd >> 16);
+		dst[MAB_TROW * j] = (uint16_t)wd; dst[MAB_TROW * j + MAB_TROW / 2] = (uint16_t)(wd >> 16);
 	}
 	__syncwarp();
 }
@@ -763,7 +763,7 @@ __device__ __forceinline__ void trace_core(DpCtx &c, Trace &w, uint8_t *tile8)
 	const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile8);
 #endif
 	stage_masks(c, b, tile8);
-	#define NIB() tile_ld8(tile8, tile_s, (mi << 6) + (int32_t)(q & qmask))
+	#define NIB() tile_ld8(tile8, tile_s, mi * MAB_TROW + (int32_t)(q & qmask))
 	nb = NIB();
 	#define POP(_v, _id) { \
 		if(_v) { g1 -= dec; } else { g0 -= dec; } \
@@ -782,6 +782,28 @@ __device__ __forceinline__ void trace_core(DpCtx &c, Trace &w, uint8_t *tile8)
 	}
 L_D_HEAD:
 	if(!(nb & 1)) { goto L_H_HEAD; }											/* h bit set */
+	{
+		/* Run of diagonal steps inside this block, looked up by all lanes at once: along a pure diagonal run the column after
+		 * s steps is known from the direction bits alone (q + popc(low 2s bits) - s), so lane s reads the flags the walk would
+		 * see after s steps, a ballot finds the first step that leaves the diagonal (v flag at D_TAIL, h flag at D_HEAD) and
+		 * the state jumps there: two path bits "01" per step, both section counters down by one in tail mode.  The run stops
+		 * short of the block end and of the section ends; those steps take the scalar path below. */
+		int32_t lim = mi >> 1;
+		if(dec) { const int32_t gl = g0 < g1 ? g0 : g1; lim = gl < lim ? gl : lim; }
+		if(lim >= 1) {
+			const uint32_t run_mask = (1u << (2 * (c.lane & 15))) - 1u, run_need = c.lane == 0 ? 1u : 3u;
+			const int32_t ms = mi - 2 * c.lane;
+			const uint32_t qs = q + (uint32_t)__popc(dir & run_mask) - (uint32_t)c.lane;
+			uint32_t ns = 0;
+			if(ms >= 0) { ns = tile_ld8(tile8, tile_s, ms * MAB_TROW + (int32_t)(qs & qmask)); }
+			const uint32_t bal = __ballot_sync(MAB_FULL, (ns & run_need) == run_need);
+			const int32_t nf = __ffs((int)~bal) - 1, n = nf < lim ? nf : lim;						/* >= 1: lane 0 re-reads nb; lanes past the block read 0 */
+			nb = __shfl_sync(MAB_FULL, ns, n); q = __shfl_sync(MAB_FULL, qs, n);
+			dir >>= 2 * n; mi -= 2 * n; g0 -= dec * n; g1 -= dec * n;
+			pacc = (pacc << (2 * n)) | (0x5555555555555555ull >> (64 - 2 * n)); nacc += 2 * n;
+			goto L_D_TAIL;
+		}
+	}
 	if(g0 == 0 || g1 == 0) { w.state = mab_ts_d; goto term; }
 	POP(0, 1);
 	POP(1, 2);

@@ -484,7 +484,7 @@ static int map_core(mab_ctx *ctx, const uint8_t *d_base, std::vector<ReadRec> &h
 			}
 			RT_MEMSET_ASYNC(&ctx->d_ctr->work_next, 0, sizeof(unsigned int), ctx->stream);
 			if(timed && round < 8) { RT_EVENT_RECORD(ctx->rev[3 * round + 1], ctx->stream); }
-			RT_LAUNCH(k_extend, ext_ctas, 32 * MAB_WARPS_PER_CTA, 1024 + 2048 * MAB_WARPS_PER_CTA, ctx->stream, P, d_base, (const uint8_t *)ctx->d_ntail, ctx->d_reads, (const uint32_t *)ctx->d_order, n_seq, ctx->d_ws,
+			RT_LAUNCH(k_extend, ext_ctas, 32 * MAB_WARPS_PER_CTA, 1024 + 4 * MAB_TILE_WORDS * MAB_WARPS_PER_CTA, ctx->stream, P, d_base, (const uint8_t *)ctx->d_ntail, ctx->d_reads, (const uint32_t *)ctx->d_order, n_seq, ctx->d_ws,
 				ctx->d_arenas, AL.total, blk_cap, ctx->d_pool, pool_words, ctx->d_ctr, round, P.n_occ - 1);
 			S.n_launches += 2;
 			if(timed && round < 8) { RT_EVENT_RECORD(ctx->rev[3 * round + 2], ctx->stream); }
@@ -716,7 +716,7 @@ extern "C" int mab_extend_pairs(mab_ctx *ctx, const uint8_t *seq_block, uint64_t
 	CK(RT_MEMCPY_H2D(d_seq, seq_block, block_size)); CK(RT_MEMCPY_H2D(d_p, pairs, sizeof(PairIn) * (uint64_t)n));
 	BatchCounters zero; memset(&zero, 0, sizeof(zero));
 	CK(RT_MEMCPY_H2D(ctx->d_ctr, &zero, sizeof(zero)));
-	RT_LAUNCH(k_extend_pairs, ctas, 32 * MAB_WARPS_PER_CTA, 1024 + 2048 * MAB_WARPS_PER_CTA, ctx->stream, P, (const uint8_t *)d_seq, (const uint8_t *)ctx->d_ntail, (const PairIn *)d_p, n, d_res, d_ao,
+	RT_LAUNCH(k_extend_pairs, ctas, 32 * MAB_WARPS_PER_CTA, 1024 + 4 * MAB_TILE_WORDS * MAB_WARPS_PER_CTA, ctx->stream, P, (const uint8_t *)d_seq, (const uint8_t *)ctx->d_ntail, (const PairIn *)d_p, n, d_res, d_ao,
 		d_ar, AL.total, blk_cap, d_pool, pool_words, ctx->d_ctr);
 	CK(RT_STREAM_SYNC(ctx->stream));
 	BatchCounters hc; CK(RT_MEMCPY_D2H(&hc, ctx->d_ctr, sizeof(hc)));

@@ -557,7 +557,7 @@ __device__ __forceinline__ SecDesc make_sec(const uint8_t *base, uint32_t len, u
 }
 
 /* ---------------------------------------------------------------- k_extend */
-/* shared memory per CTA: 1 KB score LUT + per warp a 2 KB tile (traceback nibbles / sort scratch) */
+/* shared memory per CTA: 1 KB score LUT + per warp a 2.1 KB tile (traceback nibbles / sort scratch) */
 __global__ void __launch_bounds__(32 * MAB_WARPS_PER_CTA, MAB_EXT_CTAS_PER_SM) k_extend(DevParams P, const uint8_t *base, const uint8_t *ntail, ReadRec *reads, const uint32_t *order, uint32_t n_reads, uint8_t *ws,
 	uint8_t *arenas, uint64_t arena_stride, uint32_t blk_cap, uint32_t *pool, uint64_t pool_cap, BatchCounters *ctr, uint32_t round, uint32_t last_round)
 {
@@ -566,7 +566,7 @@ __global__ void __launch_bounds__(32 * MAB_WARPS_PER_CTA, MAB_EXT_CTAS_PER_SM) k
 	/* warp-uniform indices go through a lane-0 broadcast: the compiler then knows that every pointer derived from them (arena,
 	 * tile) and every branch on data loaded through them is warp-uniform, and drops the divergence guards around the shuffles */
 	int lane = threadIdx.x & 31, wib = __shfl_sync(MAB_FULL, (int)(threadIdx.x >> 5), 0);
-	uint32_t *tile = (uint32_t *)smem + 256 + 512 * wib;
+	uint32_t *tile = (uint32_t *)smem + 256 + MAB_TILE_WORDS * wib;
 	build_lut(P, lut, threadIdx.x, blockDim.x);
 	__syncthreads();
 	uint32_t gw = __shfl_sync(MAB_FULL, (blockIdx.x * blockDim.x + threadIdx.x) >> 5, 0);
@@ -670,7 +670,7 @@ __global__ void k_extend_pairs(DevParams P, const uint8_t *base, const uint8_t *
 	MAB_DYN_SMEM(smem);
 	uint32_t *lut = (uint32_t *)smem;
 	int lane = threadIdx.x & 31, wib = __shfl_sync(MAB_FULL, (int)(threadIdx.x >> 5), 0);
-	uint32_t *tile = (uint32_t *)smem + 256 + 512 * wib;
+	uint32_t *tile = (uint32_t *)smem + 256 + MAB_TILE_WORDS * wib;
 	build_lut(P, lut, threadIdx.x, blockDim.x);
 	__syncthreads();
 	uint32_t gw = __shfl_sync(MAB_FULL, (blockIdx.x * blockDim.x + threadIdx.x) >> 5, 0), nw = (gridDim.x * blockDim.x) >> 5;
