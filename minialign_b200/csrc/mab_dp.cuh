@@ -684,24 +684,62 @@ struct Trace {
 	uint32_t pidx, nacc; int32_t widx;
 	uint64_t pacc;
 	uint32_t *path;				/* path words in the result pool */
+	int32_t sblk, pblk; uint32_t cur;	/* block held by tile buffer cur, block being prefetched into the other buffer (-1: none) */
 };
 
-/* Stage the 2 KB mask block of entry b into this warp's shared-memory tile as one flag nibble per byte, tile8[vector][cell]
- * (64 B per vector at a pitch of MAB_TROW), so that the walk below needs one byte load per popped vector.  Global reads are coalesced 128 B rows.
- * For W = 16 the cells 16..31 read as "all flags clear" like the zero-extended 16-bit mask words of the reference. */
-__device__ __forceinline__ void stage_masks(const DpCtx &c, int32_t b, uint8_t *tile8)
+/* Start the copy of the 2 KB mask block of entry b into a tile buffer: 16 asynchronous 4-byte copies per lane (coalesced
+ * 128 B rows in global memory, pitch MAB_TPITCH in shared memory), no registers and no waiting: the block the walk will need
+ * next is fetched while the current one is walked. */
+__device__ __forceinline__ void stage_issue(const DpCtx &c, int32_t b, uint8_t *buf)
 {
 	const uint32_t *src = c.masks + 512ull * b + c.lane;
-	uint16_t *dst = (uint16_t *)tile8 + c.lane;
-	const bool pad = c.W == 16 && c.lane >= 8;
-	__syncwarp();				/* every lane is done reading the previous tile (lanes are not lock-stepped on sm_70+) */
-	#pragma unroll 4
+#ifdef MAB_EMU
+	for(int j = 0; j < 16; j++) { ((uint32_t *)buf)[33 * j + c.lane] = src[32 * j]; }
+#else
+	const uint32_t dst = (uint32_t)__cvta_generic_to_shared(buf) + 4u * c.lane;
+	const unsigned long long g = (unsigned long long)__cvta_generic_to_global(src);
+	#pragma unroll
 	for(int j = 0; j < 16; j++) {
-		uint32_t wd = src[32 * j];
-		if(pad) { wd = 0x0f0f0f0fu; }
-		dst[MAB_TROW * j] = (uint16_t)wd; dst[MAB_TROW * j + MAB_TROW / 2] = (uint16_t)(wd >> 16);
+		asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst + MAB_TPITCH * j), "l"(g + 128ull * j) : "memory");
+	}
+#endif
+}
+
+/* Wait for this lane's copies and publish them to the warp.  For W = 16 the cells 16..31 read as "all flags clear" like the
+ * zero-extended 16-bit mask words of the reference. */
+__device__ __forceinline__ void stage_wait(const DpCtx &c, uint8_t *buf)
+{
+#ifndef MAB_EMU
+	asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+	if(c.W == 16 && c.lane >= 8) {
+		for(int j = 0; j < 16; j++) { ((uint32_t *)buf)[33 * j + c.lane] = 0x0f0f0f0fu; }
 	}
 	__syncwarp();
+}
+
+/* no copy may still be in flight when the tile is reused as sort scratch */
+__device__ __forceinline__ void stage_drain()
+{
+#ifndef MAB_EMU
+	asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+	__syncwarp();
+}
+
+/* Make block b the one held by the current tile buffer and start fetching b - 1, the usual successor, into the other. */
+__device__ __forceinline__ void stage_block(const DpCtx &c, Trace &w, int32_t b, uint8_t *tile8)
+{
+	if(w.sblk != b) {
+		if(w.pblk == b) { w.cur ^= 1; w.pblk = -1; }
+		else { __syncwarp(); stage_issue(c, b, tile8 + MAB_TBUF * w.cur); }		/* every lane is done reading the old contents */
+		w.sblk = b;
+		stage_wait(c, tile8 + MAB_TBUF * w.cur);
+	}
+	if(b > 0 && w.pblk != b - 1) {
+		__syncwarp();
+		stage_issue(c, b - 1, tile8 + MAB_TBUF * (w.cur ^ 1)); w.pblk = b - 1;
+	}
 }
 
 /* trace_reload_section (gaba.c:2826-2859) */
@@ -762,8 +800,11 @@ __device__ __forceinline__ void trace_core(DpCtx &c, Trace &w, uint8_t *tile8)
 #else
 	const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile8);
 #endif
-	stage_masks(c, b, tile8);
-	#define NIB() tile_ld8(tile8, tile_s, mi * MAB_TROW + (int32_t)(q & qmask))
+	stage_block(c, w, b, tile8);
+	uint32_t cofs = MAB_TBUF * w.cur;
+	/* byte of (vector m, cell x) in the raw block layout */
+	#define TIDX(_m, _x) (int32_t)(cofs + (uint32_t)((_m) >> 1) * MAB_TPITCH + (((uint32_t)(_m) & 1u) << 1) + (((_x) >> 1) << 2) + ((_x) & 1u))
+	#define NIB() tile_ld8(tile8, tile_s, TIDX(mi, q & qmask))
 	nb = NIB();
 	#define POP(_v, _id) { \
 		if(_v) { g1 -= dec; } else { g0 -= dec; } \
@@ -795,7 +836,7 @@ L_D_HEAD:
 			const int32_t ms = mi - 2 * c.lane;
 			const uint32_t qs = q + (uint32_t)__popc(dir & run_mask) - (uint32_t)c.lane;
 			uint32_t ns = 0;
-			if(ms >= 0) { ns = tile_ld8(tile8, tile_s, ms * MAB_TROW + (int32_t)(qs & qmask)); }
+			if(ms >= 0) { ns = tile_ld8(tile8, tile_s, TIDX(ms, qs & qmask)); }
 			const uint32_t bal = __ballot_sync(MAB_FULL, (ns & run_need) == run_need);
 			const int32_t nf = __ffs((int)~bal) - 1, n = nf < lim ? nf : lim;						/* >= 1: lane 0 re-reads nb; lanes past the block read 0 */
 			nb = __shfl_sync(MAB_FULL, ns, n); q = __shfl_sync(MAB_FULL, qs, n);
@@ -873,7 +914,7 @@ reload:
 		#undef TEST_BULK
 		#undef RELOAD_BLOCK
 		FLUSH_PATH();
-		stage_masks(c, b, tile8);
+		stage_block(c, w, b, tile8); cofs = MAB_TBUF * w.cur;
 		switch(ret) { case 1: goto R1; case 2: goto R2; case 3: goto R3; case 4: goto R4; case 5: goto R5; default: goto R6; }
 	}
 term:
@@ -883,6 +924,7 @@ term:
 	__syncwarp();
 	#undef POP
 	#undef NIB
+	#undef TIDX
 	#undef FLUSH_PATH
 }
 
@@ -907,6 +949,7 @@ __device__ inline uint64_t dp_trace(DpCtx &c, int32_t ti, uint32_t *pool, uint64
 	for(int i = 0; i < 2; i++) { w.gidx[i] = lf.gidx[i]; w.sgidx[i] = lf.sgidx[i]; w.tail[i] = ti; w.ofs[i] = 0; w.id[i] = 0; w.gi[i] = w.ge[i] = w.gf[i] = 0; }
 	if(plen >= 0x80000000ull) { c.err |= MAB_ERR_DP_OVF; return 0xffffffffffffffffull; }	/* 2^31 path bits: not a read */
 	w.pidx = (uint32_t)plen; w.path = rec + MAB_ALN_HDR + 8ull * sn;
+	w.sblk = w.pblk = -1; w.cur = 0;
 	w.pacc = 1; w.widx = (int32_t)(plen >> 5); w.nacc = 32u - ((uint32_t)plen & 31u);	/* sentinel bit at plen (gaba.c:3287), zeros above it */
 	if(c.lane == 0) {
 		w.path[(plen >> 5) + 1] = 0;
@@ -917,11 +960,11 @@ __device__ inline uint64_t dp_trace(DpCtx &c, int32_t ti, uint32_t *pool, uint64
 	/* the remaining-bits counter comes out of the walk, whose data-dependent branches the compiler cannot prove warp-uniform:
 	 * re-broadcast it so that this loop (and with it everything after the trace) counts as convergent code */
 	while(__shfl_sync(MAB_FULL, w.pidx, 0) != 0) {
-		if(fuel-- == 0) { c.err |= MAB_ERR_DP_OVF; return 0xffffffffffffffffull; }		/* more segments than sections: cannot happen */
+		if(fuel-- == 0) { c.err |= MAB_ERR_DP_OVF; stage_drain(); return 0xffffffffffffffffull; }		/* more segments than sections: cannot happen */
 		if(w.gidx[0] < (int32_t)((w.state & MAB_TS_H) != 0)) { trace_reload_section(c, w, 0); }
 		if(w.gidx[1] < (int32_t)((w.state & MAB_TS_V) != 0)) { trace_reload_section(c, w, 1); }
 		trace_core(c, w, (uint8_t *)tile32);
-		if(w.q >= (uint32_t)c.W) { return 0xffffffffffffffffull; }					/* out of band: abort (gaba.c:3324-3328) */
+		if(w.q >= (uint32_t)c.W) { stage_drain(); return 0xffffffffffffffffull; }					/* out of band: abort (gaba.c:3324-3328) */
 		/* trace_push_segment (gaba.c:2865-2895): slots fill from the back */
 		if(c.lane == 0 && nseg < sn) {
 			uint32_t *s = rec + MAB_ALN_HDR + 8ull * (sn - 1 - nseg);
@@ -947,7 +990,7 @@ __device__ inline uint64_t dp_trace(DpCtx &c, int32_t ti, uint32_t *pool, uint64
 		rec[11] = rec[12] = rec[13] = rec[14] = rec[15] = 0;
 	}
 	if(nseg > sn) { c.err |= MAB_ERR_POOL_OVF; }
-	__syncwarp();
+	stage_drain();
 	return (uint64_t)ofs;
 }
 

@@ -11,10 +11,13 @@ namespace mab {
 #define MAB_BLK			32
 #define MAB_KH_CAP		1024u		/* slots of the per-read dedup hash (reference starts at 256 and doubles) */
 #define MAB_MAX_TAILS	24
-/* per-warp traceback tile in shared memory: 32 vector rows of one flag byte per cell.  The row pitch is 68 B (17 banks) so
- * that the 16 lanes of the diagonal-run lookahead, which read rows 2 apart at nearly the same column, hit 16 different banks */
-#define MAB_TROW 68
-#define MAB_TILE_WORDS (MAB_TROW * 32 / 4)
+/* per-warp traceback tiles in shared memory: two buffers (the block being walked and the prefetched next one), each a raw
+ * copy of a block's mask stream: 16 rows of 32 words (row j = vectors 2j and 2j+1, one flag byte per cell, word of lane l =
+ * cells 2l, 2l+1 of both vectors).  The row pitch is 33 words so that the 16 lanes of the diagonal-run lookahead, which read
+ * consecutive rows at nearly the same column, hit different banks */
+#define MAB_TPITCH 132
+#define MAB_TBUF (16 * MAB_TPITCH)
+#define MAB_TILE_WORDS (2 * MAB_TBUF / 4)
 #define MAB_SC_SMALL		2944u		/* largest shared-memory staging of the ordinary size class of k_sortchain (16 B per seed + 2 KB = 48 KB) */
 #define MAB_SC_MAX		6016u		/* ... and of the seed-rich class (96 KB, opt-in dynamic shared memory) */
 #define MAB_WARPS_PER_CTA 4
