@@ -800,7 +800,15 @@ __device__ __forceinline__ void trace_core(DpCtx &c, Trace &w, uint8_t *tile8)
 #else
 	const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile8);
 #endif
+	/* acc, xstat, acnt, bcnt of a block entry as one word */
+	#define BLK_META(_b) (*(const uint32_t *)&c.blk[_b].acc)
+	#define META_XSTAT(_m) ((_m) >> 8)
+	#define META_ACNT(_m) ((int32_t)(int8_t)((_m) >> 16))
+	#define META_BCNT(_m) ((int32_t)(_m) >> 24)
+	#define PREFETCH_META() { if(b > 0) { pf_meta = BLK_META(b - 1); pf_dir = c.blk[b - 1].dir_mask; } }
+	uint32_t pf_meta = 0, pf_dir = 0;
 	stage_block(c, w, b, tile8);
+	PREFETCH_META();
 	uint32_t cofs = MAB_TBUF * w.cur;
 	/* byte of (vector m, cell x) in the raw block layout */
 	#define TIDX(_m, _x) (int32_t)(cofs + (uint32_t)((_m) >> 1) * MAB_TPITCH + (((uint32_t)(_m) & 1u) << 1) + (((_x) >> 1) << 2) + ((_x) & 1u))
@@ -880,19 +888,23 @@ L_V_TAIL:
 
 reload:
 	{
-		/* _trace_test_bulk (3052-3060), _trace_reload_block (3032-3043), _trace_reload_tail (3009-3026) */
+		/* _trace_test_bulk (3052-3060), _trace_reload_block (3032-3043), _trace_reload_tail (3009-3026); the header words of
+		 * entry b - 1 were fetched when block b was entered (pf_meta, pf_dir) */
+		uint32_t meta;
 		#define TEST_BULK(_ok) { \
-			int32_t _ga = g0 - c.blk[b].acnt, _gb = g1 - c.blk[b].bcnt; \
+			int32_t _ga = g0 - META_ACNT(meta), _gb = g1 - META_BCNT(meta); \
 			_ok = !(W > _ga) && !(W > _gb); \
 			if(_ok) { g0 = _ga; g1 = _gb; } \
 		}
+		#define RELOAD_HEAD() { \
+			do { b = c.blk[b].link; } while(c.blk[b].xstat & MAB_X_HEAD); \
+			meta = BLK_META(b); \
+			int _cnt = META_ACNT(meta) + META_BCNT(meta); \
+			mi = _cnt - 1; dir = c.blk[b].dir_mask >> (MAB_BLK - _cnt); \
+		}
 		#define RELOAD_BLOCK() { \
-			b--; mi = MAB_BLK - 1; dir = c.blk[b].dir_mask; \
-			if(c.blk[b].xstat & MAB_X_HEAD) { \
-				do { b = c.blk[b].link; } while(c.blk[b].xstat & MAB_X_HEAD); \
-				int _cnt = c.blk[b].acnt + c.blk[b].bcnt; \
-				mi = _cnt - 1; dir = c.blk[b].dir_mask >> (MAB_BLK - _cnt); \
-			} \
+			b--; mi = MAB_BLK - 1; dir = pf_dir; meta = pf_meta; \
+			if(META_XSTAT(meta) & MAB_X_HEAD) { RELOAD_HEAD(); } \
 		}
 		if(bulk) {																/* _trace_bulk_load_n (3070-3082) */
 			RELOAD_BLOCK();
@@ -902,19 +914,19 @@ reload:
 				g1 += (int32_t)(q - save); g0 += (int32_t)(save - q); save = HEAD_CNT; bulk = 0; dec = 1;
 			}
 		} else {																/* _trace_tail_load_n (3083-3099) */
-			if(c.blk[b - 1].xstat & MAB_X_HEAD) {
-				b--; do { b = c.blk[b].link; } while(c.blk[b].xstat & MAB_X_HEAD);
-				int cnt = c.blk[b].acnt + c.blk[b].bcnt;
-				mi = cnt - 1; dir = c.blk[b].dir_mask >> (MAB_BLK - cnt);
+			if(META_XSTAT(pf_meta) & MAB_X_HEAD) {
+				b--; RELOAD_HEAD();
 			} else {
 				RELOAD_BLOCK();
 				if(--save >= HEAD_CNT) { int ok; TEST_BULK(ok); if(ok) { save = q; bulk = 1; dec = 0; } }
 			}
 		}
+		#undef RELOAD_HEAD
 		#undef TEST_BULK
 		#undef RELOAD_BLOCK
 		FLUSH_PATH();
 		stage_block(c, w, b, tile8); cofs = MAB_TBUF * w.cur;
+		PREFETCH_META();
 		switch(ret) { case 1: goto R1; case 2: goto R2; case 3: goto R3; case 4: goto R4; case 5: goto R5; default: goto R6; }
 	}
 term:
@@ -926,6 +938,11 @@ term:
 	#undef NIB
 	#undef TIDX
 	#undef FLUSH_PATH
+	#undef BLK_META
+	#undef META_XSTAT
+	#undef META_ACNT
+	#undef META_BCNT
+	#undef PREFETCH_META
 }
 
 /* gaba_dp_trace (gaba.c:3244-3393).  Allocates the alignment record from the result pool (lane 0 bumps the pointer),
