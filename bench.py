@@ -154,7 +154,7 @@ def cpu_baseline(idx, batches, work, budget_core_s=20.0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch-reads", type=int, default=16384)
@@ -260,13 +260,22 @@ def main():
                     agg["ms_ext"] += st["ms_extend"]; agg["ms_ext_r0"] += st["ms_extend_r0"]; agg["ms_dev"] += st["ms_total"]; agg["vec"] += st["n_vectors"]
                     agg["out_words"] += words
 
-        def drive(first, count, timed):
+        def drive(first, count, timed, static=False):
             errs = []
+            nxt = iter(range(first, first + count))     # steps are handed out as contexts become free
 
             def worker(t):
                 try:
                     torch.cuda.set_device(local)
-                    for i in range(first + t, first + count, len(ms)):
+                    if static:
+                        for i in range(first + t, first + count, len(ms)):
+                            one(ms[t], i, timed)
+                        return
+                    while True:
+                        with lock:
+                            i = next(nxt, None)
+                        if i is None:
+                            break
                         one(ms[t], i, timed)
                 except Exception as e:       # a failed batch must fail the run, not shorten it
                     errs.append(e)
@@ -276,7 +285,7 @@ def main():
             if errs:
                 raise errs[0]
 
-        drive(0, len(ms), False)                       # set-up: one untimed batch per context sizes its device / pinned buffers
+        drive(0, len(ms), False, static=True)          # set-up: one untimed batch per context sizes its device / pinned buffers
         drive(len(ms), max(warmup, len(ms)), False)    # the W warm-up steps
         sampler = ClockSampler(local); sampler.start()
         # device-side timing: the events sit on torch's (idle) stream; the first is recorded after a full device sync, the second
