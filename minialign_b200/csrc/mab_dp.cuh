@@ -120,20 +120,6 @@ __device__ __forceinline__ uint32_t fetch_b(const SecDesc &s, uint32_t i)
 	return (s.rev ? 3 - c : c) << 2;
 }
 
-/* Pull the cache line that holds position i of a section towards the SM: issued by one lane at a block start for the bases
- * three blocks ahead, so that the per-block fetches above hit L1 instead of waiting for L2 / HBM.  i is clamped to the section. */
-__device__ __forceinline__ void fetch_ahead(const SecDesc &s, uint32_t i)
-{
-#ifndef MAB_EMU
-	if(s.len == 0) { return; }
-	if(i >= s.len) { i = s.len - 1; }
-	const uint8_t *p = (const uint8_t *)s.base + (s.rev ? s.len - 1 - i : i);
-	asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
-#else
-	(void)s; (void)i;
-#endif
-}
-
 /* build the 256-entry LUT: index = idx(cell 2l) | idx(cell 2l+1) << 4, value = packed sb[] pair (gaba.c:1612, 3657) */
 __device__ __forceinline__ void build_lut(const DevParams &P, uint32_t *lut, int tid, int nthreads)
 {
@@ -436,8 +422,6 @@ __device__ __forceinline__ int32_t fill_blocks(DpCtx &c, FillWork &w, Vec &v, ui
 		uint32_t an = 0, bn = 0;
 		if((uint32_t)l < w.rem[0]) { an = fetch_a(w.sec[0], w.sec[0].len - w.rem[0] + l) << 2; }
 		if((uint32_t)l < w.rem[1]) { bn = fetch_b(w.sec[1], w.sec[1].len - w.rem[1] + l) << 18; }		/* enters a high half */
-		if(l == 0) { fetch_ahead(w.sec[0], w.sec[0].len - w.rem[0] + 3 * MAB_BLK); }
-		if(l == 1) { fetch_ahead(w.sec[1], w.sec[1].len - w.rem[1] + 3 * MAB_BLK); }
 		if(l < c.nl) { b->cha[l] = (uint16_t)win_store(v.wa); b->chb[l] = (uint16_t)win_store(v.wb); }
 		if(first) { vec_load(c, v, &c.blk[bi - 1], xd); first = 0; }
 		else { v.delta = 0; v.acc = (int32_t)(int8_t)v.acc; v.dir = 0; }				/* ndrop carries over: xd == drop of the previous block */
