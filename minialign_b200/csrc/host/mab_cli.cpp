@@ -9,6 +9,7 @@
  * reference on the host (mab_index.cpp), parses FASTA/FASTQ into the reference's 1 byte/base codes (minialign.c:214-232),
  * maps batches through the C ABI (libminialign_b200.so, CUDA, no CPU fallback) and prints SAM with mab_sam.cpp.
  */
+#include <unistd.h>
 #include "../../../include/minialign_b200.h"
 #include "mab_sam.h"
 #include "mab_index.h"
@@ -378,6 +379,8 @@ int main(int argc, char **argv)
 	double tm = now() - tmap;
 	fprintf(stderr, "[M::main] mapped %llu reads / %.1f Mbases in %.3f sec (%.1f Mbases/s)\n", (unsigned long long)tot_reads, tot_bases / 1e6, tm, tot_bases / 1e6 / tm);
 	fprintf(stderr, "[M::main] Command: %s\n[M::main] Real time: %.3f sec\n", cmdline.c_str(), now() - t0);
-	mab_destroy(ctx);
-	return 0;
+	/* everything is written: leave without unpinning the host pools and freeing the DP arenas one by one (0.5-2 s for nothing;
+	 * the driver reclaims the context with the process) */
+	fflush(stdout); fflush(stderr);
+	_exit(0);
 }
