@@ -172,7 +172,7 @@ def main():
         if rank != 0:
             return
         n_b = 1
-        g, idx, blob, batches = build_workload(work, n_b, min(args.batch_reads, 4096))    # bounded sample per step: ~84 Mbases
+        g, idx, blob, batches = build_workload(work, n_b, min(args.batch_reads, 16384))   # bounded sample per step: one batch of our arm, ~338 Mbases, ~1.2 s on 16 cores
         from minialign_b200 import synth
         fa = os.path.join(work, "ref_step.fa")
         synth.write_fasta(fa, batches[0])
