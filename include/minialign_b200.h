@@ -97,6 +97,8 @@ typedef struct {
 	uint32_t n_retry;
 	float ms_wall, ms_wall_sizing, ms_wall_wait;	/* host wall clock: whole call, workspace sizing between the two device phases, blocked in stream syncs */
 	float ms_wall_submit;						/* host wall clock spent issuing copies and launches (driver calls that should not block) */
+	uint32_t n_failed;							/* reads given up on because a per-read device structure overflowed (reported unmapped) */
+	uint32_t _pad;
 } mab_stats_t;
 int mab_last_stats(const mab_ctx *ctx, mab_stats_t *out);
 

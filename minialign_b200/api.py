@@ -28,7 +28,8 @@ class MabStats(C.Structure):
                 ("ms_extend", C.c_float), ("ms_d2h", C.c_float), ("ms_post", C.c_float), ("ms_extend_r0", C.c_float),
                 ("n_vectors", C.c_uint64), ("n_fill_calls", C.c_uint64), ("n_trace", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("n_launches", C.c_uint32), ("n_retry", C.c_uint32),
-                ("ms_wall", C.c_float), ("ms_wall_sizing", C.c_float), ("ms_wall_wait", C.c_float), ("ms_wall_submit", C.c_float)]
+                ("ms_wall", C.c_float), ("ms_wall_sizing", C.c_float), ("ms_wall_wait", C.c_float), ("ms_wall_submit", C.c_float),
+                ("n_failed", C.c_uint32), ("_pad", C.c_uint32)]
 
 
 class MabPair(C.Structure):

@@ -46,6 +46,10 @@ static inline cudaError_t RT_MEMSET_ASYNC(void *d, int v, uint64_t n, RT_STREAM 
 static inline cudaError_t RT_STREAM_CREATE(RT_STREAM *s) { return cudaStreamCreateWithFlags(s, cudaStreamNonBlocking); }
 static inline cudaError_t RT_STREAM_SYNC(RT_STREAM s) { cudaError_t e = cudaStreamSynchronize(s); if(e == cudaSuccess) { e = cudaGetLastError(); } return e; }
 static inline cudaError_t RT_EVENT_CREATE(RT_EVENT *e) { return cudaEventCreate(e); }
+static inline void RT_EVENT_DESTROY(RT_EVENT e) { cudaEventDestroy(e); }
+static inline void RT_STREAM_DESTROY(RT_STREAM s) { cudaStreamDestroy(s); }
+static inline cudaError_t RT_DEVICE_SYNC() { return cudaDeviceSynchronize(); }
+static inline cudaError_t RT_EVENT_SYNC(RT_EVENT e) { return cudaEventSynchronize(e); }
 static inline void RT_EVENT_RECORD(RT_EVENT e, RT_STREAM s) { cudaEventRecord(e, s); }
 static inline float RT_EVENT_MS(RT_EVENT a, RT_EVENT b) { float ms = 0.f; if(cudaEventElapsedTime(&ms, a, b) != cudaSuccess) { ms = 0.f; cudaGetLastError(); } return ms; }
 static inline double RT_WALL_MS() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }

@@ -6,6 +6,7 @@
  */
 #include "../../include/minialign_b200.h"
 #include "mab_kernels.cuh"
+#include <new>
 #include <vector>
 #include <string>
 #include <cmath>
@@ -37,7 +38,7 @@ struct mab_ctx {
 	uint8_t *d_arenas = nullptr; uint64_t arenas_cap = 0;
 	uint32_t *d_pool = nullptr; uint64_t pool_cap = 0;
 	BatchCounters *d_ctr = nullptr;
-	RT_STREAM stream;
+	RT_STREAM stream; bool have_stream = false; int n_ev = 0;
 	RT_EVENT ev[8];
 	RT_EVENT rev[24];					/* per-round kernel boundaries: [3r] sortchain start, [3r+1] extend start, [3r+2] extend end */
 	int device_input = 0;
@@ -48,7 +49,11 @@ struct mab_ctx {
 	uint32_t *h_pool = nullptr; uint64_t h_pool_cap = 0;	/* pinned host copy of the device result pool */
 	uint8_t *pin = nullptr; uint64_t pin_cap = 0;			/* pinned bounce buffer: [ReadRec x n][order u32 x n][BatchCounters x 2] (every async copy has a
 															 * pinned host side: a pageable one blocks inside the runtime and stalls the other contexts' submissions) */
-	std::vector<ReadRec> h_reads;
+	uint64_t pin_user = 0;				/* bytes at the head of `pin` the caller of pipeline_run uses itself */
+	uint8_t *d_io = nullptr; uint64_t io_cap = 0;			/* [ofs u64 x n][len u32 x n] of the record-level entry point */
+	BatchCounters hc;					/* counters of the last batch */
+	uint32_t sc_cap1[2] = { 1536, 1536 };	/* k_sortchain: staging capacity of the ordinary size class, per round kind (adapted from batch to batch) */
+	double ws_per_base = 6.0;			/* workspace estimate: bytes per read base beyond the fixed 20 KB per read (high-water mark) */
 	mab_stats_t stats;
 };
 
@@ -166,9 +171,11 @@ extern "C" mab_ctx *mab_init(const void *mai_blob, uint64_t size, const mab_para
 	CKP(RT_MALLOC(&ctx->d_ntail, 256));
 	CKP(RT_MEMCPY_H2D(ctx->d_ntail, nt, 128));
 	CKP(RT_MALLOC(&ctx->d_ctr, sizeof(BatchCounters)));
-	CKP(RT_STREAM_CREATE(&ctx->stream));
-	for(int i = 0; i < 8; i++) { CKP(RT_EVENT_CREATE(&ctx->ev[i])); }
-	for(int i = 0; i < 24; i++) { CKP(RT_EVENT_CREATE(&ctx->rev[i])); }
+	CKP(RT_DEVICE_SYNC());								/* the uploads above ran on the legacy stream: nothing on the context's own (non-blocking) stream may overtake them */
+	CKP(RT_STREAM_CREATE(&ctx->stream)); ctx->have_stream = true;
+	for(int i = 0; i < 8; i++) { CKP(RT_EVENT_CREATE(&ctx->ev[i])); ctx->n_ev++; }
+	for(int i = 0; i < 24; i++) { CKP(RT_EVENT_CREATE(&ctx->rev[i])); ctx->n_ev++; }
+	RT_FUNC_MAX_SMEM(k_sortchain, 16 * MAB_SC_MAX + 2048);
 	ctx->n_slots = RT_EXTEND_SLOTS(ctx->n_sm);
 	if(const char *e = getenv("MAB_EXT_CTAS")) {										/* resident k_extend CTAs per SM actually launched (<= MAB_EXT_CTAS_PER_SM) */
 		int v = atoi(e);
@@ -181,8 +188,10 @@ extern "C" void mab_destroy(mab_ctx *ctx)
 {
 	if(ctx == nullptr) { return; }
 	RT_FREE(ctx->d_idx); RT_FREE(ctx->d_ntail); RT_FREE(ctx->d_ctr); RT_FREE(ctx->d_seq); RT_FREE(ctx->d_reads); RT_FREE(ctx->d_ws);
-	RT_FREE(ctx->d_frames); RT_FREE(ctx->d_order); RT_FREE(ctx->d_recs); RT_FREE(ctx->d_arenas); RT_FREE(ctx->d_pool);
+	RT_FREE(ctx->d_frames); RT_FREE(ctx->d_order); RT_FREE(ctx->d_recs); RT_FREE(ctx->d_arenas); RT_FREE(ctx->d_pool); RT_FREE(ctx->d_io);
 	RT_HOST_FREE(ctx->h_pool); RT_HOST_FREE(ctx->pin); delete[] ctx->res_words;
+	if(ctx->have_stream) { RT_STREAM_DESTROY(ctx->stream); }
+	for(int i = 0; i < ctx->n_ev; i++) { RT_EVENT_DESTROY(i < 8 ? ctx->ev[i] : ctx->rev[i - 8]); }
 	delete ctx;
 }
 
@@ -370,84 +379,34 @@ static void post_emit(const ReadPlan &pl, const PlanItem *items, uint32_t *out)
 /* ---------------------------------------------------------------- batch driver */
 static uint32_t dp_blk_cap(uint32_t maxlen) { return (uint32_t)((4ull * ((uint64_t)maxlen + 512)) / 32 + 64); }
 
-/* one pass of the device pipeline over `hr` (seq_ofs / len / rlen_in filled in); on return hr holds the device-side
- * records and ctx->h_pool (or *alt_pool) the result pool */
-static int map_core(mab_ctx *ctx, const uint8_t *d_base, std::vector<ReadRec> &hr, bool timed, std::vector<uint32_t> *alt_pool = nullptr)
+struct PipeShape { uint32_t n_seq, maxlen; uint64_t tot_len, span; };		/* what the host knows about a batch: counts, longest read, bases, size of the base block */
+
+static int pin_reserve(mab_ctx *ctx, uint64_t need)
+{
+	if(need <= ctx->pin_cap) { return MAB_OK; }
+	RT_HOST_FREE(ctx->pin); ctx->pin = nullptr; ctx->pin_cap = 0;
+	if(!RT_OK(RT_HOST_ALLOC(&ctx->pin, need + need / 4))) { g_err = std::string("pinned host allocation failed: ") + RT_ERRSTR(); return MAB_ENOMEM; }
+	ctx->pin_cap = need + need / 4;
+	return MAB_OK;
+}
+
+/* One batch through the device pipeline: scan -> size -> expand -> rounds of sort/chain + extend -> rlen verification (+ redo
+ * passes).  On entry ctx->d_reads holds n_seq records with seq_ofs / len set (k_reads_init or the text parser); nothing between
+ * the first launch and the verification needs the host: workspace offsets, the work order and the `rlen` speculation are
+ * computed on the device, buffers are sized from the shape and from high-water marks of earlier batches, and a buffer that
+ * turns out too small (result pool, workspace) is grown and the batch re-run.  On return ctx->hc holds the batch counters. */
+static int pipeline_run(mab_ctx *ctx, const uint8_t *d_base, const PipeShape &sh, uint32_t rlen_init, uint32_t init_known, bool timed)
 {
 	const DevParams &P = ctx->P;
 	mab_stats_t &S = ctx->stats;
-	uint32_t n_seq = (uint32_t)hr.size();
+	const uint32_t n_seq = sh.n_seq;
 	double t_sub = RT_WALL_MS();
-	uint32_t maxlen = 0; uint64_t tot_len = 0;
-	for(uint32_t i = 0; i < n_seq; i++) { maxlen = std::max(maxlen, hr[i].len); tot_len += hr[i].len; }
-	{ int rc = grow(&ctx->d_reads, &ctx->reads_cap, sizeof(ReadRec) * (uint64_t)n_seq); if(rc) { return rc; } }
-	const uint64_t rr_bytes = sizeof(ReadRec) * (uint64_t)n_seq;
-	{
-		uint64_t need = rr_bytes + 4ull * n_seq + 2 * sizeof(BatchCounters) + 256;
-		if(need > ctx->pin_cap) {
-			RT_HOST_FREE(ctx->pin); ctx->pin = nullptr; ctx->pin_cap = 0;
-			if(!RT_OK(RT_HOST_ALLOC(&ctx->pin, need + need / 4))) { g_err = std::string("pinned host allocation failed: ") + RT_ERRSTR(); return MAB_ENOMEM; }
-			ctx->pin_cap = need + need / 4;
-		}
-	}
-	ReadRec *pin_rr = (ReadRec *)ctx->pin;
-	uint32_t *pin_order = (uint32_t *)(ctx->pin + rr_bytes);
-	BatchCounters *pin_ctr = (BatchCounters *)(ctx->pin + ((rr_bytes + 4ull * n_seq + 127) & ~127ull));
-	memcpy(pin_rr, hr.data(), rr_bytes);
-	CK(RT_MEMCPY_H2D_ASYNC(ctx->d_reads, pin_rr, rr_bytes, ctx->stream));
-	S.h2d_bytes += sizeof(ReadRec) * (uint64_t)n_seq;
-	if(timed) { RT_EVENT_RECORD(ctx->ev[1], ctx->stream); }
-	/* count pass, workspace sizing */
-	uint32_t seed_ctas = std::max<uint32_t>(1, std::min<uint32_t>((n_seq + MAB_WARPS_PER_CTA - 1) / MAB_WARPS_PER_CTA, ctx->n_sm * 8));
-	{
-		uint64_t span = 0;
-		for(uint32_t i = 0; i < n_seq; i++) { span = std::max<uint64_t>(span, hr[i].seq_ofs + hr[i].len); }
-		int rc = grow(&ctx->d_recs, &ctx->recs_cap, 16ull * span + 256); if(rc) { return rc; }
-	}
-	RT_LAUNCH(k_seed_scan, seed_ctas, 32 * MAB_WARPS_PER_CTA, 2560 * MAB_WARPS_PER_CTA, ctx->stream, P, d_base, ctx->d_reads, n_seq, ctx->d_recs);
-	S.n_launches++;
-	CK(RT_MEMCPY_D2H_ASYNC(pin_rr, ctx->d_reads, rr_bytes, ctx->stream));
-	S.ms_wall_submit += (float)(RT_WALL_MS() - t_sub);
-	{ double tw = RT_WALL_MS(); CK(RT_STREAM_SYNC(ctx->stream)); S.ms_wall_wait += (float)(RT_WALL_MS() - tw); }
-	memcpy(hr.data(), pin_rr, rr_bytes);
-	double t_sizing = RT_WALL_MS();
-	S.d2h_bytes += sizeof(ReadRec) * (uint64_t)n_seq;
-	uint64_t ws_total = 0;
-	/* k_sortchain size classes, per round kind (round 0 stages a read's own seeds, later rounds all of them): the ordinary
-	 * reads (up to the 90th percentile of the seed bound) run with a small shared-memory footprint, the seed-rich rest in a
-	 * second launch with up to MAB_SC_MAX seeds staged */
-	struct ScCaps { uint32_t cap1, cap2, max_bound; } sc[2] = { { 64, 64, 0 }, { 64, 64, 0 } };
-	for(int kind = 0; kind < 2; kind++) {
-		std::vector<uint32_t> bnd;
-		for(uint32_t i = 0; i < n_seq; i++) { if(hr[i].state == 0) { bnd.push_back((kind == 0 ? hr[i].tot_seeds0 : hr[i].tot_seeds) + 2); } }
-		if(!bnd.empty()) {
-			size_t k90 = (bnd.size() * 9) / 10; if(k90 >= bnd.size()) { k90 = bnd.size() - 1; }
-			std::nth_element(bnd.begin(), bnd.begin() + k90, bnd.end());
-			sc[kind].cap1 = std::max<uint32_t>(64u, std::min<uint32_t>((bnd[k90] + 63u) & ~63u, MAB_SC_SMALL));
-			sc[kind].max_bound = *std::max_element(bnd.begin(), bnd.end());
-			sc[kind].cap2 = std::max<uint32_t>(sc[kind].cap1, std::min<uint32_t>((sc[kind].max_bound + 63u) & ~63u, MAB_SC_MAX));
-		}
-		if(const char *e = getenv("MAB_SC_CAP")) {									/* test hook: tiny caps push reads through the unstaged (global memory) path */
-			uint32_t v = (uint32_t)atoi(e);
-			if(v >= 64) { sc[kind].cap1 = std::min(sc[kind].cap1, v); sc[kind].cap2 = std::min(sc[kind].cap2, std::max(v, sc[kind].cap1)); }
-		}
-	}
-	for(uint32_t i = 0; i < n_seq; i++) {
-		ReadRec &r = hr[i];
-		if(r.state != 0) { continue; }
-		r.seed_cap = 2 * (r.tot_seeds + 1) + 8; r.root_cap = r.tot_seeds + 8; r.resc_cap = r.tot_resc + 4; r.bin_cap = 2 * r.tot_seeds + 128;
-		r.ws_ofs = ws_total;
-		ws_total += ws_layout(r.seed_cap, r.root_cap, r.resc_cap, r.bin_cap).total;
-	}
-	{ int rc = grow(&ctx->d_ws, &ctx->ws_cap, ws_total + 256); if(rc) { return rc; } }
+	{ int rc = pin_reserve(ctx, ctx->pin_user + 2 * sizeof(BatchCounters) + 256); if(rc) { return rc; } }
+	BatchCounters *pin_ctr = (BatchCounters *)(ctx->pin + ((ctx->pin_user + 127) & ~127ull));
+	{ int rc = grow(&ctx->d_recs, &ctx->recs_cap, 16ull * sh.span + 256); if(rc) { return rc; } }
 	{ int rc = grow(&ctx->d_frames, &ctx->frames_cap, 4ull * 8 * MAB_RS_FRAME * n_seq); if(rc) { return rc; } }
-	{	/* longest-processing-time-first work order for the persistent extend kernel (shortens its tail) */
-		int rc = grow(&ctx->d_order, &ctx->order_cap, 4ull * n_seq); if(rc) { return rc; }
-		for(uint32_t i = 0; i < n_seq; i++) { pin_order[i] = i; }
-		std::stable_sort(pin_order, pin_order + n_seq, [&](uint32_t a, uint32_t b) { return hr[a].len > hr[b].len; });
-		CK(RT_MEMCPY_H2D_ASYNC(ctx->d_order, pin_order, 4ull * n_seq, ctx->stream));
-	}
-	uint32_t blk_cap = dp_blk_cap(maxlen);
+	{ int rc = grow(&ctx->d_order, &ctx->order_cap, 4ull * n_seq); if(rc) { return rc; } }
+	uint32_t blk_cap = dp_blk_cap(sh.maxlen);
 	ArenaLayout AL = arena_layout(blk_cap);
 	uint32_t ext_ctas = std::max<uint32_t>(1, std::min<uint32_t>(ctx->n_slots / MAB_WARPS_PER_CTA, (n_seq + MAB_WARPS_PER_CTA - 1) / MAB_WARPS_PER_CTA));
 	{	/* the DP arenas are sized by the longest read of the batch (312 B per base per resident warp): with very long reads fewer
@@ -458,73 +417,100 @@ static int map_core(mab_ctx *ctx, const uint8_t *d_base, std::vector<ReadRec> &h
 		if(fit < ext_ctas) { ext_ctas = (uint32_t)std::max<uint64_t>(1, fit); }
 	}
 	{ int rc = grow(&ctx->d_arenas, &ctx->arenas_cap, AL.total * (uint64_t)ext_ctas * MAB_WARPS_PER_CTA); if(rc) { return rc; } }
-	uint64_t pool_need = tot_len / 4 + 64ull * n_seq + (1u << 16);				/* ~2 bits per base and alignment, x4 head room */
-	S.ms_wall_sizing += (float)(RT_WALL_MS() - t_sizing);
-	for(int attempt = 0; attempt < 3; attempt++) {
+	uint64_t pool_need = sh.tot_len / 4 + 64ull * n_seq + (1u << 16);				/* ~2 bits per base and alignment, x4 head room */
+	uint64_t ws_need = (uint64_t)(ctx->ws_per_base * (double)sh.tot_len) + 20480ull * n_seq + 4096;
+	uint32_t seed_ctas = std::max<uint32_t>(1, std::min<uint32_t>((n_seq + MAB_WARPS_PER_CTA - 1) / MAB_WARPS_PER_CTA, ctx->n_sm * 8));
+	uint32_t init_ctas = std::max<uint32_t>(1, std::min<uint32_t>((n_seq + 255) / 256, ctx->n_sm * 4));
+	/* k_sortchain size classes, per round kind (round 0 stages a read's own seeds, later rounds all of them): the ordinary reads
+	 * (up to the 90th percentile of the seed bound of the previous batch) run with a small shared-memory footprint, the
+	 * seed-rich rest in a second launch with up to MAB_SC_MAX seeds staged, beyond that in global memory */
+	uint32_t sc_cap1[2] = { ctx->sc_cap1[0], ctx->sc_cap1[1] }, sc_cap2[2] = { MAB_SC_MAX, MAB_SC_MAX };
+	if(const char *e = getenv("MAB_SC_CAP")) {										/* test hook: tiny caps push reads through the unstaged (global memory) path */
+		uint32_t v = (uint32_t)atoi(e);
+		if(v >= 64) { for(int k = 0; k < 2; k++) { sc_cap1[k] = std::min(sc_cap1[k], v); sc_cap2[k] = std::min(sc_cap2[k], std::max(v, sc_cap1[k])); } }
+	}
+	S.ms_wall_sizing += (float)(RT_WALL_MS() - t_sub);
+	auto rounds = [&](bool first) {
+		for(uint32_t round = 0; round < P.n_occ; round++) {
+			bool ev = timed && first && round < 8;
+			if(ev) { RT_EVENT_RECORD(ctx->rev[3 * round], ctx->stream); }
+			int kind = round == 0 ? 0 : 1;
+			RT_LAUNCH(k_sortchain, n_seq, 32, 16 * sc_cap1[kind] + 2048, ctx->stream, P, ctx->d_reads, n_seq, ctx->d_ws, ctx->d_frames, round, sc_cap1[kind], 0u, sc_cap1[kind]);
+			RT_LAUNCH(k_sortchain, n_seq, 32, 16 * sc_cap2[kind] + 2048, ctx->stream, P, ctx->d_reads, n_seq, ctx->d_ws, ctx->d_frames, round, sc_cap2[kind], sc_cap1[kind], 0xffffffffu);
+			if(first && round == 0) { RT_LAUNCH(k_rlen_predict, 1, MAB_PIPE_THREADS, 0, ctx->stream, P, ctx->d_reads, n_seq, (const uint8_t *)ctx->d_ws); S.n_launches++; }
+			RT_MEMSET_ASYNC(&ctx->d_ctr->work_next, 0, sizeof(unsigned int), ctx->stream);
+			if(ev) { RT_EVENT_RECORD(ctx->rev[3 * round + 1], ctx->stream); }
+			RT_LAUNCH(k_extend, ext_ctas, 32 * MAB_WARPS_PER_CTA, 1024 + 4 * MAB_TILE_WORDS * MAB_WARPS_PER_CTA, ctx->stream, P, d_base, (const uint8_t *)ctx->d_ntail, ctx->d_reads, (const uint32_t *)ctx->d_order, n_seq, ctx->d_ws,
+				ctx->d_arenas, AL.total, blk_cap, ctx->d_pool, ctx->pool_cap / 4, ctx->d_ctr, round, P.n_occ - 1);
+			S.n_launches += 3;
+			if(ev) { RT_EVENT_RECORD(ctx->rev[3 * round + 2], ctx->stream); }
+		}
+	};
+	RT_LAUNCH(k_order, 1, MAB_PIPE_THREADS, 0, ctx->stream, (const ReadRec *)ctx->d_reads, n_seq, ctx->d_order);
+	S.n_launches++;
+	for(int attempt = 0; ; attempt++) {
 		t_sub = RT_WALL_MS();
 		{ int rc = grow(&ctx->d_pool, &ctx->pool_cap, 4 * pool_need); if(rc) { return rc; } }
-		uint64_t pool_words = ctx->pool_cap / 4;
-		memcpy(pin_rr, hr.data(), rr_bytes);
-		CK(RT_MEMCPY_H2D_ASYNC(ctx->d_reads, pin_rr, rr_bytes, ctx->stream));
-		memset(&pin_ctr[0], 0, sizeof(BatchCounters));
-		CK(RT_MEMCPY_H2D_ASYNC(ctx->d_ctr, &pin_ctr[0], sizeof(BatchCounters), ctx->stream));
-		if(timed) { RT_EVENT_RECORD(ctx->ev[2], ctx->stream); }
-		RT_LAUNCH(k_seed_expand, seed_ctas, 32 * MAB_WARPS_PER_CTA, 0, ctx->stream, P, ctx->d_reads, n_seq, ctx->d_ws, (const uint32_t *)ctx->d_recs);
-		S.n_launches++;
-		if(timed) { RT_EVENT_RECORD(ctx->ev[3], ctx->stream); }
-		/* rounds of sort+chain / extend (minialign.c:4444-4448) */
-		for(uint32_t round = 0; round < P.n_occ; round++) {
-			if(timed && round < 8) { RT_EVENT_RECORD(ctx->rev[3 * round], ctx->stream); }
-			const ScCaps &C = sc[round == 0 ? 0 : 1];
-			RT_LAUNCH(k_sortchain, n_seq, 32, 16 * C.cap1 + 2048, ctx->stream, P, ctx->d_reads, n_seq, ctx->d_ws, ctx->d_frames, round, C.cap1, 0u, C.cap1);
-			if(C.max_bound > C.cap1) {												/* the seed-rich class (staged up to cap2 seeds, global memory beyond) */
-				RT_FUNC_MAX_SMEM(k_sortchain, 16 * MAB_SC_MAX + 2048);
-				RT_LAUNCH(k_sortchain, n_seq, 32, 16 * C.cap2 + 2048, ctx->stream, P, ctx->d_reads, n_seq, ctx->d_ws, ctx->d_frames, round, C.cap2, C.cap1, 0xffffffffu);
-				S.n_launches++;
-			}
-			RT_MEMSET_ASYNC(&ctx->d_ctr->work_next, 0, sizeof(unsigned int), ctx->stream);
-			if(timed && round < 8) { RT_EVENT_RECORD(ctx->rev[3 * round + 1], ctx->stream); }
-			RT_LAUNCH(k_extend, ext_ctas, 32 * MAB_WARPS_PER_CTA, 1024 + 4 * MAB_TILE_WORDS * MAB_WARPS_PER_CTA, ctx->stream, P, d_base, (const uint8_t *)ctx->d_ntail, ctx->d_reads, (const uint32_t *)ctx->d_order, n_seq, ctx->d_ws,
-				ctx->d_arenas, AL.total, blk_cap, ctx->d_pool, pool_words, ctx->d_ctr, round, P.n_occ - 1);
-			S.n_launches += 2;
-			if(timed && round < 8) { RT_EVENT_RECORD(ctx->rev[3 * round + 2], ctx->stream); }
+		{ int rc = grow(&ctx->d_ws, &ctx->ws_cap, ws_need); if(rc) { return rc; } }
+		if(attempt > 0) { RT_LAUNCH(k_reads_reset, init_ctas, 256, 0, ctx->stream, ctx->d_reads, n_seq); S.n_launches++; }
+		CK(RT_MEMSET_ASYNC(ctx->d_ctr, 0, sizeof(BatchCounters), ctx->stream));
+		if(timed) { RT_EVENT_RECORD(ctx->ev[1], ctx->stream); }
+		RT_LAUNCH(k_seed_scan, seed_ctas, 32 * MAB_WARPS_PER_CTA, 2560 * MAB_WARPS_PER_CTA, ctx->stream, P, d_base, ctx->d_reads, n_seq, ctx->d_recs);
+		RT_LAUNCH(k_size, 1, MAB_PIPE_THREADS, 0, ctx->stream, ctx->d_reads, n_seq, ctx->ws_cap, ctx->d_ctr);
+		S.n_launches += 2;
+		BatchCounters hc;
+		for(bool first = true; ; first = false) {
+			if(timed && first) { RT_EVENT_RECORD(ctx->ev[2], ctx->stream); }
+			RT_LAUNCH(k_seed_expand, seed_ctas, 32 * MAB_WARPS_PER_CTA, 0, ctx->stream, P, ctx->d_reads, n_seq, ctx->d_ws, (const uint32_t *)ctx->d_recs);
+			S.n_launches++;
+			if(timed && first) { RT_EVENT_RECORD(ctx->ev[3], ctx->stream); }
+			rounds(first);
+			if(timed && first) { RT_EVENT_RECORD(ctx->ev[4], ctx->stream); }
+			CK(RT_MEMSET_ASYNC(&ctx->d_ctr->n_redo, 0, sizeof(unsigned int), ctx->stream));
+			RT_LAUNCH(k_rlen_verify, 1, MAB_PIPE_THREADS, 0, ctx->stream, ctx->d_reads, n_seq, rlen_init, init_known, ctx->d_ctr);
+			S.n_launches++;
+			CK(RT_MEMCPY_D2H_ASYNC(pin_ctr, ctx->d_ctr, sizeof(BatchCounters), ctx->stream));
+			S.ms_wall_submit += (float)(RT_WALL_MS() - t_sub);
+			{ double tw = RT_WALL_MS(); CK(RT_STREAM_SYNC(ctx->stream)); S.ms_wall_wait += (float)(RT_WALL_MS() - tw); }
+			t_sub = RT_WALL_MS();
+			hc = *pin_ctr;
+			S.d2h_bytes += sizeof(hc);
+			if((hc.err_any & (MAB_ERR_POOL_OVF | MAB_ERR_WS_OVF)) || hc.pool_top > ctx->pool_cap / 4 || hc.n_redo == 0) { break; }
+			S.n_retry += hc.n_redo;
 		}
-		if(timed) { RT_EVENT_RECORD(ctx->ev[4], ctx->stream); }
-		CK(RT_MEMCPY_D2H_ASYNC(&pin_ctr[1], ctx->d_ctr, sizeof(BatchCounters), ctx->stream));
-		CK(RT_MEMCPY_D2H_ASYNC(pin_rr, ctx->d_reads, rr_bytes, ctx->stream));
-		S.ms_wall_submit += (float)(RT_WALL_MS() - t_sub);
-		{ double tw = RT_WALL_MS(); CK(RT_STREAM_SYNC(ctx->stream)); S.ms_wall_wait += (float)(RT_WALL_MS() - tw); }
-		BatchCounters hc = pin_ctr[1];
-		memcpy(hr.data(), pin_rr, rr_bytes);
-		uint32_t err = 0;
-		for(uint32_t i = 0; i < n_seq; i++) { err |= hr[i].err; }
-		S.n_vectors += hc.n_vectors; S.n_fill_calls += hc.n_fill; S.n_trace += hc.n_trace;
-		if((err & MAB_ERR_POOL_OVF) || hc.pool_top > pool_words) {
-			pool_need *= 4; S.n_retry++;
-			for(uint32_t i = 0; i < n_seq; i++) { ReadRec &r = hr[i]; if(r.len >= P.k && (double)r.len * P.mcoef >= (double)P.min_score) { r.state = 0; } r.err = 0; r.result_words = 0; r.n_res = 0; r.nbin = 0; }
-			if(attempt == 2) { g_err = "result pool overflow after retries"; return MAB_EOVERFLOW; }
+		if(hc.ws_need > ctx->ws_cap || (hc.err_any & MAB_ERR_WS_OVF)) {					/* workspace estimate too small: now it is known exactly */
+			ws_need = hc.ws_need + hc.ws_need / 8 + 4096; S.n_retry++;
+			if(attempt >= 3) { g_err = "workspace overflow after retries"; return MAB_EOVERFLOW; }
 			continue;
 		}
-		if(err) { g_err = "device workspace overflow (error bits " + std::to_string(err) + ")"; return MAB_EOVERFLOW; }
-		uint64_t top = hc.pool_top;
-		uint32_t *dst;
-		if(alt_pool) { alt_pool->resize((size_t)top + 4); dst = alt_pool->data(); }			/* re-mapped reads (rare): pageable side buffer */
-		else {
-			if(4 * (top + 4) > ctx->h_pool_cap) {
-				RT_HOST_FREE(ctx->h_pool); ctx->h_pool = nullptr; ctx->h_pool_cap = 0;
-				uint64_t nb = 4 * (top + 4) + (top + 4);									/* 25 % head room */
-				if(!RT_OK(RT_HOST_ALLOC(&ctx->h_pool, nb))) { g_err = std::string("pinned host allocation failed: ") + RT_ERRSTR(); return MAB_ENOMEM; }
-				ctx->h_pool_cap = nb;
-			}
-			dst = ctx->h_pool;
+		if((hc.err_any & MAB_ERR_POOL_OVF) || hc.pool_top > ctx->pool_cap / 4) {
+			pool_need = std::max<uint64_t>(4 * pool_need, hc.pool_top + hc.pool_top / 2); S.n_retry++;
+			if(attempt >= 3) { g_err = "result pool overflow after retries"; return MAB_EOVERFLOW; }
+			continue;
 		}
-		if(top) { CK(RT_MEMCPY_D2H_ASYNC(dst, ctx->d_pool, 4 * top, ctx->stream)); }
-		if(timed) { RT_EVENT_RECORD(ctx->ev[5], ctx->stream); }
-		{ double tw = RT_WALL_MS(); CK(RT_STREAM_SYNC(ctx->stream)); S.ms_wall_wait += (float)(RT_WALL_MS() - tw); }
-		S.d2h_bytes += 4 * top + sizeof(ReadRec) * (uint64_t)n_seq + sizeof(hc);
+		ctx->hc = hc;
+		S.n_vectors += hc.n_vectors; S.n_fill_calls += hc.n_fill; S.n_trace += hc.n_trace;
+		if(sh.tot_len) {																	/* high-water mark for the next batch's estimate */
+			double per_base = ((double)hc.ws_need - 20480.0 * n_seq) / (double)sh.tot_len;
+			if(per_base * 1.25 > ctx->ws_per_base) { ctx->ws_per_base = per_base * 1.25; }
+		}
 		break;
 	}
 	return MAB_OK;
+}
+
+/* size classes of k_sortchain for the next batch from this batch's per-read seed bounds */
+static void update_sc_caps(mab_ctx *ctx, const ReadRec *hr, uint32_t n_seq)
+{
+	for(int kind = 0; kind < 2; kind++) {
+		std::vector<uint32_t> bnd;
+		bnd.reserve(n_seq);
+		for(uint32_t i = 0; i < n_seq; i++) { if(hr[i].len >= ctx->P.k && hr[i].seed_cap != 0) { bnd.push_back((kind == 0 ? hr[i].tot_seeds0 : hr[i].tot_seeds) + 2); } }
+		if(bnd.size() < 16) { continue; }
+		size_t k90 = (bnd.size() * 9) / 10; if(k90 >= bnd.size()) { k90 = bnd.size() - 1; }
+		std::nth_element(bnd.begin(), bnd.begin() + k90, bnd.end());
+		ctx->sc_cap1[kind] = std::max<uint32_t>(64u, std::min<uint32_t>((bnd[k90] + 63u) & ~63u, MAB_SC_SMALL));
+	}
 }
 
 extern "C" int mab_map_batch(mab_ctx *ctx, const uint8_t *seq_block, uint64_t block_size, const uint64_t *seq_ofs, const uint32_t *seq_len, uint32_t n_seq)
@@ -532,9 +518,15 @@ extern "C" int mab_map_batch(mab_ctx *ctx, const uint8_t *seq_block, uint64_t bl
 	mab_stats_t &S = ctx->stats;
 	memset(&S, 0, sizeof(S));
 	const double t_call = RT_WALL_MS();
-	ctx->res_ofs.assign((size_t)n_seq + 1, 0);
+	try { ctx->res_ofs.assign((size_t)n_seq + 1, 0); } catch(const std::bad_alloc &) { g_err = "host allocation failed"; return MAB_ENOMEM; }
 	if(n_seq == 0) { return MAB_OK; }
 	CK(RT_USE_DEVICE(ctx->device));
+	PipeShape sh; sh.n_seq = n_seq; sh.maxlen = 0; sh.tot_len = 0; sh.span = 0;
+	for(uint32_t i = 0; i < n_seq; i++) {
+		sh.maxlen = std::max(sh.maxlen, seq_len[i]); sh.tot_len += seq_len[i]; sh.span = std::max<uint64_t>(sh.span, seq_ofs[i] + seq_len[i]);
+		/* contract (header): ascending, non-overlapping, >= 64 bytes of margin behind every read, inside the block */
+		if(seq_ofs[i] + seq_len[i] + 64 > block_size || (i > 0 && seq_ofs[i] < seq_ofs[i - 1] + seq_len[i - 1] + 64)) { g_err = "mab_map_batch: reads must be ascending, non-overlapping and followed by 64 bytes of margin inside the block"; return MAB_EINVAL; }
+	}
 	RT_EVENT_RECORD(ctx->ev[0], ctx->stream);
 	const uint8_t *d_base;
 	if(ctx->device_input) { d_base = seq_block; }
@@ -543,72 +535,76 @@ extern "C" int mab_map_batch(mab_ctx *ctx, const uint8_t *seq_block, uint64_t bl
 		CK(RT_MEMCPY_H2D_ASYNC(ctx->d_seq, seq_block, block_size, ctx->stream));
 		d_base = ctx->d_seq; S.h2d_bytes += block_size;
 	}
-	std::vector<ReadRec> &hr = ctx->h_reads;
-	hr.assign(n_seq, ReadRec());
-	for(uint32_t i = 0; i < n_seq; i++) { memset(&hr[i], 0, sizeof(ReadRec)); hr[i].seq_ofs = seq_ofs[i]; hr[i].len = seq_len[i]; hr[i].rlen_in = MAB_RLEN_OWN; }
-	{ int rc = map_core(ctx, d_base, hr, true); if(rc) { return rc; } }
-	double t0 = RT_WALL_MS();
-	/* verify the rlen speculation in read order (the reference's -t1 semantics); re-map the reads whose first root test would
-	 * have gone the other way with the true stale value.  Their results land in side pools; src[i] = pool read i refers to. */
-	std::vector<const uint32_t *> src(n_seq, ctx->h_pool);
-	std::vector<std::vector<uint32_t>> side;
-	side.reserve(8);
-	for(int iter = 0; iter < 8; iter++) {
-		std::vector<uint32_t> redo;
-		uint32_t prev = ctx->rlen_last;
-		for(uint32_t i = 0; i < n_seq; i++) {
-			ReadRec &r = hr[i];
-			if(!(r.dep_flags & 1)) { continue; }					/* no chain was loaded: rlen unchanged */
-			bool used = (r.dep_apos >= r.rlen_used) || (r.dep_flags & 2), actual = (r.dep_apos >= prev) || (r.dep_flags & 2);
-			if(used != actual) { redo.push_back(i); }
-			prev = r.rlen_cur;										/* value left behind by this read (may change after a redo) */
-		}
-		if(redo.empty()) { break; }
-		S.n_retry += (uint32_t)redo.size();
-		/* true stale value for each read to redo, given the current view of its predecessors */
-		std::vector<ReadRec> sub(redo.size());
-		prev = ctx->rlen_last;
-		size_t k = 0;
-		for(uint32_t i = 0; i < n_seq && k < redo.size(); i++) {
-			if(i == redo[k]) { memset(&sub[k], 0, sizeof(ReadRec)); sub[k].seq_ofs = hr[i].seq_ofs; sub[k].len = hr[i].len; sub[k].rlen_in = prev; k++; }
-			if(hr[i].dep_flags & 1) { prev = hr[i].rlen_cur; }
-		}
-		side.emplace_back();
-		{ int rc = map_core(ctx, d_base, sub, false, &side.back()); if(rc) { return rc; } }
-		for(size_t j = 0; j < redo.size(); j++) { hr[redo[j]] = sub[j]; src[redo[j]] = side.back().data(); }
+	const uint64_t rr_bytes = sizeof(ReadRec) * (uint64_t)n_seq;
+	ctx->pin_user = rr_bytes;																/* [ReadRec x n] doubles as [ofs u64 x n][len u32 x n] on the way in */
+	{ int rc = pin_reserve(ctx, ctx->pin_user + 2 * sizeof(BatchCounters) + 256); if(rc) { return rc; } }
+	{ int rc = grow(&ctx->d_reads, &ctx->reads_cap, rr_bytes); if(rc) { return rc; } }
+	{ int rc = grow(&ctx->d_io, &ctx->io_cap, 12ull * n_seq + 64); if(rc) { return rc; } }
+	{
+		uint64_t *po = (uint64_t *)ctx->pin; uint32_t *pl = (uint32_t *)(ctx->pin + 8ull * n_seq);
+		memcpy(po, seq_ofs, 8ull * n_seq); memcpy(pl, seq_len, 4ull * n_seq);
+		CK(RT_MEMCPY_H2D_ASYNC(ctx->d_io, ctx->pin, 12ull * n_seq, ctx->stream));
+		S.h2d_bytes += 12ull * n_seq;
+		uint32_t init_ctas = std::max<uint32_t>(1, std::min<uint32_t>((n_seq + 255) / 256, ctx->n_sm * 4));
+		RT_LAUNCH(k_reads_init, init_ctas, 256, 0, ctx->stream, ctx->d_reads, n_seq, (const uint64_t *)ctx->d_io, (const uint32_t *)(ctx->d_io + 8ull * n_seq));
+		S.n_launches++;
 	}
-	for(uint32_t i = 0; i < n_seq; i++) { if(hr[i].dep_flags & 1) { ctx->rlen_last = hr[i].rlen_cur; } }
+	{ int rc = pipeline_run(ctx, d_base, sh, ctx->rlen_last, 1u, true); if(rc) { return rc; } }
+	const BatchCounters &hc = ctx->hc;
+	if(hc.chain_valid) { ctx->rlen_last = hc.chain_rlen; }
+	/* results: per-read records and the pool */
+	ReadRec *pin_rr = (ReadRec *)ctx->pin;
+	uint64_t top = hc.pool_top;
+	if(4 * (top + 4) > ctx->h_pool_cap) {
+		RT_HOST_FREE(ctx->h_pool); ctx->h_pool = nullptr; ctx->h_pool_cap = 0;
+		uint64_t nb = 4 * (top + 4) + (top + 4);											/* 25 % head room */
+		if(!RT_OK(RT_HOST_ALLOC(&ctx->h_pool, nb))) { g_err = std::string("pinned host allocation failed: ") + RT_ERRSTR(); return MAB_ENOMEM; }
+		ctx->h_pool_cap = nb;
+	}
+	CK(RT_MEMCPY_D2H_ASYNC(pin_rr, ctx->d_reads, rr_bytes, ctx->stream));
+	if(top) { CK(RT_MEMCPY_D2H_ASYNC(ctx->h_pool, ctx->d_pool, 4 * top, ctx->stream)); }
+	RT_EVENT_RECORD(ctx->ev[5], ctx->stream);
+	{ double tw = RT_WALL_MS(); CK(RT_STREAM_SYNC(ctx->stream)); S.ms_wall_wait += (float)(RT_WALL_MS() - tw); }
+	S.d2h_bytes += 4 * top + rr_bytes;
+	const ReadRec *hr = pin_rr;
+	update_sc_caps(ctx, hr, n_seq);
+	uint32_t n_failed = 0;
+	for(uint32_t i = 0; i < n_seq; i++) { n_failed += hr[i].err != 0; }
+	S.n_failed = n_failed;																	/* reads given up on (a per-read device structure overflowed): reported unmapped */
+	double t0 = RT_WALL_MS();
 	/* host post-processing, fanned out over the host cores: plan every read (no copying), prefix-sum the sizes, then write the
 	 * flat records straight into their final place */
 	uint32_t hw = std::thread::hardware_concurrency();
 	if(const char *e = getenv("MAB_HOST_THREADS")) { int v = atoi(e); if(v > 0) { hw = (uint32_t)v; } }
 	uint32_t nth = std::max(1u, std::min<uint32_t>(std::min<uint32_t>(hw, 32u), n_seq / 64 + 1));
-	std::vector<std::vector<PlanItem>> items(nth);
-	std::vector<ReadPlan> plan(n_seq);
-	auto run_par = [&](auto &&fn) {
-		std::vector<std::thread> th;
-		for(uint32_t t = 1; t < nth; t++) { th.emplace_back(fn, t); }
-		fn(0u);
-		for(auto &x : th) { x.join(); }
-	};
-	run_par([&](uint32_t t) {
-		for(uint32_t i = t; i < n_seq; i += nth) {
-			if(hr[i].result_words != 0) { plan[i] = post_plan(ctx, src[i], src[i] + hr[i].result_ofs, items[t]); }
-			else { plan[i].first = 0; plan[i].count = 0; plan[i].n_uniq = 0; plan[i].words = 0; }
-		}
-	});
-	uint64_t total = 0;
-	for(uint32_t i = 0; i < n_seq; i++) { ctx->res_ofs[i] = total; total += plan[i].words; }
-	ctx->res_ofs[n_seq] = total;
-	if(total > ctx->res_cap) { delete[] ctx->res_words; ctx->res_cap = total + total / 4 + 1024; ctx->res_words = new uint32_t[ctx->res_cap]; }
-	run_par([&](uint32_t t) {
-		for(uint32_t i = t; i < n_seq; i += nth) {
-			if(plan[i].words != 0) { post_emit(plan[i], items[t].data() + plan[i].first, ctx->res_words + ctx->res_ofs[i]); }
-		}
-	});
+	try {
+		std::vector<std::vector<PlanItem>> items(nth);
+		std::vector<ReadPlan> plan(n_seq);
+		auto run_par = [&](auto &&fn) {
+			std::vector<std::thread> th;
+			for(uint32_t t = 1; t < nth; t++) { th.emplace_back(fn, t); }
+			fn(0u);
+			for(auto &x : th) { x.join(); }
+		};
+		run_par([&](uint32_t t) {
+			for(uint32_t i = t; i < n_seq; i += nth) {
+				if(hr[i].result_words != 0 && hr[i].err == 0) { plan[i] = post_plan(ctx, ctx->h_pool, ctx->h_pool + hr[i].result_ofs, items[t]); }
+				else { plan[i].first = 0; plan[i].count = 0; plan[i].n_uniq = 0; plan[i].words = 0; }
+			}
+		});
+		uint64_t total = 0;
+		for(uint32_t i = 0; i < n_seq; i++) { ctx->res_ofs[i] = total; total += plan[i].words; }
+		ctx->res_ofs[n_seq] = total;
+		if(total > ctx->res_cap) { delete[] ctx->res_words; ctx->res_words = nullptr; ctx->res_cap = 0; ctx->res_words = new uint32_t[total + total / 4 + 1024]; ctx->res_cap = total + total / 4 + 1024; }
+		run_par([&](uint32_t t) {
+			for(uint32_t i = t; i < n_seq; i += nth) {
+				if(plan[i].words != 0) { post_emit(plan[i], items[t].data() + plan[i].first, ctx->res_words + ctx->res_ofs[i]); }
+			}
+		});
+	} catch(const std::bad_alloc &) { g_err = "host allocation failed"; return MAB_ENOMEM; }
 	S.ms_post = (float)(RT_WALL_MS() - t0);
 	S.ms_h2d = RT_EVENT_MS(ctx->ev[0], ctx->ev[1]);
-	S.ms_seed = RT_EVENT_MS(ctx->ev[2], ctx->ev[3]);
+	S.ms_seed = RT_EVENT_MS(ctx->ev[1], ctx->ev[3]);
 	S.ms_sortchain = 0.f; S.ms_extend = 0.f; S.ms_extend_r0 = 0.f;
 	for(uint32_t r = 0; r < ctx->P.n_occ && r < 8; r++) {
 		S.ms_sortchain += RT_EVENT_MS(ctx->rev[3 * r], ctx->rev[3 * r + 1]);
@@ -652,12 +648,13 @@ extern "C" uint64_t mab_sketch(mab_ctx *ctx, const uint8_t *seq, uint32_t len, u
 {
 	uint8_t *d_seq = nullptr; uint64_t *d_out = nullptr, *d_n = nullptr;
 	uint64_t n = 0, dcap = (uint64_t)len + 8;
+	if(!RT_OK(RT_USE_DEVICE(ctx->device))) { return 0; }
 	if(!RT_OK(RT_MALLOC(&d_seq, (uint64_t)len + 64)) || !RT_OK(RT_MALLOC(&d_out, 8 * dcap)) || !RT_OK(RT_MALLOC(&d_n, 8))) { return 0; }
-	RT_MEMCPY_H2D(d_seq, seq, len);
+	RT_MEMCPY_H2D_ASYNC(d_seq, seq, len, ctx->stream);
 	RT_LAUNCH(k_sketch_words, 1, 32, 512, ctx->stream, ctx->P, (const uint8_t *)d_seq, len, d_out, dcap, d_n);
 	RT_STREAM_SYNC(ctx->stream);
-	RT_MEMCPY_D2H(&n, d_n, 8);
-	if(n <= cap) { RT_MEMCPY_D2H(out, d_out, 8 * n); }
+	RT_MEMCPY_D2H_ASYNC(&n, d_n, 8, ctx->stream);
+	if(n <= cap) { RT_MEMCPY_D2H_ASYNC(out, d_out, 8 * n, ctx->stream); }
 	RT_FREE(d_seq); RT_FREE(d_out); RT_FREE(d_n);
 	return n;
 }
@@ -667,30 +664,31 @@ extern "C" uint64_t mab_seed_chain(mab_ctx *ctx, const uint8_t *seq, uint32_t le
 {
 	const DevParams &P = ctx->P;
 	*n_total = 0; *n_root = 0;
+	if(!RT_OK(RT_USE_DEVICE(ctx->device))) { return 0; }
 	uint8_t *d_seq = nullptr; ReadRec *d_r = nullptr; uint8_t *d_ws = nullptr; uint32_t *d_fr = nullptr;
 	if(!RT_OK(RT_MALLOC(&d_seq, (uint64_t)len + 256)) || !RT_OK(RT_MALLOC(&d_r, sizeof(ReadRec))) || !RT_OK(RT_MALLOC(&d_fr, 4ull * 8 * MAB_RS_FRAME))) { return 0; }
-	RT_MEMCPY_H2D(d_seq, seq, len);
+	RT_MEMCPY_H2D_ASYNC(d_seq, seq, len, ctx->stream);
 	ReadRec r; memset(&r, 0, sizeof(r)); r.len = len;
-	RT_MEMCPY_H2D(d_r, &r, sizeof(r));
+	RT_MEMCPY_H2D_ASYNC(d_r, &r, sizeof(r), ctx->stream);
 	uint32_t *d_rec = nullptr;
 	if(!RT_OK(RT_MALLOC(&d_rec, 16ull * len + 256))) { RT_FREE(d_seq); RT_FREE(d_r); RT_FREE(d_fr); return 0; }
 	RT_LAUNCH(k_seed_scan, 1, 32, 2560, ctx->stream, P, (const uint8_t *)d_seq, d_r, 1u, d_rec);
 	RT_STREAM_SYNC(ctx->stream);
-	RT_MEMCPY_D2H(&r, d_r, sizeof(r));
+	RT_MEMCPY_D2H_ASYNC(&r, d_r, sizeof(r), ctx->stream);
 	uint64_t ns = 0;
 	if(r.state == 0) {
 		r.seed_cap = 2 * (r.tot_seeds + 1) + 8; r.root_cap = r.tot_seeds + 8; r.resc_cap = r.tot_resc + 4; r.bin_cap = 2 * r.tot_seeds + 128; r.ws_ofs = 0;
 		WsLayout L = ws_layout(r.seed_cap, r.root_cap, r.resc_cap, r.bin_cap);
 		RT_MALLOC(&d_ws, L.total + 256);
-		RT_MEMCPY_H2D(d_r, &r, sizeof(r));
+		RT_MEMCPY_H2D_ASYNC(d_r, &r, sizeof(r), ctx->stream);
 		RT_LAUNCH(k_seed_expand, 1, 32, 0, ctx->stream, P, d_r, 1u, d_ws, (const uint32_t *)d_rec);
 		{ uint32_t sc_cap = std::max<uint32_t>(64u, std::min<uint32_t>(r.tot_seeds + 2, MAB_SC_SMALL)); for(uint32_t i = 0; i <= round && i < P.n_occ; i++) { RT_LAUNCH(k_sortchain, 1, 32, 16 * sc_cap + 2048, ctx->stream, P, d_r, 1u, d_ws, d_fr, i, sc_cap, 0u, 0xffffffffu); } }
 		RT_STREAM_SYNC(ctx->stream);
-		RT_MEMCPY_D2H(&r, d_r, sizeof(r));
+		RT_MEMCPY_D2H_ASYNC(&r, d_r, sizeof(r), ctx->stream);
 		if(r.n_seed) {
 			ns = r.n_seed; *n_total = r.seed_n; *n_root = r.n_root;
-			if(r.seed_n <= seed_cap) { RT_MEMCPY_D2H(seeds, d_ws + L.seed, 16ull * r.seed_n); }
-			if(r.n_root && r.n_root <= root_cap) { RT_MEMCPY_D2H(roots, d_ws + L.root, 8ull * r.n_root); }
+			if(r.seed_n <= seed_cap) { RT_MEMCPY_D2H_ASYNC(seeds, d_ws + L.seed, 16ull * r.seed_n, ctx->stream); }
+			if(r.n_root && r.n_root <= root_cap) { RT_MEMCPY_D2H_ASYNC(roots, d_ws + L.root, 8ull * r.n_root, ctx->stream); }
 		}
 		RT_FREE(d_ws);
 	}
@@ -703,6 +701,7 @@ extern "C" int mab_extend_pairs(mab_ctx *ctx, const uint8_t *seq_block, uint64_t
 {
 	const DevParams &P = ctx->P;
 	if(n == 0) { aln_ofs[0] = 0; return MAB_OK; }
+	CK(RT_USE_DEVICE(ctx->device));
 	uint32_t maxlen = 0; uint64_t tot = 0;
 	for(uint32_t i = 0; i < n; i++) { maxlen = std::max(maxlen, std::max(pairs[i].alen, pairs[i].blen)); tot += pairs[i].alen + pairs[i].blen; }
 	uint32_t blk_cap = dp_blk_cap(maxlen);
@@ -713,17 +712,17 @@ extern "C" int mab_extend_pairs(mab_ctx *ctx, const uint8_t *seq_block, uint64_t
 	static_assert(sizeof(PairIn) == sizeof(mab_pair_t), "pair layout");
 	CK(RT_MALLOC(&d_seq, block_size + 256)); CK(RT_MALLOC(&d_ar, AL.total * (uint64_t)ctas * MAB_WARPS_PER_CTA)); CK(RT_MALLOC(&d_p, sizeof(PairIn) * (uint64_t)n));
 	CK(RT_MALLOC(&d_res, 64ull * n)); CK(RT_MALLOC(&d_pool, 4 * pool_words)); CK(RT_MALLOC(&d_ao, 8ull * n));
-	CK(RT_MEMCPY_H2D(d_seq, seq_block, block_size)); CK(RT_MEMCPY_H2D(d_p, pairs, sizeof(PairIn) * (uint64_t)n));
+	CK(RT_MEMCPY_H2D_ASYNC(d_seq, seq_block, block_size, ctx->stream)); CK(RT_MEMCPY_H2D_ASYNC(d_p, pairs, sizeof(PairIn) * (uint64_t)n, ctx->stream));
 	BatchCounters zero; memset(&zero, 0, sizeof(zero));
-	CK(RT_MEMCPY_H2D(ctx->d_ctr, &zero, sizeof(zero)));
+	CK(RT_MEMCPY_H2D_ASYNC(ctx->d_ctr, &zero, sizeof(zero), ctx->stream));
 	RT_LAUNCH(k_extend_pairs, ctas, 32 * MAB_WARPS_PER_CTA, 1024 + 4 * MAB_TILE_WORDS * MAB_WARPS_PER_CTA, ctx->stream, P, (const uint8_t *)d_seq, (const uint8_t *)ctx->d_ntail, (const PairIn *)d_p, n, d_res, d_ao,
 		d_ar, AL.total, blk_cap, d_pool, pool_words, ctx->d_ctr);
 	CK(RT_STREAM_SYNC(ctx->stream));
-	BatchCounters hc; CK(RT_MEMCPY_D2H(&hc, ctx->d_ctr, sizeof(hc)));
+	BatchCounters hc; CK(RT_MEMCPY_D2H_ASYNC(&hc, ctx->d_ctr, sizeof(hc), ctx->stream));
 	std::vector<uint32_t> pool((size_t)std::min<uint64_t>(hc.pool_top, pool_words) + 4);
 	std::vector<uint64_t> ao(n);
-	CK(RT_MEMCPY_D2H(res, d_res, 64ull * n)); CK(RT_MEMCPY_D2H(ao.data(), d_ao, 8ull * n));
-	if(hc.pool_top) { CK(RT_MEMCPY_D2H(pool.data(), d_pool, 4 * std::min<uint64_t>(hc.pool_top, pool_words))); }
+	CK(RT_MEMCPY_D2H_ASYNC(res, d_res, 64ull * n, ctx->stream)); CK(RT_MEMCPY_D2H_ASYNC(ao.data(), d_ao, 8ull * n, ctx->stream));
+	if(hc.pool_top) { CK(RT_MEMCPY_D2H_ASYNC(pool.data(), d_pool, 4 * std::min<uint64_t>(hc.pool_top, pool_words), ctx->stream)); }
 	ctx->stats.n_vectors = hc.n_vectors;
 	uint64_t o = 0;
 	int rc = (hc.err_any || hc.pool_top > pool_words) ? MAB_EOVERFLOW : MAB_OK;
@@ -770,11 +769,12 @@ extern "C" int mab_fill_peak(mab_ctx *ctx, int masks, uint32_t n_blocks, double 
 extern "C" int mab_selftest(mab_ctx *ctx, uint32_t *out)
 {
 	uint32_t *d = nullptr;
+	CK(RT_USE_DEVICE(ctx->device));
 	CK(RT_MALLOC(&d, 4ull * 64 * 32));
 	CK(RT_MEMSET_ASYNC(d, 0, 4ull * 64 * 32, ctx->stream));
 	RT_LAUNCH(k_selftest, 1, 32, 0, ctx->stream, d);
 	CK(RT_STREAM_SYNC(ctx->stream));
-	CK(RT_MEMCPY_D2H(out, d, 4ull * 64 * 32));
+	CK(RT_MEMCPY_D2H_ASYNC(out, d, 4ull * 64 * 32, ctx->stream));
 	RT_FREE(d);
 	return MAB_OK;
 }

@@ -13,6 +13,7 @@
  */
 #pragma once
 #include "mab_dp.cuh"
+#include "mab_pipe.cuh"
 
 namespace mab {
 
@@ -651,6 +652,7 @@ __global__ void __launch_bounds__(32 * MAB_WARPS_PER_CTA, MAB_EXT_CTAS_PER_SM) k
 			r->rlen_cur = st.rlen;
 			if(c.err) { r->err |= c.err; }
 			if(r->n_res > 0 || round == last_round || r->err) { finalize_read(x, ctr, pool_cap); }
+			if(r->err) { atomicOr(&ctr->err_any, r->err); }
 		}
 		__syncwarp();
 	}

@@ -41,6 +41,7 @@ namespace mab {
 #define MAB_ERR_POOL_OVF	0x08u
 #define MAB_ERR_DP_OVF		0x10u
 #define MAB_ERR_TAIL_OVF	0x20u
+#define MAB_ERR_WS_OVF		0x40u		/* the batch's workspace buffer was too small for this read (host grows it and re-runs) */
 
 /* root (phantom) vectors of one band width: gaba_init_diff_vectors / gaba_init_middle_delta / gaba_init_phantom
  * (gaba.c:3684-3791) evaluated on the host once per context */
@@ -162,6 +163,11 @@ struct BatchCounters {
 	unsigned int work_next;			/* persistent-warp work counter */
 	unsigned int err_any;
 	unsigned long long n_vectors, n_fill, n_trace;
+	unsigned long long ws_need;		/* k_size: bytes of per-read workspace the batch asks for */
+	unsigned int n_redo;			/* k_rlen_verify: reads whose first-root test was mis-speculated (re-activated for a redo pass) */
+	unsigned int chain_valid, chain_rlen;	/* the reference thread's `rlen` after the last chain-loading read of the batch */
+	unsigned int fd_valid, fd_idx, fd_apos, fd_flags, fd_used;	/* first chain-loading read: its predecessor lives in the previous batch */
+	unsigned int _pad;
 };
 
 }  // namespace mab

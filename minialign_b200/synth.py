@@ -15,10 +15,17 @@ for _a, _b in zip(b"ACGTN", b"TGCAN"):
     _COMP[_a] = _b
 
 
-def make_genome(length: int, n_contigs: int = 1, seed: int = 1, repeats=((7, 5000), (40, 1500)), divergence: float = 0.02):
-    """Return a list of (name, uint8 ASCII array) contigs."""
+def make_genome(length: int, n_contigs: int = 1, seed: int = 1, repeats=((7, 5000), (40, 1500)), divergence: float = 0.02, weights=None):
+    """Return a list of (name, uint8 ASCII array) contigs.  weights: relative contig sizes (default: equal); unequal contigs
+    matter for parity because the reference tests a read's first seed against the PREVIOUS chain's reference length
+    (minialign.c:3865 runs before 3873)."""
     rng = np.random.default_rng(seed)
-    sizes = np.full(n_contigs, length // n_contigs, dtype=np.int64)
+    if weights is None:
+        sizes = np.full(n_contigs, length // n_contigs, dtype=np.int64)
+    else:
+        w = np.asarray(weights, dtype=np.float64)
+        assert w.size == n_contigs
+        sizes = np.maximum(1, (length * w / w.sum()).astype(np.int64))
     sizes[-1] += length - sizes.sum()
     contigs = []
     for ci, sz in enumerate(sizes):

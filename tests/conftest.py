@@ -19,7 +19,7 @@ def pytest_configure(config):
 def build_emu():
     """g++ build of the product's device + host sources against the CUDA-on-CPU shim (tests/emu)."""
     srcs = [os.path.join(ROOT, "tests/emu", f) for f in ("mab_emu.cpp", "cuda_emu.cpp", "cuda_emu.h")]
-    srcs += [os.path.join(ROOT, "minialign_b200/csrc", f) for f in ("mab_host.inl", "mab_kernels.cuh", "mab_dp.cuh", "mab_scalar.cuh", "mab_types.h")]
+    srcs += [os.path.join(ROOT, "minialign_b200/csrc", f) for f in sorted(f for f in os.listdir(os.path.join(ROOT, "minialign_b200/csrc")) if f.endswith((".inl", ".cuh", ".h")))]
     if not os.path.exists(EMU_SO) or any(os.path.getmtime(s) > os.path.getmtime(EMU_SO) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-pthread", "-shared", "-I" + os.path.join(ROOT, "tests/emu"),
                                os.path.join(ROOT, "tests/emu/mab_emu.cpp"), os.path.join(ROOT, "tests/emu/cuda_emu.cpp"), "-o", EMU_SO])

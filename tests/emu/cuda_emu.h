@@ -19,6 +19,7 @@
 #define __global__
 #define __device__
 #define __host__
+#define __shared__ static
 #define __forceinline__ inline
 #define __noinline__
 #define __restrict__

@@ -100,3 +100,40 @@ def test_emu_map_batch_state_carries_across_batches(gold):
     m.close()
     for e, g in zip(exp, got):
         assert np.array_equal(e, g)
+
+
+def _uneven_genome_index(tmp_path, total=90_000, seed=61):
+    """Contigs of very different lengths + an index built by the product's own host builder (`minialign-b200 -d`)."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    from minialign_b200 import mai, synth
+    g = synth.make_genome(total, 6, seed=seed, repeats=((6, 600), (20, 200)), weights=[30, 3, 14, 2, 9, 5])
+    fa, idx = str(tmp_path / "g.fa"), str(tmp_path / "g.mai")
+    synth.write_fasta(fa, g, 60)
+    subprocess.check_call(["make", "-s", "-f", "minialign_b200/csrc/host/Makefile"], cwd=ROOT)
+    subprocess.check_call([os.path.join(ROOT, "minialign_b200", "minialign-b200"), "-xpacbio", "-d", idx, fa], stderr=subprocess.DEVNULL)
+    return g, mai.load_mai(idx)
+
+
+def test_emu_rlen_chain_on_uneven_contigs(tmp_path):
+    """The reference thread's stale `rlen` (first seed of a read tested against the previous chain's reference length): with
+    contigs of very different lengths the test flips often.  Device-side prediction + verification + redo passes must give the
+    oracle's sequential (-t1) results, also across batch boundaries."""
+    from minialign_b200 import mai, synth
+    g, blob = _uneven_genome_index(tmp_path)
+    hdr = mai.parse_header(blob)
+    reads = synth.make_reads(g, 70_000, seed=62, len_mean=900, len_sd=400, len_min=60, len_max=2500) + synth.make_hard_reads(g, seed=63, n=16)
+    enc = [synth.encode_2bit(r) for _, r in reads]
+    o = ora.Oracle(dict(ora.PACBIO, occ=hdr["occ"][:3]), blob)
+    exp = [o.align(s) for s in enc]
+    o.close()
+    m = api.Mapper(blob, "pacbio", lib_path=build_emu())
+    got = m.map_batch(enc[:37])
+    n_retry = m.stats()["n_retry"]
+    got += m.map_batch(enc[37:])
+    m.close()
+    assert sum(len(e) > 0 for e in exp) > 30
+    for e, x in zip(exp, got):
+        assert np.array_equal(e, x)
+    print("redo reads in the first batch:", n_retry)
