@@ -34,7 +34,8 @@ extern "C" {
 #define MAB_ENODEV   -1		/* no usable CUDA device / CUDA runtime error (message via mab_last_error) */
 #define MAB_EINVAL   -2		/* bad argument / unsupported parameter set (e.g. non-combined gap model) */
 #define MAB_ENOMEM   -3		/* device or host allocation failed */
-#define MAB_EOVERFLOW -4	/* a per-read device workspace overflowed even after the retry */
+#define MAB_EOVERFLOW -4	/* a batch-level device buffer (result pool, workspace) overflowed even after it was grown and the batch re-run */
+#define MAB_EFORMAT  -5		/* text path: a record layout the device reader does not take (see mab_text_begin) */
 
 /* mapping parameters: the subset of mm_align_params_t (minialign.c:2517-2524) + gaba_params_t (gaba.h:90-110) the hot
  * path reads.  k, w, b, occ[] come from the index itself. */
@@ -104,6 +105,44 @@ int mab_last_stats(const mab_ctx *ctx, mab_stats_t *out);
 
 /* When set, mab_map_batch takes seq_block as a DEVICE pointer already resident in HBM (bench.py's kernel-only arm). */
 int mab_set_device_input(mab_ctx *ctx, int on);
+
+/* ---- text path: FASTA / FASTQ bytes in, SAM bytes out ----------------------------------------------------------------------
+ * One call sequence replaces, for one chunk of the input file, the reference's source -> worker -> drain pipeline stage
+ * (mm_align_source: bseq_read, minialign.c:4565-4583, 1996-2164; mm_align_worker, 4589-4601; mm_align_drain_intl ->
+ * mm_print_mapped, 4607-4626, 5095-5426): the records are parsed, mapped, post-processed and printed on the device; the host
+ * hands over text and gets text back.
+ *
+ * text: n_bytes of FASTA or FASTQ holding whole records (the caller cuts the file at record boundaries), starting with the
+ * delimiter ('>' or '@').  Taken as is: '\n' line ends, FASTA sequences on any number of lines, FASTQ with four lines per
+ * record; anything else gives MAB_EFORMAT and the caller falls back to its own reader + mab_map_batch.
+ * flags: the tag bits of mab_sam.h (MAB_TAG_*, MAB_OMIT_REP) | MAB_TEXT_* below.
+ *
+ * The reference worker thread carries one word of state from read to read (`rlen`, minialign.c:3865 vs 3873; with -t1 that is
+ * file order).  Chunks mapped concurrently (several contexts, several GPUs) stay byte-identical to the -t1 run by passing it on:
+ *   mab_text_begin(ctx, ..., rlen_prev, rlen_known = 0)   map without knowing what the previous chunk left behind
+ *   mab_text_commit(ctx, rlen_prev, &rlen_next)           ... once the previous chunk's value is known (re-maps the rare read
+ *                                                         whose first seed test depended on it); rlen_next goes to the next chunk
+ *   mab_text_finish(ctx, ...)                             post-processing + SAM formatting + copy out
+ * A single context used sequentially calls mab_map_text, which chains the value through the context. */
+enum { MAB_TAG_RG = 1 << 0, MAB_TAG_NH = 1 << 2, MAB_TAG_IH = 1 << 3, MAB_TAG_AS = 1 << 4, MAB_TAG_XS = 1 << 5, MAB_TAG_NM = 1 << 6, MAB_TAG_SA = 1 << 7, MAB_TAG_MD = 1 << 8,
+       MAB_OMIT_REP = 1 << 30 };		/* optional SAM tags (-T, minialign.c:2527-2537) and -R */
+#define MAB_TEXT_KEEP_QUAL   0x01000000u	/* -Q: print FASTQ qualities (default: '*', minialign.c:6145, 5134, 5187) */
+#define MAB_TEXT_DEVICE_OUT  0x02000000u	/* leave the SAM text on the device (kernel-side measurements): no copy out */
+typedef struct {
+	uint64_t n_reads, n_bases;			/* records kept (non-empty sequence) and their bases */
+	uint64_t sam_bytes;					/* valid after mab_text_finish */
+	uint32_t rlen_valid, rlen_next;		/* the value this chunk leaves behind (rlen_valid = 0: it loaded no chain, pass the previous one on) */
+} mab_text_info_t;
+int mab_text_begin(mab_ctx *ctx, const char *text, uint64_t n_bytes, uint32_t flags, uint32_t rlen_prev, int rlen_known, mab_text_info_t *info);
+int mab_text_commit(mab_ctx *ctx, uint32_t rlen_prev, mab_text_info_t *info);
+/* sam_out = NULL: the text is left in a pinned buffer owned by the context, *sam_ptr points at it (valid until the next begin) */
+int mab_text_finish(mab_ctx *ctx, char *sam_out, uint64_t sam_cap, const char **sam_ptr, mab_text_info_t *info);
+int mab_map_text(mab_ctx *ctx, const char *text, uint64_t n_bytes, uint32_t flags, char *sam_out, uint64_t sam_cap, const char **sam_ptr, mab_text_info_t *info);
+/* the SAM header (@HD, @SQ, @PG; minialign.c:5095-5120) for this context's index; returns the length, writes at most cap bytes */
+uint64_t mab_sam_header_text(const mab_ctx *ctx, const char *version, const char *cmdline, char *out, uint64_t cap);
+/* page-locked host memory for text / SAM buffers (copies from / to pageable memory are staged by the driver and block) */
+void *mab_host_alloc(uint64_t bytes);
+void mab_host_free(void *p);
 
 /* ---- stage-level entry points (parity tests; same semantics as the reference functions named above) ---- */
 /* sketch of one read: writes the minimizer words followed by the 4-word cap; returns #words (may exceed cap) */

@@ -32,6 +32,23 @@ class MabStats(C.Structure):
                 ("n_failed", C.c_uint32), ("_pad", C.c_uint32)]
 
 
+class MabTextInfo(C.Structure):
+    _fields_ = [("n_reads", C.c_uint64), ("n_bases", C.c_uint64), ("sam_bytes", C.c_uint64), ("rlen_valid", C.c_uint32), ("rlen_next", C.c_uint32)]
+
+
+# optional SAM tags (include/minialign_b200.h) and text-path flags
+TAGS = {"RG": 1 << 0, "NH": 1 << 2, "IH": 1 << 3, "AS": 1 << 4, "XS": 1 << 5, "NM": 1 << 6, "SA": 1 << 7, "MD": 1 << 8}
+OMIT_REP = 1 << 30
+TEXT_KEEP_QUAL, TEXT_DEVICE_OUT = 0x01000000, 0x02000000
+
+
+def parse_tags(s: str) -> int:
+    t = 0
+    for tok in s.replace(";", ",").replace(":", ",").replace("/", ",").split(","):
+        t |= TAGS.get(tok, 0)
+    return t
+
+
 class MabPair(C.Structure):
     _fields_ = [("a_ofs", C.c_uint64), ("b_ofs", C.c_uint64), ("alen", C.c_uint32), ("blen", C.c_uint32), ("apos", C.c_uint32),
                 ("bpos", C.c_uint32), ("brev", C.c_uint32), ("narrow", C.c_uint32), ("min_score", C.c_int64)]
@@ -90,6 +107,20 @@ def load_library(lib_path: str | None = None):
     L.mab_fill_peak.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.POINTER(C.c_double)]
     L.mab_selftest.restype = C.c_int
     L.mab_selftest.argtypes = [C.c_void_p, u32p]
+    ti = C.POINTER(MabTextInfo)
+    L.mab_text_begin.restype = C.c_int
+    L.mab_text_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, ti]
+    L.mab_text_commit.restype = C.c_int
+    L.mab_text_commit.argtypes = [C.c_void_p, C.c_uint32, ti]
+    L.mab_text_finish.restype = C.c_int
+    L.mab_text_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), ti]
+    L.mab_map_text.restype = C.c_int
+    L.mab_map_text.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), ti]
+    L.mab_sam_header_text.restype = C.c_uint64
+    L.mab_sam_header_text.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_uint64]
+    L.mab_host_alloc.restype = C.c_void_p
+    L.mab_host_alloc.argtypes = [C.c_uint64]
+    L.mab_host_free.argtypes = [C.c_void_p]
     return L
 
 
@@ -142,6 +173,42 @@ class Mapper:
         out = [self.result(i) for i in range(len(reads))]
         self.lib.mab_release_batch(self.h)
         return out
+
+    # ---- text path: FASTA / FASTQ bytes in, SAM bytes out (mab_text_* in include/minialign_b200.h) ----
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed ({rc}): " + self.lib.mab_last_error().decode())
+
+    def map_text(self, text: bytes, tags: int = 0, keep_qual: bool = False) -> bytes:
+        """One chunk, sequential use: the reference thread's state is chained through the context."""
+        info, ptr = MabTextInfo(), C.c_void_p()
+        flags = tags | (TEXT_KEEP_QUAL if keep_qual else 0)
+        buf = C.create_string_buffer(text, len(text)) if not isinstance(text, C.Array) else text
+        self._check(self.lib.mab_map_text(self.h, C.addressof(buf), len(text), flags, None, 0, C.byref(ptr), C.byref(info)), "mab_map_text")
+        self.last_info = info
+        return C.string_at(ptr.value, info.sam_bytes) if info.sam_bytes else b""
+
+    def text_begin(self, ptr: int, n: int, flags: int = 0, rlen_prev: int = 0, rlen_known: bool = False) -> MabTextInfo:
+        info = MabTextInfo()
+        self._check(self.lib.mab_text_begin(self.h, ptr, n, flags, rlen_prev, 1 if rlen_known else 0, C.byref(info)), "mab_text_begin")
+        return info
+
+    def text_commit(self, rlen_prev: int) -> MabTextInfo:
+        info = MabTextInfo()
+        self._check(self.lib.mab_text_commit(self.h, rlen_prev, C.byref(info)), "mab_text_commit")
+        return info
+
+    def text_finish(self, out_ptr: int = 0, out_cap: int = 0):
+        """-> (info, pointer to the SAM text).  out_ptr = 0: the text stays in the context's pinned buffer."""
+        info, ptr = MabTextInfo(), C.c_void_p()
+        self._check(self.lib.mab_text_finish(self.h, out_ptr or None, out_cap, C.byref(ptr), C.byref(info)), "mab_text_finish")
+        return info, ptr.value
+
+    def sam_header(self, cmdline: str = "", version: str = "0.6.0-devel") -> bytes:
+        n = self.lib.mab_sam_header_text(self.h, version.encode(), cmdline.encode(), None, 0)
+        buf = C.create_string_buffer(n)
+        self.lib.mab_sam_header_text(self.h, version.encode(), cmdline.encode(), buf, n)
+        return buf.raw[:n]
 
     def stats(self) -> dict:
         s = MabStats()

@@ -3,6 +3,7 @@
  * (minialign.c:5095-5426) and path parser (gaba_parse.h:107-263), fed with the flat per-read results of mab_result().
  */
 #pragma once
+#include "../../../include/minialign_b200.h"
 #include <cstdint>
 #include <string>
 #include <vector>
@@ -10,8 +11,7 @@
 struct MabSamRef { const char *name; uint32_t l_name; uint32_t l_seq; const uint8_t *seq; };		/* mm_idx_seq_t view */
 struct MabSamRead { const char *name; uint32_t l_name; const uint8_t *seq; uint32_t l_seq; const char *qual; };	/* bseq_seq_t view; qual may be null */
 
-enum { MAB_TAG_RG = 1 << 0, MAB_TAG_NH = 1 << 2, MAB_TAG_IH = 1 << 3, MAB_TAG_AS = 1 << 4, MAB_TAG_XS = 1 << 5, MAB_TAG_NM = 1 << 6, MAB_TAG_SA = 1 << 7, MAB_TAG_MD = 1 << 8,
-       MAB_OMIT_REP = 1 << 30 };
+/* tag bits (MAB_TAG_*, MAB_OMIT_REP): include/minialign_b200.h */
 
 extern "C" {
 /* header: @HD, @SQ per reference, @PG with the command line (minialign.c:5095-5120) */

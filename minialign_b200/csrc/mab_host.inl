@@ -20,6 +20,14 @@ using namespace mab;
 static thread_local std::string g_err;
 extern "C" const char *mab_last_error(void) { return g_err.c_str(); }
 
+struct PipeShape { uint32_t n_seq, maxlen; uint64_t tot_len, span; };		/* what the host knows about a batch: counts, longest read, bases, size of the base block */
+/* launch geometry and buffer shapes of the batch in flight (kept in the context: redo passes may be issued by a later call) */
+struct RunState {
+	PipeShape sh; const uint8_t *d_base;
+	uint32_t blk_cap, ext_ctas, seed_ctas, init_ctas, sc_cap1[2], sc_cap2[2];
+	uint64_t arena_stride;
+};
+
 struct mab_ctx {
 	int device;
 	DevParams P;
@@ -52,6 +60,21 @@ struct mab_ctx {
 	uint64_t pin_user = 0;				/* bytes at the head of `pin` the caller of pipeline_run uses itself */
 	uint8_t *d_io = nullptr; uint64_t io_cap = 0;			/* [ofs u64 x n][len u32 x n] of the record-level entry point */
 	BatchCounters hc;					/* counters of the last batch */
+	RunState rs;
+	/* text path (mab_text_*): the chunk, its index, the packed read block, the SAM text */
+	uint8_t *d_text = nullptr; uint64_t text_cap = 0;
+	uint8_t *d_base = nullptr; uint64_t base_cap = 0;
+	uint32_t *d_marks = nullptr; uint64_t marks_cap = 0;
+	uint32_t *d_tiles = nullptr; uint64_t tiles_cap = 0;
+	TextRec *d_trec = nullptr; uint64_t trec_cap = 0;
+	TextCounters *d_tc = nullptr;
+	double *d_thr = nullptr;			/* MAPQ step table (mab_post.cuh) */
+	bool thr_ok = false;
+	uint8_t *d_sam = nullptr; uint64_t sam_cap = 0;
+	uint8_t *h_sam = nullptr; uint64_t h_sam_cap = 0;		/* pinned; used when the caller passes no output buffer */
+	uint64_t mark_hw = 0, rec_hw = 0;	/* high-water marks of the parser's arrays */
+	double sam_per_byte = 1.3;			/* SAM bytes per input byte (high-water mark, sizes d_sam) */
+	struct TextState { const uint8_t *d_text; uint64_t n_text, n_kept, sam_total; uint32_t n_rec, flags, stage; bool rlen_known; TextCounters tc; } tx;
 	uint32_t sc_cap1[2] = { 1536, 1536 };	/* k_sortchain: staging capacity of the ordinary size class, per round kind (adapted from batch to batch) */
 	double ws_per_base = 6.0;			/* workspace estimate: bytes per read base beyond the fixed 20 KB per read (high-water mark) */
 	mab_stats_t stats;
@@ -137,6 +160,8 @@ inline uint32_t rd32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v;
 inline uint16_t rd16(const uint8_t *p) { uint16_t v; memcpy(&v, p, 2); return v; }
 }  // namespace
 
+static int text_init(struct mab_ctx *ctx);
+static void text_destroy(struct mab_ctx *ctx);
 #define CK(call) do { if(!RT_OK(call)) { g_err = std::string(#call) + ": " + RT_ERRSTR(); return MAB_ENODEV; } } while(0)
 #define CKP(call) do { if(!RT_OK(call)) { g_err = std::string(#call) + ": " + RT_ERRSTR(); mab_destroy(ctx); return nullptr; } } while(0)
 
@@ -162,7 +187,7 @@ extern "C" mab_ctx *mab_init(const void *mai_blob, uint64_t size, const mab_para
 	P.min_score = params->min_score; P.min_ratio = params->min_ratio;
 	double mc = 0.0, xc = 0.0;																/* minialign.c:4676-4681 */
 	for(int i = 0; i < 16; i++) { if((i & 3) == (i >> 3)) { mc += params->score_matrix[0]; } else { xc += params->score_matrix[0]; } }
-	P.mcoef = mc / 4.0; ctx->xcoef = xc / 12.0;
+	P.mcoef = mc / 4.0; ctx->xcoef = xc / 12.0; P.xcoef = ctx->xcoef;
 	init_gaba_consts(P, params);
 	CKP(RT_MALLOC(&ctx->d_idx, size + 256));
 	CKP(RT_MEMCPY_H2D(ctx->d_idx, b, size));
@@ -176,6 +201,7 @@ extern "C" mab_ctx *mab_init(const void *mai_blob, uint64_t size, const mab_para
 	for(int i = 0; i < 8; i++) { CKP(RT_EVENT_CREATE(&ctx->ev[i])); ctx->n_ev++; }
 	for(int i = 0; i < 24; i++) { CKP(RT_EVENT_CREATE(&ctx->rev[i])); ctx->n_ev++; }
 	RT_FUNC_MAX_SMEM(k_sortchain, 16 * MAB_SC_MAX + 2048);
+	if(text_init(ctx) != MAB_OK) { mab_destroy(ctx); return nullptr; }
 	ctx->n_slots = RT_EXTEND_SLOTS(ctx->n_sm);
 	if(const char *e = getenv("MAB_EXT_CTAS")) {										/* resident k_extend CTAs per SM actually launched (<= MAB_EXT_CTAS_PER_SM) */
 		int v = atoi(e);
@@ -190,6 +216,7 @@ extern "C" void mab_destroy(mab_ctx *ctx)
 	RT_FREE(ctx->d_idx); RT_FREE(ctx->d_ntail); RT_FREE(ctx->d_ctr); RT_FREE(ctx->d_seq); RT_FREE(ctx->d_reads); RT_FREE(ctx->d_ws);
 	RT_FREE(ctx->d_frames); RT_FREE(ctx->d_order); RT_FREE(ctx->d_recs); RT_FREE(ctx->d_arenas); RT_FREE(ctx->d_pool); RT_FREE(ctx->d_io);
 	RT_HOST_FREE(ctx->h_pool); RT_HOST_FREE(ctx->pin); delete[] ctx->res_words;
+	text_destroy(ctx);
 	if(ctx->have_stream) { RT_STREAM_DESTROY(ctx->stream); }
 	for(int i = 0; i < ctx->n_ev; i++) { RT_EVENT_DESTROY(i < 8 ? ctx->ev[i] : ctx->rev[i - 8]); }
 	delete ctx;
@@ -379,7 +406,6 @@ static void post_emit(const ReadPlan &pl, const PlanItem *items, uint32_t *out)
 /* ---------------------------------------------------------------- batch driver */
 static uint32_t dp_blk_cap(uint32_t maxlen) { return (uint32_t)((4ull * ((uint64_t)maxlen + 512)) / 32 + 64); }
 
-struct PipeShape { uint32_t n_seq, maxlen; uint64_t tot_len, span; };		/* what the host knows about a batch: counts, longest read, bases, size of the base block */
 
 static int pin_reserve(mab_ctx *ctx, uint64_t need)
 {
@@ -387,6 +413,56 @@ static int pin_reserve(mab_ctx *ctx, uint64_t need)
 	RT_HOST_FREE(ctx->pin); ctx->pin = nullptr; ctx->pin_cap = 0;
 	if(!RT_OK(RT_HOST_ALLOC(&ctx->pin, need + need / 4))) { g_err = std::string("pinned host allocation failed: ") + RT_ERRSTR(); return MAB_ENOMEM; }
 	ctx->pin_cap = need + need / 4;
+	return MAB_OK;
+}
+
+static void pipe_rounds(mab_ctx *ctx, bool first, bool timed)
+{
+	const DevParams &P = ctx->P; const RunState &R = ctx->rs; mab_stats_t &S = ctx->stats;
+	const uint32_t n_seq = R.sh.n_seq;
+	if(timed && first) { RT_EVENT_RECORD(ctx->ev[2], ctx->stream); }
+	RT_LAUNCH(k_seed_expand, R.seed_ctas, 32 * MAB_WARPS_PER_CTA, 0, ctx->stream, P, ctx->d_reads, n_seq, ctx->d_ws, (const uint32_t *)ctx->d_recs);
+	S.n_launches++;
+	if(timed && first) { RT_EVENT_RECORD(ctx->ev[3], ctx->stream); }
+	for(uint32_t round = 0; round < P.n_occ; round++) {
+		bool ev = timed && first && round < 8;
+		if(ev) { RT_EVENT_RECORD(ctx->rev[3 * round], ctx->stream); }
+		int kind = round == 0 ? 0 : 1;
+		RT_LAUNCH(k_sortchain, n_seq, 32, 16 * R.sc_cap1[kind] + 2048, ctx->stream, P, ctx->d_reads, n_seq, ctx->d_ws, ctx->d_frames, round, R.sc_cap1[kind], 0u, R.sc_cap1[kind]);
+		RT_LAUNCH(k_sortchain, n_seq, 32, 16 * R.sc_cap2[kind] + 2048, ctx->stream, P, ctx->d_reads, n_seq, ctx->d_ws, ctx->d_frames, round, R.sc_cap2[kind], R.sc_cap1[kind], 0xffffffffu);
+		if(first && round == 0) { RT_LAUNCH(k_rlen_predict, 1, MAB_PIPE_THREADS, 0, ctx->stream, P, ctx->d_reads, n_seq, (const uint8_t *)ctx->d_ws); S.n_launches++; }
+		RT_MEMSET_ASYNC(&ctx->d_ctr->work_next, 0, sizeof(unsigned int), ctx->stream);
+		if(ev) { RT_EVENT_RECORD(ctx->rev[3 * round + 1], ctx->stream); }
+		RT_LAUNCH(k_extend, R.ext_ctas, 32 * MAB_WARPS_PER_CTA, 1024 + 4 * MAB_TILE_WORDS * MAB_WARPS_PER_CTA, ctx->stream, P, R.d_base, (const uint8_t *)ctx->d_ntail, ctx->d_reads, (const uint32_t *)ctx->d_order, n_seq, ctx->d_ws,
+			ctx->d_arenas, R.arena_stride, R.blk_cap, ctx->d_pool, ctx->pool_cap / 4, ctx->d_ctr, round, P.n_occ - 1);
+		S.n_launches += 3;
+		if(ev) { RT_EVENT_RECORD(ctx->rev[3 * round + 2], ctx->stream); }
+	}
+	if(timed && first) { RT_EVENT_RECORD(ctx->ev[4], ctx->stream); }
+}
+
+/* verification of the rlen speculation (+ redo passes until it holds) against the value the previous batch left behind;
+ * init_known = 0: that value is not known yet, the first chain-loading read is only reported (ctx->hc.fd_*).  Ends with the
+ * batch counters in ctx->hc; a buffer overflow is left for the caller to see there. */
+static int pipe_verify(mab_ctx *ctx, uint32_t rlen_init, uint32_t init_known)
+{
+	mab_stats_t &S = ctx->stats;
+	BatchCounters *pin_ctr = (BatchCounters *)(ctx->pin + ((ctx->pin_user + 127) & ~127ull));
+	for(;;) {
+		double t_sub = RT_WALL_MS();
+		CK(RT_MEMSET_ASYNC(&ctx->d_ctr->n_redo, 0, sizeof(unsigned int), ctx->stream));
+		RT_LAUNCH(k_rlen_verify, 1, MAB_PIPE_THREADS, 0, ctx->stream, ctx->d_reads, ctx->rs.sh.n_seq, rlen_init, init_known, ctx->d_ctr);
+		S.n_launches++;
+		CK(RT_MEMCPY_D2H_ASYNC(pin_ctr, ctx->d_ctr, sizeof(BatchCounters), ctx->stream));
+		S.ms_wall_submit += (float)(RT_WALL_MS() - t_sub);
+		{ double tw = RT_WALL_MS(); CK(RT_STREAM_SYNC(ctx->stream)); S.ms_wall_wait += (float)(RT_WALL_MS() - tw); }
+		ctx->hc = *pin_ctr;
+		S.d2h_bytes += sizeof(BatchCounters);
+		const BatchCounters &hc = ctx->hc;
+		if((hc.err_any & (MAB_ERR_POOL_OVF | MAB_ERR_WS_OVF)) || hc.pool_top > ctx->pool_cap / 4 || hc.n_redo == 0) { break; }
+		S.n_retry += hc.n_redo;
+		pipe_rounds(ctx, false, false);
+	}
 	return MAB_OK;
 }
 
@@ -399,85 +475,55 @@ static int pipeline_run(mab_ctx *ctx, const uint8_t *d_base, const PipeShape &sh
 {
 	const DevParams &P = ctx->P;
 	mab_stats_t &S = ctx->stats;
+	RunState &R = ctx->rs;
 	const uint32_t n_seq = sh.n_seq;
 	double t_sub = RT_WALL_MS();
+	R.sh = sh; R.d_base = d_base;
 	{ int rc = pin_reserve(ctx, ctx->pin_user + 2 * sizeof(BatchCounters) + 256); if(rc) { return rc; } }
-	BatchCounters *pin_ctr = (BatchCounters *)(ctx->pin + ((ctx->pin_user + 127) & ~127ull));
 	{ int rc = grow(&ctx->d_recs, &ctx->recs_cap, 16ull * sh.span + 256); if(rc) { return rc; } }
-	{ int rc = grow(&ctx->d_frames, &ctx->frames_cap, 4ull * 8 * MAB_RS_FRAME * n_seq); if(rc) { return rc; } }
+	{ int rc = grow(&ctx->d_frames, &ctx->frames_cap, 4ull * 8 * MAB_RS_FRAME * ((uint64_t)n_seq + 8)); if(rc) { return rc; } }
 	{ int rc = grow(&ctx->d_order, &ctx->order_cap, 4ull * n_seq); if(rc) { return rc; } }
-	uint32_t blk_cap = dp_blk_cap(sh.maxlen);
-	ArenaLayout AL = arena_layout(blk_cap);
-	uint32_t ext_ctas = std::max<uint32_t>(1, std::min<uint32_t>(ctx->n_slots / MAB_WARPS_PER_CTA, (n_seq + MAB_WARPS_PER_CTA - 1) / MAB_WARPS_PER_CTA));
+	R.blk_cap = dp_blk_cap(sh.maxlen);
+	ArenaLayout AL = arena_layout(R.blk_cap);
+	R.arena_stride = AL.total;
+	R.ext_ctas = std::max<uint32_t>(1, std::min<uint32_t>(ctx->n_slots / MAB_WARPS_PER_CTA, (n_seq + MAB_WARPS_PER_CTA - 1) / MAB_WARPS_PER_CTA));
 	{	/* the DP arenas are sized by the longest read of the batch (312 B per base per resident warp): with very long reads fewer
 		 * warps stay resident rather than asking for more than MAB_ARENA_BUDGET bytes of HBM per context */
 		uint64_t budget = 40ull << 30;
 		if(const char *e = getenv("MAB_ARENA_BUDGET_MB")) { long v = atol(e); if(v > 0) { budget = (uint64_t)v << 20; } }
 		uint64_t fit = budget / (AL.total * MAB_WARPS_PER_CTA);
-		if(fit < ext_ctas) { ext_ctas = (uint32_t)std::max<uint64_t>(1, fit); }
+		if(fit < R.ext_ctas) { R.ext_ctas = (uint32_t)std::max<uint64_t>(1, fit); }
 	}
-	{ int rc = grow(&ctx->d_arenas, &ctx->arenas_cap, AL.total * (uint64_t)ext_ctas * MAB_WARPS_PER_CTA); if(rc) { return rc; } }
+	{ int rc = grow(&ctx->d_arenas, &ctx->arenas_cap, AL.total * (uint64_t)R.ext_ctas * MAB_WARPS_PER_CTA); if(rc) { return rc; } }
 	uint64_t pool_need = sh.tot_len / 4 + 64ull * n_seq + (1u << 16);				/* ~2 bits per base and alignment, x4 head room */
 	uint64_t ws_need = (uint64_t)(ctx->ws_per_base * (double)sh.tot_len) + 20480ull * n_seq + 4096;
-	uint32_t seed_ctas = std::max<uint32_t>(1, std::min<uint32_t>((n_seq + MAB_WARPS_PER_CTA - 1) / MAB_WARPS_PER_CTA, ctx->n_sm * 8));
-	uint32_t init_ctas = std::max<uint32_t>(1, std::min<uint32_t>((n_seq + 255) / 256, ctx->n_sm * 4));
+	R.seed_ctas = std::max<uint32_t>(1, std::min<uint32_t>((n_seq + MAB_WARPS_PER_CTA - 1) / MAB_WARPS_PER_CTA, ctx->n_sm * 8));
+	R.init_ctas = std::max<uint32_t>(1, std::min<uint32_t>((n_seq + 255) / 256, ctx->n_sm * 4));
 	/* k_sortchain size classes, per round kind (round 0 stages a read's own seeds, later rounds all of them): the ordinary reads
 	 * (up to the 90th percentile of the seed bound of the previous batch) run with a small shared-memory footprint, the
 	 * seed-rich rest in a second launch with up to MAB_SC_MAX seeds staged, beyond that in global memory */
-	uint32_t sc_cap1[2] = { ctx->sc_cap1[0], ctx->sc_cap1[1] }, sc_cap2[2] = { MAB_SC_MAX, MAB_SC_MAX };
+	for(int k = 0; k < 2; k++) { R.sc_cap1[k] = ctx->sc_cap1[k]; R.sc_cap2[k] = MAB_SC_MAX; }
 	if(const char *e = getenv("MAB_SC_CAP")) {										/* test hook: tiny caps push reads through the unstaged (global memory) path */
 		uint32_t v = (uint32_t)atoi(e);
-		if(v >= 64) { for(int k = 0; k < 2; k++) { sc_cap1[k] = std::min(sc_cap1[k], v); sc_cap2[k] = std::min(sc_cap2[k], std::max(v, sc_cap1[k])); } }
+		if(v >= 64) { for(int k = 0; k < 2; k++) { R.sc_cap1[k] = std::min(R.sc_cap1[k], v); R.sc_cap2[k] = std::min(R.sc_cap2[k], std::max(v, R.sc_cap1[k])); } }
 	}
 	S.ms_wall_sizing += (float)(RT_WALL_MS() - t_sub);
-	auto rounds = [&](bool first) {
-		for(uint32_t round = 0; round < P.n_occ; round++) {
-			bool ev = timed && first && round < 8;
-			if(ev) { RT_EVENT_RECORD(ctx->rev[3 * round], ctx->stream); }
-			int kind = round == 0 ? 0 : 1;
-			RT_LAUNCH(k_sortchain, n_seq, 32, 16 * sc_cap1[kind] + 2048, ctx->stream, P, ctx->d_reads, n_seq, ctx->d_ws, ctx->d_frames, round, sc_cap1[kind], 0u, sc_cap1[kind]);
-			RT_LAUNCH(k_sortchain, n_seq, 32, 16 * sc_cap2[kind] + 2048, ctx->stream, P, ctx->d_reads, n_seq, ctx->d_ws, ctx->d_frames, round, sc_cap2[kind], sc_cap1[kind], 0xffffffffu);
-			if(first && round == 0) { RT_LAUNCH(k_rlen_predict, 1, MAB_PIPE_THREADS, 0, ctx->stream, P, ctx->d_reads, n_seq, (const uint8_t *)ctx->d_ws); S.n_launches++; }
-			RT_MEMSET_ASYNC(&ctx->d_ctr->work_next, 0, sizeof(unsigned int), ctx->stream);
-			if(ev) { RT_EVENT_RECORD(ctx->rev[3 * round + 1], ctx->stream); }
-			RT_LAUNCH(k_extend, ext_ctas, 32 * MAB_WARPS_PER_CTA, 1024 + 4 * MAB_TILE_WORDS * MAB_WARPS_PER_CTA, ctx->stream, P, d_base, (const uint8_t *)ctx->d_ntail, ctx->d_reads, (const uint32_t *)ctx->d_order, n_seq, ctx->d_ws,
-				ctx->d_arenas, AL.total, blk_cap, ctx->d_pool, ctx->pool_cap / 4, ctx->d_ctr, round, P.n_occ - 1);
-			S.n_launches += 3;
-			if(ev) { RT_EVENT_RECORD(ctx->rev[3 * round + 2], ctx->stream); }
-		}
-	};
 	RT_LAUNCH(k_order, 1, MAB_PIPE_THREADS, 0, ctx->stream, (const ReadRec *)ctx->d_reads, n_seq, ctx->d_order);
 	S.n_launches++;
 	for(int attempt = 0; ; attempt++) {
 		t_sub = RT_WALL_MS();
 		{ int rc = grow(&ctx->d_pool, &ctx->pool_cap, 4 * pool_need); if(rc) { return rc; } }
 		{ int rc = grow(&ctx->d_ws, &ctx->ws_cap, ws_need); if(rc) { return rc; } }
-		if(attempt > 0) { RT_LAUNCH(k_reads_reset, init_ctas, 256, 0, ctx->stream, ctx->d_reads, n_seq); S.n_launches++; }
+		if(attempt > 0) { RT_LAUNCH(k_reads_reset, R.init_ctas, 256, 0, ctx->stream, ctx->d_reads, n_seq); S.n_launches++; }
 		CK(RT_MEMSET_ASYNC(ctx->d_ctr, 0, sizeof(BatchCounters), ctx->stream));
 		if(timed) { RT_EVENT_RECORD(ctx->ev[1], ctx->stream); }
-		RT_LAUNCH(k_seed_scan, seed_ctas, 32 * MAB_WARPS_PER_CTA, 2560 * MAB_WARPS_PER_CTA, ctx->stream, P, d_base, ctx->d_reads, n_seq, ctx->d_recs);
+		RT_LAUNCH(k_seed_scan, R.seed_ctas, 32 * MAB_WARPS_PER_CTA, 2560 * MAB_WARPS_PER_CTA, ctx->stream, P, d_base, ctx->d_reads, n_seq, ctx->d_recs);
 		RT_LAUNCH(k_size, 1, MAB_PIPE_THREADS, 0, ctx->stream, ctx->d_reads, n_seq, ctx->ws_cap, ctx->d_ctr);
 		S.n_launches += 2;
-		BatchCounters hc;
-		for(bool first = true; ; first = false) {
-			if(timed && first) { RT_EVENT_RECORD(ctx->ev[2], ctx->stream); }
-			RT_LAUNCH(k_seed_expand, seed_ctas, 32 * MAB_WARPS_PER_CTA, 0, ctx->stream, P, ctx->d_reads, n_seq, ctx->d_ws, (const uint32_t *)ctx->d_recs);
-			S.n_launches++;
-			if(timed && first) { RT_EVENT_RECORD(ctx->ev[3], ctx->stream); }
-			rounds(first);
-			if(timed && first) { RT_EVENT_RECORD(ctx->ev[4], ctx->stream); }
-			CK(RT_MEMSET_ASYNC(&ctx->d_ctr->n_redo, 0, sizeof(unsigned int), ctx->stream));
-			RT_LAUNCH(k_rlen_verify, 1, MAB_PIPE_THREADS, 0, ctx->stream, ctx->d_reads, n_seq, rlen_init, init_known, ctx->d_ctr);
-			S.n_launches++;
-			CK(RT_MEMCPY_D2H_ASYNC(pin_ctr, ctx->d_ctr, sizeof(BatchCounters), ctx->stream));
-			S.ms_wall_submit += (float)(RT_WALL_MS() - t_sub);
-			{ double tw = RT_WALL_MS(); CK(RT_STREAM_SYNC(ctx->stream)); S.ms_wall_wait += (float)(RT_WALL_MS() - tw); }
-			t_sub = RT_WALL_MS();
-			hc = *pin_ctr;
-			S.d2h_bytes += sizeof(hc);
-			if((hc.err_any & (MAB_ERR_POOL_OVF | MAB_ERR_WS_OVF)) || hc.pool_top > ctx->pool_cap / 4 || hc.n_redo == 0) { break; }
-			S.n_retry += hc.n_redo;
-		}
+		pipe_rounds(ctx, true, timed);
+		S.ms_wall_submit += (float)(RT_WALL_MS() - t_sub);
+		{ int rc = pipe_verify(ctx, rlen_init, init_known); if(rc) { return rc; } }
+		const BatchCounters &hc = ctx->hc;
 		if(hc.ws_need > ctx->ws_cap || (hc.err_any & MAB_ERR_WS_OVF)) {					/* workspace estimate too small: now it is known exactly */
 			ws_need = hc.ws_need + hc.ws_need / 8 + 4096; S.n_retry++;
 			if(attempt >= 3) { g_err = "workspace overflow after retries"; return MAB_EOVERFLOW; }
@@ -488,7 +534,6 @@ static int pipeline_run(mab_ctx *ctx, const uint8_t *d_base, const PipeShape &sh
 			if(attempt >= 3) { g_err = "result pool overflow after retries"; return MAB_EOVERFLOW; }
 			continue;
 		}
-		ctx->hc = hc;
 		S.n_vectors += hc.n_vectors; S.n_fill_calls += hc.n_fill; S.n_trace += hc.n_trace;
 		if(sh.tot_len) {																	/* high-water mark for the next batch's estimate */
 			double per_base = ((double)hc.ws_need - 20480.0 * n_seq) / (double)sh.tot_len;
@@ -778,3 +823,5 @@ extern "C" int mab_selftest(mab_ctx *ctx, uint32_t *out)
 	RT_FREE(d);
 	return MAB_OK;
 }
+
+#include "mab_text_host.inl"

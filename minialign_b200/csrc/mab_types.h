@@ -58,7 +58,7 @@ struct DevParams {
 	uint32_t b, w, k, n_occ, occ[8], n_ref;
 	uint32_t twlen, tglen, min_score;
 	float min_ratio;
-	double mcoef, imx, xmx;
+	double mcoef, xcoef, imx, xmx;
 	int8_t sb[16];
 	int32_t adjh, adjv, ofsh, ofsv, gfh, gfv, tx;
 	/* the same constants as packed H8 pairs (value in the high byte of both 16-bit halves; "+1" = plus one ulp, see mab_dp.cuh)
@@ -168,6 +168,30 @@ struct BatchCounters {
 	unsigned int chain_valid, chain_rlen;	/* the reference thread's `rlen` after the last chain-loading read of the batch */
 	unsigned int fd_valid, fd_idx, fd_apos, fd_flags, fd_used;	/* first chain-loading read: its predecessor lives in the previous batch */
 	unsigned int _pad;
+};
+
+/* ---- text path (FASTA/FASTQ bytes in, SAM bytes out) ---- */
+/* one record of a text chunk (bseq_seq_t, minialign.c:1589-1596, as offsets into the chunk) */
+struct TextRec {
+	uint64_t name_ofs;				/* first byte of the name */
+	uint64_t seq_beg, seq_end;		/* text range of the sequence lines (newlines inside are skipped) */
+	uint64_t qual_ofs;				/* FASTQ: first byte of the quality line */
+	uint32_t name_len, len;			/* len = number of bases */
+	uint32_t flags, _pad;
+	uint64_t sam_ofs;				/* where this read's SAM lines start in the output */
+	uint64_t sam_len;
+};
+#define MAB_TR_DROPPED	1u			/* shorter than the reader's min_len (1): the record vanishes (minialign.c:2077) */
+#define MAB_TR_HASQUAL	2u
+
+#define MAB_TXT_EFORMAT	1u			/* record layout the device parser does not take (see mab_text.cuh) */
+#define MAB_TXT_EMARKS	2u			/* mark array too small (host grows it and parses again) */
+#define MAB_TXT_ERECS	4u			/* record array too small (ditto) */
+struct TextCounters {
+	unsigned long long n_mark;		/* record starts (FASTA) or line ends (FASTQ) found */
+	unsigned long long tot_len, span, sam_total;
+	unsigned int n_rec, maxlen, err, fastq;
+	unsigned int mapq_flag, _pad[3];
 };
 
 }  // namespace mab

@@ -147,3 +147,4 @@ template <class T> static inline T atomicExch(T *p, T v) { T o = *p; *p = v; ret
 static inline void __threadfence() {}
 static inline void __threadfence_block() {}
 static inline void __trap() { fprintf(stderr, "emu: __trap()\n"); abort(); }
+static inline unsigned __float2uint_rz(float x) { return (unsigned)x; }
