@@ -55,6 +55,9 @@ typedef struct mab_ctx mab_ctx;
 /* blob = raw (inflated) .mai payload after the 12-byte {magic,size} header: the relocatable mm_idx_t image
  * (minialign.c:3070-3167).  Copied to HBM; the host copy is only read during the call. device = CUDA ordinal. */
 mab_ctx *mab_init(const void *mai_blob, uint64_t size, const mab_params_t *params, int device);
+/* another context on the same device sharing the parent's index image (several batches in flight per GPU cost one index copy);
+ * the parent must outlive its clones.  One host thread per context at a time. */
+mab_ctx *mab_clone(mab_ctx *parent);
 void mab_destroy(mab_ctx *ctx);
 const char *mab_last_error(void);
 
@@ -85,6 +88,11 @@ typedef struct mab_results mab_results;
 mab_results *mab_detach_batch(mab_ctx *ctx);
 uint64_t mab_results_get(const mab_results *r, uint32_t i, const uint32_t **words);
 void mab_results_free(mab_results *r);
+
+/* The one word of state the reference's worker thread carries from read to read (`rlen`, see the text path below): mab_map_batch
+ * chains it through the context; a caller that spreads consecutive batches over several contexts moves it by hand. */
+uint32_t mab_get_rlen(const mab_ctx *ctx);
+void mab_set_rlen(mab_ctx *ctx, uint32_t rlen);
 
 /* device-side statistics of the last batch (for bench.py / roofline): kernel milliseconds measured with CUDA events
  * on the context's stream, DP vectors filled, bytes moved each way */

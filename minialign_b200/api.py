@@ -81,6 +81,8 @@ def load_library(lib_path: str | None = None):
     u8p, u32p, u64p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
     L.mab_init.restype = C.c_void_p
     L.mab_init.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(MabParams), C.c_int]
+    L.mab_clone.restype = C.c_void_p
+    L.mab_clone.argtypes = [C.c_void_p]
     L.mab_destroy.argtypes = [C.c_void_p]
     L.mab_last_error.restype = C.c_char_p
     L.mab_n_ref.restype = C.c_uint32
@@ -146,6 +148,15 @@ class Mapper:
         self.h = self.lib.mab_init(self.blob.ctypes.data, self.blob.size, C.byref(self.params), device)
         if not self.h:
             raise RuntimeError("mab_init failed: " + self.lib.mab_last_error().decode())
+
+    def clone(self) -> "Mapper":
+        """Another context on the same device sharing this one's index image (keep this one alive while the clone is used)."""
+        m = Mapper.__new__(Mapper)
+        m.lib, m.params, m.blob = self.lib, self.params, self.blob
+        m.h = self.lib.mab_clone(self.h)
+        if not m.h:
+            raise RuntimeError("mab_clone failed: " + self.lib.mab_last_error().decode())
+        return m
 
     def close(self):
         if self.h:

@@ -19,6 +19,10 @@
 #include <chrono>
 #include <condition_variable>
 #include <deque>
+#include <map>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <cerrno>
 #include <memory>
 #include <mutex>
 #include <thread>
@@ -84,10 +88,16 @@ struct Rec { std::string name, qual; std::vector<uint8_t> seq; };
 struct SeqReader {
 	gzFile fp; std::vector<char> buf; size_t pos = 0, end = 0; bool eof = false;
 	std::string line; bool have = false;
+	bool keep_qual = false;			/* -Q (minialign.c:5964, 2064): without it the quality lines are skipped */
 	uint8_t enc[256];
+	/* records out of a chunk of text already in memory */
+	SeqReader(const char *mem, size_t n) : buf(mem, mem + n) { fp = nullptr; end = n; eof = true; init_enc(); }
 	explicit SeqReader(const char *path) : buf(4 << 20) {
 		fp = strcmp(path, "-") == 0 ? gzdopen(0, "rb") : gzopen(path, "rb");
 		if(fp) { gzbuffer(fp, 1 << 20); }
+		init_enc();
+	}
+	void init_enc() {
 		uint8_t e16[16]; memset(e16, 0, sizeof(e16));
 		e16['A' & 15] = 0; e16['C' & 15] = 1; e16['G' & 15] = 2; e16['T' & 15] = 3; e16['U' & 15] = 3; e16['N' & 15] = 4;
 		for(int i = 0; i < 256; i++) { enc[i] = e16[i & 15]; }
@@ -135,15 +145,61 @@ struct SeqReader {
 				size_t o = r.seq.size(); r.seq.resize(o + n);
 				for(size_t i = 0; i < n; i++) { r.seq[o + i] = enc[(uint8_t)b[i]]; }
 			}
-			if(fq) { while(r.qual.size() < r.seq.size() && getline(&b, &n)) { r.qual.append(b, n); } }
+			if(fq) { std::string q; while(q.size() < r.seq.size() && getline(&b, &n)) { q.append(b, n); } if(keep_qual) { r.qual.swap(q); } }
 			return true;
 		}
 		return false;
 	}
 };
 
+/* ---- raw bytes of a read file (gzip transparent), for the text path ---- */
+struct ByteSource {
+	int fd = -1; gzFile gz = nullptr;
+	explicit ByteSource(const char *path) {
+		if(strcmp(path, "-") == 0) { gz = gzdopen(0, "rb"); if(gz) { gzbuffer(gz, 1 << 20); } return; }
+		fd = open(path, O_RDONLY);
+		if(fd < 0) { return; }
+		unsigned char m[2] = { 0, 0 };
+		ssize_t n = pread(fd, m, 2, 0);
+		if(n == 2 && m[0] == 0x1f && m[1] == 0x8b) { close(fd); fd = -1; gz = gzopen(path, "rb"); if(gz) { gzbuffer(gz, 1 << 20); } }
+	}
+	~ByteSource() { if(fd >= 0) { close(fd); } if(gz) { gzclose(gz); } }
+	bool ok() const { return fd >= 0 || gz != nullptr; }
+	int64_t read(char *dst, uint64_t n) {
+		if(n > (1u << 30)) { n = 1u << 30; }
+		if(gz) { return gzread(gz, dst, (unsigned)n); }
+		return ::read(fd, dst, n);
+	}
+};
+
+/* [0, cut) = whole records of buf[0, fill): the start of the last record header that can be told for sure.  FASTA: the last
+ * '>' at a line start.  FASTQ: the last '@' at a line start whose line after next starts with '+' (a quality line may start
+ * with '@' too, but then the line after next is a sequence).  0 = no such place. */
+static uint64_t record_cut(const char *buf, uint64_t fill)
+{
+	if(fill < 2) { return 0; }
+	const char delim = buf[0];
+	for(uint64_t p = fill - 1; p > 0; p--) {
+		if(buf[p] != delim || buf[p - 1] != '\n') { continue; }
+		if(delim != '@') { return p; }
+		const char *e1 = (const char *)memchr(buf + p, '\n', fill - p);
+		if(!e1) { continue; }
+		const char *e2 = (const char *)memchr(e1 + 1, '\n', fill - (uint64_t)(e1 + 1 - buf));
+		if(!e2 || (uint64_t)(e2 + 1 - buf) >= fill) { continue; }
+		if(e2[1] == '+') { return p; }
+	}
+	return 0;
+}
+
+static int write_all(int fd, const char *p, uint64_t n)
+{
+	while(n) { ssize_t w = write(fd, p, n > (1u << 30) ? (1u << 30) : n); if(w < 0) { if(errno == EINTR) { continue; } return -1; } p += w; n -= (uint64_t)w; }
+	return 0;
+}
+
 struct Opts {
 	mab_params_t p; uint32_t tags = 0; int device = 0; uint32_t batch_reads = 16384; uint64_t batch_bases = 400ull << 20;
+	bool keep_qual = false; unsigned contexts = 3; std::vector<int> devices; double chunk_mb = 320;
 	MabIdxParams ip; bool w_set = false; std::string dump;
 	std::vector<std::string> pos;
 };
@@ -210,10 +266,46 @@ static bool apply_opt(Opts &o, char c, const char *arg)
 			return o.ip.n_frq > 0;
 		}
 		case 'd': o.dump = arg; return true;
-		case 'g': o.device = atoi(arg); return true;
+		case 'g': {												/* device ordinal, or a comma-separated list: the chunks are dealt to all of them */
+			o.devices.clear();
+			for(const char *q = arg; *q;) { o.devices.push_back(atoi(q)); const char *cm = strchr(q, ','); if(!cm) { break; } q = cm + 1; }
+			if(o.devices.empty()) { return false; }
+			o.device = o.devices[0];
+			return true;
+		}
+		case 'Q': o.keep_qual = true; return true;				/* keep the FASTQ qualities (minialign.c:5964) */
+		case 'c': o.contexts = (unsigned)std::max(1, atoi(arg)); return true;	/* chunks in flight per GPU */
+		case 'N': o.chunk_mb = std::max(0.001, atof(arg)); return true;	/* chunk size in MiB of read file */
 		case 'n': o.batch_reads = (uint32_t)atoi(arg); return true;
 		default: return false;
 	}
+}
+
+/* a chunk the device reader does not take: host reader -> record-level mapper -> host formatter (runs in file order, the
+ * context's rlen word is set by hand) */
+static bool map_chunk_on_host(mab_ctx *ctx, const char *buf, uint64_t len, const Opts &o, const std::vector<MabSamRef> &refs, uint32_t rlen_in, uint32_t *rlen_out,
+	std::string &out, uint64_t *n_reads, uint64_t *n_bases)
+{
+	SeqReader rd(buf, len); rd.keep_qual = o.keep_qual;
+	std::vector<Rec> recs; Rec r;
+	uint64_t bases = 0;
+	while(rd.next(r)) { if(r.seq.empty()) { continue; } bases += r.seq.size(); recs.push_back(std::move(r)); }
+	*n_reads = recs.size(); *n_bases = bases; *rlen_out = rlen_in;
+	if(recs.empty()) { return true; }
+	std::vector<uint8_t> block(64 + bases + 64ull * recs.size() + 64, 0);
+	std::vector<uint64_t> ofs(recs.size()); std::vector<uint32_t> lens(recs.size());
+	uint64_t p = 64;
+	for(size_t i = 0; i < recs.size(); i++) { ofs[i] = p; lens[i] = (uint32_t)recs[i].seq.size(); memcpy(block.data() + p, recs[i].seq.data(), lens[i]); p += lens[i] + 64; }
+	mab_set_rlen(ctx, rlen_in);
+	if(mab_map_batch(ctx, block.data(), block.size(), ofs.data(), lens.data(), (uint32_t)recs.size()) != MAB_OK) { return false; }
+	*rlen_out = mab_get_rlen(ctx);
+	for(size_t i = 0; i < recs.size(); i++) {
+		const uint32_t *w = nullptr; uint64_t nw = mab_result(ctx, (uint32_t)i, &w);
+		MabSamRead q = { recs[i].name.c_str(), (uint32_t)recs[i].name.size(), block.data() + ofs[i], lens[i], recs[i].qual.empty() ? nullptr : recs[i].qual.c_str() };
+		mab_sam_record(out, refs.data(), &q, w, nw, o.tags);
+	}
+	mab_release_batch(ctx);
+	return true;
 }
 
 int main(int argc, char **argv)
@@ -228,7 +320,7 @@ int main(int argc, char **argv)
 		const char *a = argv[i];
 		if(a[0] == '-' && a[1] != '\0') {
 			if(a[1] == 'v') { fprintf(stderr, "[M::main] Version: 0.6.0-devel, Build: B200 (sm_100a)\n"); return 0; }
-			const char *arg = a[2] ? a + 2 : (i + 1 < argc ? argv[++i] : "");
+			const char *arg = a[1] == 'Q' ? "" : (a[2] ? a + 2 : (i + 1 < argc ? argv[++i] : ""));
 			if(!apply_opt(o, a[1], arg)) { fprintf(stderr, "[E::main] unknown or unsupported option `-%c'.\n", a[1]); return 1; }
 		} else { o.pos.push_back(a); }
 	}
@@ -249,133 +341,186 @@ int main(int argc, char **argv)
 		fprintf(stderr, "[M::main] Command: %s\n[M::main] Real time: %.3f sec\n", cmdline.c_str(), now() - t0);
 		return 0;
 	}
-	/* Pipeline: a reader thread parses and packs the next batches (reads already sit 1 byte/base with 64 B margins, the layout of
-	 * bseq_t, minialign.c:2109-2146) while this thread maps the current one; the SAM text of a batch is formatted by all host
-	 * cores, one slice of reads each, and written in input order.  One context, batches in input order: the reference's
-	 * per-thread state (rlen) carries over exactly as with -t1. */
-	struct Batch { std::vector<Rec> recs; std::vector<uint8_t> block; std::vector<uint64_t> ofs; std::vector<uint32_t> len; uint64_t bases = 0; size_t file = 0; bool last_of_file = false; bool open_failed = false; };
-	std::mutex mu; std::condition_variable cv;
-	std::deque<std::unique_ptr<Batch>> queue; bool done = false, stop = false;
-	std::thread reader([&]() {
-		for(size_t qi = 1; qi < o.pos.size(); qi++) {
-			SeqReader rd(o.pos[qi].c_str());
-			if(!rd.fp) { auto bt = std::make_unique<Batch>(); bt->file = qi; bt->open_failed = true; std::unique_lock<std::mutex> lk(mu); queue.push_back(std::move(bt)); cv.notify_all(); break; }
-			bool more = true;
-			while(more) {
-				auto bt = std::make_unique<Batch>(); bt->file = qi;
-				Rec r;
-				while(bt->recs.size() < o.batch_reads && bt->bases < o.batch_bases && (more = rd.next(r))) { if(r.seq.empty()) { continue; } bt->bases += r.seq.size(); bt->recs.push_back(std::move(r)); }
-				bt->last_of_file = !more;
-				if(!bt->recs.empty()) {
-					bt->block.assign(64 + bt->bases + 64ull * bt->recs.size() + 64, 0);
-					bt->ofs.resize(bt->recs.size()); bt->len.resize(bt->recs.size());
-					uint64_t p = 64;
-					for(size_t i = 0; i < bt->recs.size(); i++) {
-						bt->ofs[i] = p; bt->len[i] = (uint32_t)bt->recs[i].seq.size();
-						memcpy(bt->block.data() + p, bt->recs[i].seq.data(), bt->len[i]); p += bt->len[i] + 64;
-						std::vector<uint8_t>().swap(bt->recs[i].seq);
-					}
-				}
-				std::unique_lock<std::mutex> lk(mu);
-				cv.wait(lk, [&]() { return queue.size() < 2 || stop; });
-				if(stop) { return; }
-				queue.push_back(std::move(bt)); cv.notify_all();
-			}
-		}
-		std::unique_lock<std::mutex> lk(mu); done = true; cv.notify_all();
-	});
+	/* Pipeline (the reference's source -> workers -> drain, minialign.c:4565-4643, with the workers' job done by the GPU):
+	 *   reader   one thread: the read files in big blocks straight into page-locked chunk buffers, cut at record boundaries
+	 *   workers  one thread per context (several contexts per GPU, any number of GPUs): chunk -> mab_text_begin (parse, map) ->
+	 *            wait for its turn in file order -> mab_text_commit with the `rlen` word the previous chunk left behind (the
+	 *            reference thread's state, DESIGN.md: this keeps the output identical to the -t1 run however the chunks are
+	 *            spread) -> mab_text_finish (post-processing, SAM text) into a page-locked output buffer
+	 *   writer   one thread: write(2) the SAM text of the chunks in file order
+	 * A chunk the device reader does not take (MAB_EFORMAT: wrapped FASTQ, ...) is parsed on the host and goes through the
+	 * record-level entry point and the host formatter instead. */
+	const uint64_t chunk_bytes = std::max<uint64_t>(1024, (uint64_t)(o.chunk_mb * 1048576.0));
+	std::vector<int> devices = o.devices.empty() ? std::vector<int>{ o.device } : o.devices;
+	const unsigned n_ctx = std::max(1u, o.contexts) * (unsigned)devices.size();
 	double t_idx = now() - t0;
-	mab_ctx *ctx = mab_init(blob.data(), blob.size(), &o.p, o.device);
-	if(!ctx) {
-		fprintf(stderr, "[E::main_align] failed to instanciate alignment context: %s\n", mab_last_error());
-		{ std::unique_lock<std::mutex> lk(mu); stop = true; cv.notify_all(); }
-		reader.join();
-		return 1;
+	std::vector<mab_ctx *> ctxs(n_ctx, nullptr);
+	{	/* one parent context per device (uploads the index), clones share its image; devices are set up in parallel */
+		std::vector<std::thread> th; std::vector<std::string> errs(devices.size());
+		for(size_t d = 0; d < devices.size(); d++) {
+			th.emplace_back([&, d]() {
+				mab_ctx *p = mab_init(blob.data(), blob.size(), &o.p, devices[d]);
+				if(!p) { errs[d] = mab_last_error(); return; }
+				ctxs[d] = p;
+				for(unsigned c = 1; c < std::max(1u, o.contexts); c++) { mab_ctx *q = mab_clone(p); if(!q) { errs[d] = mab_last_error(); return; } ctxs[c * devices.size() + d] = q; }
+			});
+		}
+		for(auto &x : th) { x.join(); }
+		for(auto &e : errs) { if(!e.empty()) { fprintf(stderr, "[E::main_align] failed to instanciate alignment context: %s\n", e.c_str()); return 1; } }
 	}
-	uint32_t n_ref = mab_n_ref(ctx);
+	mab_ctx *ctx0 = ctxs[0];
+	uint32_t n_ref = mab_n_ref(ctx0);
 	std::vector<MabSamRef> refs(n_ref);
-	for(uint32_t i = 0; i < n_ref; i++) { mab_ref_info(ctx, i, &refs[i].name, &refs[i].l_name, &refs[i].l_seq, &refs[i].seq); }
-	fprintf(stderr, "[M::main_align::%.3f] loaded/built index for %u target sequence(s) (index file %.3f s, device context %.3f s).\n", now() - t0, n_ref, t_idx, now() - t0 - t_idx);
-	double tmap = now(); uint64_t tot_bases = 0, tot_reads = 0;
-	std::string out; out.reserve(64 << 20);
-	mab_sam_header(out, refs.data(), n_ref, "0.6.0-devel", cmdline.c_str());
-	unsigned nfmt = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
-	/* writer stage: takes (batch, detached results) in input order, formats the SAM text on all cores, writes it */
-	struct Done { std::unique_ptr<Batch> bt; mab_results *res; };
-	std::mutex wmu; std::condition_variable wcv; std::deque<Done> wq; bool wdone = false;
-	double t_fmt = 0, t_wr = 0;
-	std::thread writer([&]() {
-		std::vector<std::string> parts(nfmt);									/* per-slice SAM text, reused from batch to batch */
-		if(!out.empty()) { fwrite(out.data(), 1, out.size(), stdout); out.clear(); }		/* the header */
-		while(true) {
-			Done d;
-			{
-				std::unique_lock<std::mutex> lk(wmu);
-				wcv.wait(lk, [&]() { return !wq.empty() || wdone; });
-				if(wq.empty()) { break; }
-				d = std::move(wq.front()); wq.pop_front(); wcv.notify_all();
-			}
-			Batch *bt = d.bt.get();
-			double tm0 = now();
-			size_t n = bt->recs.size(), nsl = std::min<size_t>(nfmt, (n + 63) / 64);
-			for(auto &pz : parts) { pz.clear(); }
-			auto fmt = [&](size_t t) {
-				std::string &dst = parts[t];
-				size_t lo = n * t / nsl, hi = n * (t + 1) / nsl, est = 0;
-				for(size_t i = lo; i < hi; i++) { est += bt->len[i] + bt->len[i] / 3 + 512; }
-				if(dst.capacity() < est) { dst.reserve(est + est / 8); }
-				for(size_t i = lo; i < hi; i++) {
-					const uint32_t *w = nullptr; uint64_t nw = mab_results_get(d.res, (uint32_t)i, &w);
-					MabSamRead q = { bt->recs[i].name.c_str(), (uint32_t)bt->recs[i].name.size(), bt->block.data() + bt->ofs[i], bt->len[i], bt->recs[i].qual.empty() ? nullptr : bt->recs[i].qual.c_str() };
-					mab_sam_record(dst, refs.data(), &q, w, nw, o.tags);
+	for(uint32_t i = 0; i < n_ref; i++) { mab_ref_info(ctx0, i, &refs[i].name, &refs[i].l_name, &refs[i].l_seq, &refs[i].seq); }
+	fprintf(stderr, "[M::main_align::%.3f] loaded/built index for %u target sequence(s) (index file %.3f s, %u device context(s) on %zu GPU(s) %.3f s).\n", now() - t0, n_ref, t_idx, n_ctx, devices.size(), now() - t0 - t_idx);
+	double tmap = now();
+	struct Chunk { char *buf = nullptr; uint64_t cap = 0, len = 0; uint64_t id = 0; size_t file = 0; bool last_of_file = false, open_failed = false; };
+	struct Out { char *buf = nullptr; uint64_t cap = 0, len = 0; std::string spill; uint64_t id = 0; unsigned owner = 0; bool busy = false; };	/* buf: page-locked, the SAM text is copied from the device straight into it */
+	std::mutex mu; std::condition_variable cv;
+	std::deque<Chunk *> free_chunks, ready; std::map<uint64_t, Out *> done_outs;
+	bool read_done = false, failed = false;
+	std::vector<Chunk> chunk_pool(n_ctx + 2); std::vector<Out> out_pool(2 * n_ctx);			/* two output buffers per context: one being written while the next is filled */
+	for(auto &c : chunk_pool) { c.cap = chunk_bytes + (16 << 20); c.buf = (char *)mab_host_alloc(c.cap); if(!c.buf) { fprintf(stderr, "[E::main_align] %s\n", mab_last_error()); return 1; } free_chunks.push_back(&c); }
+	for(unsigned i = 0; i < 2 * n_ctx; i++) { out_pool[i].owner = i / 2; }
+	struct stat st_out; const bool out_is_file = fstat(1, &st_out) == 0 && S_ISREG(st_out.st_mode);
+	uint64_t out_ofs = out_is_file ? (uint64_t)std::max<off_t>(0, lseek(1, 0, SEEK_CUR)) : 0;	/* regular file: the writers pwrite() concurrently at known offsets */
+	uint64_t next_commit = 0, next_write = 0, tot_bases = 0, tot_reads = 0, n_chunks_total = 0;
+	uint32_t rlen_chain = 0;												/* a fresh reference thread starts with rlen = 0 (calloc'ed mm_tbuf_t) */
+	std::string header;
+	{ uint64_t n = mab_sam_header_text(ctx0, "0.6.0-devel", cmdline.c_str(), nullptr, 0); header.resize(n); mab_sam_header_text(ctx0, "0.6.0-devel", cmdline.c_str(), &header[0], n); }
+	std::thread reader([&]() {
+		uint64_t id = 0;
+		std::string carry;													/* the cut-off tail of the previous block: start of the next chunk */
+		for(size_t qi = 1; qi < o.pos.size(); qi++) {
+			ByteSource src(o.pos[qi].c_str());
+			if(!src.ok()) { std::unique_lock<std::mutex> lk(mu); Chunk *c = nullptr; cv.wait(lk, [&]() { return !free_chunks.empty() || failed; }); if(failed) { return; } c = free_chunks.front(); free_chunks.pop_front(); c->len = 0; c->id = id++; c->file = qi; c->open_failed = true; c->last_of_file = true; ready.push_back(c); cv.notify_all(); break; }
+			bool eof = false; carry.clear();
+			while(!eof) {
+				Chunk *c;
+				{ std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&]() { return !free_chunks.empty() || failed; }); if(failed) { return; } c = free_chunks.front(); free_chunks.pop_front(); }
+				uint64_t fill = carry.size();
+				if(fill > c->cap) { c->len = 0; }							/* (cannot happen: the carry is cut below the capacity) */
+				memcpy(c->buf, carry.data(), fill); carry.clear();
+				while(fill < chunk_bytes && !eof) { int64_t n = src.read(c->buf + fill, (chunk_bytes - fill)); if(n <= 0) { eof = true; break; } fill += (uint64_t)n; }
+				uint64_t cut = fill;
+				if(!eof) {
+					cut = record_cut(c->buf, fill);
+					while(cut == 0 && !eof) {								/* one record longer than the chunk: keep reading until it ends */
+						if(fill + (1 << 20) > c->cap) { break; }
+						int64_t n = src.read(c->buf + fill, std::min<uint64_t>(c->cap - fill, 1 << 20)); if(n <= 0) { eof = true; break; } fill += (uint64_t)n;
+						cut = eof ? fill : record_cut(c->buf, fill);
+					}
+					if(eof) { cut = fill; }
+					if(cut == 0) { cut = fill; }							/* give up cutting: the device reader will reject what is not whole records */
 				}
-			};
-			std::vector<std::thread> th;
-			for(size_t t = 1; t < nsl; t++) { th.emplace_back(fmt, t); }
-			if(nsl) { fmt(0); }
-			for(auto &x : th) { x.join(); }
-			mab_results_free(d.res);
-			t_fmt += now() - tm0; tm0 = now();
-			for(size_t t = 0; t < nsl; t++) { fwrite(parts[t].data(), 1, parts[t].size(), stdout); }
-			t_wr += now() - tm0;
+				carry.assign(c->buf + cut, fill - cut);
+				while(cut > 0 && eof && c->buf[cut - 1] == '\n' && cut > 1 && c->buf[cut - 2] == '\n') { cut--; }	/* blank lines at the end of the file */
+				c->len = cut; c->id = id++; c->file = qi; c->last_of_file = eof; c->open_failed = false;
+				std::unique_lock<std::mutex> lk(mu); ready.push_back(c); cv.notify_all();
+			}
 		}
+		std::unique_lock<std::mutex> lk(mu); read_done = true; n_chunks_total = id; cv.notify_all();
 	});
-	int rc_main = 0;
-	double t_wait = 0, t_map = 0, t_wwait = 0;
-	while(true) {
-		std::unique_ptr<Batch> bt;
-		double tq = now();
-		{
-			std::unique_lock<std::mutex> lk(mu);
-			cv.wait(lk, [&]() { return !queue.empty() || done; });
-			if(queue.empty()) { break; }
-			bt = std::move(queue.front()); queue.pop_front(); cv.notify_all();
-		}
-		t_wait += now() - tq;
-		if(rc_main) { continue; }												/* drain the queue after an error */
-		if(bt->open_failed) { fprintf(stderr, "[E::main_align] failed to open sequence file `%s'. Please check file path and format.\n", o.pos[bt->file].c_str()); rc_main = 1; continue; }
-		bool last = bt->last_of_file; size_t file = bt->file;
-		if(!bt->recs.empty()) {
+	double t_wr = 0;
+	if(write_all(1, header.data(), header.size()) != 0) { fprintf(stderr, "[E::main_align] failed to write the SAM header\n"); return 1; }
+	out_ofs += header.size();
+	auto writer_fn = [&]() {
+		while(true) {
+			Out *x; uint64_t ofs;
+			{
+				std::unique_lock<std::mutex> lk(mu);
+				cv.wait(lk, [&]() { return done_outs.count(next_write) || failed || (read_done && next_write == n_chunks_total); });
+				if(failed || !done_outs.count(next_write)) { return; }
+				x = done_outs[next_write]; done_outs.erase(next_write);
+				uint64_t len = x->spill.empty() ? x->len : x->spill.size();
+				ofs = out_ofs; out_ofs += len;
+				if(out_is_file) { next_write++; cv.notify_all(); }			/* the next chunk's writer may start: the offsets are fixed */
+			}
 			double tm0 = now();
-			int rc = mab_map_batch(ctx, bt->block.data(), bt->block.size(), bt->ofs.data(), bt->len.data(), (uint32_t)bt->recs.size());
-			t_map += now() - tm0;
-			if(rc != MAB_OK) { fprintf(stderr, "[E::main_align] failed to map sequence file `%s': %s\n", o.pos[bt->file].c_str(), mab_last_error()); rc_main = 1; continue; }
-			tot_bases += bt->bases; tot_reads += bt->recs.size();
-			Done d; d.res = mab_detach_batch(ctx); d.bt = std::move(bt);
-			tm0 = now();
-			std::unique_lock<std::mutex> lk(wmu);
-			wcv.wait(lk, [&]() { return wq.size() < 2; });
-			wq.push_back(std::move(d)); wcv.notify_all();
-			t_wwait += now() - tm0;
+			const char *p = x->spill.empty() ? x->buf : x->spill.data(); uint64_t len = x->spill.empty() ? x->len : x->spill.size();
+			int rc = 0;
+			if(out_is_file) { while(len) { ssize_t w = pwrite(1, p, len > (1u << 30) ? (1u << 30) : len, (off_t)ofs); if(w < 0) { if(errno == EINTR) { continue; } rc = -1; break; } p += w; len -= (uint64_t)w; ofs += (uint64_t)w; } }
+			else { rc = write_all(1, p, len); }
+			std::unique_lock<std::mutex> lk(mu);
+			t_wr += now() - tm0;
+			if(rc != 0) { failed = true; }
+			x->spill.clear(); x->len = 0; x->busy = false;
+			if(!out_is_file) { next_write++; }
+			cv.notify_all();
 		}
-		if(last) { fprintf(stderr, "[M::main_align::%.3f] finished mapping `%s' onto `%s'.\n", now() - t0, o.pos[file].c_str(), o.pos[0].c_str()); }
-	}
-	{ std::unique_lock<std::mutex> lk(wmu); wdone = true; wcv.notify_all(); }
-	writer.join();
-	reader.join();
-	if(rc_main) { mab_destroy(ctx); return rc_main; }
-	fprintf(stderr, "[M::main_align] host pipeline: mapper waited for the reader %.3f s and for the writer %.3f s, mapping %.3f s; writer: SAM formatting %.3f s, writing %.3f s\n", t_wait, t_wwait, t_map, t_fmt, t_wr);
-	fwrite(out.data(), 1, out.size(), stdout);
+	};
+	std::vector<std::thread> writers;
+	for(unsigned i = 0; i < (out_is_file ? std::min(4u, n_ctx) : 1u); i++) { writers.emplace_back(writer_fn); }
+	std::vector<double> t_begin(n_ctx, 0), t_turn(n_ctx, 0), t_finish(n_ctx, 0);
+	std::atomic<uint64_t> n_redo(0), n_fallback(0), n_failed_reads(0);
+	auto worker = [&](unsigned w) {
+		mab_ctx *ctx = ctxs[w];
+		while(true) {
+			Chunk *c; Out *x;
+			{
+				std::unique_lock<std::mutex> lk(mu);
+				auto my_out = [&]() -> Out * { for(unsigned i = 0; i < 2; i++) { if(!out_pool[2 * w + i].busy) { return &out_pool[2 * w + i]; } } return nullptr; };
+				cv.wait(lk, [&]() { return (!ready.empty() && my_out() != nullptr) || failed || (read_done && ready.empty()); });
+				if(failed || ready.empty()) { return; }
+				c = ready.front(); ready.pop_front(); x = my_out(); x->busy = true;
+			}
+			x->id = c->id; x->len = 0; x->spill.clear();
+			auto fail = [&](const std::string &msg) { fprintf(stderr, "%s\n", msg.c_str()); std::unique_lock<std::mutex> lk(mu); failed = true; cv.notify_all(); };
+			if(c->open_failed) { fail("[E::main_align] failed to open sequence file `" + o.pos[c->file] + "'. Please check file path and format."); return; }
+			mab_text_info_t info; memset(&info, 0, sizeof(info));
+			double tm0 = now();
+			const uint32_t flags = o.tags | (o.keep_qual ? MAB_TEXT_KEEP_QUAL : 0);
+			int rc = c->len ? mab_text_begin(ctx, c->buf, c->len, flags, 0, 0, &info) : MAB_OK;
+			bool host_path = rc == MAB_EFORMAT;
+			if(rc != MAB_OK && !host_path) { fail(std::string("[E::main_align] failed to map sequence file `") + o.pos[c->file] + "': " + mab_last_error()); return; }
+			t_begin[w] += now() - tm0; tm0 = now();
+			{ std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&]() { return next_commit == c->id || failed; }); if(failed) { return; } }
+			t_turn[w] += now() - tm0; tm0 = now();
+			uint64_t reads_here = 0, bases_here = 0;
+			uint32_t rlen_next = rlen_chain;
+			if(host_path) {													/* host reader + record-level mapper + host formatter, in turn (the context's own chain is set by hand) */
+				n_fallback++;
+				if(!map_chunk_on_host(ctx, c->buf, c->len, o, refs, rlen_chain, &rlen_next, x->spill, &reads_here, &bases_here)) { fail(std::string("[E::main_align] failed to map sequence file `") + o.pos[c->file] + "': " + mab_last_error()); return; }
+			} else if(c->len) {
+				rc = mab_text_commit(ctx, rlen_chain, &info);
+				if(rc != MAB_OK) { fail(std::string("[E::main_align] failed to map sequence file `") + o.pos[c->file] + "': " + mab_last_error()); return; }
+				if(info.rlen_valid) { rlen_next = info.rlen_next; }
+			}
+			{ std::unique_lock<std::mutex> lk(mu); rlen_chain = rlen_next; next_commit++; cv.notify_all(); }
+			if(!host_path && c->len) {
+				const char *ptr = nullptr;
+				if(x->buf == nullptr) { x->cap = c->len + c->len / 2 + (1 << 20); x->buf = (char *)mab_host_alloc(x->cap); if(!x->buf) { fail(std::string("[E::main_align] ") + mab_last_error()); return; } }
+				rc = mab_text_finish(ctx, x->buf, x->cap, &ptr, &info);		/* device -> this page-locked buffer; the context is free for the next chunk afterwards */
+				if(rc == MAB_ENOMEM && info.sam_bytes > x->cap) {			/* more text than estimated: a larger buffer, format again */
+					mab_host_free(x->buf); x->cap = info.sam_bytes + info.sam_bytes / 8 + (1 << 20); x->buf = (char *)mab_host_alloc(x->cap);
+					if(!x->buf) { fail(std::string("[E::main_align] ") + mab_last_error()); return; }
+					rc = mab_text_finish(ctx, x->buf, x->cap, &ptr, &info);
+				}
+				if(rc != MAB_OK) { fail(std::string("[E::main_align] failed to format the alignments of `") + o.pos[c->file] + "': " + mab_last_error()); return; }
+				x->len = info.sam_bytes;
+				reads_here = info.n_reads; bases_here = info.n_bases;
+				mab_stats_t st; mab_last_stats(ctx, &st); n_redo += st.n_retry; n_failed_reads += st.n_failed;
+			}
+			t_finish[w] += now() - tm0;
+			bool last = c->last_of_file; size_t file = c->file;
+			{
+				std::unique_lock<std::mutex> lk(mu);
+				tot_reads += reads_here; tot_bases += bases_here;
+				free_chunks.push_back(c); done_outs[x->id] = x; cv.notify_all();
+			}
+			if(last) { fprintf(stderr, "[M::main_align::%.3f] finished mapping `%s' onto `%s'.\n", now() - t0, o.pos[file].c_str(), o.pos[0].c_str()); }
+		}
+	};
+	std::vector<std::thread> workers;
+	for(unsigned w = 0; w < n_ctx; w++) { workers.emplace_back(worker, w); }
+	for(auto &x : workers) { x.join(); }
+	{ std::unique_lock<std::mutex> lk(mu); cv.notify_all(); }
+	reader.join(); for(auto &x : writers) { x.join(); }
+	if(failed) { return 1; }
+	double sb = 0, st = 0, sf = 0; for(unsigned w = 0; w < n_ctx; w++) { sb += t_begin[w]; st += t_turn[w]; sf += t_finish[w]; }
+	fprintf(stderr, "[M::main_align] host pipeline: %u context(s); per context on average: parse+map %.3f s, waiting for its turn %.3f s, post+SAM+copy %.3f s; writer: writing %.3f s; reads re-mapped for the rlen chain: %llu; chunks parsed on the host: %llu\n",
+		n_ctx, sb / n_ctx, st / n_ctx, sf / n_ctx, t_wr, (unsigned long long)n_redo.load(), (unsigned long long)n_fallback.load());
+	if(n_failed_reads.load()) { fprintf(stderr, "[W::main_align] %llu read(s) overflowed a per-read device structure and are reported unmapped\n", (unsigned long long)n_failed_reads.load()); }
 	double tm = now() - tmap;
 	fprintf(stderr, "[M::main] mapped %llu reads / %.1f Mbases in %.3f sec (%.1f Mbases/s)\n", (unsigned long long)tot_reads, tot_bases / 1e6, tm, tot_bases / 1e6 / tm);
 	fprintf(stderr, "[M::main] Command: %s\n[M::main] Real time: %.3f sec\n", cmdline.c_str(), now() - t0);

@@ -7,6 +7,7 @@
 #include "../../include/minialign_b200.h"
 #include "mab_kernels.cuh"
 #include <new>
+#include <memory>
 #include <vector>
 #include <string>
 #include <cmath>
@@ -31,7 +32,8 @@ struct RunState {
 struct mab_ctx {
 	int device;
 	DevParams P;
-	std::vector<uint8_t> blob;			/* host copy of the index image (reference names / sequences for the printer) */
+	std::shared_ptr<std::vector<uint8_t>> blob;	/* host copy of the index image (reference names / sequences for the printer); shared by clones */
+	mab_ctx *parent = nullptr;			/* clone: d_idx / d_ntail / d_thr belong to the parent */
 	uint8_t *d_idx = nullptr, *d_ntail = nullptr;
 	uint32_t n_sm = 0, n_slots = 0;
 	mab_params_t prm;
@@ -47,6 +49,7 @@ struct mab_ctx {
 	uint32_t *d_pool = nullptr; uint64_t pool_cap = 0;
 	BatchCounters *d_ctr = nullptr;
 	RT_STREAM stream; bool have_stream = false; int n_ev = 0;
+	RT_EVENT sync_ev; bool have_sync_ev = false;	/* the host waits on this one asleep (blocking-sync event) instead of spinning in a stream synchronize */
 	RT_EVENT ev[8];
 	RT_EVENT rev[24];					/* per-round kernel boundaries: [3r] sortchain start, [3r+1] extend start, [3r+2] extend end */
 	int device_input = 0;
@@ -165,6 +168,32 @@ static void text_destroy(struct mab_ctx *ctx);
 #define CK(call) do { if(!RT_OK(call)) { g_err = std::string(#call) + ": " + RT_ERRSTR(); return MAB_ENODEV; } } while(0)
 #define CKP(call) do { if(!RT_OK(call)) { g_err = std::string(#call) + ": " + RT_ERRSTR(); mab_destroy(ctx); return nullptr; } } while(0)
 
+/* wait for everything queued on the context's stream with the host thread asleep: several contexts per GPU and several GPUs
+ * per process each have a thread waiting most of the time, and spinning waits would eat the cores the reader needs */
+static inline auto ctx_sync(mab_ctx *ctx) -> decltype(RT_STREAM_SYNC(ctx->stream))
+{
+	if(!ctx->have_sync_ev) { return RT_STREAM_SYNC(ctx->stream); }
+	RT_EVENT_RECORD(ctx->sync_ev, ctx->stream);
+	return RT_EVENT_SYNC(ctx->sync_ev);
+}
+
+/* the per-context part of the set-up: counters, stream, events, launch shape */
+static int ctx_private_init(mab_ctx *ctx)
+{
+	CK(RT_MALLOC(&ctx->d_ctr, sizeof(BatchCounters)));
+	CK(RT_STREAM_CREATE(&ctx->stream)); ctx->have_stream = true;
+	for(int i = 0; i < 8; i++) { CK(RT_EVENT_CREATE(&ctx->ev[i])); ctx->n_ev++; }
+	for(int i = 0; i < 24; i++) { CK(RT_EVENT_CREATE(&ctx->rev[i])); ctx->n_ev++; }
+	CK(RT_SYNC_EVENT_CREATE(&ctx->sync_ev)); ctx->have_sync_ev = true;
+	RT_FUNC_MAX_SMEM(k_sortchain, 16 * MAB_SC_MAX + 2048);
+	ctx->n_slots = RT_EXTEND_SLOTS(ctx->n_sm);
+	if(const char *e = getenv("MAB_EXT_CTAS")) {										/* resident k_extend CTAs per SM actually launched (<= MAB_EXT_CTAS_PER_SM) */
+		int v = atoi(e);
+		if(v >= 1 && v <= MAB_EXT_CTAS_PER_SM) { ctx->n_slots = ctx->n_sm * MAB_WARPS_PER_CTA * (uint32_t)v; }
+	}
+	return MAB_OK;
+}
+
 extern "C" mab_ctx *mab_init(const void *mai_blob, uint64_t size, const mab_params_t *params, int device)
 {
 	if(mai_blob == nullptr || size < 64 || params == nullptr) { g_err = "mab_init: bad arguments"; return nullptr; }
@@ -175,7 +204,7 @@ extern "C" mab_ctx *mab_init(const void *mai_blob, uint64_t size, const mab_para
 	if(!RT_OK(RT_SET_DEVICE(device))) { g_err = std::string("no usable CUDA device: ") + RT_ERRSTR(); delete ctx; return nullptr; }
 	ctx->n_sm = RT_SM_COUNT(device);
 	const uint8_t *b = (const uint8_t *)mai_blob;
-	ctx->blob.assign(b, b + size);
+	try { ctx->blob = std::make_shared<std::vector<uint8_t>>(b, b + size); } catch(const std::bad_alloc &) { g_err = "host allocation failed"; delete ctx; return nullptr; }
 	DevParams &P = ctx->P;
 	memset(&P, 0, sizeof(P));
 	P.bkt_ofs = rd64(b); P.bkt_mask = rd64(b + 8);
@@ -195,24 +224,34 @@ extern "C" mab_ctx *mab_init(const void *mai_blob, uint64_t size, const mab_para
 	uint8_t nt[128]; memset(nt, 4, sizeof(nt));
 	CKP(RT_MALLOC(&ctx->d_ntail, 256));
 	CKP(RT_MEMCPY_H2D(ctx->d_ntail, nt, 128));
-	CKP(RT_MALLOC(&ctx->d_ctr, sizeof(BatchCounters)));
-	CKP(RT_DEVICE_SYNC());								/* the uploads above ran on the legacy stream: nothing on the context's own (non-blocking) stream may overtake them */
-	CKP(RT_STREAM_CREATE(&ctx->stream)); ctx->have_stream = true;
-	for(int i = 0; i < 8; i++) { CKP(RT_EVENT_CREATE(&ctx->ev[i])); ctx->n_ev++; }
-	for(int i = 0; i < 24; i++) { CKP(RT_EVENT_CREATE(&ctx->rev[i])); ctx->n_ev++; }
-	RT_FUNC_MAX_SMEM(k_sortchain, 16 * MAB_SC_MAX + 2048);
 	if(text_init(ctx) != MAB_OK) { mab_destroy(ctx); return nullptr; }
-	ctx->n_slots = RT_EXTEND_SLOTS(ctx->n_sm);
-	if(const char *e = getenv("MAB_EXT_CTAS")) {										/* resident k_extend CTAs per SM actually launched (<= MAB_EXT_CTAS_PER_SM) */
-		int v = atoi(e);
-		if(v >= 1 && v <= MAB_EXT_CTAS_PER_SM) { ctx->n_slots = ctx->n_sm * MAB_WARPS_PER_CTA * (uint32_t)v; }
-	}
+	CKP(RT_DEVICE_SYNC());								/* the uploads above ran on the legacy stream: nothing on the context's own (non-blocking) stream may overtake them */
+	if(ctx_private_init(ctx) != MAB_OK) { mab_destroy(ctx); return nullptr; }
+	return ctx;
+}
+
+/* a second (third, ...) context on the parent's device that shares its index image: batches in flight at the same time cost one
+ * copy of the index, not one each.  The parent must outlive its clones. */
+extern "C" mab_ctx *mab_clone(mab_ctx *parent)
+{
+	if(parent == nullptr) { g_err = "mab_clone: bad arguments"; return nullptr; }
+	while(parent->parent != nullptr) { parent = parent->parent; }
+	mab_ctx *ctx = new mab_ctx();
+	ctx->parent = parent; ctx->device = parent->device; ctx->prm = parent->prm; ctx->P = parent->P; ctx->xcoef = parent->xcoef; ctx->n_sm = parent->n_sm;
+	ctx->blob = parent->blob; ctx->d_idx = parent->d_idx; ctx->d_ntail = parent->d_ntail; ctx->d_thr = parent->d_thr; ctx->thr_ok = parent->thr_ok;
+	memset(&ctx->stats, 0, sizeof(ctx->stats));
+	if(!RT_OK(RT_USE_DEVICE(ctx->device))) { g_err = std::string("no usable CUDA device: ") + RT_ERRSTR(); delete ctx; return nullptr; }
+	CKP(RT_MALLOC(&ctx->d_tc, sizeof(TextCounters)));
+	if(ctx_private_init(ctx) != MAB_OK) { mab_destroy(ctx); return nullptr; }
 	return ctx;
 }
 
 extern "C" void mab_destroy(mab_ctx *ctx)
 {
 	if(ctx == nullptr) { return; }
+	RT_USE_DEVICE(ctx->device);
+	if(ctx->parent != nullptr) { ctx->d_idx = nullptr; ctx->d_ntail = nullptr; ctx->d_thr = nullptr; }	/* the parent's */
+	if(ctx->have_sync_ev) { RT_EVENT_DESTROY(ctx->sync_ev); }
 	RT_FREE(ctx->d_idx); RT_FREE(ctx->d_ntail); RT_FREE(ctx->d_ctr); RT_FREE(ctx->d_seq); RT_FREE(ctx->d_reads); RT_FREE(ctx->d_ws);
 	RT_FREE(ctx->d_frames); RT_FREE(ctx->d_order); RT_FREE(ctx->d_recs); RT_FREE(ctx->d_arenas); RT_FREE(ctx->d_pool); RT_FREE(ctx->d_io);
 	RT_HOST_FREE(ctx->h_pool); RT_HOST_FREE(ctx->pin); delete[] ctx->res_words;
@@ -226,7 +265,7 @@ extern "C" uint32_t mab_n_ref(const mab_ctx *ctx) { return ctx->P.n_ref; }
 extern "C" int mab_ref_info(const mab_ctx *ctx, uint32_t rid, const char **name, uint32_t *l_name, uint32_t *l_seq, const uint8_t **seq)
 {
 	if(rid >= ctx->P.n_ref) { return MAB_EINVAL; }
-	const uint8_t *b = ctx->blob.data(), *s = b + ctx->P.seq_ofs + 24ull * rid;
+	const uint8_t *b = ctx->blob->data(), *s = b + ctx->P.seq_ofs + 24ull * rid;
 	if(seq) { *seq = b + rd64(s); }
 	if(name) { *name = (const char *)(b + rd64(s + 8)); }
 	if(l_seq) { *l_seq = rd32(s + 16); }
@@ -239,6 +278,8 @@ extern "C" int mab_index_params(const mab_ctx *ctx, uint32_t *k, uint32_t *w, ui
 	if(occ) { for(int i = 0; i < 7; i++) { occ[i] = ctx->P.occ[i]; } }
 	return MAB_OK;
 }
+extern "C" uint32_t mab_get_rlen(const mab_ctx *ctx) { return ctx->rlen_last; }
+extern "C" void mab_set_rlen(mab_ctx *ctx, uint32_t rlen) { ctx->rlen_last = rlen; }
 extern "C" int mab_set_device_input(mab_ctx *ctx, int on) { ctx->device_input = on; return MAB_OK; }
 extern "C" int mab_last_stats(const mab_ctx *ctx, mab_stats_t *out) { *out = ctx->stats; return MAB_OK; }
 
@@ -455,7 +496,7 @@ static int pipe_verify(mab_ctx *ctx, uint32_t rlen_init, uint32_t init_known)
 		S.n_launches++;
 		CK(RT_MEMCPY_D2H_ASYNC(pin_ctr, ctx->d_ctr, sizeof(BatchCounters), ctx->stream));
 		S.ms_wall_submit += (float)(RT_WALL_MS() - t_sub);
-		{ double tw = RT_WALL_MS(); CK(RT_STREAM_SYNC(ctx->stream)); S.ms_wall_wait += (float)(RT_WALL_MS() - tw); }
+		{ double tw = RT_WALL_MS(); CK(ctx_sync(ctx)); S.ms_wall_wait += (float)(RT_WALL_MS() - tw); }
 		ctx->hc = *pin_ctr;
 		S.d2h_bytes += sizeof(BatchCounters);
 		const BatchCounters &hc = ctx->hc;
@@ -609,7 +650,7 @@ extern "C" int mab_map_batch(mab_ctx *ctx, const uint8_t *seq_block, uint64_t bl
 	CK(RT_MEMCPY_D2H_ASYNC(pin_rr, ctx->d_reads, rr_bytes, ctx->stream));
 	if(top) { CK(RT_MEMCPY_D2H_ASYNC(ctx->h_pool, ctx->d_pool, 4 * top, ctx->stream)); }
 	RT_EVENT_RECORD(ctx->ev[5], ctx->stream);
-	{ double tw = RT_WALL_MS(); CK(RT_STREAM_SYNC(ctx->stream)); S.ms_wall_wait += (float)(RT_WALL_MS() - tw); }
+	{ double tw = RT_WALL_MS(); CK(ctx_sync(ctx)); S.ms_wall_wait += (float)(RT_WALL_MS() - tw); }
 	S.d2h_bytes += 4 * top + rr_bytes;
 	const ReadRec *hr = pin_rr;
 	update_sc_caps(ctx, hr, n_seq);
@@ -697,7 +738,7 @@ extern "C" uint64_t mab_sketch(mab_ctx *ctx, const uint8_t *seq, uint32_t len, u
 	if(!RT_OK(RT_MALLOC(&d_seq, (uint64_t)len + 64)) || !RT_OK(RT_MALLOC(&d_out, 8 * dcap)) || !RT_OK(RT_MALLOC(&d_n, 8))) { return 0; }
 	RT_MEMCPY_H2D_ASYNC(d_seq, seq, len, ctx->stream);
 	RT_LAUNCH(k_sketch_words, 1, 32, 512, ctx->stream, ctx->P, (const uint8_t *)d_seq, len, d_out, dcap, d_n);
-	RT_STREAM_SYNC(ctx->stream);
+	ctx_sync(ctx);
 	RT_MEMCPY_D2H_ASYNC(&n, d_n, 8, ctx->stream);
 	if(n <= cap) { RT_MEMCPY_D2H_ASYNC(out, d_out, 8 * n, ctx->stream); }
 	RT_FREE(d_seq); RT_FREE(d_out); RT_FREE(d_n);
@@ -718,7 +759,7 @@ extern "C" uint64_t mab_seed_chain(mab_ctx *ctx, const uint8_t *seq, uint32_t le
 	uint32_t *d_rec = nullptr;
 	if(!RT_OK(RT_MALLOC(&d_rec, 16ull * len + 256))) { RT_FREE(d_seq); RT_FREE(d_r); RT_FREE(d_fr); return 0; }
 	RT_LAUNCH(k_seed_scan, 1, 32, 2560, ctx->stream, P, (const uint8_t *)d_seq, d_r, 1u, d_rec);
-	RT_STREAM_SYNC(ctx->stream);
+	ctx_sync(ctx);
 	RT_MEMCPY_D2H_ASYNC(&r, d_r, sizeof(r), ctx->stream);
 	uint64_t ns = 0;
 	if(r.state == 0) {
@@ -728,7 +769,7 @@ extern "C" uint64_t mab_seed_chain(mab_ctx *ctx, const uint8_t *seq, uint32_t le
 		RT_MEMCPY_H2D_ASYNC(d_r, &r, sizeof(r), ctx->stream);
 		RT_LAUNCH(k_seed_expand, 1, 32, 0, ctx->stream, P, d_r, 1u, d_ws, (const uint32_t *)d_rec);
 		{ uint32_t sc_cap = std::max<uint32_t>(64u, std::min<uint32_t>(r.tot_seeds + 2, MAB_SC_SMALL)); for(uint32_t i = 0; i <= round && i < P.n_occ; i++) { RT_LAUNCH(k_sortchain, 1, 32, 16 * sc_cap + 2048, ctx->stream, P, d_r, 1u, d_ws, d_fr, i, sc_cap, 0u, 0xffffffffu); } }
-		RT_STREAM_SYNC(ctx->stream);
+		ctx_sync(ctx);
 		RT_MEMCPY_D2H_ASYNC(&r, d_r, sizeof(r), ctx->stream);
 		if(r.n_seed) {
 			ns = r.n_seed; *n_total = r.seed_n; *n_root = r.n_root;
@@ -762,7 +803,7 @@ extern "C" int mab_extend_pairs(mab_ctx *ctx, const uint8_t *seq_block, uint64_t
 	CK(RT_MEMCPY_H2D_ASYNC(ctx->d_ctr, &zero, sizeof(zero), ctx->stream));
 	RT_LAUNCH(k_extend_pairs, ctas, 32 * MAB_WARPS_PER_CTA, 1024 + 4 * MAB_TILE_WORDS * MAB_WARPS_PER_CTA, ctx->stream, P, (const uint8_t *)d_seq, (const uint8_t *)ctx->d_ntail, (const PairIn *)d_p, n, d_res, d_ao,
 		d_ar, AL.total, blk_cap, d_pool, pool_words, ctx->d_ctr);
-	CK(RT_STREAM_SYNC(ctx->stream));
+	CK(ctx_sync(ctx));
 	BatchCounters hc; CK(RT_MEMCPY_D2H_ASYNC(&hc, ctx->d_ctr, sizeof(hc), ctx->stream));
 	std::vector<uint32_t> pool((size_t)std::min<uint64_t>(hc.pool_top, pool_words) + 4);
 	std::vector<uint64_t> ao(n);
@@ -802,7 +843,7 @@ extern "C" int mab_fill_peak(mab_ctx *ctx, int masks, uint32_t n_blocks, double 
 		if(masks) { RT_LAUNCH((k_fill_peak<true>), ctas, 32 * MAB_WARPS_PER_CTA, 1024, ctx->stream, ctx->P, d_ring, n_blocks, d_sink); }
 		else { RT_LAUNCH((k_fill_peak<false>), ctas, 32 * MAB_WARPS_PER_CTA, 1024, ctx->stream, ctx->P, d_ring, n_blocks, d_sink); }
 		RT_EVENT_RECORD(ctx->ev[7], ctx->stream);
-		CK(RT_STREAM_SYNC(ctx->stream));
+		CK(ctx_sync(ctx));
 	}
 	float ms = RT_EVENT_MS(ctx->ev[6], ctx->ev[7]);
 	RT_FREE(d_ring); RT_FREE(d_sink);
@@ -818,7 +859,7 @@ extern "C" int mab_selftest(mab_ctx *ctx, uint32_t *out)
 	CK(RT_MALLOC(&d, 4ull * 64 * 32));
 	CK(RT_MEMSET_ASYNC(d, 0, 4ull * 64 * 32, ctx->stream));
 	RT_LAUNCH(k_selftest, 1, 32, 0, ctx->stream, d);
-	CK(RT_STREAM_SYNC(ctx->stream));
+	CK(ctx_sync(ctx));
 	CK(RT_MEMCPY_D2H_ASYNC(out, d, 4ull * 64 * 32, ctx->stream));
 	RT_FREE(d);
 	return MAB_OK;

@@ -99,7 +99,7 @@ extern "C" int mab_text_begin(mab_ctx *ctx, const char *text, uint64_t n_bytes, 
 		d_text = (const uint8_t *)text;
 		uint8_t fl[2];
 		CK(RT_MEMCPY_D2H_ASYNC(&fl[0], d_text, 1, ctx->stream)); CK(RT_MEMCPY_D2H_ASYNC(&fl[1], d_text + n_bytes - 1, 1, ctx->stream));
-		CK(RT_STREAM_SYNC(ctx->stream));
+		CK(ctx_sync(ctx));
 		first = fl[0]; last = fl[1];
 		if(last != '\n') { g_err = "mab_text_begin: a device-resident chunk must end with a newline"; return MAB_EINVAL; }
 	} else {
@@ -134,7 +134,7 @@ extern "C" int mab_text_begin(mab_ctx *ctx, const char *text, uint64_t n_bytes, 
 		RT_LAUNCH(k_text_layout, 1, MAB_PIPE_THREADS, 0, ctx->stream, (const TextRec *)ctx->d_trec, ctx->d_reads, ctx->d_tc);
 		S.n_launches += 5;
 		CK(RT_MEMCPY_D2H_ASYNC(pin_tc, ctx->d_tc, sizeof(TextCounters), ctx->stream));
-		{ double tw = RT_WALL_MS(); CK(RT_STREAM_SYNC(ctx->stream)); S.ms_wall_wait += (float)(RT_WALL_MS() - tw); }
+		{ double tw = RT_WALL_MS(); CK(ctx_sync(ctx)); S.ms_wall_wait += (float)(RT_WALL_MS() - tw); }
 		tc = *pin_tc;
 		S.d2h_bytes += sizeof(TextCounters);
 		if(tc.err & (MAB_TXT_EMARKS | MAB_TXT_ERECS)) {
@@ -194,10 +194,9 @@ extern "C" int mab_text_finish(mab_ctx *ctx, char *sam_out, uint64_t sam_cap, co
 {
 	mab_stats_t &S = ctx->stats;
 	if(ctx->tx.stage != 2) { g_err = "mab_text_finish: call mab_text_begin (and mab_text_commit) first"; return MAB_EINVAL; }
-	ctx->tx.stage = 0;
 	if(sam_ptr) { *sam_ptr = nullptr; }
 	const uint32_t n = ctx->tx.n_rec;
-	if(n == 0) { ctx->tx.sam_total = 0; text_fill_info(ctx, info); return MAB_OK; }
+	if(n == 0) { ctx->tx.sam_total = 0; ctx->tx.stage = 0; text_fill_info(ctx, info); return MAB_OK; }
 	CK(RT_USE_DEVICE(ctx->device));
 	const double t_call = RT_WALL_MS();
 	const uint32_t flags = ctx->tx.flags, tags = flags & ~(MAB_TEXT_KEEP_QUAL | MAB_TEXT_DEVICE_OUT), keep_qual = (flags & MAB_TEXT_KEEP_QUAL) != 0;
@@ -215,7 +214,7 @@ extern "C" int mab_text_finish(mab_ctx *ctx, char *sam_out, uint64_t sam_cap, co
 	/* the output buffer is sized from earlier chunks; the size pass usually confirms it while the write pass is already queued */
 	uint64_t est = (uint64_t)(ctx->sam_per_byte * (double)ctx->tx.n_text) + 512ull * n + 4096;
 	{ int rc = grow(&ctx->d_sam, &ctx->sam_cap, est); if(rc) { return rc; } }
-	{ double tw = RT_WALL_MS(); CK(RT_STREAM_SYNC(ctx->stream)); S.ms_wall_wait += (float)(RT_WALL_MS() - tw); }
+	{ double tw = RT_WALL_MS(); CK(ctx_sync(ctx)); S.ms_wall_wait += (float)(RT_WALL_MS() - tw); }
 	const uint64_t total = pin_tc->sam_total;
 	S.d2h_bytes += sizeof(TextCounters);
 	{ int rc = grow(&ctx->d_sam, &ctx->sam_cap, total + 64); if(rc) { return rc; } }
@@ -237,13 +236,16 @@ extern "C" int mab_text_finish(mab_ctx *ctx, char *sam_out, uint64_t sam_cap, co
 				ctx->h_sam_cap = nb;
 			}
 			dst = (char *)ctx->h_sam;
-		} else if(total > sam_cap) { g_err = "mab_text_finish: output buffer too small (" + std::to_string(total) + " bytes needed)"; return MAB_ENOMEM; }
+		} else if(total > sam_cap) {										/* the chunk stays in flight: call again with info->sam_bytes of room */
+			g_err = "mab_text_finish: output buffer too small (" + std::to_string(total) + " bytes needed)";
+			CK(ctx_sync(ctx)); text_fill_info(ctx, info); return MAB_ENOMEM;
+		}
 		if(total) { CK(RT_MEMCPY_D2H_ASYNC(dst, ctx->d_sam, total, ctx->stream)); }
 		S.d2h_bytes += total;
 		if(sam_ptr) { *sam_ptr = dst; }
 	}
 	RT_EVENT_RECORD(ctx->ev[5], ctx->stream);
-	{ double tw = RT_WALL_MS(); CK(RT_STREAM_SYNC(ctx->stream)); S.ms_wall_wait += (float)(RT_WALL_MS() - tw); }
+	{ double tw = RT_WALL_MS(); CK(ctx_sync(ctx)); S.ms_wall_wait += (float)(RT_WALL_MS() - tw); }
 	update_sc_caps(ctx, pin_rr, n);
 	uint32_t n_failed = 0; uint64_t kept = 0;
 	for(uint32_t i = 0; i < n; i++) { n_failed += pin_rr[i].err != 0; kept += pin_rr[i].len != 0; }
@@ -260,6 +262,7 @@ extern "C" int mab_text_finish(mab_ctx *ctx, char *sam_out, uint64_t sam_cap, co
 	S.ms_d2h = RT_EVENT_MS(ctx->ev[7], ctx->ev[5]);
 	S.ms_total = RT_EVENT_MS(ctx->ev[0], ctx->ev[5]);
 	S.ms_wall += (float)(RT_WALL_MS() - t_call);
+	ctx->tx.stage = 0;
 	text_fill_info(ctx, info);
 	return MAB_OK;
 }

@@ -26,6 +26,20 @@ def build_emu():
     return EMU_SO
 
 
+EMU_CLI = os.path.join(ROOT, "tests", "emu", "minialign-emu")
+
+
+def build_emu_cli():
+    """the product's command line (host pipeline: reader, contexts, rlen chain, writers) linked against the emulation build"""
+    so = build_emu()
+    host = os.path.join(ROOT, "minialign_b200/csrc/host")
+    srcs = [os.path.join(host, f) for f in os.listdir(host)] + [so, os.path.join(ROOT, "include/minialign_b200.h")]
+    if not os.path.exists(EMU_CLI) or any(os.path.getmtime(s) > os.path.getmtime(EMU_CLI) for s in srcs):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", EMU_CLI, *[os.path.join(host, f) for f in ("mab_cli.cpp", "mab_sam.cpp", "mab_index.cpp")],
+                               "-L" + os.path.join(ROOT, "tests/emu"), "-lmab_emu", "-lz", "-pthread", "-Wl,-rpath,$ORIGIN"])
+    return EMU_CLI
+
+
 def unpack(words, ofs):
     return [words[ofs[i]:ofs[i + 1]] for i in range(len(ofs) - 1)]
 

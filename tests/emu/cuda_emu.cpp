@@ -1,5 +1,6 @@
 /* cuda_emu.cpp -- fiber scheduler behind cuda_emu.h (test infrastructure, see the header). */
 #include "cuda_emu.h"
+#include <mutex>
 
 namespace emu {
 Fiber *g_cur = nullptr;
@@ -80,6 +81,8 @@ static void trampoline()
 
 void launch(emu_dim3 grid, emu_dim3 block, size_t smem, const std::function<void()> &body)
 {
+	static std::mutex launch_mu;			/* one kernel at a time: the scheduler state is global (contexts on several host threads share it) */
+	std::lock_guard<std::mutex> launch_lock(launch_mu);
 	unsigned nt = block.x * block.y * block.z;
 	static std::vector<uint8_t *> stacks;
 	while(stacks.size() < nt) { stacks.push_back((uint8_t *)aligned_alloc(64, STACK)); }

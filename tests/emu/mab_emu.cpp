@@ -30,6 +30,7 @@ static inline void RT_EVENT_DESTROY(RT_EVENT) {}
 static inline void RT_STREAM_DESTROY(RT_STREAM) {}
 static inline int RT_DEVICE_SYNC() { return 0; }
 static inline int RT_EVENT_SYNC(RT_EVENT) { return 0; }
+static inline int RT_SYNC_EVENT_CREATE(RT_EVENT *e) { *e = 0; return 0; }
 static inline void RT_EVENT_RECORD(RT_EVENT, RT_STREAM) {}
 static inline float RT_EVENT_MS(RT_EVENT, RT_EVENT) { return 0.f; }
 static inline double RT_WALL_MS() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
