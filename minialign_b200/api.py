@@ -212,7 +212,10 @@ class Mapper:
     def text_finish(self, out_ptr: int = 0, out_cap: int = 0):
         """-> (info, pointer to the SAM text).  out_ptr = 0: the text stays in the context's pinned buffer."""
         info, ptr = MabTextInfo(), C.c_void_p()
-        self._check(self.lib.mab_text_finish(self.h, out_ptr or None, out_cap, C.byref(ptr), C.byref(info)), "mab_text_finish")
+        rc = self.lib.mab_text_finish(self.h, out_ptr or None, out_cap, C.byref(ptr), C.byref(info))
+        if rc == -3 and out_ptr and info.sam_bytes > out_cap:
+            return info, None           # buffer too small: the chunk stays in flight, call again with info.sam_bytes of room
+        self._check(rc, "mab_text_finish")
         return info, ptr.value
 
     def sam_header(self, cmdline: str = "", version: str = "0.6.0-devel") -> bytes:

@@ -77,7 +77,7 @@ struct mab_ctx {
 	uint8_t *h_sam = nullptr; uint64_t h_sam_cap = 0;		/* pinned; used when the caller passes no output buffer */
 	uint64_t mark_hw = 0, rec_hw = 0;	/* high-water marks of the parser's arrays */
 	double sam_per_byte = 1.3;			/* SAM bytes per input byte (high-water mark, sizes d_sam) */
-	struct TextState { const uint8_t *d_text; uint64_t n_text, n_kept, sam_total; uint32_t n_rec, flags, stage; bool rlen_known; TextCounters tc; } tx;
+	struct TextState { const uint8_t *d_text; uint64_t n_text, n_kept, sam_total; uint32_t n_rec, flags, stage, rlen_committed; bool rlen_known; TextCounters tc; } tx;
 	uint32_t sc_cap1[2] = { 1536, 1536 };	/* k_sortchain: staging capacity of the ordinary size class, per round kind (adapted from batch to batch) */
 	double ws_per_base = 6.0;			/* workspace estimate: bytes per read base beyond the fixed 20 KB per read (high-water mark) */
 	mab_stats_t stats;

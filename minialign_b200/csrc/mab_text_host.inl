@@ -161,7 +161,7 @@ extern "C" int mab_text_begin(mab_ctx *ctx, const char *text, uint64_t n_bytes, 
 		if(rc) { return rc; }
 	}
 	ctx->tx.n_kept = tc.n_rec;						/* dropped (empty) records are counted out in finish, where the records come back */
-	ctx->tx.stage = rlen_known ? 2 : 1;
+	ctx->tx.stage = rlen_known ? 2 : 1; ctx->tx.rlen_committed = rlen_prev;
 	if(rlen_known && ctx->hc.chain_valid) { ctx->rlen_last = ctx->hc.chain_rlen; }
 	text_fill_info(ctx, info);
 	S.ms_wall = (float)(RT_WALL_MS() - t_call);
@@ -170,22 +170,25 @@ extern "C" int mab_text_begin(mab_ctx *ctx, const char *text, uint64_t n_bytes, 
 
 extern "C" int mab_text_commit(mab_ctx *ctx, uint32_t rlen_prev, mab_text_info_t *info)
 {
-	if(ctx->tx.stage == 2) { text_fill_info(ctx, info); return MAB_OK; }			/* begun with a known value (or empty): nothing to check */
-	if(ctx->tx.stage != 1) { g_err = "mab_text_commit: no chunk in flight"; return MAB_EINVAL; }
+	if(ctx->tx.stage != 1 && ctx->tx.stage != 2) { g_err = "mab_text_commit: no chunk in flight"; return MAB_EINVAL; }
 	CK(RT_USE_DEVICE(ctx->device));
-	if(ctx->tx.n_rec != 0 && ctx->hc.fd_valid) {
-		/* the first chain-loading read was mapped assuming its own reference's length; only if the true value flips its first seed
-		 * test does anything have to be redone (the verification pass finds that out, and what follows from it) */
-		const BatchCounters &hc = ctx->hc;
-		bool used = (hc.fd_apos >= hc.fd_used) || (hc.fd_flags & 2), actual = (hc.fd_apos >= rlen_prev) || (hc.fd_flags & 2);
-		if(used != actual) {
-			uint64_t pool_before = ctx->hc.pool_top;
-			int rc = pipe_verify(ctx, rlen_prev, 1u); if(rc) { return rc; }
-			if((ctx->hc.err_any & (MAB_ERR_POOL_OVF | MAB_ERR_WS_OVF)) || ctx->hc.pool_top > ctx->pool_cap / 4) { g_err = "result pool overflow while re-mapping a read"; return MAB_EOVERFLOW; }
-			(void)pool_before;
-		}
+	bool check = false;
+	if(ctx->tx.n_rec != 0) {
+		if(ctx->tx.stage == 1) {
+			/* the first chain-loading read was mapped assuming its own reference's length; only if the true value flips its first
+			 * seed test does anything have to be redone (the verification pass finds that out, and what follows from it) */
+			const BatchCounters &hc = ctx->hc;
+			if(hc.fd_valid) {
+				bool used = (hc.fd_apos >= hc.fd_used) || (hc.fd_flags & 2), actual = (hc.fd_apos >= rlen_prev) || (hc.fd_flags & 2);
+				check = used != actual;
+			}
+		} else { check = rlen_prev != ctx->tx.rlen_committed; }				/* committed before with another value (a predecessor was corrected): verify again */
 	}
-	ctx->tx.stage = 2;
+	if(check) {
+		int rc = pipe_verify(ctx, rlen_prev, 1u); if(rc) { return rc; }
+		if((ctx->hc.err_any & (MAB_ERR_POOL_OVF | MAB_ERR_WS_OVF)) || ctx->hc.pool_top > ctx->pool_cap / 4) { g_err = "result pool overflow while re-mapping a read"; return MAB_EOVERFLOW; }
+	}
+	ctx->tx.stage = 2; ctx->tx.rlen_committed = rlen_prev;
 	text_fill_info(ctx, info);
 	return MAB_OK;
 }

@@ -1,30 +1,97 @@
-"""Read sharding across the GPUs of one box: contiguous input batches dealt round-robin to ranks, a
-full index copy per GPU, and ONE exchange step: an all-gather of each rank's output byte count per batch wave followed by an
-exclusive prefix sum, so every rank knows where its slice of the merged, input-ordered output stream starts.  The exchange
-is 8 bytes per rank (latency-bound); NCCL on the GPU box, gloo in the CPU tests."""
+"""Read sharding across ranks (one process per GPU): the exchange step of the mapping path.
+
+The chunks of ONE read file are dealt round-robin: wave w = chunks w*N .. w*N+N-1, rank r maps chunk w*N + r.  Reads are
+independent except for the single word of state the reference's worker thread carries from read to read (`rlen`, minialign.c:3865
+vs 3873; with -t1 that is file order), and the merged SAM needs every chunk's byte offset.  Both are a few bytes per rank per
+wave and both are prefix problems in chunk order:
+
+  rlen chain      each rank contributes (loaded-a-chain?, value it leaves behind); chunk c starts from the value left by the last
+                  chain-loading chunk before it.  A rank whose chunk's first seed test flips under the true value re-maps that read
+                  (mab_text_commit); in the rare case this changes what the chunk leaves behind, a second round propagates it.
+  output offsets  all-gather of the SAM byte counts -> exclusive prefix sum -> every rank pwrite()s its text at its own offset.
+
+The collectives are torch.distributed all_gathers of a handful of int64 (NCCL over NVLink on the GPU box, gloo in the CPU tests).
+Everything else -- the index, the reads, the DP -- stays on the rank's own GPU: no data-path collective.
+"""
 from __future__ import annotations
 
 import torch
 import torch.distributed as dist
 
 
-def batches_of(rank: int, world: int, n_batches: int):
-    """Batch ids handled by `rank`: round-robin, so wave w = batches [w*world, (w+1)*world)."""
-    return list(range(rank, n_batches, world))
+def deal_chunks(n_chunks: int, world: int, rank: int):
+    """Chunk ids of this rank, in wave order."""
+    return list(range(rank, n_chunks, world))
 
 
-def output_offsets(local_bytes: int, device: torch.device | str = "cpu", group=None):
-    """Exclusive prefix sum of the per-rank byte counts of one wave -> (my offset, total bytes of the wave)."""
-    if not (dist.is_available() and dist.is_initialized()):
-        return 0, int(local_bytes)
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
-    mine = torch.tensor([int(local_bytes)], dtype=torch.int64, device=device)
-    allv = torch.zeros(world, dtype=torch.int64, device=device)
-    dist.all_gather_into_tensor(allv, mine, group=group)
-    allv = allv.cpu()
-    return int(allv[:rank].sum()), int(allv.sum())
+def exclusive_offsets(sizes):
+    out, acc = [], 0
+    for s in sizes:
+        out.append(acc)
+        acc += int(s)
+    return out, acc
 
 
-def merged_order(n_batches: int, world: int):
-    """(batch id, owning rank) in output order: the reference drains batches strictly by id (minialign.c:4638-4643)."""
-    return [(b, b % world) for b in range(n_batches)]
+class WaveExchange:
+    """The per-wave collectives.  Every rank must call the methods in the same order, once per wave (ranks without a chunk in the
+    last, partial wave pass valid=False / 0 bytes)."""
+
+    def __init__(self, device=None):
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.device = device
+        self.rlen = 0               # a fresh reference thread starts with rlen = 0
+        self.out_base = 0           # bytes of SAM text before this wave
+        self.n_collectives = 0
+
+    def _gather(self, vals):
+        if self.world == 1:
+            return [list(vals)]
+        t = torch.tensor(list(vals), dtype=torch.int64, device=self.device)
+        out = torch.empty(self.world * t.numel(), dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(out, t)
+        self.n_collectives += 1
+        return out.view(self.world, -1).tolist()
+
+    def rlen_inputs(self, valid: bool, value: int):
+        """(valid, value) = what this rank's chunk leaves behind under its current assumption.  Returns the value this rank's chunk
+        must be committed with; `self.rlen` is not advanced before settle() confirms the wave."""
+        rows = self._gather((1 if valid else 0, int(value)))
+        run, mine = self.rlen, None
+        for q, (v, x) in enumerate(rows):
+            if q == self.rank:
+                mine = run
+            if v:
+                run = x
+        self._pending = run
+        return mine
+
+    def settle(self, commit):
+        """commit(rlen_in) -> (valid, value) re-maps whatever depends on rlen_in and returns what the chunk then leaves behind.
+        Repeats the exchange until no rank's value moved (normally one round: a corrected first read almost never is the last
+        chain-loading read of its chunk).  Advances self.rlen to the wave's final value."""
+        valid, value = self._last
+        while True:
+            rlen_in = self.rlen_inputs(valid, value)
+            nv, nx = commit(rlen_in)
+            changed = (bool(nv), int(nx)) != (bool(valid), int(value))
+            valid, value = nv, nx
+            if self.world == 1:
+                any_changed = changed
+            else:
+                any_changed = any(r[0] for r in self._gather((1 if changed else 0,)))
+            if not any_changed:
+                break
+        self.rlen = self._pending
+        return rlen_in
+
+    def begin_wave(self, valid: bool, value: int):
+        self._last = (bool(valid), int(value))
+
+    def offsets(self, n_bytes: int):
+        """SAM bytes of this rank's chunk -> (absolute offset of this rank's text, total bytes of the wave)."""
+        rows = self._gather((int(n_bytes),))
+        ofs, total = exclusive_offsets([r[0] for r in rows])
+        mine = self.out_base + ofs[self.rank]
+        self.out_base += total
+        return mine, total

@@ -218,3 +218,44 @@ uint64_t refh_extend_dump(void *_h, uint8_t const *seq, uint32_t len, uint32_t *
 	}
 	return(n);
 }
+
+/* refh_align_many: mm_align_seq (minialign.c:4427) over n reads on n_threads of the reference's own worker buffers (the
+ * context must have been opened with -t<n_threads>): thread j maps reads j, j + n_threads, ...; results are freed, nothing is
+ * read or printed.  Returns the wall-clock seconds of the parallel section: the reference's hot path alone, no I/O
+ * (bench.py's cpu_baseline.hot_path). */
+#include <pthread.h>
+#include <time.h>
+typedef struct { refh_t *h; uint32_t tid, nth, n; uint8_t const *block; uint64_t const *ofs; uint32_t const *len; uint64_t n_mapped; } refh_job_t;
+static void *refh_align_many_worker(void *arg)
+{
+	refh_job_t *j = (refh_job_t *)arg;
+	lmm_t *lmm = lmm_init_margin(NULL, 512 * 1024, sizeof(mm_aln_t), 0);
+	for(uint32_t i = j->tid; i < j->n; i += j->nth) {
+		mm_reg_t const *reg = mm_align_seq(j->h->aln->t[j->tid], j->len[i], j->block + j->ofs[i], i, lmm);
+		if(reg == NULL) { continue; }
+		j->n_mapped++;
+		for(uint32_t k = 0; k < reg->n_all; k++) { lmm_free(lmm, (void *)reg->aln[k]->a); }
+		lmm_free(lmm, (void *)reg);
+	}
+	lmm_clean(lmm);
+	return(NULL);
+}
+double refh_align_many(void *_h, uint8_t const *block, uint64_t const *ofs, uint32_t const *len, uint32_t n, uint32_t n_threads, uint64_t *n_mapped)
+{
+	refh_t *h = (refh_t *)_h;
+	if(n_threads == 0 || n_threads > pt_nth(h->o->pt)) { return(-1.0); }
+	pthread_t *th = calloc(n_threads, sizeof(pthread_t));
+	refh_job_t *job = calloc(n_threads, sizeof(refh_job_t));
+	struct timespec t0, t1;
+	clock_gettime(CLOCK_MONOTONIC, &t0);
+	for(uint32_t t = 0; t < n_threads; t++) {
+		job[t] = (refh_job_t){ .h = h, .tid = t, .nth = n_threads, .n = n, .block = block, .ofs = ofs, .len = len, .n_mapped = 0 };
+		pthread_create(&th[t], NULL, refh_align_many_worker, &job[t]);
+	}
+	uint64_t m = 0;
+	for(uint32_t t = 0; t < n_threads; t++) { pthread_join(th[t], NULL); m += job[t].n_mapped; }
+	clock_gettime(CLOCK_MONOTONIC, &t1);
+	if(n_mapped) { *n_mapped = m; }
+	free(th); free(job);
+	return((double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec));
+}
