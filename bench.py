@@ -1,20 +1,27 @@
 #!/usr/bin/env python
-"""bench.py -- Mbases aligned / s of the read->reference mapping hot path (BASELINE.json metric).
+"""bench.py -- Mbases aligned / s of the read->reference mapping path (BASELINE.json metric), FASTA text to SAM text.
 
   python bench.py --gpus N --steps K --warmup W            our arm (CUDA, one process per GPU)
   python bench.py --impl reference --gpus N --steps K ...   the reference's own CPU implementation (oracle/_ref/minialign)
 
-Workload (config.workload): BASELINE.json configs[1] -- E.coli-MG1655-sized reference (4.64 Mb, synthetic: no genomes or
+Workload (config.workload): N = 1: BASELINE.json configs[1] -- E.coli-MG1655-sized reference (4.64 Mb, synthetic: no genomes or
 PBSIM exist offline) x100 coverage of PBSIM-CLR-like reads (20k +- 2k, accuracy 0.88 +- 0.07), -xpacbio.
-A step = one pass of the hot path (seed -> sort/chain -> extend -> results) over one batch of `--batch-reads` reads; batches
-cycle through the read set, every batch's reads + DP state are far larger than L2 (config.l2 says so).
-value   : kernel-side throughput, reads already resident in HBM when the timed region starts (device-input mode of the C ABI)
-e2e     : the same through mab_map_batch with HOST (pinned) buffers, H2D of the reads and D2H of the results inside the timing
-roofline: the dominant kernel (k_extend, round 0) timed with CUDA events on its own stream inside the library
+N > 1: configs[2] -- sacCer3-sized reference (12.1 Mb, 17 contigs of the yeast chromosomes' sizes), same read model, ONE read
+set cut into chunks that are dealt round-robin to the ranks (weak scaling: one chunk per rank and step).
+A step = one chunk of `--batch-reads` reads per rank through the whole path: FASTA text -> parse -> seed -> sort/chain -> extend ->
+post-processing -> SAM text.  Chunks cycle through a few distinct ones, each far larger than L2 (config.l2).
+value   : kernel-side throughput, the FASTA text already resident in HBM when the timed region starts, SAM text left in HBM
+e2e     : the same through the public text API (mab_text_begin / commit / finish) with HOST buffers: FASTA bytes in page-locked
+          host memory in, SAM bytes in page-locked host memory out, both copies and (N > 1) the per-wave NCCL exchange of the rlen
+          chain and the output offsets inside the timed region
+roofline: the dominant kernel (k_extend, round 0) timed alone with CUDA events on its own stream inside the library, against the
+          integer ceiling of its own DP step (k_fill_peak) -- the bound SURVEY.md section 8d names; HBM figures as secondary keys
+After the timed runs the SAM text of a full-size chunk is checked against the reference CLI (-t1) on a sample of its reads.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import re
@@ -28,34 +35,49 @@ sys.path.insert(0, ROOT)
 
 import numpy as np
 
-GENOME_BP = 4_640_000
+GENOMES = {
+    "ecoli": dict(bp=4_640_000, contigs=1, weights=None,
+                  name="ecoli-like 4.64 Mb synthetic reference x100 PBSIM-CLR-like reads (20k+-2k, acc 0.88+-0.07), -xpacbio (BASELINE configs[1])"),
+    "saccer3": dict(bp=12_100_000, contigs=17, weights=[230, 813, 317, 1532, 577, 270, 1091, 563, 440, 746, 667, 1078, 924, 784, 1091, 948, 86],
+                    name="sacCer3-like 12.1 Mb / 17 contigs synthetic reference x100 PBSIM-CLR-like reads (20k+-2k, acc 0.88+-0.07), -xpacbio, one read set sharded by chunk (BASELINE configs[2])"),
+}
 BYTES_PER_BASE = 160.0          # algorithmic HBM bytes per read base
 TRAFFIC_PER_BASE = 292.0        # dram__bytes_read.sum + dram__bytes_write.sum of k_extend per read base, ncu --set full capture
-                                # in profiles/r01_ncu_k_extend_full.json (49.3 GB for the 169 Mbase launch)
+                                # (profiles/r01_ncu_k_extend_full.json: 49.3 GB for the 169 Mbase launch)
+NCU_PIPE_ALU_PCT = 62.6         # sm__inst_executed_pipe_alu of k_extend in the same capture
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "minialign")
+OUR_BIN = os.path.join(ROOT, "minialign_b200", "minialign-b200")
 
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-def build_workload(work: str, n_batches: int, batch_reads: int, rank: int = 0, seed: int = 1):
-    """Synthetic genome + index (built by the reference, like BASELINE.md section 3 step 3) + read batches."""
+def build_genome(work: str, which: str, seed: int = 1):
+    """Synthetic genome + index (built by the reference, like BASELINE.md section 3 step 3; by the product's own host builder when
+    the reference binary is absent)."""
     from minialign_b200 import mai, synth
+    G = GENOMES[which]
     os.makedirs(work, exist_ok=True)
-    g = synth.make_genome(GENOME_BP, 1, seed=seed)
-    fa, idx = os.path.join(work, "ecoli_like.fa"), os.path.join(work, "ecoli_like.mai")
+    g = synth.make_genome(G["bp"], G["contigs"], seed=seed, weights=G["weights"])
+    fa, idx = os.path.join(work, f"{which}_like.fa"), os.path.join(work, f"{which}_like.mai")
     if not os.path.exists(idx):
         tmp = idx + f".tmp{os.getpid()}.mai"
         synth.write_fasta(fa + f".{os.getpid()}", g, 80)
-        subprocess.check_call([REF_BIN, "-xpacbio", "-d", tmp, fa + f".{os.getpid()}"], stderr=subprocess.DEVNULL)
+        builder = REF_BIN if os.path.exists(REF_BIN) else OUR_BIN
+        subprocess.check_call([builder, "-xpacbio", "-d", tmp, fa + f".{os.getpid()}"], stderr=subprocess.DEVNULL)
         os.replace(tmp, idx)
-    blob = mai.load_mai(idx)
-    batches = []
-    for b in range(n_batches):
-        reads = synth.make_reads(g, batch_reads * 20_600, seed=1000 + b)[:batch_reads]
-        batches.append(reads)
-    return g, idx, blob, batches
+    return g, idx, mai.load_mai(idx)
+
+
+def chunk_reads(g, chunk_id: int, batch_reads: int):
+    """reads of chunk `chunk_id` of the (virtual) read file: seeded by the chunk id, so every rank can produce its own share"""
+    from minialign_b200 import synth
+    return synth.make_reads(g, batch_reads * 20_600, seed=1000 + chunk_id)[:batch_reads]
+
+
+def fasta_bytes(reads, chunk_id: int = 0) -> bytes:
+    return b"".join(b">c%d_" % chunk_id + n.encode() + b"\n" + s.tobytes() + b"\n" for n, s in reads)
 
 
 class ClockSampler(threading.Thread):
@@ -116,10 +138,10 @@ class ClockSampler(threading.Thread):
                 "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
-def ref_run(idx: str, fasta: str, threads: int):
+def ref_run(idx: str, fasta: str, threads: int, out=None, extra=()):
     """One run of the reference CLI; returns mapping seconds = final Real time - index-load timestamp."""
-    with open(os.devnull, "wb") as null:
-        p = subprocess.run([REF_BIN, "-xpacbio", f"-t{threads}", idx, fasta], stdout=null, stderr=subprocess.PIPE, text=True)
+    with open(out or os.devnull, "wb") as sink:
+        p = subprocess.run([REF_BIN, "-xpacbio", f"-t{threads}", *extra, idx, fasta], stdout=sink, stderr=subprocess.PIPE, text=True)
     m1 = re.search(r"main_align::([0-9.]+)\*[0-9.]+\] loaded/built index", p.stderr)
     m2 = re.search(r"Real time: ([0-9.]+) sec", p.stderr)
     if p.returncode != 0 or not m1 or not m2:
@@ -131,24 +153,89 @@ def host_threads():
     return max(1, min(os.cpu_count() or 1, 127))          # MAX_THREADS requires -t < 128 (minialign.c:23, 5971)
 
 
-def cpu_baseline(idx, batches, work, budget_core_s=20.0):
+def ref_hot_path(idx: str, reads, threads: int):
+    """The reference's mm_align_seq alone (no file I/O, no SAM text) over all host cores, through oracle/_ref/libref_harness.so
+    (refh_align_many): the like-for-like number for the C-ABI record-level call."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import refh
+    from minialign_b200 import api, synth
+    if not refh.available():
+        return None
+    h = refh.RefHarness(idx, args=("-xpacbio", f"-t{threads}"))
+    L = h.lib
+    if not hasattr(L, "refh_align_many"):
+        h.close()
+        return None
+    L.refh_align_many.restype = C.c_double
+    L.refh_align_many.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]
+    block, ofs, lens = api.pack_reads([synth.encode_2bit(s) for _, s in reads])
+    nm = C.c_uint64(0)
+    best = None
+    for _ in range(2):
+        secs = L.refh_align_many(h.h, block.ctypes.data, ofs.ctypes.data_as(C.POINTER(C.c_uint64)), lens.ctypes.data_as(C.POINTER(C.c_uint32)), len(lens), threads, C.byref(nm))
+        best = secs if best is None else min(best, secs)
+    h.close()
+    return {"value": float(lens.sum()) / 1e6 / best, "unit": "Mbases/s", "cores": threads, "mapped": int(nm.value),
+            "what": "mm_align_seq over all cores through libref_harness.so: reads pre-parsed in memory, results freed, no SAM text, best of 2"}
+
+
+def cpu_baseline(idx, reads, work, budget_core_s=20.0):
     from minialign_b200 import synth
     thr = host_threads()
     # ~10 Mbases/s/core (SURVEY 6.2): bound the sample to roughly `budget_core_s` core-seconds
-    reads, bases = [], 0
-    for b in batches:
-        for r in b:
-            reads.append(r); bases += r[1].size
-            if bases >= budget_core_s * 10e6:
-                break
+    sample, bases = [], 0
+    for r in reads:
+        sample.append(r); bases += r[1].size
         if bases >= budget_core_s * 10e6:
             break
     fa = os.path.join(work, f"cpu_sample.{os.getpid()}.fa")
-    synth.write_fasta(fa, reads)
+    synth.write_fasta(fa, sample)
     secs = min(ref_run(idx, fa, thr) for _ in range(2))
     os.remove(fa)
-    return {"value": bases / 1e6 / secs, "unit": "Mbases/s", "cores": thr, "kind": "reference",
-            "sample": f"{len(reads)} reads / {bases / 1e6:.1f} Mbases of the same workload, oracle/_ref/minialign -xpacbio -t{thr}, best of 2, index load excluded"}
+    out = {"value": bases / 1e6 / secs, "unit": "Mbases/s", "cores": thr, "kind": "reference",
+           "sample": f"{len(sample)} reads / {bases / 1e6:.1f} Mbases of the same workload, oracle/_ref/minialign -xpacbio -t{thr} FASTA file -> SAM text, best of 2, index load excluded"}
+    try:
+        hp = ref_hot_path(idx, sample, thr)
+        if hp:
+            out["hot_path"] = hp
+    except Exception as e:
+        out["hot_path"] = {"value": None, "unavailable": str(e)}
+    return out
+
+
+class _Solo:
+    """rank-local stand-in for the wave exchange (the untimed parity pass runs on rank 0 alone)"""
+
+    def __init__(self):
+        self.rlen, self.out_base, self.n_collectives, self.world, self.rank = 0, 0, 0, 1, 0
+
+    def begin_wave(self, valid, value):
+        self._last = (valid, value)
+
+    def settle(self, commit):
+        v = commit(self.rlen)
+        if v[0]:
+            self.rlen = v[1]
+
+    def offsets(self, n):
+        o = self.out_base
+        self.out_base += n
+        return o, n
+
+
+def parity_check(idx, reads, work, text: bytes, n_sample=384):
+    """Untimed: the SAM text of a full-size chunk must start with exactly the lines the reference CLI (-t1) prints for the first
+    `n_sample` reads of that chunk (the reference's results do not depend on what follows a read)."""
+    from minialign_b200 import synth
+    fa, sam = os.path.join(work, f"parity.{os.getpid()}.fa"), os.path.join(work, f"parity.{os.getpid()}.sam")
+    sample = reads[:n_sample]
+    with open(fa, "wb") as f:
+        f.write(fasta_bytes(sample, 0))
+    ref_run(idx, fa, 1, out=sam)
+    exp = b"".join(l for l in open(sam, "rb") if not l.startswith(b"@"))
+    os.remove(fa); os.remove(sam)
+    ok = text[:len(exp)] == exp and len(exp) > 0
+    return {"ok": bool(ok), "reads": len(sample), "bytes": len(exp), "against": "oracle/_ref/minialign -xpacbio -t1, every SAM line of the first reads of a timed full-size chunk"}
 
 
 def main():
@@ -159,35 +246,44 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch-reads", type=int, default=16384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--contexts", type=int, default=3, help="mapper contexts (in-flight batches) per GPU")
+    ap.add_argument("--contexts", type=int, default=3, help="mapper contexts (in-flight chunks) per GPU")
+    ap.add_argument("--workload", default=None, choices=[None, "ecoli", "saccer3"], help="default: ecoli at one GPU (configs[1]), saccer3 across GPUs (configs[2])")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
-    config = {"workload": "ecoli-like 4.64 Mb synthetic reference x100 PBSIM-CLR-like reads (20k+-2k, acc 0.88+-0.07), -xpacbio (BASELINE configs[1])",
-              "batch_reads": args.batch_reads, "read_model": "len N(20000,2000) acc N(0.88,0.07) sub:ins:del 10:60:30",
-              "parallelism": f"read-shard x{world}", "contexts_per_gpu": args.contexts, "setup": "one untimed allocation batch per context before the warm-up steps", "l2": "every step maps a different batch; reads + DP state per batch >> 126 MB L2"}
+    which = args.workload or ("ecoli" if max(world, args.gpus) == 1 else "saccer3")
+    config = {"workload": GENOMES[which]["name"], "batch_reads": args.batch_reads, "read_model": "len N(20000,2000) acc N(0.88,0.07) sub:ins:del 10:60:30",
+              "parallelism": f"read-shard x{world}: chunk c of the read set on rank c mod {world}", "contexts_per_gpu": args.contexts,
+              "path": "FASTA text -> device reader -> seed/chain/extend -> device post-processing -> device SAM printer -> SAM text",
+              "setup": "one untimed chunk per context before the warm-up steps (buffer allocation)", "l2": "every step maps a different chunk; text + reads + DP state per chunk >> 126 MB L2"}
     work = os.environ.get("MAB_BENCH_DIR", "/tmp/mab_bench")
 
     if args.impl == "reference":
         if rank != 0:
             return
-        n_b = 1
-        g, idx, blob, batches = build_workload(work, n_b, min(args.batch_reads, 16384))   # bounded sample per step: one batch of our arm, ~338 Mbases, ~1.2 s on 16 cores
         from minialign_b200 import synth
+        g, idx, blob = build_genome(work, which)
+        reads = chunk_reads(g, 0, min(args.batch_reads, 16384))      # bounded sample per step: one chunk of our arm, ~338 Mbases, ~1.2 s on 16 cores
         fa = os.path.join(work, "ref_step.fa")
-        synth.write_fasta(fa, batches[0])
-        bases = sum(r[1].size for r in batches[0])
+        synth.write_fasta(fa, reads)
+        bases = sum(r[1].size for r in reads)
         thr = host_threads()
         for _ in range(args.warmup):
             ref_run(idx, fa, thr)
         t = [ref_run(idx, fa, thr) for _ in range(args.steps)]
         secs = sum(t)
         v = bases * args.steps / 1e6 / secs
+        cb = {"value": v, "unit": "Mbases/s", "cores": thr, "kind": "reference",
+              "sample": f"{len(reads)} reads / {bases / 1e6:.1f} Mbases per step, oracle/_ref/minialign -xpacbio -t{thr} FASTA file -> SAM text, index load excluded"}
+        try:
+            hp = ref_hot_path(idx, reads[:max(256, len(reads) // 4)], thr)
+            if hp:
+                cb["hot_path"] = hp
+        except Exception as e:
+            cb["hot_path"] = {"value": None, "unavailable": str(e)}
         print(json.dumps({"impl": "reference", "metric": "Mbases aligned/sec", "value": v, "unit": "Mbases/s", "n_gpus": args.gpus, "steps": args.steps,
                           "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                          "dtype": "int8", "data": "synthetic", "config": dict(config, batch_reads=len(batches[0])),
-                          "cpu_baseline": {"value": v, "unit": "Mbases/s", "cores": thr, "kind": "reference",
-                                           "sample": f"{len(batches[0])} reads / {bases / 1e6:.1f} Mbases per step, oracle/_ref/minialign -xpacbio -t{thr}, index load excluded"},
+                          "dtype": "int8", "data": "synthetic", "config": dict(config, batch_reads=len(reads)), "cpu_baseline": cb,
                           "e2e": {"value": v, "unit": "Mbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
@@ -201,34 +297,34 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from minialign_b200 import api, shard
+    from minialign_b200 import api, pipeline, shard
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
-    os.environ.setdefault("MAB_HOST_THREADS", str(max(2, (os.cpu_count() or 2) // (world * max(1, args.contexts)))))
+    dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    n_b = min(3, args.warmup + args.steps)
+        dist.init_process_group("nccl", device_id=dev)
+    n_distinct = min(3, args.warmup + args.steps)
     t0 = time.time()
-    g, idx, blob, batches = build_workload(work + f"/r{rank}", n_b, args.batch_reads, rank, seed=1)
-    # weak scaling: every rank maps its own batches (different read seeds per rank)
-    if world > 1:
-        from minialign_b200 import synth
-        batches = [synth.make_reads(g, args.batch_reads * 20_600, seed=1000 + 100 * rank + b)[:args.batch_reads] for b in range(n_b)]
-    from minialign_b200 import synth
-    packed = []
-    for b in batches:
-        block, ofs, lens = api.pack_reads([synth.encode_2bit(r) for _, r in b])
-        pinned = torch.from_numpy(block).pin_memory()
-        packed.append((pinned, ofs, lens, int(lens.sum())))
-    log(f"[rank {rank}] workload ready in {time.time() - t0:.1f}s: {n_b} batches x {args.batch_reads} reads")
-    # two mapper contexts per GPU, each driven by its own host thread: while one batch sits in D2H / host post-processing
-    # (MAPQ etc., minialign.c:4175-4396) the other one's kernels run -- the reference's source/worker/drain pipeline in two stages
-    # the pipelined contexts launch 5 of the 6 possible k_extend CTAs per SM: the registers / shared memory left over let the next
-    # batch's scan and sort/chain kernels run under the current batch's extend (+3 % end to end); alone, 6 is faster
+    g, idx, blob = build_genome(work + f"/r{rank}", which)
+    # the (virtual) read file: chunk c = reads seeded by c; this rank maps chunks rank, rank + world, ... (a few distinct ones, cycled)
+    my_reads = [chunk_reads(g, d * world + rank, args.batch_reads) for d in range(n_distinct)]
+    texts = [fasta_bytes(r, d * world + rank) for d, r in enumerate(my_reads)]
+    bases_of = [int(sum(s.size for _, s in r)) for r in my_reads]
+    pinned = []
+    for t in texts:
+        p = torch.empty(len(t) + 64, dtype=torch.uint8).pin_memory()
+        p[:len(t)] = torch.frombuffer(bytearray(t), dtype=torch.uint8)
+        p[len(t):] = 10
+        pinned.append(p)
+    log(f"[rank {rank}] workload ready in {time.time() - t0:.1f}s: {n_distinct} chunks x {args.batch_reads} reads, {len(texts[0]) / 1e6:.0f} MB of FASTA each")
+    # three mapper contexts per GPU, each driven by its own host thread (pipeline.py): while one chunk is being parsed / copied / printed,
+    # another one's extension runs.  The pipelined contexts launch 5 of the 6 possible k_extend CTAs per SM: the registers / shared
+    # memory left over let the other chunks' small kernels run under the current extension; alone, 6 is faster
     ext_pipe = os.environ.get("MAB_EXT_CTAS", "5" if args.contexts > 1 else "6")
     os.environ["MAB_EXT_CTAS"] = ext_pipe
-    ms = [api.Mapper(blob, "pacbio", device=local) for _ in range(max(1, args.contexts))]
+    m0 = api.Mapper(blob, "pacbio", device=local)
+    ms = [m0] + [m0.clone() for _ in range(max(1, args.contexts) - 1)]
     config["extend_ctas_per_sm"] = int(ext_pipe)
 
     def barrier():
@@ -237,99 +333,105 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    last_out = {}
+
     def run(mode_device: bool, steps: int, warmup: int):
         for m in ms:
             m.lib.mab_set_device_input(m.h, 1 if mode_device else 0)
-        dev_blocks = [p[0].cuda(non_blocking=False) for p in packed] if mode_device else None
-        agg = dict(bases=0, launches=0, h2d=0, d2h=0, ms_ext=0.0, ms_ext_r0=0.0, ms_dev=0.0, vec=0, out_words=0)
-        lock = threading.Lock()
+        dev_text = [p.cuda(non_blocking=False) for p in pinned] if mode_device else None
+        flags = api.TEXT_DEVICE_OUT if mode_device else 0
 
-        def one(m, i, timed):
-            p = packed[i % n_b]
-            tw = time.perf_counter()
-            m.map_packed(dev_blocks[i % n_b].data_ptr() if mode_device else p[0].data_ptr(), p[0].numel(), p[1], p[2])
-            st = m.stats()
-            st["py_call_ms"] = 1e3 * (time.perf_counter() - tw)
-            words = sum(int(m.lib.mab_result(m.h, j, None)) for j in range(0, len(p[2]), max(1, len(p[2]) // 64)))
-            m.lib.mab_release_batch(m.h)
-            if timed:
-                if os.environ.get("MAB_BENCH_VERBOSE"):
-                    log(f"[rank {rank}] step {i} device={mode_device} " + " ".join(f"{k}={v:.2f}" if isinstance(v, float) else f"{k}={v}" for k, v in st.items()))
-                with lock:
-                    agg["bases"] += p[3]; agg["launches"] += st["n_launches"]; agg["h2d"] += st["h2d_bytes"]; agg["d2h"] += st["d2h_bytes"]
-                    agg["ms_ext"] += st["ms_extend"]; agg["ms_ext_r0"] += st["ms_extend_r0"]; agg["ms_dev"] += st["ms_total"]; agg["vec"] += st["n_vectors"]
-                    agg["out_words"] += words
+        def get_chunk(first):
+            def f(w):
+                d = (first + w) % n_distinct
+                return pipeline.Chunk(dev_text[d].data_ptr() if mode_device else pinned[d].data_ptr(), len(texts[d]))
+            return f
 
-        def drive(first, count, timed, static=False):
-            errs = []
-            nxt = iter(range(first, first + count))     # steps are handed out as contexts become free
+        def sink(first):
+            def f(w, ptr, n, ofs):
+                if not mode_device:
+                    last_out[(first + w) % n_distinct] = (ptr, n)       # stays valid until the context's next finish: only read after the run
+            return f
 
-            def worker(t):
-                try:
-                    torch.cuda.set_device(local)
-                    if static:
-                        for i in range(first + t, first + count, len(ms)):
-                            one(ms[t], i, timed)
-                        return
-                    while True:
-                        with lock:
-                            i = next(nxt, None)
-                        if i is None:
-                            break
-                        one(ms[t], i, timed)
-                except Exception as e:       # a failed batch must fail the run, not shorten it
-                    errs.append(e)
-            th = [threading.Thread(target=worker, args=(t,)) for t in range(len(ms))]
-            [x.start() for x in th]
-            [x.join() for x in th]
-            if errs:
-                raise errs[0]
+        def drive(first, count):
+            ex = shard.WaveExchange(device=dev)
+            pipe = pipeline.WavePipeline(ms, ex, flags, device_index=local)
+            pipe.out, pipe.out_cap = run.out, run.out_cap                # page-locked output buffers live across drives
+            tot = pipe.run(count, get_chunk(first), sink(first))
+            run.out, run.out_cap = pipe.out, pipe.out_cap
+            tot["collectives"] = ex.n_collectives
+            return tot
 
-        drive(0, len(ms), False, static=True)          # set-up: one untimed batch per context sizes its device / pinned buffers
-        drive(len(ms), max(warmup, len(ms)), False)    # the W warm-up steps
+        drive(0, len(ms))                                   # set-up: one untimed chunk per context sizes its device / pinned buffers
+        drive(len(ms), max(warmup, len(ms)))                # the W warm-up steps
         sampler = ClockSampler(local); sampler.start()
         # device-side timing: the events sit on torch's (idle) stream; the first is recorded after a full device sync, the second
         # after the next one, so the interval covers everything the contexts ran on their own streams in between
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         ev0.record()
-        drive(warmup, steps, True)
+        tot = drive(warmup, steps)
         torch.cuda.synchronize()
         ev1.record(); ev1.synchronize()
         secs = ev0.elapsed_time(ev1) / 1e3
-        # the one exchange step of the sharded path: output offsets of this wave (8 B per rank)
-        shard.output_offsets(4 * agg["out_words"], device=torch.device("cuda", local))
         barrier()
         sampler.stop_flag = True; sampler.join(timeout=2)
         if world > 1:
             tt = torch.tensor([secs], dtype=torch.float64, device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.MAX); secs = float(tt.item())
-            bb = torch.tensor([agg["bases"]], dtype=torch.float64, device="cuda"); dist.all_reduce(bb); total_bases = float(bb.item())
+            bb = torch.tensor([tot["bases"]], dtype=torch.float64, device="cuda"); dist.all_reduce(bb); total_bases = float(bb.item())
         else:
-            total_bases = float(agg["bases"])
-        return secs, total_bases, agg, sampler.summary()
+            total_bases = float(tot["bases"])
+        return secs, total_bases, tot, sampler.summary()
+    run.out, run.out_cap = [None] * len(ms), [0] * len(ms)
 
-    # (the integer roofline of the DP step -- the product's own step code on register-resident state, k_fill_peak, traced variant --
-    # is measured in the solo pass after the timed runs)
-    secs_dev, bases_dev, agg_dev, clocks = run(True, args.steps, args.warmup)
-    secs_e2e, bases_e2e, agg_e2e, _ = run(False, args.steps, args.warmup)
+    secs_dev, bases_dev, tot_dev, clocks = run(True, args.steps, args.warmup)
+    secs_e2e, bases_e2e, tot_e2e, _ = run(False, args.steps, args.warmup)
+    # untimed parity: (1) a full-size chunk mapped from a fresh reference-thread state (rlen = 0, like the reference CLI's first read)
+    # must start with exactly the lines the reference prints for a sample of its reads; (2) the text the TIMED run produced for the same
+    # chunk must equal it from the second read on (in the timed run the chunk's first read inherits the previous chunk's rlen word)
+    parity = None
+    if rank == 0:
+        try:
+            d = sorted(last_out)[0]
+            timed = C.string_at(*last_out[d])
+            for m in ms:
+                m.lib.mab_set_device_input(m.h, 0)
+            fresh = {}
+            pipe = pipeline.WavePipeline(ms, shard.WaveExchange(device=dev) if world == 1 else _Solo(), 0, device_index=local)
+            pipe.out, pipe.out_cap = run.out, run.out_cap
+            pipe.run(1, lambda w: pipeline.Chunk(pinned[d].data_ptr(), len(texts[d])), lambda w, ptr, n, ofs: fresh.update(t=C.string_at(ptr, n)))
+            run.out, run.out_cap = pipe.out, pipe.out_cap
+            second = b"\nc%d_%s\t" % (d * world + rank, my_reads[d][1][0].encode())
+            a, b = timed.find(second), fresh["t"].find(second)
+            parity = {"timed_equals_fresh_from_second_read": bool(a > 0 and b > 0 and timed[a:] == fresh["t"][b:]), "sam_bytes": len(timed)}
+            if os.path.exists(REF_BIN):
+                parity.update(parity_check(idx, [(f"c{d * world + rank}_" + nm, sq) for nm, sq in my_reads[d]], work, fresh["t"]))
+            else:
+                parity.update({"ok": None, "against": "oracle/_ref/minialign not present"})
+        except Exception as e:
+            parity = {"ok": False, "error": repr(e)}
+        if parity.get("ok") is False or parity.get("timed_equals_fresh_from_second_read") is False:
+            raise SystemExit(f"bench.py: SAM text of the timed path differs from the reference: {parity}")
 
     # roofline pass: the dominant kernel timed ALONE (one context, CUDA events on its stream inside the library); in the pipelined
-    # runs above the kernels of two contexts overlap on the GPU, which stretches every per-kernel event interval
+    # runs above the kernels of three contexts overlap on the GPU, which stretches every per-kernel event interval
     def solo(n):
         os.environ["MAB_EXT_CTAS"] = "6"
         m = api.Mapper(blob, "pacbio", device=local)
         os.environ["MAB_EXT_CTAS"] = ext_pipe
-        m.lib.mab_set_device_input(m.h, 1)
-        p = packed[0]; d = p[0].cuda()
-        m.map_packed(d.data_ptr(), p[0].numel(), p[1], p[2]); m.lib.mab_release_batch(m.h)        # warm-up: allocations
+        a = dict(bases=0, ms_ext_r0=0.0, ms_ext=0.0, vec=0, ms_post=0.0, ms_total=0.0)
+        m.map_text(pinned[0][:len(texts[0])].numpy().tobytes()[:1 << 22].rsplit(b"\n>", 1)[0] + b"\n")      # warm-up: small allocations
         peak = m.fill_peak(True, 4000)
-        a = dict(bases=0, ms_ext_r0=0.0, ms_ext=0.0, vec=0)
-        for i in range(n):
-            p = packed[i % n_b]
-            d = p[0].cuda()
-            m.map_packed(d.data_ptr(), p[0].numel(), p[1], p[2])
-            st = m.stats(); m.lib.mab_release_batch(m.h)
-            a["bases"] += p[3]; a["ms_ext_r0"] += st["ms_extend_r0"]; a["ms_ext"] += st["ms_extend"]; a["vec"] += st["n_vectors"]
+        info = api.MabTextInfo()
+        for i in range(n + 1):
+            d = i % n_distinct
+            rc = m.lib.mab_map_text(m.h, pinned[d].data_ptr(), len(texts[d]), 0, None, 0, None, C.byref(info))
+            if rc != 0:
+                raise RuntimeError("mab_map_text failed: " + m.lib.mab_last_error().decode())
+            st = m.stats()
+            if i == 0:
+                continue                                    # allocation pass
+            a["bases"] += bases_of[d]; a["ms_ext_r0"] += st["ms_extend_r0"]; a["ms_ext"] += st["ms_extend"]; a["vec"] += st["n_vectors"]; a["ms_post"] += st["ms_post"]; a["ms_total"] += st["ms_total"]
         m.close()
         return a, n, peak
     for m in ms[1:]:
@@ -341,32 +443,37 @@ def main():
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     k_s = agg_solo["ms_ext_r0"] / 1e3 / n_solo                             # average k_extend (round 0) launch duration, kernel alone
     alg_bytes = BYTES_PER_BASE * agg_solo["bases"] / n_solo                # algorithmic bytes one launch processes
-    achieved = alg_bytes / k_s / 1e9 if k_s > 0 else 0.0
+    hbm_achieved = alg_bytes / k_s / 1e9 if k_s > 0 else 0.0
+    gcups = 64.0 * agg_solo["vec"] / max(1e-9, agg_solo["ms_ext"] / 1e3) / 1e9
+    peak_gcups = 64.0 * peak_vps / 1e9
     line = {
         "metric": "Mbases aligned/sec", "value": bases_dev / 1e6 / secs_dev, "unit": "Mbases/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * secs_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8",
         "data": "synthetic", "config": config, "clocks": clocks,
-        "e2e": {"value": bases_e2e / 1e6 / secs_e2e, "unit": "Mbases/s", "h2d_bytes_per_step": agg_e2e["h2d"] // args.steps, "d2h_bytes_per_step": agg_e2e["d2h"] // args.steps},
-        "gpu_launches": agg_dev["launches"],
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": TRAFFIC_PER_BASE * agg_solo["bases"] / n_solo,
-                     "traffic_source": "profiles/r01_ncu_k_extend_full.json: 292 B per read base (mask stream widened to 1 B per cell, DESIGN.md section 5)",
-                     "kernel": "k_extend (round 0)", "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-                     "note": "algorithmic bytes = 160 B/read base (SURVEY 8d); the kernel is integer-issue bound, not HBM bound: see DESIGN.md section 5",
-                     "ms_per_launch": 1e3 * k_s, "gcups": 64.0 * agg_solo["vec"] / max(1e-9, agg_solo["ms_ext"] / 1e3) / 1e9,
+        "e2e": {"value": bases_e2e / 1e6 / secs_e2e, "unit": "Mbases/s", "h2d_bytes_per_step": tot_e2e["h2d"] // args.steps, "d2h_bytes_per_step": tot_e2e["d2h"] // args.steps,
+                "what": "FASTA bytes in page-locked host memory -> mab_text_begin/commit/finish -> SAM bytes in page-locked host memory", "sam_bytes_per_step": tot_e2e["sam_bytes"] // args.steps,
+                "collectives_in_timed_region": tot_e2e["collectives"], "reads_remapped_for_rlen_chain": tot_e2e["redo"]},
+        "gpu_launches": tot_dev["launches"],
+        # the bound that limits the dominant kernel: issue slots of the integer pipes.  peak = cell updates/s of the DP step
+        # alone (k_fill_peak: the product's own traced step code, register-resident, k_extend's launch shape), achieved = what k_extend
+        # sustains including block bookkeeping, search, trace and the state machine
+        "roofline": {"bound": "int-alu", "achieved": gcups, "peak": peak_gcups, "unit": "GCUPS", "frac": gcups / peak_gcups if peak_gcups else None,
+                     "traffic": TRAFFIC_PER_BASE * agg_solo["bases"] / n_solo, "kernel": "k_extend (round 0)", "ms_per_launch": 1e3 * k_s,
+                     "peak_source": "k_fill_peak microbenchmark, same run (profiles/: SASS opcode histogram of the step and the ceiling derived from it)",
+                     "ncu_pipe_alu_pct": NCU_PIPE_ALU_PCT, "traffic_source": "ncu --set full capture under profiles/: dram bytes per read base x bases per launch",
                      "timing": "k_extend timed alone (one context, all 6 CTAs per SM resident) after the pipelined runs, CUDA events on its stream",
-                     # the bound that actually limits k_extend: issue slots of the integer pipes.  peak = vectors/s of the DP step alone
-                     # (k_fill_peak, same code, no memory), achieved = vectors/s k_extend sustains including search, trace and bookkeeping
-                     "integer": {"achieved_gcups": 64.0 * agg_solo["vec"] / max(1e-9, agg_solo["ms_ext"] / 1e3) / 1e9, "peak_gcups": 64.0 * peak_vps / 1e9,
-                                 "frac": (agg_solo["vec"] / max(1e-9, agg_solo["ms_ext"] / 1e3)) / peak_vps if peak_vps else None,
-                                 "peak_source": "k_fill_peak microbenchmark (traced DP step, register-resident, k_extend launch shape), same run"}},
+                     "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak if hbm_peak else None,
+                             "algorithmic_bytes_per_base": BYTES_PER_BASE, "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s"},
+                     "text_stages_ms_per_chunk": {"post+sam kernels": agg_solo["ms_post"] / n_solo, "whole chunk, one context": agg_solo["ms_total"] / n_solo}},
+        "parity": parity,
     }
     if rank == 0:
         if not args.no_cpu_baseline and os.path.exists(REF_BIN):
             try:
-                line["cpu_baseline"] = cpu_baseline(idx, batches, work)
+                line["cpu_baseline"] = cpu_baseline(idx, my_reads[0], work)
             except Exception as e:   # the reference binary is test infrastructure: report its absence, never fake it
                 line["cpu_baseline"] = {"value": None, "unit": "Mbases/s", "cores": host_threads(), "kind": "reference", "sample": f"unavailable: {e}"}
         emit(line)

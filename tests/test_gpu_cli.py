@@ -40,7 +40,7 @@ def test_cli_matches_live_reference_on_20kb_reads(tmp_path, preset):
     ref = subprocess.run([refh.BIN, "-x" + preset, "-t1", "-TAS,XS,NM,MD,SA", idx, rd], capture_output=True)
     assert ref.returncode == 0
     exp = [l for l in ref.stdout.decode().split("\n") if not l.startswith("@PG")]
-    got = run_cli(["-x" + preset, "-TAS,XS,NM,MD,SA", "-n", "97", idx, rd])          # odd batch size: state must carry across batches
+    got = run_cli(["-x" + preset, "-TAS,XS,NM,MD,SA", "-c2", "-N1.3", idx, rd])        # several chunks: state must carry across chunks and contexts
     assert len(got) == len(exp)
     bad = [i for i, (a, b) in enumerate(zip(got, exp)) if a != b]
     assert not bad, (len(bad), got[bad[0]][:200], exp[bad[0]][:200])
@@ -72,7 +72,7 @@ def test_cli_matches_live_reference_multi_contig_repeats(tmp_path):
     """BASELINE config 2 in small (sacCer3-like: 17 contigs) with heavier planted repeat families, so that the rescue rounds
     (occ thresholds), secondary / supplementary records and the seed-rich sort class are exercised; reference run with -t1."""
     from minialign_b200 import synth
-    g = synth.make_genome(6_000_000, 17, seed=31, repeats=((30, 4000), (120, 1200), (400, 300)))
+    g = synth.make_genome(6_000_000, 17, seed=31, repeats=((30, 4000), (120, 1200), (400, 300)), weights=[7, 2, 9, 1, 5, 3, 8, 2, 6, 4, 1, 9, 3, 5, 2, 7, 1])
     reads = synth.make_reads(g, 8_000_000, seed=32) + synth.make_hard_reads(g, seed=33)
     fa, rd, idx = str(tmp_path / "g.fa"), str(tmp_path / "r.fa"), str(tmp_path / "g.mai")
     synth.write_fasta(fa, g, 80); synth.write_fasta(rd, reads)
