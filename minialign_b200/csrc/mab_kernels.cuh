@@ -518,7 +518,7 @@ __device__ inline void finalize_read(RCtx &x, BatchCounters *ctr, uint64_t pool_
 	uint64_t words = 1, n_aln = 0;
 	for(uint32_t i = 0; i < r->n_res; i++) { uint32_t na = BIN_NALN(x, x.root[2ull * i + 1]); words += 5 + 2ull * na; n_aln += na; }
 	/* behind the record: room for the post-processing kernel (mab_post.cuh): 4 words of scratch per result and the output plan */
-	uint64_t room = words + 4ull * r->n_res + 2 + 4 * n_aln;
+	uint64_t room = words + 1 + 4ull * r->n_res + 2 + 4 * n_aln;			/* + 1: the scratch is 8-byte aligned (sorted as u32 pairs) */
 	unsigned long long ofs = atomicAdd(&ctr->pool_top, (unsigned long long)room);
 	if(ofs + room > pool_cap) { r->err |= MAB_ERR_POOL_OVF; r->result_words = 0; return; }
 	uint32_t *o = x.pool + ofs;

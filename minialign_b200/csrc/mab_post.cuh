@@ -36,13 +36,20 @@ __device__ __forceinline__ uint32_t mapq_lookup(const double *thr, double v)
 	return lo;
 }
 
+/* the scratch / plan area behind a read's result record, 8-byte aligned (the sort moves u32 pairs) */
+__device__ __forceinline__ uint32_t *post_scratch(uint32_t *rec, uint32_t result_words)
+{
+	uint32_t *p = rec + result_words;
+	return p + (((uintptr_t)p >> 2) & 1);
+}
+
 __device__ __forceinline__ int32_t post_sc(uint32_t x) { return (int32_t)0x40000000 - (int32_t)x; }
 
 __device__ inline void post_read(const DevParams &P, uint32_t *pool, ReadRec *r, const double *thr, uint32_t *frames, uint32_t *sm, int lane)
 {
 	uint32_t *rec = pool + r->result_ofs;
 	uint32_t n_res = rec[0];
-	uint32_t *res = rec + r->result_words, *boff = res + 2ull * n_res, *mq = boff + n_res, *plan = mq + n_res;
+	uint32_t *res = post_scratch(rec, r->result_words), *boff = res + 2ull * n_res, *mq = boff + n_res, *plan = mq + n_res;
 	if(lane == 0) {
 		uint32_t p = 1;
 		for(uint32_t i = 0; i < n_res; i++) { boff[i] = p; res[2 * i] = rec[p]; res[2 * i + 1] = i; mq[i] = 0; p += 5 + 2 * rec[p + 1]; }

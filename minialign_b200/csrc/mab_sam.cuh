@@ -289,7 +289,7 @@ __global__ void k_sam(DevParams P, const uint32_t *pool, const ReadRec *reads, T
 			const uint32_t *plan = nullptr;
 			if(r->result_words != 0 && r->err == 0) {
 				const uint32_t *rec = pool + r->result_ofs;
-				plan = rec + r->result_words + 4ull * rec[0];
+				plan = post_scratch(const_cast<uint32_t *>(rec), r->result_words) + 4ull * rec[0];
 			}
 			sam_read(o, P, pool, plan, q, tags);
 		}

@@ -97,6 +97,7 @@ extern "C" int mab_text_begin(mab_ctx *ctx, const char *text, uint64_t n_bytes, 
 	if(ctx->device_input) {
 		/* caller contract in this mode: the device buffer ends with '\n' and has 64 readable bytes behind it */
 		d_text = (const uint8_t *)text;
+		if(((uintptr_t)text & 15) != 0) { g_err = "mab_text_begin: a device-resident chunk must be 16-byte aligned"; return MAB_EINVAL; }
 		uint8_t fl[2];
 		CK(RT_MEMCPY_D2H_ASYNC(&fl[0], d_text, 1, ctx->stream)); CK(RT_MEMCPY_D2H_ASYNC(&fl[1], d_text + n_bytes - 1, 1, ctx->stream));
 		CK(ctx_sync(ctx));

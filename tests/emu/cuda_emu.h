@@ -29,8 +29,8 @@
 
 struct emu_dim3 { unsigned x, y, z; emu_dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 typedef emu_dim3 dim3;
-struct uint4 { unsigned x, y, z, w; };
-struct uint2 { unsigned x, y; };
+struct __attribute__((aligned(16))) uint4 { unsigned x, y, z, w; };
+struct __attribute__((aligned(8))) uint2 { unsigned x, y; };
 
 namespace emu {
 struct Warp {
