@@ -223,14 +223,14 @@ class _Solo:
         return o, n
 
 
-def parity_check(idx, reads, work, text: bytes, n_sample=384):
+def parity_check(idx, reads, chunk_id, work, text: bytes, n_sample=384):
     """Untimed: the SAM text of a full-size chunk must start with exactly the lines the reference CLI (-t1) prints for the first
     `n_sample` reads of that chunk (the reference's results do not depend on what follows a read)."""
     from minialign_b200 import synth
     fa, sam = os.path.join(work, f"parity.{os.getpid()}.fa"), os.path.join(work, f"parity.{os.getpid()}.sam")
     sample = reads[:n_sample]
     with open(fa, "wb") as f:
-        f.write(fasta_bytes(sample, 0))
+        f.write(fasta_bytes(sample, chunk_id))
     ref_run(idx, fa, 1, out=sam)
     exp = b"".join(l for l in open(sam, "rb") if not l.startswith(b"@"))
     os.remove(fa); os.remove(sam)
@@ -405,7 +405,7 @@ def main():
             a, b = timed.find(second), fresh["t"].find(second)
             parity = {"timed_equals_fresh_from_second_read": bool(a > 0 and b > 0 and timed[a:] == fresh["t"][b:]), "sam_bytes": len(timed)}
             if os.path.exists(REF_BIN):
-                parity.update(parity_check(idx, [(f"c{d * world + rank}_" + nm, sq) for nm, sq in my_reads[d]], work, fresh["t"]))
+                parity.update(parity_check(idx, my_reads[d], d * world + rank, work, fresh["t"]))
             else:
                 parity.update({"ok": None, "against": "oracle/_ref/minialign not present"})
         except Exception as e:
