@@ -101,15 +101,92 @@ __device__ __forceinline__ void parse_rv(const PathBits &pb, unsigned long long 
 	}
 }
 
+/* decimal digits of v at p (per-lane helper of the warp-parallel CIGAR); returns their number */
+__device__ __forceinline__ uint32_t sam_ndigits(uint32_t v)
+{
+	return v < 10u ? 1u : v < 100u ? 2u : v < 1000u ? 3u : v < 10000u ? 4u : v < 100000u ? 5u : v < 1000000u ? 6u : v < 10000000u ? 7u : v < 100000000u ? 8u : v < 1000000000u ? 9u : 10u;
+}
+__device__ __forceinline__ void sam_put_dec(uint8_t *p, uint32_t v, uint32_t nd)
+{
+	for(uint32_t i = nd; i > 0; i--) { uint32_t q = v / 10; p[i - 1] = (uint8_t)('0' + (v - 10 * q)); v = q; }
+}
+
+/* CIGAR of path bits [ppos, ppos + plen), written from the top bit down (the reference parses alignments in reverse:
+ * _parser_loop_rv, gaba_parse.h:162-184, driven by gaba_dump_cigar_reverse).
+ *
+ * What the serial parser (parse_rv above, used for the MD walk) produces is a run-length encoding of a purely local
+ * classification of the path bits, scanning downwards: a 0 directly above a 1 and that 1 form a diagonal step (M); every other 1 is
+ * an insertion (I), every other 0 a deletion (D).  (The parser counts a run of zeros and keeps the last one for the pair it forms
+ * with the following 1 -- `m - (m > 0)` --, counts a run of ones as insertions, then eats "01" pairs; below bit 0 it reads the
+ * words in front of the path, a 0 then a 1 (PathBits), so zeros at the bottom are deletions.)  Consecutive steps of one kind make
+ * one CIGAR operation.  That makes the CIGAR data-parallel: every lane classifies 32 positions with a few bit operations, marks the
+ * positions that start a new run, and formats the runs that end at its own starts; run lengths come from the previous start
+ * (warp scan, carried from chunk to chunk), output offsets from a warp scan of the text lengths.  1024 positions per iteration. */
 template <bool W>
 __device__ __forceinline__ void sam_cigar_rv(SamW<W> &o, const PathBits &pb, unsigned long long ppos, unsigned long long plen)
 {
-	unsigned long long mrun = 0;
-	parse_rv(pb, ppos, plen,
-		[&](unsigned long long c) { if(c) { if(mrun) { o.num(mrun); o.c('M'); mrun = 0; } o.num(c); o.c('D'); } },
-		[&](unsigned long long c) { if(c) { if(mrun) { o.num(mrun); o.c('M'); mrun = 0; } o.num(c); o.c('I'); } },
-		[&](unsigned long long c) { mrun += c; });
-	if(mrun) { o.num(mrun); o.c('M'); }
+	const int lane = o.lane;
+	const long long len = (long long)plen;
+	if(len <= 0) { return; }
+	long long prev_q = -1; uint32_t prev_cls = 0;				/* the latest run start so far (downward coordinate q = len - 1 - position) and its class */
+	uint32_t cls_above = 3;										/* class of the position just above the chunk (3 = none: the top position always starts a run) */
+	for(long long hi = len - 1; hi >= 0; hi -= 1024) {
+		const long long base = hi - 32ll * lane - 31;			/* position of bit 0 of this lane's 32 positions; bit 31 is the topmost */
+		unsigned long long x = base > -32 ? pb.at((long long)ppos + base - 1) : 0ull;		/* bit 0: lower neighbour of position base; bit 33: upper neighbour of base + 31 */
+		uint32_t Wd = (uint32_t)(x >> 1), Lw = (uint32_t)x, Uw = (uint32_t)(x >> 2);
+		if(base + 31 == len - 1) { Uw |= 0x80000000u; }			/* nothing above the top of the segment: a 1 there is an insertion */
+		const uint32_t valid = base >= 0 ? 0xffffffffu : (base <= -32 ? 0u : (0xffffffffu << (uint32_t)(-base)));
+		const uint32_t Mm = ((Wd & ~Uw) | (~Wd & Lw)) & valid, Im = (Wd & Uw) & valid, Dm = (~Wd & ~Lw) & valid;
+		const uint32_t cls0 = (Mm & 1u) ? 0u : (Im & 1u) ? 1u : (Dm & 1u) ? 2u : 3u;
+		uint32_t up = __shfl_up_sync(0xffffffffu, cls0, 1);
+		if(lane == 0) { up = cls_above; }
+		cls_above = __shfl_sync(0xffffffffu, cls0, 31);
+		const uint32_t start = valid & ~((Mm & ((Mm >> 1) | ((uint32_t)(up == 0) << 31))) | (Im & ((Im >> 1) | ((uint32_t)(up == 1) << 31))) | (Dm & ((Dm >> 1) | ((uint32_t)(up == 2) << 31))));
+		/* the latest start above this lane's positions: exclusive maximum over the lanes (q grows downwards), else the carry */
+		unsigned long long mine = 0;
+		if(start) {
+			int k = __ffs((int)start) - 1;
+			uint32_t c = (Mm >> k) & 1u ? 0u : (Im >> k) & 1u ? 1u : 2u;
+			mine = ((unsigned long long)(len - 1 - base - k) + 1) << 2 | c;
+		}
+		unsigned long long inc = mine;
+		for(int d = 1; d < 32; d <<= 1) { unsigned long long y = __shfl_up_sync(0xffffffffu, inc, d); if(lane >= d && y > inc) { inc = y; } }
+		unsigned long long exc = __shfl_up_sync(0xffffffffu, inc, 1);
+		if(lane == 0) { exc = 0; }
+		const unsigned long long last = __shfl_sync(0xffffffffu, inc, 31);
+		long long pq0 = exc ? (long long)(exc >> 2) - 1 : prev_q; uint32_t pc0 = exc ? (uint32_t)(exc & 3) : prev_cls;
+		/* text bytes of the runs that end at this lane's starts */
+		uint32_t bytes = 0;
+		{
+			long long pq = pq0; uint32_t pc = pc0;
+			for(uint32_t m = start; m; ) {
+				int k = 31 - __clz((int)m); m &= ~(1u << k);
+				long long q = len - 1 - base - k;
+				if(pq >= 0) { uint32_t run = (uint32_t)(q - pq); bytes += sam_ndigits(pc == 0 ? run >> 1 : run) + 1; }
+				pq = q; pc = (Mm >> k) & 1u ? 0u : (Im >> k) & 1u ? 1u : 2u;
+			}
+		}
+		uint32_t tot, ofs = warp_excl_scan(bytes, lane, &tot);
+		if(W) {
+			uint8_t *p = o.p + o.n + ofs;
+			long long pq = pq0; uint32_t pc = pc0;
+			for(uint32_t m = start; m; ) {
+				int k = 31 - __clz((int)m); m &= ~(1u << k);
+				long long q = len - 1 - base - k;
+				if(pq >= 0) {
+					uint32_t run = (uint32_t)(q - pq), v = pc == 0 ? run >> 1 : run, nd = sam_ndigits(v);
+					sam_put_dec(p, v, nd); p[nd] = pc == 0 ? 'M' : pc == 1 ? 'I' : 'D'; p += nd + 1;
+				}
+				pq = q; pc = (Mm >> k) & 1u ? 0u : (Im >> k) & 1u ? 1u : 2u;
+			}
+		}
+		o.n += tot;
+		if(last) { prev_q = (long long)(last >> 2) - 1; prev_cls = (uint32_t)(last & 3); }
+	}
+	if(prev_q >= 0) {											/* the last run reaches the bottom of the segment */
+		uint32_t run = (uint32_t)(len - prev_q);
+		o.num(prev_cls == 0 ? run >> 1 : run); o.c(prev_cls == 0 ? 'M' : prev_cls == 1 ? 'I' : 'D');
+	}
 }
 
 struct SamRead { const uint8_t *name; uint32_t l_name; const uint8_t *seq; uint32_t l_seq; const uint8_t *qual; };
