@@ -246,7 +246,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch-reads", type=int, default=16384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--contexts", type=int, default=3, help="mapper contexts (in-flight chunks) per GPU")
+    ap.add_argument("--contexts", type=int, default=4, help="mapper contexts (in-flight chunks) per GPU")
     ap.add_argument("--workload", default=None, choices=[None, "ecoli", "saccer3"], help="default: ecoli at one GPU (configs[1]), saccer3 across GPUs (configs[2])")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -318,10 +318,11 @@ def main():
         p[len(t):] = 10
         pinned.append(p)
     log(f"[rank {rank}] workload ready in {time.time() - t0:.1f}s: {n_distinct} chunks x {args.batch_reads} reads, {len(texts[0]) / 1e6:.0f} MB of FASTA each")
-    # three mapper contexts per GPU, each driven by its own host thread (pipeline.py): while one chunk is being parsed / copied / printed,
-    # another one's extension runs.  The pipelined contexts launch 5 of the 6 possible k_extend CTAs per SM: the registers / shared
-    # memory left over let the other chunks' small kernels run under the current extension; alone, 6 is faster
-    ext_pipe = os.environ.get("MAB_EXT_CTAS", "5" if args.contexts > 1 else "6")
+    # four mapper contexts per GPU, each driven by its own host thread (pipeline.py): while one chunk is being parsed / copied / printed,
+    # another one's extension runs.  The pipelined contexts launch 4 of the 6 possible k_extend CTAs per SM: the registers / shared
+    # memory left over let the other chunks' kernels (and the next chunk's extension) run under the current one; alone, 6 is faster
+    # (sweep under profiles/r02_sweep_contexts.txt)
+    ext_pipe = os.environ.get("MAB_EXT_CTAS", "4" if args.contexts > 1 else "6")
     os.environ["MAB_EXT_CTAS"] = ext_pipe
     m0 = api.Mapper(blob, "pacbio", device=local)
     ms = [m0] + [m0.clone() for _ in range(max(1, args.contexts) - 1)]
