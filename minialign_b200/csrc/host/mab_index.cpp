@@ -6,7 +6,7 @@
  * The mapping results depend on the index through (a) the minimizer set, (b) the ORDER of the occurrences of a minimizer
  * (seeds are generated in that order and the unstable seed sort keeps ties in generation order) and (c) the occurrence
  * thresholds occ[].  (b) is fixed by the reference's unstable radix sort of every first-stage bucket (ksort.h:82-131), whose
- * permutation cycles are reproduced literally below; the second-stage hash tables only have to be valid linear-probing tables
+ * permutation cycles are followed step by step below; the second-stage hash tables only have to be valid linear-probing tables
  * for the probe in mab_scalar.cuh (idx_get), their slot order is not observable.
  *
  * Blob layout = the payload of a .mai index block: mm_idx_t (64 B) | buckets 32 B x 2^b | sequence
@@ -62,42 +62,51 @@ void sketch(const uint8_t *seq, uint32_t len, uint32_t k, uint32_t w, std::vecto
 	}
 }
 
-/* ---- the reference's unstable radix sort, 16-byte elements keyed by their first u64 (radix_sort_128x) ---- */
-void rs_insertion(Mini *beg, Mini *end)
+/* ---- bucket sort of the minimizers by their key remainder ----
+ * The order in which equal keys (the occurrences of one minimizer) end up is observable: it is the order of the occurrence array
+ * in the index and from there of the seeds.  The reference sorts with an in-place MSD radix sort whose distribution pass is not
+ * stable, so the permutation it performs is followed here step by step, in the same index-based form as the device and host
+ * sorts of the mapping path (mab_scalar.cuh radix_sort_exact_warp, mab_host.inl rs_sort64): digit histogram -> [head, tail)
+ * range per digit -> for every digit in turn, the element at the head is carried along its displacement cycle until one that
+ * belongs here comes back -> ranges above 64 elements recurse on the next digit, smaller ones are finished by insertion. */
+inline unsigned digit_of(const Mini &m, int shift) { return (unsigned)(m.hrem >> shift) & 255u; }
+
+void insertion_by_key(Mini *a, size_t n)
 {
-	for(Mini *i = beg + 1; i < end; ++i) {
-		if(i->hrem < (i - 1)->hrem) {
-			Mini *j, tmp = *i;
-			for(j = i; j > beg && tmp.hrem < (j - 1)->hrem; --j) { *j = *(j - 1); }
-			*j = tmp;
-		}
+	for(size_t i = 1; i < n; i++) {
+		if(!(a[i].hrem < a[i - 1].hrem)) { continue; }
+		Mini t = a[i];
+		size_t j = i;
+		while(j > 0 && t.hrem < a[j - 1].hrem) { a[j] = a[j - 1]; j--; }
+		a[j] = t;
 	}
 }
-void rs_sort(Mini *beg, Mini *end, int s)
+
+void flag_sort(Mini *a, size_t n, int shift)
 {
-	struct Bk { Mini *b, *e; } b[256], *be = b + 256, *k;
-	for(k = b; k != be; ++k) { k->b = k->e = beg; }
-	for(Mini *i = beg; i != end; ++i) { ++b[(i->hrem >> s) & 255].e; }
-	for(k = b + 1; k != be; ++k) { k->e += (k - 1)->e - beg; k->b = (k - 1)->e; }
-	for(k = b; k != be;) {
-		if(k->b != k->e) {
-			Bk *l;
-			if((l = b + ((k->b->hrem >> s) & 255)) != k) {
-				Mini tmp = *k->b, swap;
-				do { swap = tmp; tmp = *l->b; *l->b++ = swap; l = b + ((tmp.hrem >> s) & 255); } while(l != k);
-				*k->b++ = tmp;
-			} else { ++k->b; }
-		} else { ++k; }
+	size_t head[256], tail[256];
+	memset(tail, 0, sizeof(tail));
+	for(size_t i = 0; i < n; i++) { tail[digit_of(a[i], shift)]++; }
+	head[0] = 0;
+	for(int d = 1; d < 256; d++) { tail[d] += tail[d - 1]; head[d] = tail[d - 1]; }
+	for(int d = 0; d < 256; ) {
+		if(head[d] == tail[d]) { d++; continue; }
+		unsigned t = digit_of(a[head[d]], shift);
+		if(t == (unsigned)d) { head[d]++; continue; }
+		Mini carried = a[head[d]];								/* displacement cycle: put it where it belongs, pick up what was there */
+		while(t != (unsigned)d) { std::swap(carried, a[head[t]]); head[t]++; t = digit_of(carried, shift); }
+		a[head[d]++] = carried;
 	}
-	for(b->b = beg, k = b + 1; k != be; ++k) { k->b = (k - 1)->e; }
-	if(s) {
-		s = s > 8 ? s - 8 : 0;
-		for(k = b; k != be; ++k) {
-			if(k->e - k->b > 64) { rs_sort(k->b, k->e, s); } else if(k->e - k->b > 1) { rs_insertion(k->b, k->e); }
-		}
+	if(shift == 0) { return; }
+	const int next = shift > 8 ? shift - 8 : 0;
+	size_t beg = 0;
+	for(int d = 0; d < 256; d++) {
+		size_t sz = tail[d] - beg;
+		if(sz > 64) { flag_sort(a + beg, sz, next); } else if(sz > 1) { insertion_by_key(a + beg, sz); }
+		beg = tail[d];
 	}
 }
-void radix_sort_128x(Mini *p, size_t l) { if(l <= 64) { rs_insertion(p, p + l); } else { rs_sort(p, p + l, 56); } }
+void radix_sort_128x(Mini *p, size_t l) { if(l <= 64) { insertion_by_key(p, l); } else { flag_sort(p, l, 56); } }
 
 void put64(std::vector<uint8_t> &v, size_t ofs, uint64_t x) { memcpy(v.data() + ofs, &x, 8); }
 void put32(std::vector<uint8_t> &v, size_t ofs, uint32_t x) { memcpy(v.data() + ofs, &x, 4); }
