@@ -361,6 +361,7 @@ def main():
             tot = pipe.run(count, get_chunk(first), sink(first))
             run.out, run.out_cap = pipe.out, pipe.out_cap
             tot["collectives"] = ex.n_collectives
+            tot["collective_ms"] = 1e3 * ex.t_collectives
             return tot
 
         drive(0, len(ms))                                   # set-up: one untimed chunk per context sizes its device / pinned buffers
@@ -456,7 +457,7 @@ def main():
         "data": "synthetic", "config": config, "clocks": clocks,
         "e2e": {"value": bases_e2e / 1e6 / secs_e2e, "unit": "Mbases/s", "h2d_bytes_per_step": tot_e2e["h2d"] // args.steps, "d2h_bytes_per_step": tot_e2e["d2h"] // args.steps,
                 "what": "FASTA bytes in page-locked host memory -> mab_text_begin/commit/finish -> SAM bytes in page-locked host memory", "sam_bytes_per_step": tot_e2e["sam_bytes"] // args.steps,
-                "collectives_in_timed_region": tot_e2e["collectives"], "reads_remapped_for_rlen_chain": tot_e2e["redo"]},
+                "collectives_in_timed_region": tot_e2e["collectives"], "collective_ms_per_step": tot_e2e["collective_ms"] / args.steps, "reads_remapped_for_rlen_chain": tot_e2e["redo"]},
         "gpu_launches": tot_dev["launches"],
         # the bound that limits the dominant kernel: issue slots of the integer pipes.  peak = cell updates/s of the DP step
         # alone (k_fill_peak: the product's own traced step code, register-resident, k_extend's launch shape), achieved = what k_extend

@@ -43,15 +43,20 @@ class WaveExchange:
         self.rlen = 0               # a fresh reference thread starts with rlen = 0
         self.out_base = 0           # bytes of SAM text before this wave
         self.n_collectives = 0
+        self.t_collectives = 0.0    # seconds the calling thread spent inside the collectives
 
     def _gather(self, vals):
         if self.world == 1:
             return [list(vals)]
+        import time
+        t0 = time.perf_counter()
         t = torch.tensor(list(vals), dtype=torch.int64, device=self.device)
         out = torch.empty(self.world * t.numel(), dtype=torch.int64, device=self.device)
         dist.all_gather_into_tensor(out, t)
+        rows = out.view(self.world, -1).tolist()
         self.n_collectives += 1
-        return out.view(self.world, -1).tolist()
+        self.t_collectives += time.perf_counter() - t0
+        return rows
 
     def rlen_inputs(self, valid: bool, value: int):
         """(valid, value) = what this rank's chunk leaves behind under its current assumption.  Returns the value this rank's chunk
