@@ -302,8 +302,10 @@ def main():
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    host_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        host_group = dist.new_group(backend="gloo") if os.environ.get("MAB_RLEN_OVER_NCCL") is None else None
     n_distinct = min(3, args.warmup + args.steps)
     t0 = time.time()
     g, idx, blob = build_genome(work + f"/r{rank}", which)
@@ -355,7 +357,7 @@ def main():
             return f
 
         def drive(first, count):
-            ex = shard.WaveExchange(device=dev)
+            ex = shard.WaveExchange(device=dev, host_group=host_group)
             pipe = pipeline.WavePipeline(ms, ex, flags, device_index=local)
             pipe.out, pipe.out_cap = run.out, run.out_cap                # page-locked output buffers live across drives
             tot = pipe.run(count, get_chunk(first), sink(first))

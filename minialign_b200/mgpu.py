@@ -185,7 +185,8 @@ def main(argv=None):
         dist.barrier()
     if out_fd is None:
         out_fd = os.open(o["out"], os.O_WRONLY)
-    ex = shard.WaveExchange(device=dev)
+    host_group = dist.new_group(backend="gloo") if world > 1 and backend == "nccl" else None
+    ex = shard.WaveExchange(device=dev, host_group=host_group)
     ex.out_base = len(header)
     chunk_bytes = max(1024, int(o["chunk_mb"] * 1048576))
     tot = dict(reads=0, bases=0)

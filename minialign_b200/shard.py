@@ -36,24 +36,35 @@ class WaveExchange:
     """The per-wave collectives.  Every rank must call the methods in the same order, once per wave (ranks without a chunk in the
     last, partial wave pass valid=False / 0 bytes)."""
 
-    def __init__(self, device=None):
+    def __init__(self, device=None, host_group=None):
+        """device: where the default group's tensors live (cuda device for NCCL, None for gloo).  host_group: an optional gloo group
+        for the rlen chain -- that exchange is on the critical path of every wave (the chunks cannot be printed before it) and its
+        payload is host data; an NCCL kernel for it would queue behind the mapping kernels that keep the GPU full.  The byte-count
+        all-gather for the output offsets stays on the default (NCCL) group: nothing waits for it but the writer."""
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.device = device
+        self.host_group = host_group
         self.rlen = 0               # a fresh reference thread starts with rlen = 0
         self.out_base = 0           # bytes of SAM text before this wave
         self.n_collectives = 0
         self.t_collectives = 0.0    # seconds the calling thread spent inside the collectives
 
-    def _gather(self, vals):
+    def _gather(self, vals, host=False):
         if self.world == 1:
             return [list(vals)]
         import time
         t0 = time.perf_counter()
-        t = torch.tensor(list(vals), dtype=torch.int64, device=self.device)
-        out = torch.empty(self.world * t.numel(), dtype=torch.int64, device=self.device)
-        dist.all_gather_into_tensor(out, t)
-        rows = out.view(self.world, -1).tolist()
+        if host and self.host_group is not None:
+            t = torch.tensor(list(vals), dtype=torch.int64)
+            parts = [torch.empty_like(t) for _ in range(self.world)]
+            dist.all_gather(parts, t, group=self.host_group)
+            rows = [p.tolist() for p in parts]
+        else:
+            t = torch.tensor(list(vals), dtype=torch.int64, device=self.device)
+            out = torch.empty(self.world * t.numel(), dtype=torch.int64, device=self.device)
+            dist.all_gather_into_tensor(out, t)
+            rows = out.view(self.world, -1).tolist()
         self.n_collectives += 1
         self.t_collectives += time.perf_counter() - t0
         return rows
@@ -61,7 +72,7 @@ class WaveExchange:
     def rlen_inputs(self, valid: bool, value: int):
         """(valid, value) = what this rank's chunk leaves behind under its current assumption.  Returns the value this rank's chunk
         must be committed with; `self.rlen` is not advanced before settle() confirms the wave."""
-        rows = self._gather((1 if valid else 0, int(value)))
+        rows = self._gather((1 if valid else 0, int(value)), host=True)
         run, mine = self.rlen, None
         for q, (v, x) in enumerate(rows):
             if q == self.rank:
@@ -84,7 +95,7 @@ class WaveExchange:
             if self.world == 1:
                 any_changed = changed
             else:
-                any_changed = any(r[0] for r in self._gather((1 if changed else 0,)))
+                any_changed = any(r[0] for r in self._gather((1 if changed else 0,), host=True))
             if not any_changed:
                 break
         self.rlen = self._pending
