@@ -305,7 +305,7 @@ def main():
     host_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-        host_group = dist.new_group(backend="gloo") if os.environ.get("MAB_RLEN_OVER_NCCL") is None else None
+        host_group = dist.new_group(backend="gloo")      # rlen chain (host data, on the critical path); its own group: the two exchanges run on different threads
     n_distinct = min(3, args.warmup + args.steps)
     t0 = time.time()
     g, idx, blob = build_genome(work + f"/r{rank}", which)

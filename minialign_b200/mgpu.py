@@ -185,7 +185,7 @@ def main(argv=None):
         dist.barrier()
     if out_fd is None:
         out_fd = os.open(o["out"], os.O_WRONLY)
-    host_group = dist.new_group(backend="gloo") if world > 1 and backend == "nccl" else None
+    host_group = dist.new_group(backend="gloo") if world > 1 else None      # its own group: the two exchanges run on different threads
     ex = shard.WaveExchange(device=dev, host_group=host_group)
     ex.out_base = len(header)
     chunk_bytes = max(1024, int(o["chunk_mb"] * 1048576))

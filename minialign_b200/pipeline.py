@@ -127,15 +127,28 @@ class WavePipeline:
                     q.put(("stop", None))
                 raise errors[0]
 
-        def settle_offsets(w):
-            evs[w]["f"].wait(); check()
-            info = finished[w][0]
-            ofs, _total = self.ex.offsets(int(info.sam_bytes) if info is not None else 0)
-            cmd[w % K].put(("sink", ofs))
+        # the offsets exchange (byte counts -> prefix sum) runs on its own thread, in wave order: nothing but the sink of a wave waits
+        # for it, so the commit loop below never blocks behind a collective that has to find room on a busy GPU
+        def offsets_loop():
+            try:
+                if self.device_index is not None:
+                    import torch
+                    torch.cuda.set_device(self.device_index)
+                for w in range(n_waves):
+                    evs[w]["f"].wait()
+                    if errors:
+                        return
+                    info = finished[w][0]
+                    ofs, _total = self.ex.offsets(int(info.sam_bytes) if info is not None else 0)
+                    cmd[w % K].put(("sink", ofs))
+            except Exception as e:
+                errors.append(e)
+                for q in cmd:
+                    q.put(("stop", None))
 
+        ot = threading.Thread(target=offsets_loop, daemon=True)
+        ot.start()
         for w in range(n_waves):
-            if K == 1 and w >= 1:
-                settle_offsets(w - 1)       # a single context cannot start wave w before wave w - 1 is out
             evs[w]["b"].wait(); check()
             info = begun[w]
             self.ex.begin_wave(bool(info.rlen_valid) if info is not None else False, int(info.rlen_next) if info is not None else 0)
@@ -146,10 +159,7 @@ class WavePipeline:
                 return (bool(r.rlen_valid), int(r.rlen_next)) if r is not None else (False, 0)
             self.ex.settle(commit)
             cmd[w % K].put(("finish", None))
-            if K > 1 and w >= 1:
-                settle_offsets(w - 1)
-        if n_waves:
-            settle_offsets(n_waves - 1)
+        ot.join()
         [t.join() for t in threads]
         check()
         return self.totals

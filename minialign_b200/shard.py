@@ -55,7 +55,9 @@ class WaveExchange:
             return [list(vals)]
         import time
         t0 = time.perf_counter()
-        if host and self.host_group is not None:
+        if host and self.host_group is None and self.world > 1:
+            raise RuntimeError("WaveExchange: the rlen chain needs its own (gloo) group when world > 1")
+        if host:
             t = torch.tensor(list(vals), dtype=torch.int64)
             parts = [torch.empty_like(t) for _ in range(self.world)]
             dist.all_gather(parts, t, group=self.host_group)

@@ -21,7 +21,7 @@ def _exchange_worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    ex = shard.WaveExchange()
+    ex = shard.WaveExchange(host_group=dist.new_group(backend="gloo"))
     log = []
     # wave 0: rank 0 leaves 700 behind, rank 1 loads no chain; wave 1: rank 0's value moves when it is committed (700 -> 650 -> 640),
     # rank 1 must see the corrected one; wave 2: partial (rank 1 has no chunk)
