@@ -25,7 +25,7 @@ struct PipeShape { uint32_t n_seq, maxlen; uint64_t tot_len, span; };		/* what t
 /* launch geometry and buffer shapes of the batch in flight (kept in the context: redo passes may be issued by a later call) */
 struct RunState {
 	PipeShape sh; const uint8_t *d_base;
-	uint32_t blk_cap, ext_ctas, seed_ctas, init_ctas, sc_cap1[2], sc_cap2[2];
+	uint32_t blk_cap, ext_ctas, seed_ctas, init_ctas, sc_cap1[2], sc_cap2[2], rlen_init, init_known;
 	uint64_t arena_stride;
 };
 
@@ -471,7 +471,7 @@ static void pipe_rounds(mab_ctx *ctx, bool first, bool timed)
 		int kind = round == 0 ? 0 : 1;
 		RT_LAUNCH(k_sortchain, n_seq, 32, 16 * R.sc_cap1[kind] + 2048, ctx->stream, P, ctx->d_reads, n_seq, ctx->d_ws, ctx->d_frames, round, R.sc_cap1[kind], 0u, R.sc_cap1[kind]);
 		RT_LAUNCH(k_sortchain, n_seq, 32, 16 * R.sc_cap2[kind] + 2048, ctx->stream, P, ctx->d_reads, n_seq, ctx->d_ws, ctx->d_frames, round, R.sc_cap2[kind], R.sc_cap1[kind], 0xffffffffu);
-		if(first && round == 0) { RT_LAUNCH(k_rlen_predict, 1, MAB_PIPE_THREADS, 0, ctx->stream, P, ctx->d_reads, n_seq, (const uint8_t *)ctx->d_ws); S.n_launches++; }
+		if(first && round == 0) { RT_LAUNCH(k_rlen_predict, 1, MAB_PIPE_THREADS, 0, ctx->stream, P, ctx->d_reads, n_seq, (const uint8_t *)ctx->d_ws, R.rlen_init, R.init_known); S.n_launches++; }
 		RT_MEMSET_ASYNC(&ctx->d_ctr->work_next, 0, sizeof(unsigned int), ctx->stream);
 		if(ev) { RT_EVENT_RECORD(ctx->rev[3 * round + 1], ctx->stream); }
 		RT_LAUNCH(k_extend, R.ext_ctas, 32 * MAB_WARPS_PER_CTA, 1024 + 4 * MAB_TILE_WORDS * MAB_WARPS_PER_CTA, ctx->stream, P, R.d_base, (const uint8_t *)ctx->d_ntail, ctx->d_reads, (const uint32_t *)ctx->d_order, n_seq, ctx->d_ws,
@@ -519,7 +519,7 @@ static int pipeline_run(mab_ctx *ctx, const uint8_t *d_base, const PipeShape &sh
 	RunState &R = ctx->rs;
 	const uint32_t n_seq = sh.n_seq;
 	double t_sub = RT_WALL_MS();
-	R.sh = sh; R.d_base = d_base;
+	R.sh = sh; R.d_base = d_base; R.rlen_init = rlen_init; R.init_known = init_known;
 	{ int rc = pin_reserve(ctx, ctx->pin_user + 2 * sizeof(BatchCounters) + 256); if(rc) { return rc; } }
 	{ int rc = grow(&ctx->d_recs, &ctx->recs_cap, 16ull * sh.span + 256); if(rc) { return rc; } }
 	{ int rc = grow(&ctx->d_frames, &ctx->frames_cap, 4ull * 8 * MAB_RS_FRAME * ((uint64_t)n_seq + 8)); if(rc) { return rc; } }
@@ -559,8 +559,9 @@ static int pipeline_run(mab_ctx *ctx, const uint8_t *d_base, const PipeShape &sh
 		CK(RT_MEMSET_ASYNC(ctx->d_ctr, 0, sizeof(BatchCounters), ctx->stream));
 		if(timed) { RT_EVENT_RECORD(ctx->ev[1], ctx->stream); }
 		RT_LAUNCH(k_seed_scan, R.seed_ctas, 32 * MAB_WARPS_PER_CTA, 2560 * MAB_WARPS_PER_CTA, ctx->stream, P, d_base, ctx->d_reads, n_seq, ctx->d_recs);
+		RT_LAUNCH(k_seed_probe, R.seed_ctas, 32 * MAB_WARPS_PER_CTA, 0, ctx->stream, P, ctx->d_reads, n_seq, ctx->d_recs);
 		RT_LAUNCH(k_size, 1, MAB_PIPE_THREADS, 0, ctx->stream, ctx->d_reads, n_seq, ctx->ws_cap, ctx->d_ctr);
-		S.n_launches += 2;
+		S.n_launches += 3;
 		pipe_rounds(ctx, true, timed);
 		S.ms_wall_submit += (float)(RT_WALL_MS() - t_sub);
 		{ int rc = pipe_verify(ctx, rlen_init, init_known); if(rc) { return rc; } }
@@ -759,6 +760,7 @@ extern "C" uint64_t mab_seed_chain(mab_ctx *ctx, const uint8_t *seq, uint32_t le
 	uint32_t *d_rec = nullptr;
 	if(!RT_OK(RT_MALLOC(&d_rec, 16ull * len + 256))) { RT_FREE(d_seq); RT_FREE(d_r); RT_FREE(d_fr); return 0; }
 	RT_LAUNCH(k_seed_scan, 1, 32, 2560, ctx->stream, P, (const uint8_t *)d_seq, d_r, 1u, d_rec);
+	RT_LAUNCH(k_seed_probe, 1, 32, 0, ctx->stream, P, d_r, 1u, d_rec);
 	ctx_sync(ctx);
 	RT_MEMCPY_D2H_ASYNC(&r, d_r, sizeof(r), ctx->stream);
 	uint64_t ns = 0;

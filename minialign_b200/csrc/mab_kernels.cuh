@@ -32,11 +32,10 @@ __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t x, int lane, uint32_
 }
 
 /* ---------------------------------------------------------------- k_seed_scan / k_seed_expand */
-/* k_seed_scan: the sketch + probe pass.  Every minimizer with 0 < n <= occ[n_occ - 1] occurrences leaves a 16 B record
- * {qs, n, byte offset of its occurrence array in the index image (lo, hi)} in emission order at recs[4 * (seq_ofs + j)]
- * (a read emits at most one minimizer per base, so its slice of the block-sized record array cannot overflow), and the
- * per-read totals size the workspaces.  k_seed_expand then only replays the records (mm_collect_seed / mm_expand,
- * minialign.c:3420-3493): no second sketch, no second probe.
+/* k_seed_scan: the sketch pass.  Every minimizer the read emits leaves a 16 B record {hash (lo, hi), qs, 0} in emission order at
+ * recs[4 * (seq_ofs + j)] (a read emits at most one minimizer per base, so its slice of the block-sized record array cannot
+ * overflow).  k_seed_probe turns the records into {qs, n, occurrence array offset} (one batched probe pass), k_seed_expand
+ * replays them (mm_collect_seed / mm_expand, minialign.c:3420-3493): one sketch, one probe per minimizer.
  * shared memory per warp: five 64-entry rings of encoded minimizer candidates (u64): 2560 B */
 __global__ void k_seed_scan(DevParams P, const uint8_t *base, ReadRec *reads, uint32_t n_reads, uint32_t *recs)
 {
@@ -45,7 +44,6 @@ __global__ void k_seed_scan(DevParams P, const uint8_t *base, ReadRec *reads, ui
 	uint64_t *ring = (uint64_t *)smem + 320 * wib;
 	uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
 	uint64_t const k = P.k, w = P.w, kk = k - 1, shift1 = 2 * kk, mask = (1ull << (2 * k)) - 1;
-	uint32_t const max_occ = P.occ[P.n_occ - 1], resc_occ = P.occ[0];
 	for(uint32_t rid = gw; rid < n_reads; rid += nw) {
 		ReadRec *r = &reads[rid];
 		uint32_t len = r->len;
@@ -56,7 +54,7 @@ __global__ void k_seed_scan(DevParams P, const uint8_t *base, ReadRec *reads, ui
 		const uint8_t *seq = base + r->seq_ofs;
 		uint32_t *rec = recs + 4ull * r->seq_ofs;
 		uint32_t npos = len - (uint32_t)kk;
-		uint32_t tot_seeds = 0, tot_seeds0 = 0, tot_resc = 0, n_words = 0, n_rec = 0;
+		uint32_t n_words = 0, n_rec = 0;
 		uint64_t vcarry = 0;				/* u: previous window minimum */
 		uint32_t idx_carry = (uint32_t)w;	/* decoder state: previous emitted in-block index (v = w), number of block starts */
 		uint32_t nblk_carry = 0;
@@ -141,27 +139,49 @@ __global__ void k_seed_scan(DevParams P, const uint8_t *base, ReadRec *reads, ui
 			uint32_t blkcnt = nblk_carry + (uint32_t)__popc(nbm & ((2u << lane) - 1));		/* inclusive */
 			if(em) { int last = 31 - __clz((int)em); idx_carry = __shfl_sync(MAB_FULL, myidx, last); }
 			nblk_carry += (uint32_t)__popc(nbm);
-			/* probe */
-			uint32_t n = 0; const uint8_t *occ = nullptr; uint32_t qs = 0;
+			/* leave the minimizer for the probe pass: {hash (lo, hi), query position word, 0} in emission order */
 			if(emit) {
 				uint64_t fr = (v >> 7) & 1, h = v >> 8;
 				uint64_t bpos = (uint64_t)(blkcnt - 1) * w + myidx;
-				occ = idx_get(P, h, &n);
-				qs = (uint32_t)((bpos + (k & (0 - fr))) ^ (0 - fr));
-				if(n > max_occ) { n = 0; occ = nullptr; }
+				uint32_t qs = (uint32_t)((bpos + (k & (0 - fr))) ^ (0 - fr));
+				uint4 e; e.x = (uint32_t)h; e.y = (uint32_t)(h >> 32); e.z = qs; e.w = 0;
+				((uint4 *)rec)[n_rec + (uint32_t)__popc(em & ((1u << lane) - 1))] = e;
 			}
-			uint32_t hit = __ballot_sync(MAB_FULL, n != 0);
-			if(n != 0) {
-				uint32_t *s = rec + 4ull * (n_rec + (uint32_t)__popc(hit & ((1u << lane) - 1)));
-				uint64_t ofs = (uint64_t)(occ - P.idx);
-				s[0] = qs; s[1] = n; s[2] = (uint32_t)ofs; s[3] = (uint32_t)(ofs >> 32);
-				tot_seeds += n; tot_seeds0 += n > resc_occ ? 0 : n; tot_resc += n > resc_occ;
-			}
-			n_rec += (uint32_t)__popc(hit);
+			n_rec += (uint32_t)__popc(em);
 			__syncwarp();
 		}
+		if(lane == 0) { r->n_words = n_words; r->n_rec = n_rec; }
+	}
+}
+
+/* k_seed_probe: the index probes of a read, 32 minimizers at a time (mm_idx_get, minialign.c:2727-2748).  Sketching and probing
+ * are separate passes on purpose: inside the sketch loop a probe is three dependent loads that only the ~6 emitting lanes of a
+ * 32-position step issue and that the whole warp then waits for; here every lane has its own minimizer, a warp keeps 32
+ * independent probe chains in flight and nothing else waits for them.  A record becomes {qs, n, byte offset of the occurrence
+ * array in the index image (lo, hi)}; n = 0 drops the minimizer (absent, or more frequent than occ[n_occ - 1], 3479); the
+ * per-read totals size the workspaces. */
+__global__ void k_seed_probe(DevParams P, ReadRec *reads, uint32_t n_reads, uint32_t *recs)
+{
+	int lane = threadIdx.x & 31;
+	uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+	uint32_t const max_occ = P.occ[P.n_occ - 1], resc_occ = P.occ[0];
+	for(uint32_t rid = gw; rid < n_reads; rid += nw) {
+		ReadRec *r = &reads[rid];
+		if(r->state != 0) { continue; }
+		uint4 *rec = (uint4 *)(recs + 4ull * r->seq_ofs);
+		uint32_t n_rec = r->n_rec, tot_seeds = 0, tot_seeds0 = 0, tot_resc = 0;
+		for(uint32_t j = lane; j < n_rec; j += 32) {
+			uint4 e = rec[j];
+			uint32_t n = 0;
+			const uint8_t *occ = idx_get(P, (uint64_t)e.x | (uint64_t)e.y << 32, &n);
+			if(n > max_occ) { n = 0; }
+			uint64_t ofs = n ? (uint64_t)(occ - P.idx) : 0;
+			uint4 o; o.x = e.z; o.y = n; o.z = (uint32_t)ofs; o.w = (uint32_t)(ofs >> 32);
+			rec[j] = o;
+			tot_seeds += n; tot_seeds0 += n > resc_occ ? 0 : n; tot_resc += n > resc_occ;
+		}
 		tot_seeds = __reduce_add_sync(MAB_FULL, tot_seeds); tot_seeds0 = __reduce_add_sync(MAB_FULL, tot_seeds0); tot_resc = __reduce_add_sync(MAB_FULL, tot_resc);
-		if(lane == 0) { r->tot_seeds = tot_seeds; r->tot_seeds0 = tot_seeds0; r->tot_resc = tot_resc; r->n_words = n_words; r->n_rec = n_rec; }
+		if(lane == 0) { r->tot_seeds = tot_seeds; r->tot_seeds0 = tot_seeds0; r->tot_resc = tot_resc; }
 	}
 }
 

@@ -140,7 +140,7 @@ __global__ void k_size(ReadRec *reads, uint32_t n, uint64_t ws_cap, BatchCounter
  * (mm_search_load_root, minialign.c:3838-3848) and leaves the reference length of the last one it loaded behind; which chains
  * those are is known from the list alone.  Reads that only load a chain in a rescue round, exhausted chain budgets and the first
  * reads of the batch (their predecessor is in the previous batch) are what k_rlen_verify is for. */
-__global__ void k_rlen_predict(DevParams P, ReadRec *reads, uint32_t n, const uint8_t *ws)
+__global__ void k_rlen_predict(DevParams P, ReadRec *reads, uint32_t n, const uint8_t *ws, uint32_t rlen_init, uint32_t init_known)
 {
 	__shared__ uint64_t sm[34];
 	uint64_t carry = 0;
@@ -165,7 +165,7 @@ __global__ void k_rlen_predict(DevParams P, ReadRec *reads, uint32_t n, const ui
 		}
 		uint64_t tot, e = block_excl_max(x, sm, &tot);
 		if(carry > e) { e = carry; }
-		if(active) { uint32_t v = e != 0 ? (uint32_t)e : MAB_RLEN_OWN; r->rlen_in = v; r->rlen_cur = v; r->rlen_used = v; }
+		if(active) { uint32_t v = e != 0 ? (uint32_t)e : (init_known ? rlen_init : MAB_RLEN_OWN); r->rlen_in = v; r->rlen_cur = v; r->rlen_used = v; }
 		if(tot > carry) { carry = tot; }
 	}
 }
