@@ -135,6 +135,11 @@ struct StepK {
 	uint32_t selR, selD;		/* PRMT selectors of the two band shifts: the edge lane pulls in a zero byte instead of its neighbour */
 	uint32_t insA, insB;		/* bit-select masks that drop the new base into cell 0 (lane 0, low half) / cell W-1 (last lane, high half) */
 	uint32_t accw;				/* DP4A weights: lane 0 contributes +delta[0], the last lane -delta[W-1] to the direction accumulator */
+	/* the packed step constants as plain 32-bit vector registers.  The assembler keeps a warp-uniform 16x2 operand as two 16-bit
+	 * halves in uniform registers (LDCU.U16) and rebuilds the pair with two moves and a PRMT in front of every use: 5 PRMT + 7
+	 * moves per anti-diagonal.  OR-ing in a per-lane word that is zero on every lane, but not provably so (lane (lane + 1) & 1), makes the
+	 * value thread-varying in its eyes: one ordinary register, usable as it is. */
+	uint32_t gfh1, gfv1, adjh1, adjv1, ofs;
 	const uint8_t *lut;
 };
 __device__ __forceinline__ StepK make_stepk(const DpCtx &c)
@@ -145,9 +150,15 @@ __device__ __forceinline__ StepK make_stepk(const DpCtx &c)
 	k.selR = is0 ? 0x5444u : 0x5432u; k.selD = isL ? 0x0032u : 0x5432u;
 	k.insA = is0 ? 0x0000ffffu : 0u; k.insB = isL ? 0xffff0000u : 0u;
 	k.accw = is0 ? 0x00000100u : (isL ? 0xff000000u : 0u);
+	const DevParams &P = *c.P;
 #ifndef MAB_EMU
 	/* keep the per-lane words in registers: without the barrier the compiler re-derives them from the lane id every step */
 	asm volatile("" : "+r"(k.selR), "+r"(k.selD), "+r"(k.insA), "+r"(k.insB), "+r"(k.accw));
+#endif
+	const uint32_t lane_zero = ((uint32_t)c.lane * ((uint32_t)c.lane + 1u)) & 1u;	/* a product of consecutive numbers is even */
+	k.gfh1 = P.K_GFH1 | lane_zero; k.gfv1 = P.K_GFV1 | lane_zero; k.adjh1 = P.K_ADJH1 | lane_zero; k.adjv1 = P.K_ADJV1 | lane_zero; k.ofs = P.K_OFS | lane_zero;
+#ifndef MAB_EMU
+	asm volatile("" : "+r"(k.gfh1), "+r"(k.gfv1), "+r"(k.adjh1), "+r"(k.adjv1), "+r"(k.ofs));
 #endif
 	return k;
 }
@@ -185,11 +196,11 @@ __device__ __forceinline__ uint32_t vec_core(const DevParams &P, const StepK &k,
 	const uint32_t EPS = 0x00010001u, ONE = 0x00010001u;
 	uint32_t x = v.wa | v.wb;
 	uint32_t S = *(const uint32_t *)(k.lut + ((x | (x >> 12)) & 0x3fcu));
-	uint32_t dfh = __vadd2(v.V, P.K_GFH1), dfv = __vadd2(v.A, P.K_GFV1);
+	uint32_t dfh = __vadd2(v.V, k.gfh1), dfv = __vadd2(v.A, k.gfv1);
 	uint32_t T = __vimax3_s16x2(S, dfh, dfv);
 	T = __viaddmax_s16x2(v.E, EPS, T);
 	T = __viaddmax_s16x2(v.F, EPS, T);
-	uint32_t TE = __viaddmax_s16x2(v.E, P.K_ADJH1, T), TF = __viaddmax_s16x2(v.F, P.K_ADJV1, T);
+	uint32_t TE = __viaddmax_s16x2(v.E, k.adjh1, T), TF = __viaddmax_s16x2(v.F, k.adjv1, T);
 	uint32_t bits = 0;
 	if(MASKS) {
 		/* T is the maximum, so T - x is 0..255 in the high byte and "min.u16 against ONE" leaves ONE set <=> not equal */
@@ -203,7 +214,7 @@ __device__ __forceinline__ uint32_t vec_core(const DevParams &P, const StepK &k,
 	uint32_t Pp = not_fma(v.A, P.K_M1), N = not_fma(v.V, P.K_M1);
 	v.E = __vadd2(TE, Pp); v.F = __vadd2(TF, N);
 	v.V = __vadd2(Pp, T); v.A = __vadd2(T, N);
-	uint32_t dH = __vadd2(P.K_OFS, DOWN ? v.V : v.A);										/* _fill_update_delta (ofsh == ofsv) */
+	uint32_t dH = __vadd2(k.ofs, DOWN ? v.V : v.A);										/* _fill_update_delta (ofsh == ofsv) */
 	v.delta = __vadd2(v.delta, dH);														/* wraps like int8 */
 	v.ndrop = __vmaxs2(__viaddmin_s16x2(v.ndrop, h8_to_s16(dH), 0x00800080u), 0xff81ff81u);	/* -(drop subs delta), saturating */
 	v.acc += __reduce_add_sync(MAB_FULL, dp4a_ss(dH, k.accw, 0));							/* _dir_update */

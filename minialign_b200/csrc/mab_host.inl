@@ -64,6 +64,7 @@ struct mab_ctx {
 	uint8_t *d_io = nullptr; uint64_t io_cap = 0;			/* [ofs u64 x n][len u32 x n] of the record-level entry point */
 	BatchCounters hc;					/* counters of the last batch */
 	RunState rs;
+	bool ext_wide = true;				/* MAB_EXT_WIDE=0: always the 80-register build of k_extend (A/B switch) */
 	/* text path (mab_text_*): the chunk, its index, the packed read block, the SAM text */
 	uint8_t *d_text = nullptr; uint64_t text_cap = 0;
 	uint8_t *d_base = nullptr; uint64_t base_cap = 0;
@@ -187,6 +188,7 @@ static int ctx_private_init(mab_ctx *ctx)
 	CK(RT_SYNC_EVENT_CREATE(&ctx->sync_ev)); ctx->have_sync_ev = true;
 	RT_FUNC_MAX_SMEM(k_sortchain, 16 * MAB_SC_MAX + 2048);
 	ctx->n_slots = RT_EXTEND_SLOTS(ctx->n_sm);
+	if(const char *e = getenv("MAB_EXT_WIDE")) { ctx->ext_wide = atoi(e) != 0; }
 	if(const char *e = getenv("MAB_EXT_CTAS")) {										/* resident k_extend CTAs per SM actually launched (<= MAB_EXT_CTAS_PER_SM) */
 		int v = atoi(e);
 		if(v >= 1 && v <= MAB_EXT_CTAS_PER_SM) { ctx->n_slots = ctx->n_sm * MAB_WARPS_PER_CTA * (uint32_t)v; }
@@ -474,8 +476,13 @@ static void pipe_rounds(mab_ctx *ctx, bool first, bool timed)
 		if(first && round == 0) { RT_LAUNCH(k_rlen_predict, 1, MAB_PIPE_THREADS, 0, ctx->stream, P, ctx->d_reads, n_seq, (const uint8_t *)ctx->d_ws, R.rlen_init, R.init_known); S.n_launches++; }
 		RT_MEMSET_ASYNC(&ctx->d_ctr->work_next, 0, sizeof(unsigned int), ctx->stream);
 		if(ev) { RT_EVENT_RECORD(ctx->rev[3 * round + 1], ctx->stream); }
-		RT_LAUNCH(k_extend, R.ext_ctas, 32 * MAB_WARPS_PER_CTA, 1024 + 4 * MAB_TILE_WORDS * MAB_WARPS_PER_CTA, ctx->stream, P, R.d_base, (const uint8_t *)ctx->d_ntail, ctx->d_reads, (const uint32_t *)ctx->d_order, n_seq, ctx->d_ws,
-			ctx->d_arenas, R.arena_stride, R.blk_cap, ctx->d_pool, ctx->pool_cap / 4, ctx->d_ctr, round, P.n_occ - 1);
+		if(ctx->n_slots <= ctx->n_sm * MAB_WARPS_PER_CTA * 4 && ctx->ext_wide) {
+			RT_LAUNCH((k_extend<4>), R.ext_ctas, 32 * MAB_WARPS_PER_CTA, 1024 + 4 * MAB_TILE_WORDS * MAB_WARPS_PER_CTA, ctx->stream, P, R.d_base, (const uint8_t *)ctx->d_ntail, ctx->d_reads, (const uint32_t *)ctx->d_order, n_seq, ctx->d_ws,
+				ctx->d_arenas, R.arena_stride, R.blk_cap, ctx->d_pool, ctx->pool_cap / 4, ctx->d_ctr, round, P.n_occ - 1);
+		} else {
+			RT_LAUNCH((k_extend<MAB_EXT_CTAS_PER_SM>), R.ext_ctas, 32 * MAB_WARPS_PER_CTA, 1024 + 4 * MAB_TILE_WORDS * MAB_WARPS_PER_CTA, ctx->stream, P, R.d_base, (const uint8_t *)ctx->d_ntail, ctx->d_reads, (const uint32_t *)ctx->d_order, n_seq, ctx->d_ws,
+				ctx->d_arenas, R.arena_stride, R.blk_cap, ctx->d_pool, ctx->pool_cap / 4, ctx->d_ctr, round, P.n_occ - 1);
+		}
 		S.n_launches += 3;
 		if(ev) { RT_EVENT_RECORD(ctx->rev[3 * round + 2], ctx->stream); }
 	}

@@ -581,7 +581,10 @@ __device__ __forceinline__ SecDesc make_sec(const uint8_t *base, uint32_t len, u
 
 /* ---------------------------------------------------------------- k_extend */
 /* shared memory per CTA: 1 KB score LUT + per warp two 2.1 KB tiles (traceback mask blocks, double-buffered; the first doubles as sort scratch) */
-__global__ void __launch_bounds__(32 * MAB_WARPS_PER_CTA, MAB_EXT_CTAS_PER_SM) k_extend(DevParams P, const uint8_t *base, const uint8_t *ntail, ReadRec *reads, const uint32_t *order, uint32_t n_reads, uint8_t *ws,
+/* CTAS = resident CTAs per SM the register budget is cut for: 6 (80 registers) when the kernel has the GPU to itself, 4 (128
+ * registers, no spills) for the pipelined contexts, which launch 4 per SM anyway and leave the rest of the SM to the other chunks */
+template <int CTAS>
+__global__ void __launch_bounds__(32 * MAB_WARPS_PER_CTA, CTAS) k_extend(DevParams P, const uint8_t *base, const uint8_t *ntail, ReadRec *reads, const uint32_t *order, uint32_t n_reads, uint8_t *ws,
 	uint8_t *arenas, uint64_t arena_stride, uint32_t blk_cap, uint32_t *pool, uint64_t pool_cap, BatchCounters *ctr, uint32_t round, uint32_t last_round)
 {
 	MAB_DYN_SMEM(smem);
