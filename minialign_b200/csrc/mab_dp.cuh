@@ -140,6 +140,7 @@ struct StepK {
 	 * moves per anti-diagonal.  OR-ing in a per-lane word that is zero on every lane, but not provably so (lane (lane + 1) & 1), makes the
 	 * value thread-varying in its eyes: one ordinary register, usable as it is. */
 	uint32_t gfh1, gfv1, adjh1, adjv1, ofs;
+	uint32_t one, two;			/* 1 and 2 as run-time values (multipliers of the FMA-pipe increments / packs) */
 	const uint8_t *lut;
 };
 __device__ __forceinline__ StepK make_stepk(const DpCtx &c)
@@ -156,6 +157,7 @@ __device__ __forceinline__ StepK make_stepk(const DpCtx &c)
 	asm volatile("" : "+r"(k.selR), "+r"(k.selD), "+r"(k.insA), "+r"(k.insB), "+r"(k.accw));
 #endif
 	const uint32_t lane_zero = ((uint32_t)c.lane * ((uint32_t)c.lane + 1u)) & 1u;	/* a product of consecutive numbers is even */
+	k.one = 0u - P.K_M1; k.two = k.one + k.one;
 	k.gfh1 = P.K_GFH1 | lane_zero; k.gfv1 = P.K_GFV1 | lane_zero; k.adjh1 = P.K_ADJH1 | lane_zero; k.adjv1 = P.K_ADJV1 | lane_zero; k.ofs = P.K_OFS | lane_zero;
 #ifndef MAB_EMU
 	asm volatile("" : "+r"(k.gfh1), "+r"(k.gfv1), "+r"(k.adjh1), "+r"(k.adjv1), "+r"(k.ofs));
@@ -169,6 +171,41 @@ __device__ __forceinline__ int dp4a_ss(uint32_t a, uint32_t b, int c)
 	return c;
 #else
 	return __dp4a((int)a, (int)b, c);
+#endif
+}
+
+/* byte offset into the score LUT from the OR of the two windows: (x | x >> 12) & 0x3fc as one shift and one three-input
+ * logic operation (the compiler ORs the two windows in again and masks separately: one ALU instruction more per step) */
+__device__ __forceinline__ uint32_t lut_index(uint32_t x)
+{
+#ifdef MAB_EMU
+	return (x | (x >> 12)) & 0x3fcu;
+#else
+	uint32_t d;
+	asm("lop3.b32 %0, %1, %2, 0x3fc, 0xA8;" : "=r"(d) : "r"(x >> 12), "r"(x));		/* (a | b) & c */
+	return d;
+#endif
+}
+/* x + 1 on the FMA pipe (the step is bound by the ALU pipe; `one` is a run-time 1 the assembler cannot fold into an add) */
+__device__ __forceinline__ uint32_t inc_fma(uint32_t x, uint32_t one)
+{
+#ifdef MAB_EMU
+	(void)one; return x + 1;
+#else
+	uint32_t d;
+	asm("mad.lo.u32 %0, %1, %2, %2;" : "=r"(d) : "r"(x), "r"(one));
+	return d;
+#endif
+}
+
+__device__ __forceinline__ uint32_t mad_fma(uint32_t a, uint32_t m, uint32_t b)		/* a * m + b with a run-time multiplier: stays an IMAD */
+{
+#ifdef MAB_EMU
+	return a * m + b;
+#else
+	uint32_t d;
+	asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(m), "r"(b));
+	return d;
 #endif
 }
 
@@ -195,7 +232,7 @@ __device__ __forceinline__ uint32_t vec_core(const DevParams &P, const StepK &k,
 {
 	const uint32_t EPS = 0x00010001u, ONE = 0x00010001u;
 	uint32_t x = v.wa | v.wb;
-	uint32_t S = *(const uint32_t *)(k.lut + ((x | (x >> 12)) & 0x3fcu));
+	uint32_t S = *(const uint32_t *)(k.lut + lut_index(x));
 	uint32_t dfh = __vadd2(v.V, k.gfh1), dfv = __vadd2(v.A, k.gfv1);
 	uint32_t T = __vimax3_s16x2(S, dfh, dfv);
 	T = __viaddmax_s16x2(v.E, EPS, T);
@@ -209,7 +246,7 @@ __device__ __forceinline__ uint32_t vec_core(const DevParams &P, const StepK &k,
 		uint32_t g_e = __vminu2(TE ^ T, ONE), g_f = __vminu2(TF ^ T, ONE);				/* set <=> te != t */
 		uint32_t NH = n_fh & n_e, NV = n_fv & n_f;										/* ~h, ~v */
 		uint32_t NE = (n_e | ~n_fh) & g_e, NF = (n_f | ~n_fv) & g_f;						/* ~e, ~f */
-		bits = (NF * 2 + NE) * 4 + (NV * 2 + NH);										/* disjoint bits: three IMADs pack the nibble */
+		bits = (mad_fma(NF, k.two, NE)) * 4 + (NV * 2 + NH);								/* disjoint bits: three IMADs pack the nibble */
 	}
 	uint32_t Pp = not_fma(v.A, P.K_M1), N = not_fma(v.V, P.K_M1);
 	v.E = __vadd2(TE, Pp); v.F = __vadd2(TF, N);
@@ -228,10 +265,10 @@ template <bool MASKS>
 __device__ __forceinline__ uint32_t bulk_step(const DevParams &P, const StepK &k, Vec &v, uint32_t an, uint32_t bn, BulkCnt &n)
 {
 	if(v.acc < 0) {																		/* warp-uniform */
-		n.dir = n.dir * 2 + 1; shift_down(k, v, __shfl_sync(MAB_FULL, bn, n.bcnt)); n.bcnt++;
+		n.dir = n.dir * 2 + 1; shift_down(k, v, __shfl_sync(MAB_FULL, bn, n.bcnt)); n.bcnt = inc_fma(n.bcnt, k.one);
 		return vec_core<true, MASKS>(P, k, v);
 	}
-	n.dir = n.dir * 2; shift_right(k, v, __shfl_sync(MAB_FULL, an, n.acnt)); n.acnt++;
+	n.dir = n.dir * 2; shift_right(k, v, __shfl_sync(MAB_FULL, an, n.acnt)); n.acnt = inc_fma(n.acnt, k.one);
 	return vec_core<false, MASKS>(P, k, v);
 }
 template <bool MASKS>
