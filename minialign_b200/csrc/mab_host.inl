@@ -618,8 +618,8 @@ extern "C" int mab_map_batch(mab_ctx *ctx, const uint8_t *seq_block, uint64_t bl
 	PipeShape sh; sh.n_seq = n_seq; sh.maxlen = 0; sh.tot_len = 0; sh.span = 0;
 	for(uint32_t i = 0; i < n_seq; i++) {
 		sh.maxlen = std::max(sh.maxlen, seq_len[i]); sh.tot_len += seq_len[i]; sh.span = std::max<uint64_t>(sh.span, seq_ofs[i] + seq_len[i]);
-		/* contract (header): ascending, non-overlapping, >= 64 bytes of margin behind every read, inside the block */
-		if(seq_ofs[i] + seq_len[i] + 64 > block_size || (i > 0 && seq_ofs[i] < seq_ofs[i - 1] + seq_len[i - 1] + 64)) { g_err = "mab_map_batch: reads must be ascending, non-overlapping and followed by 64 bytes of margin inside the block"; return MAB_EINVAL; }
+		/* contract (header): ascending, non-overlapping, 64 readable bytes behind the last read inside the block */
+		if(seq_ofs[i] + seq_len[i] + 64 > block_size || (i > 0 && seq_ofs[i] < seq_ofs[i - 1] + seq_len[i - 1])) { g_err = "mab_map_batch: reads must be ascending and non-overlapping, with 64 bytes of margin behind the last one inside the block"; return MAB_EINVAL; }
 	}
 	RT_EVENT_RECORD(ctx->ev[0], ctx->stream);
 	const uint8_t *d_base;
