@@ -42,9 +42,9 @@ GENOMES = {
                     name="sacCer3-like 12.1 Mb / 17 contigs synthetic reference x100 PBSIM-CLR-like reads (20k+-2k, acc 0.88+-0.07), -xpacbio, one read set sharded by chunk (BASELINE configs[2])"),
 }
 BYTES_PER_BASE = 160.0          # algorithmic HBM bytes per read base
-TRAFFIC_PER_BASE = 292.0        # dram__bytes_read.sum + dram__bytes_write.sum of k_extend per read base, ncu --set full capture
-                                # (profiles/r01_ncu_k_extend_full.json: 49.3 GB for the 169 Mbase launch)
-NCU_PIPE_ALU_PCT = 62.6         # sm__inst_executed_pipe_alu of k_extend in the same capture
+TRAFFIC_PER_BASE = 293.0        # dram__bytes_read.sum + dram__bytes_write.sum of k_extend per read base, ncu --set full capture
+                                # (profiles/r02_ncu_k_extend_full.json: 47.0 + 52.0 GB for the 337.5 Mbase launch)
+NCU_PIPE_ALU_PCT = 62.0         # sm__inst_executed_pipe_alu of k_extend in the same capture (issue slots busy 75.1 %)
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "minialign")
 OUR_BIN = os.path.join(ROOT, "minialign_b200", "minialign-b200")
 
