@@ -47,8 +47,11 @@ typedef struct {
 	int8_t gi, ge, gfa, gfb;	/* positive penalties; combined (piecewise-affine) model: all non-zero */
 	int8_t xdrop;				/* -Y */
 	uint8_t _pad[3];
-	uint32_t flags;				/* reserved, must be 0 */
+	uint32_t flags;				/* MAB_FLAG_* */
 } mab_params_t;
+
+/* the caller keeps the index image alive and unchanged for the lifetime of the context (and its clones): no host copy is made */
+#define MAB_FLAG_BORROW_INDEX 1u
 
 typedef struct mab_ctx mab_ctx;
 

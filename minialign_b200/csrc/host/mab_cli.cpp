@@ -22,6 +22,7 @@
 #include <map>
 #include <fcntl.h>
 #include <sys/stat.h>
+#include <sys/mman.h>
 #include <cerrno>
 #include <memory>
 #include <mutex>
@@ -35,49 +36,61 @@
 static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 /* ---- .mai loader ---- */
-/* The container is a sequence of independently deflated frames (<= 1 MiB raw each): read them all, inflate them on all host
- * cores (the reference does the same with its worker threads), concatenate. */
-static bool load_mai(const char *path, std::vector<uint8_t> &blob)
+/* The container is a sequence of independently deflated frames of 1 MiB raw each (PG_BLOCK_SIZE, minialign.c:1137; the last one
+ * shorter).  The file is mapped, the frame table read off it, and every frame is inflated by one of the host threads straight
+ * into its place in the image: no intermediate copies (a human-sized index is ~15 GB raw). */
+struct MaiImage {
+	uint8_t *raw = nullptr; size_t raw_size = 0;		/* the inflated stream: 12-byte {magic, size} header + payload */
+	const uint8_t *blob = nullptr; size_t size = 0;	/* the payload: what mab_init takes */
+	std::vector<uint8_t> own;							/* payload built here (FASTA reference) */
+	~MaiImage() { free(raw); }
+};
+static bool load_mai(const char *path, MaiImage &im)
 {
-	FILE *fp = fopen(path, "rb");
-	if(!fp) { return false; }
-	std::vector<std::vector<uint8_t>> frames;
-	while(true) {
-		char magic[4]; uint32_t len;
-		if(fread(magic, 1, 4, fp) != 4 || memcmp(magic, "PG00", 4) != 0) { break; }
-		if(fread(&len, 4, 1, fp) != 1 || len == 0xffffffffu || len == 0) { break; }
-		frames.emplace_back(len);
-		if(fread(frames.back().data(), 1, len, fp) != len) { fclose(fp); return false; }
+	int fd = open(path, O_RDONLY);
+	if(fd < 0) { return false; }
+	struct stat st;
+	if(fstat(fd, &st) != 0 || st.st_size < 8) { close(fd); return false; }
+	const size_t fsz = (size_t)st.st_size;
+	const uint8_t *file = (const uint8_t *)mmap(nullptr, fsz, PROT_READ, MAP_PRIVATE, fd, 0);
+	close(fd);
+	if(file == MAP_FAILED) { return false; }
+	struct Frame { size_t ofs; uint32_t len; };
+	std::vector<Frame> frames;
+	for(size_t p = 0; p + 8 <= fsz;) {
+		uint32_t len; memcpy(&len, file + p + 4, 4);
+		if(memcmp(file + p, "PG00", 4) != 0 || len == 0xffffffffu || len == 0 || p + 8 + len > fsz) { break; }
+		frames.push_back({ p + 8, len }); p += 8 + (size_t)len;
 	}
-	fclose(fp);
-	if(frames.empty()) { return false; }
-	std::vector<std::vector<uint8_t>> raws(frames.size());
+	if(frames.empty()) { munmap((void *)file, fsz); return false; }
+	const size_t BS = 1 << 20;
+	im.raw = (uint8_t *)malloc(frames.size() * BS + 64);
+	if(!im.raw) { munmap((void *)file, fsz); return false; }
+	std::vector<uint32_t> out_len(frames.size(), 0);
 	std::atomic<size_t> next(0); std::atomic<bool> ok(true);
 	auto work = [&]() {
-		std::vector<uint8_t> obuf(1 << 21);
 		for(size_t i; (i = next.fetch_add(1)) < frames.size();) {
 			z_stream zs; memset(&zs, 0, sizeof(zs));
-			zs.next_in = frames[i].data(); zs.avail_in = (uInt)frames[i].size(); zs.next_out = obuf.data(); zs.avail_out = (uInt)obuf.size();
+			zs.next_in = (Bytef *)(file + frames[i].ofs); zs.avail_in = (uInt)frames[i].len; zs.next_out = im.raw + i * BS; zs.avail_out = (uInt)BS;
 			if(inflateInit2(&zs, 15) != Z_OK) { ok = false; return; }
 			int rc = inflate(&zs, Z_FINISH); inflateEnd(&zs);
 			if(rc != Z_STREAM_END) { ok = false; return; }
-			raws[i].assign(obuf.data(), obuf.data() + (obuf.size() - zs.avail_out));
+			out_len[i] = (uint32_t)(BS - zs.avail_out);
 		}
 	};
-	unsigned nth = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+	unsigned nth = std::max(1u, std::min(std::thread::hardware_concurrency(), 64u));
 	std::vector<std::thread> th;
 	for(unsigned t = 1; t < nth; t++) { th.emplace_back(work); }
 	work();
 	for(auto &x : th) { x.join(); }
+	munmap((void *)file, fsz);
 	if(!ok) { return false; }
-	std::vector<uint8_t> raw;
-	size_t tot = 0; for(auto &r : raws) { tot += r.size(); }
-	raw.reserve(tot);
-	for(auto &r : raws) { raw.insert(raw.end(), r.begin(), r.end()); }
-	if(raw.size() < 12) { return false; }
-	uint32_t magic; uint64_t size; memcpy(&magic, raw.data(), 4); memcpy(&size, raw.data() + 4, 8);
-	if(magic != 0x0849414du || raw.size() < 12 + size) { return false; }
-	blob.assign(raw.begin() + 12, raw.begin() + 12 + size);
+	for(size_t i = 0; i + 1 < frames.size(); i++) { if(out_len[i] != BS) { return false; } }		/* not the layout the reference writes */
+	im.raw_size = (frames.size() - 1) * BS + out_len.back();
+	if(im.raw_size < 12) { return false; }
+	uint32_t magic; uint64_t size; memcpy(&magic, im.raw, 4); memcpy(&size, im.raw + 4, 8);
+	if(magic != 0x0849414du || im.raw_size < 12 + size) { return false; }
+	im.blob = im.raw + 12; im.size = (size_t)size;
 	return true;
 }
 
@@ -326,18 +339,19 @@ int main(int argc, char **argv)
 	}
 	if(!o.w_set) { o.ip.w = (uint32_t)(int)(2.0 / 3.0 * o.ip.k + .499); }							/* default window size when -w is absent (minialign.c:6111) */
 	if(o.pos.size() < (o.dump.empty() ? 2u : 1u)) { fprintf(stderr, "usage: minialign-b200 [-x preset] [-T tags] <ref.fa|ref.mai> <reads.fa> [...] > out.sam\n       minialign-b200 [-x preset] -d <out.mai> <ref.fa>\n"); return 1; }
-	std::vector<uint8_t> blob;
-	if(!load_mai(o.pos[0].c_str(), blob)) {															/* not an index: a FASTA reference, build it here */
+	MaiImage im;
+	if(!load_mai(o.pos[0].c_str(), im)) {															/* not an index: a FASTA reference, build it here */
 		SeqReader rr(o.pos[0].c_str());
 		if(!rr.fp) { fprintf(stderr, "[E::main_align] failed to open index file `%s'. Please check file path and it exists.\n", o.pos[0].c_str()); return 1; }
 		std::vector<MabIdxSeq> refs; Rec r;
 		while(rr.next(r)) { if(r.seq.empty()) { continue; } MabIdxSeq q; q.name = r.name; q.seq = std::move(r.seq); refs.push_back(std::move(q)); }
 		std::string err;
-		if(!mab_build_index(refs, o.ip, blob, err)) { fprintf(stderr, "[E::main_index] failed to build index from `%s': %s\n", o.pos[0].c_str(), err.c_str()); return 1; }
+		if(!mab_build_index(refs, o.ip, im.own, err)) { fprintf(stderr, "[E::main_index] failed to build index from `%s': %s\n", o.pos[0].c_str(), err.c_str()); return 1; }
 		fprintf(stderr, "[M::main_index::%.3f] built index for %zu target sequence(s).\n", now() - t0, refs.size());
+		im.blob = im.own.data(); im.size = im.own.size();
 	}
 	if(!o.dump.empty()) {
-		if(!mab_write_mai(o.dump.c_str(), blob)) { fprintf(stderr, "[E::main_index] failed to write index to `%s'.\n", o.dump.c_str()); return 1; }
+		if(!mab_write_mai(o.dump.c_str(), std::vector<uint8_t>(im.blob, im.blob + im.size))) { fprintf(stderr, "[E::main_index] failed to write index to `%s'.\n", o.dump.c_str()); return 1; }
 		fprintf(stderr, "[M::main] Command: %s\n[M::main] Real time: %.3f sec\n", cmdline.c_str(), now() - t0);
 		return 0;
 	}
@@ -359,7 +373,8 @@ int main(int argc, char **argv)
 		std::vector<std::thread> th; std::vector<std::string> errs(devices.size());
 		for(size_t d = 0; d < devices.size(); d++) {
 			th.emplace_back([&, d]() {
-				mab_ctx *p = mab_init(blob.data(), blob.size(), &o.p, devices[d]);
+				mab_params_t prm = o.p; prm.flags |= MAB_FLAG_BORROW_INDEX;			/* `im` outlives the contexts */
+				mab_ctx *p = mab_init(im.blob, im.size, &prm, devices[d]);
 				if(!p) { errs[d] = mab_last_error(); return; }
 				ctxs[d] = p;
 				for(unsigned c = 1; c < std::max(1u, o.contexts); c++) { mab_ctx *q = mab_clone(p); if(!q) { errs[d] = mab_last_error(); return; } ctxs[c * devices.size() + d] = q; }

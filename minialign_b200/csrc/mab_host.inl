@@ -33,6 +33,7 @@ struct mab_ctx {
 	int device;
 	DevParams P;
 	std::shared_ptr<std::vector<uint8_t>> blob;	/* host copy of the index image (reference names / sequences for the printer); shared by clones */
+	const uint8_t *blob_ptr = nullptr;	/* = blob->data(), or the caller's image when it lends it (MAB_FLAG_BORROW_INDEX) */
 	mab_ctx *parent = nullptr;			/* clone: d_idx / d_ntail / d_thr belong to the parent */
 	uint8_t *d_idx = nullptr, *d_ntail = nullptr;
 	uint32_t n_sm = 0, n_slots = 0;
@@ -206,7 +207,11 @@ extern "C" mab_ctx *mab_init(const void *mai_blob, uint64_t size, const mab_para
 	if(!RT_OK(RT_SET_DEVICE(device))) { g_err = std::string("no usable CUDA device: ") + RT_ERRSTR(); delete ctx; return nullptr; }
 	ctx->n_sm = RT_SM_COUNT(device);
 	const uint8_t *b = (const uint8_t *)mai_blob;
-	try { ctx->blob = std::make_shared<std::vector<uint8_t>>(b, b + size); } catch(const std::bad_alloc &) { g_err = "host allocation failed"; delete ctx; return nullptr; }
+	if(params->flags & MAB_FLAG_BORROW_INDEX) { ctx->blob_ptr = b; }
+	else {
+		try { ctx->blob = std::make_shared<std::vector<uint8_t>>(b, b + size); } catch(const std::bad_alloc &) { g_err = "host allocation failed"; delete ctx; return nullptr; }
+		ctx->blob_ptr = ctx->blob->data();
+	}
 	DevParams &P = ctx->P;
 	memset(&P, 0, sizeof(P));
 	P.bkt_ofs = rd64(b); P.bkt_mask = rd64(b + 8);
@@ -240,7 +245,7 @@ extern "C" mab_ctx *mab_clone(mab_ctx *parent)
 	while(parent->parent != nullptr) { parent = parent->parent; }
 	mab_ctx *ctx = new mab_ctx();
 	ctx->parent = parent; ctx->device = parent->device; ctx->prm = parent->prm; ctx->P = parent->P; ctx->xcoef = parent->xcoef; ctx->n_sm = parent->n_sm;
-	ctx->blob = parent->blob; ctx->d_idx = parent->d_idx; ctx->d_ntail = parent->d_ntail; ctx->d_thr = parent->d_thr; ctx->thr_ok = parent->thr_ok;
+	ctx->blob = parent->blob; ctx->blob_ptr = parent->blob_ptr; ctx->d_idx = parent->d_idx; ctx->d_ntail = parent->d_ntail; ctx->d_thr = parent->d_thr; ctx->thr_ok = parent->thr_ok;
 	memset(&ctx->stats, 0, sizeof(ctx->stats));
 	if(!RT_OK(RT_USE_DEVICE(ctx->device))) { g_err = std::string("no usable CUDA device: ") + RT_ERRSTR(); delete ctx; return nullptr; }
 	CKP(RT_MALLOC(&ctx->d_tc, sizeof(TextCounters)));
@@ -267,7 +272,7 @@ extern "C" uint32_t mab_n_ref(const mab_ctx *ctx) { return ctx->P.n_ref; }
 extern "C" int mab_ref_info(const mab_ctx *ctx, uint32_t rid, const char **name, uint32_t *l_name, uint32_t *l_seq, const uint8_t **seq)
 {
 	if(rid >= ctx->P.n_ref) { return MAB_EINVAL; }
-	const uint8_t *b = ctx->blob->data(), *s = b + ctx->P.seq_ofs + 24ull * rid;
+	const uint8_t *b = ctx->blob_ptr, *s = b + ctx->P.seq_ofs + 24ull * rid;
 	if(seq) { *seq = b + rd64(s); }
 	if(name) { *name = (const char *)(b + rd64(s + 8)); }
 	if(l_seq) { *l_seq = rd32(s + 16); }
