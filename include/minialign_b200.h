@@ -114,6 +114,11 @@ typedef struct {
 } mab_stats_t;
 int mab_last_stats(const mab_ctx *ctx, mab_stats_t *out);
 
+/* Memory: free / total bytes of the context's device; the HBM the DP arenas of this context may take (default 40 GB; with very
+ * long reads or many contexts per GPU fewer warps stay resident instead of over-allocating: 8 MB per resident warp at 25 kb reads). */
+int mab_device_memory(const mab_ctx *ctx, uint64_t *free_bytes, uint64_t *total_bytes);
+void mab_set_arena_budget(mab_ctx *ctx, uint64_t bytes);
+
 /* When set, mab_map_batch takes seq_block as a DEVICE pointer already resident in HBM (bench.py's kernel-only arm). */
 int mab_set_device_input(mab_ctx *ctx, int on);
 

@@ -84,6 +84,9 @@ def load_library(lib_path: str | None = None):
     L.mab_clone.restype = C.c_void_p
     L.mab_clone.argtypes = [C.c_void_p]
     L.mab_destroy.argtypes = [C.c_void_p]
+    L.mab_device_memory.restype = C.c_int
+    L.mab_device_memory.argtypes = [C.c_void_p, u64p, u64p]
+    L.mab_set_arena_budget.argtypes = [C.c_void_p, C.c_uint64]
     L.mab_last_error.restype = C.c_char_p
     L.mab_n_ref.restype = C.c_uint32
     L.mab_n_ref.argtypes = [C.c_void_p]

@@ -368,6 +368,7 @@ int main(int argc, char **argv)
 	std::vector<int> devices = o.devices.empty() ? std::vector<int>{ o.device } : o.devices;
 	const unsigned n_ctx = std::max(1u, o.contexts) * (unsigned)devices.size();
 	double t_idx = now() - t0;
+	if(o.contexts > 1 && getenv("MAB_EXT_CTAS") == nullptr) { setenv("MAB_EXT_CTAS", "4", 1); }	/* contexts that run side by side launch 4 of the 6 possible extend CTAs per SM each */
 	std::vector<mab_ctx *> ctxs(n_ctx, nullptr);
 	{	/* one parent context per device (uploads the index), clones share its image; devices are set up in parallel */
 		std::vector<std::thread> th; std::vector<std::string> errs(devices.size());
@@ -378,6 +379,13 @@ int main(int argc, char **argv)
 				if(!p) { errs[d] = mab_last_error(); return; }
 				ctxs[d] = p;
 				for(unsigned c = 1; c < std::max(1u, o.contexts); c++) { mab_ctx *q = mab_clone(p); if(!q) { errs[d] = mab_last_error(); return; } ctxs[c * devices.size() + d] = q; }
+				/* what is free next to the index is shared by the contexts of this GPU: 60 % of a context's share for its DP arenas, the
+				 * rest for its text, read block, minimizer records, workspaces, result pool and SAM text */
+				uint64_t fr = 0, tot = 0;
+				if(mab_device_memory(p, &fr, &tot) == MAB_OK && fr > (8ull << 30)) {
+					uint64_t share = (fr - (4ull << 30)) / std::max(1u, o.contexts);
+					for(unsigned c = 0; c < std::max(1u, o.contexts); c++) { mab_set_arena_budget(ctxs[c * devices.size() + d], share * 6 / 10); }
+				}
 			});
 		}
 		for(auto &x : th) { x.join(); }

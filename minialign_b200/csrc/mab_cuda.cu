@@ -48,6 +48,7 @@ static inline cudaError_t RT_STREAM_SYNC(RT_STREAM s) { cudaError_t e = cudaStre
 static inline cudaError_t RT_EVENT_CREATE(RT_EVENT *e) { return cudaEventCreate(e); }
 static inline void RT_EVENT_DESTROY(RT_EVENT e) { cudaEventDestroy(e); }
 static inline void RT_STREAM_DESTROY(RT_STREAM s) { cudaStreamDestroy(s); }
+static inline cudaError_t RT_MEM_INFO(size_t *f, size_t *t) { return cudaMemGetInfo(f, t); }
 static inline cudaError_t RT_DEVICE_SYNC() { return cudaDeviceSynchronize(); }
 static inline cudaError_t RT_EVENT_SYNC(RT_EVENT e) { cudaError_t r = cudaEventSynchronize(e); if(r == cudaSuccess) { r = cudaGetLastError(); } return r; }
 static inline cudaError_t RT_SYNC_EVENT_CREATE(RT_EVENT *e) { return cudaEventCreateWithFlags(e, cudaEventBlockingSync | cudaEventDisableTiming); }

@@ -65,6 +65,7 @@ struct mab_ctx {
 	uint8_t *d_io = nullptr; uint64_t io_cap = 0;			/* [ofs u64 x n][len u32 x n] of the record-level entry point */
 	BatchCounters hc;					/* counters of the last batch */
 	RunState rs;
+	uint64_t arena_budget = 40ull << 30;	/* HBM the DP arenas of this context may take (mab_set_arena_budget) */
 	bool ext_wide = true;				/* MAB_EXT_WIDE=0: always the 80-register build of k_extend (A/B switch) */
 	/* text path (mab_text_*): the chunk, its index, the packed read block, the SAM text */
 	uint8_t *d_text = nullptr; uint64_t text_cap = 0;
@@ -287,6 +288,15 @@ extern "C" int mab_index_params(const mab_ctx *ctx, uint32_t *k, uint32_t *w, ui
 }
 extern "C" uint32_t mab_get_rlen(const mab_ctx *ctx) { return ctx->rlen_last; }
 extern "C" void mab_set_rlen(mab_ctx *ctx, uint32_t rlen) { ctx->rlen_last = rlen; }
+extern "C" int mab_device_memory(const mab_ctx *ctx, uint64_t *free_bytes, uint64_t *total_bytes)
+{
+	CK(RT_USE_DEVICE(ctx->device));
+	size_t f = 0, t = 0;
+	CK(RT_MEM_INFO(&f, &t));
+	if(free_bytes) { *free_bytes = f; } if(total_bytes) { *total_bytes = t; }
+	return MAB_OK;
+}
+extern "C" void mab_set_arena_budget(mab_ctx *ctx, uint64_t bytes) { ctx->arena_budget = bytes < (256ull << 20) ? (256ull << 20) : bytes; }
 extern "C" int mab_set_device_input(mab_ctx *ctx, int on) { ctx->device_input = on; return MAB_OK; }
 extern "C" int mab_last_stats(const mab_ctx *ctx, mab_stats_t *out) { *out = ctx->stats; return MAB_OK; }
 
@@ -542,7 +552,7 @@ static int pipeline_run(mab_ctx *ctx, const uint8_t *d_base, const PipeShape &sh
 	R.ext_ctas = std::max<uint32_t>(1, std::min<uint32_t>(ctx->n_slots / MAB_WARPS_PER_CTA, (n_seq + MAB_WARPS_PER_CTA - 1) / MAB_WARPS_PER_CTA));
 	{	/* the DP arenas are sized by the longest read of the batch (312 B per base per resident warp): with very long reads fewer
 		 * warps stay resident rather than asking for more than MAB_ARENA_BUDGET bytes of HBM per context */
-		uint64_t budget = 40ull << 30;
+		uint64_t budget = ctx->arena_budget;
 		if(const char *e = getenv("MAB_ARENA_BUDGET_MB")) { long v = atol(e); if(v > 0) { budget = (uint64_t)v << 20; } }
 		uint64_t fit = budget / (AL.total * MAB_WARPS_PER_CTA);
 		if(fit < R.ext_ctas) { R.ext_ctas = (uint32_t)std::max<uint64_t>(1, fit); }

@@ -28,6 +28,7 @@ static inline int RT_STREAM_SYNC(RT_STREAM) { return 0; }
 static inline int RT_EVENT_CREATE(RT_EVENT *e) { *e = 0; return 0; }
 static inline void RT_EVENT_DESTROY(RT_EVENT) {}
 static inline void RT_STREAM_DESTROY(RT_STREAM) {}
+static inline int RT_MEM_INFO(size_t *f, size_t *t) { *f = 64ull << 30; *t = 64ull << 30; return 0; }
 static inline int RT_DEVICE_SYNC() { return 0; }
 static inline int RT_EVENT_SYNC(RT_EVENT) { return 0; }
 static inline int RT_SYNC_EVENT_CREATE(RT_EVENT *e) { *e = 0; return 0; }
