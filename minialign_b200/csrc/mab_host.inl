@@ -25,7 +25,7 @@ struct PipeShape { uint32_t n_seq, maxlen; uint64_t tot_len, span; };		/* what t
 /* launch geometry and buffer shapes of the batch in flight (kept in the context: redo passes may be issued by a later call) */
 struct RunState {
 	PipeShape sh; const uint8_t *d_base;
-	uint32_t blk_cap, ext_ctas, seed_ctas, init_ctas, sc_cap1[2], sc_cap2[2], rlen_init, init_known;
+	uint32_t blk_cap, ext_ctas, seed_ctas, init_ctas, sc_cls[2][MAB_SC_CLASSES], sc_ncls[2], rlen_init, init_known;
 	uint64_t arena_stride;
 };
 
@@ -81,7 +81,7 @@ struct mab_ctx {
 	uint64_t mark_hw = 0, rec_hw = 0;	/* high-water marks of the parser's arrays */
 	double sam_per_byte = 1.3;			/* SAM bytes per input byte (high-water mark, sizes d_sam) */
 	struct TextState { const uint8_t *d_text; uint64_t n_text, n_kept, sam_total; uint32_t n_rec, flags, stage, rlen_committed; bool rlen_known; TextCounters tc; } tx;
-	uint32_t sc_cap1[2] = { 1536, 1536 };	/* k_sortchain: staging capacity of the ordinary size class, per round kind (adapted from batch to batch) */
+	uint32_t sc_c0[2] = { 1280, 1280 };	/* k_sortchain: staging capacity of the smallest size class (median seed bound of the previous batch), per round kind */
 	double ws_per_base = 6.0;			/* workspace estimate: bytes per read base beyond the fixed 20 KB per read (high-water mark) */
 	mab_stats_t stats;
 };
@@ -486,8 +486,11 @@ static void pipe_rounds(mab_ctx *ctx, bool first, bool timed)
 		bool ev = timed && first && round < 8;
 		if(ev) { RT_EVENT_RECORD(ctx->rev[3 * round], ctx->stream); }
 		int kind = round == 0 ? 0 : 1;
-		RT_LAUNCH(k_sortchain, n_seq, 32, 16 * R.sc_cap1[kind] + 2048, ctx->stream, P, ctx->d_reads, n_seq, ctx->d_ws, ctx->d_frames, round, R.sc_cap1[kind], 0u, R.sc_cap1[kind]);
-		RT_LAUNCH(k_sortchain, n_seq, 32, 16 * R.sc_cap2[kind] + 2048, ctx->stream, P, ctx->d_reads, n_seq, ctx->d_ws, ctx->d_frames, round, R.sc_cap2[kind], R.sc_cap1[kind], 0xffffffffu);
+		for(uint32_t ci = 0, lo = 0; ci < R.sc_ncls[kind]; ci++) {					/* one launch per size class: shared memory cut to the class */
+			const uint32_t cap = R.sc_cls[kind][ci], hi = ci + 1 == R.sc_ncls[kind] ? 0xffffffffu : cap;
+			RT_LAUNCH(k_sortchain, n_seq, 32, 16 * cap + 2048, ctx->stream, P, ctx->d_reads, n_seq, ctx->d_ws, ctx->d_frames, round, cap, lo, hi);
+			lo = cap; S.n_launches++;
+		}
 		if(first && round == 0) { RT_LAUNCH(k_rlen_predict, 1, MAB_PIPE_THREADS, 0, ctx->stream, P, ctx->d_reads, n_seq, (const uint8_t *)ctx->d_ws, R.rlen_init, R.init_known); S.n_launches++; }
 		RT_MEMSET_ASYNC(&ctx->d_ctr->work_next, 0, sizeof(unsigned int), ctx->stream);
 		if(ev) { RT_EVENT_RECORD(ctx->rev[3 * round + 1], ctx->stream); }
@@ -498,7 +501,7 @@ static void pipe_rounds(mab_ctx *ctx, bool first, bool timed)
 			RT_LAUNCH((k_extend<MAB_EXT_CTAS_PER_SM>), R.ext_ctas, 32 * MAB_WARPS_PER_CTA, 1024 + 4 * MAB_TILE_WORDS * MAB_WARPS_PER_CTA, ctx->stream, P, R.d_base, (const uint8_t *)ctx->d_ntail, ctx->d_reads, (const uint32_t *)ctx->d_order, n_seq, ctx->d_ws,
 				ctx->d_arenas, R.arena_stride, R.blk_cap, ctx->d_pool, ctx->pool_cap / 4, ctx->d_ctr, round, P.n_occ - 1);
 		}
-		S.n_launches += 3;
+		S.n_launches += 1;
 		if(ev) { RT_EVENT_RECORD(ctx->rev[3 * round + 2], ctx->stream); }
 	}
 	if(timed && first) { RT_EVENT_RECORD(ctx->ev[4], ctx->stream); }
@@ -562,13 +565,19 @@ static int pipeline_run(mab_ctx *ctx, const uint8_t *d_base, const PipeShape &sh
 	uint64_t ws_need = (uint64_t)(ctx->ws_per_base * (double)sh.tot_len) + 20480ull * n_seq + 4096;
 	R.seed_ctas = std::max<uint32_t>(1, std::min<uint32_t>((n_seq + MAB_WARPS_PER_CTA - 1) / MAB_WARPS_PER_CTA, ctx->n_sm * 8));
 	R.init_ctas = std::max<uint32_t>(1, std::min<uint32_t>((n_seq + 255) / 256, ctx->n_sm * 4));
-	/* k_sortchain size classes, per round kind (round 0 stages a read's own seeds, later rounds all of them): the ordinary reads
-	 * (up to the 90th percentile of the seed bound of the previous batch) run with a small shared-memory footprint, the
-	 * seed-rich rest in a second launch with up to MAB_SC_MAX seeds staged, beyond that in global memory */
-	for(int k = 0; k < 2; k++) { R.sc_cap1[k] = ctx->sc_cap1[k]; R.sc_cap2[k] = MAB_SC_MAX; }
+	/* k_sortchain size classes, per round kind (round 0 stages a read's own seeds, later rounds all of them).  A read's seed array
+	 * is staged in shared memory, so the reads resident per SM are what 228 KB holds: every class is launched with the footprint of
+	 * its largest member.  Classes: the median seed bound of the previous batch, then steps of x1.4 up to MAB_SC_MAX seeds (96 KB);
+	 * beyond that the read works in global memory. */
+	for(int k = 0; k < 2; k++) {
+		uint32_t c = std::max<uint32_t>(64u, std::min<uint32_t>(ctx->sc_c0[k], MAB_SC_MAX)), n = 0;
+		while(n + 1 < MAB_SC_CLASSES && c < MAB_SC_MAX) { R.sc_cls[k][n++] = c; c = std::min<uint32_t>(MAB_SC_MAX, ((c * 7 / 5) + 63u) & ~63u); }
+		R.sc_cls[k][n++] = MAB_SC_MAX;
+		R.sc_ncls[k] = n;
+	}
 	if(const char *e = getenv("MAB_SC_CAP")) {										/* test hook: tiny caps push reads through the unstaged (global memory) path */
 		uint32_t v = (uint32_t)atoi(e);
-		if(v >= 64) { for(int k = 0; k < 2; k++) { R.sc_cap1[k] = std::min(R.sc_cap1[k], v); R.sc_cap2[k] = std::min(R.sc_cap2[k], std::max(v, R.sc_cap1[k])); } }
+		if(v >= 64) { for(int k = 0; k < 2; k++) { R.sc_cls[k][0] = v; R.sc_ncls[k] = 1; } }
 	}
 	S.ms_wall_sizing += (float)(RT_WALL_MS() - t_sub);
 	RT_LAUNCH(k_order, 1, MAB_PIPE_THREADS, 0, ctx->stream, (const ReadRec *)ctx->d_reads, n_seq, ctx->d_order);
@@ -616,9 +625,9 @@ static void update_sc_caps(mab_ctx *ctx, const ReadRec *hr, uint32_t n_seq)
 		bnd.reserve(n_seq);
 		for(uint32_t i = 0; i < n_seq; i++) { if(hr[i].len >= ctx->P.k && hr[i].seed_cap != 0) { bnd.push_back((kind == 0 ? hr[i].tot_seeds0 : hr[i].tot_seeds) + 2); } }
 		if(bnd.size() < 16) { continue; }
-		size_t k90 = (bnd.size() * 9) / 10; if(k90 >= bnd.size()) { k90 = bnd.size() - 1; }
-		std::nth_element(bnd.begin(), bnd.begin() + k90, bnd.end());
-		ctx->sc_cap1[kind] = std::max<uint32_t>(64u, std::min<uint32_t>((bnd[k90] + 63u) & ~63u, MAB_SC_SMALL));
+		size_t k50 = bnd.size() / 2;
+		std::nth_element(bnd.begin(), bnd.begin() + k50, bnd.end());
+		ctx->sc_c0[kind] = std::max<uint32_t>(64u, std::min<uint32_t>((bnd[k50] + 63u) & ~63u, MAB_SC_SMALL));
 	}
 }
 

@@ -20,6 +20,7 @@ namespace mab {
 #define MAB_TILE_WORDS (2 * MAB_TBUF / 4)
 #define MAB_SC_SMALL		2944u		/* largest shared-memory staging of the ordinary size class of k_sortchain (16 B per seed + 2 KB = 48 KB) */
 #define MAB_SC_MAX		6016u		/* ... and of the seed-rich class (96 KB, opt-in dynamic shared memory) */
+#define MAB_SC_CLASSES		8u			/* size classes of k_sortchain (one launch each) */
 #define MAB_WARPS_PER_CTA 4
 #ifndef MAB_EXT_CTAS_PER_SM
 #define MAB_EXT_CTAS_PER_SM 6		/* resident CTAs of the persistent extend kernel per SM (register budget = 65536 / (128 x this)) */
