@@ -89,6 +89,15 @@ m8 = re.search(r"mapped (\d+) reads / ([0-9.]+) Mbases in ([0-9.]+) sec \(([0-9.
 if m8:
     S["ours_x%d_map_s" % REP], S["ours_x%d_mbases_per_s" % REP] = float(m8.group(3)), float(m8.group(4))
 log("ours x%d" % REP, S.get("ours_x%d_mbases_per_s" % REP))
+S["contexts_sweep_mbases_per_s"] = {}
+for nc in [int(x) for x in os.environ.get("HUMAN_CTX_SWEEP", "").split(",") if x]:
+    for ctas in ("4", "6"):
+        with open(os.devnull, "wb") as f:
+            pc = subprocess.run([CLI, "-xpacbio", f"-c{nc}", idx] + [rd] * REP, stdout=f, stderr=subprocess.PIPE, text=True, env=dict(os.environ, MAB_EXT_CTAS=ctas))
+        mc = re.search(r"in ([0-9.]+) sec \(([0-9.]+) Mbases/s\)", pc.stderr)
+        S["contexts_sweep_mbases_per_s"][f"c{nc}_ctas{ctas}"] = float(mc.group(2)) if mc else pc.stderr[-200:]
+        log("sweep", nc, ctas, S["contexts_sweep_mbases_per_s"][f"c{nc}_ctas{ctas}"])
+save()
 m = re.search(r"mapped (\d+) reads / ([0-9.]+) Mbases in ([0-9.]+) sec \(([0-9.]+) Mbases/s\)", p.stderr)
 if m:
     S["ours_map_s"], S["ours_mbases_per_s"] = float(m.group(3)), float(m.group(4))
