@@ -40,6 +40,9 @@ GENOMES = {
                   name="ecoli-like 4.64 Mb synthetic reference x100 PBSIM-CLR-like reads (20k+-2k, acc 0.88+-0.07), -xpacbio (BASELINE configs[1])"),
     "saccer3": dict(bp=12_100_000, contigs=17, weights=[230, 813, 317, 1532, 577, 270, 1091, 563, 440, 746, 667, 1078, 924, 784, 1091, 948, 86],
                     name="sacCer3-like 12.1 Mb / 17 contigs synthetic reference x100 PBSIM-CLR-like reads (20k+-2k, acc 0.88+-0.07), -xpacbio, one read set sharded by chunk (BASELINE configs[2])"),
+    # configs[3]: D.melanogaster dm6-sized (143 Mb, ~1.9 k contigs: 7 chromosome arms holding ~96 % + a long tail of scaffolds), -xont.1dsq
+    "dm6": dict(bp=143_000_000, contigs=1870, weights=[23500, 25300, 28100, 32100, 23500, 1350, 3670] + [max(1.0, 60.0 * 0.9985 ** i) for i in range(1863)], preset="ont.1dsq",
+                name="dm6-like 143 Mb / 1870 contigs synthetic reference x20 PBSIM-CLR-like reads (20k+-2k, acc 0.88+-0.07), -xont.1dsq, one read set sharded by chunk (BASELINE configs[3])"),
 }
 BYTES_PER_BASE = 160.0          # algorithmic HBM bytes per read base
 TRAFFIC_PER_BASE = 293.0        # dram__bytes_read.sum + dram__bytes_write.sum of k_extend per read base, ncu --set full capture
@@ -65,7 +68,7 @@ def build_genome(work: str, which: str, seed: int = 1):
         tmp = idx + f".tmp{os.getpid()}.mai"
         synth.write_fasta(fa + f".{os.getpid()}", g, 80)
         builder = REF_BIN if os.path.exists(REF_BIN) else OUR_BIN
-        subprocess.check_call([builder, "-xpacbio", "-d", tmp, fa + f".{os.getpid()}"], stderr=subprocess.DEVNULL)
+        subprocess.check_call([builder, "-x" + G.get("preset", "pacbio"), "-d", tmp, fa + f".{os.getpid()}"], stderr=subprocess.DEVNULL)
         os.replace(tmp, idx)
     return g, idx, mai.load_mai(idx)
 
@@ -138,10 +141,13 @@ class ClockSampler(threading.Thread):
                 "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
+PRESET = "pacbio"           # set from the workload in main()
+
+
 def ref_run(idx: str, fasta: str, threads: int, out=None, extra=()):
     """One run of the reference CLI; returns mapping seconds = final Real time - index-load timestamp."""
     with open(out or os.devnull, "wb") as sink:
-        p = subprocess.run([REF_BIN, "-xpacbio", f"-t{threads}", *extra, idx, fasta], stdout=sink, stderr=subprocess.PIPE, text=True)
+        p = subprocess.run([REF_BIN, "-x" + PRESET, f"-t{threads}", *extra, idx, fasta], stdout=sink, stderr=subprocess.PIPE, text=True)
     m1 = re.search(r"main_align::([0-9.]+)\*[0-9.]+\] loaded/built index", p.stderr)
     m2 = re.search(r"Real time: ([0-9.]+) sec", p.stderr)
     if p.returncode != 0 or not m1 or not m2:
@@ -161,7 +167,7 @@ def ref_hot_path(idx: str, reads, threads: int):
     from minialign_b200 import api, synth
     if not refh.available():
         return None
-    h = refh.RefHarness(idx, args=("-xpacbio", f"-t{threads}"))
+    h = refh.RefHarness(idx, args=("-x" + PRESET, f"-t{threads}"))
     L = h.lib
     if not hasattr(L, "refh_align_many"):
         h.close()
@@ -193,7 +199,7 @@ def cpu_baseline(idx, reads, work, budget_core_s=20.0):
     secs = min(ref_run(idx, fa, thr) for _ in range(2))
     os.remove(fa)
     out = {"value": bases / 1e6 / secs, "unit": "Mbases/s", "cores": thr, "kind": "reference",
-           "sample": f"{len(sample)} reads / {bases / 1e6:.1f} Mbases of the same workload, oracle/_ref/minialign -xpacbio -t{thr} FASTA file -> SAM text, best of 2, index load excluded"}
+           "sample": f"{len(sample)} reads / {bases / 1e6:.1f} Mbases of the same workload, oracle/_ref/minialign -x{PRESET} -t{thr} FASTA file -> SAM text, best of 2, index load excluded"}
     try:
         hp = ref_hot_path(idx, sample, thr)
         if hp:
@@ -235,7 +241,7 @@ def parity_check(idx, reads, chunk_id, work, text: bytes, n_sample=384):
     exp = b"".join(l for l in open(sam, "rb") if not l.startswith(b"@"))
     os.remove(fa); os.remove(sam)
     ok = text[:len(exp)] == exp and len(exp) > 0
-    return {"ok": bool(ok), "reads": len(sample), "bytes": len(exp), "against": "oracle/_ref/minialign -xpacbio -t1, every SAM line of the first reads of a timed full-size chunk"}
+    return {"ok": bool(ok), "reads": len(sample), "bytes": len(exp), "against": "oracle/_ref/minialign -x" + PRESET + " -t1, every SAM line of the first reads of a timed full-size chunk"}
 
 
 def main():
@@ -247,11 +253,13 @@ def main():
     ap.add_argument("--batch-reads", type=int, default=16384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--contexts", type=int, default=4, help="mapper contexts (in-flight chunks) per GPU")
-    ap.add_argument("--workload", default=None, choices=[None, "ecoli", "saccer3"], help="default: ecoli at one GPU (configs[1]), saccer3 across GPUs (configs[2])")
+    ap.add_argument("--workload", default=None, choices=[None, "ecoli", "saccer3", "dm6"], help="default: ecoli at one GPU (configs[1]), saccer3 across GPUs (configs[2])")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     which = args.workload or ("ecoli" if max(world, args.gpus) == 1 else "saccer3")
+    global PRESET
+    PRESET = GENOMES[which].get("preset", "pacbio")
     config = {"workload": GENOMES[which]["name"], "batch_reads": args.batch_reads, "read_model": "len N(20000,2000) acc N(0.88,0.07) sub:ins:del 10:60:30",
               "parallelism": f"read-shard x{world}: chunk c of the read set on rank c mod {world}", "contexts_per_gpu": args.contexts,
               "path": "FASTA text -> device reader -> seed/chain/extend -> device post-processing -> device SAM printer -> SAM text",
@@ -274,7 +282,7 @@ def main():
         secs = sum(t)
         v = bases * args.steps / 1e6 / secs
         cb = {"value": v, "unit": "Mbases/s", "cores": thr, "kind": "reference",
-              "sample": f"{len(reads)} reads / {bases / 1e6:.1f} Mbases per step, oracle/_ref/minialign -xpacbio -t{thr} FASTA file -> SAM text, index load excluded"}
+              "sample": f"{len(reads)} reads / {bases / 1e6:.1f} Mbases per step, oracle/_ref/minialign -x{PRESET} -t{thr} FASTA file -> SAM text, index load excluded"}
         try:
             hp = ref_hot_path(idx, reads[:max(256, len(reads) // 4)], thr)
             if hp:
@@ -326,7 +334,7 @@ def main():
     # (sweep under profiles/r02_sweep_contexts.txt)
     ext_pipe = os.environ.get("MAB_EXT_CTAS", "4" if args.contexts > 1 else "6")
     os.environ["MAB_EXT_CTAS"] = ext_pipe
-    m0 = api.Mapper(blob, "pacbio", device=local)
+    m0 = api.Mapper(blob, PRESET, device=local)
     ms = [m0] + [m0.clone() for _ in range(max(1, args.contexts) - 1)]
     config["extend_ctas_per_sm"] = int(ext_pipe)
 
@@ -421,7 +429,7 @@ def main():
     # runs above the kernels of three contexts overlap on the GPU, which stretches every per-kernel event interval
     def solo(n):
         os.environ["MAB_EXT_CTAS"] = "6"
-        m = api.Mapper(blob, "pacbio", device=local)
+        m = api.Mapper(blob, PRESET, device=local)
         os.environ["MAB_EXT_CTAS"] = ext_pipe
         a = dict(bases=0, ms_ext_r0=0.0, ms_ext=0.0, vec=0, ms_post=0.0, ms_total=0.0)
         m.map_text(pinned[0][:len(texts[0])].numpy().tobytes()[:1 << 22].rsplit(b"\n>", 1)[0] + b"\n")      # warm-up: small allocations
