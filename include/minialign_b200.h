@@ -149,6 +149,10 @@ typedef struct {
 	uint64_t sam_bytes;					/* valid after mab_text_finish */
 	uint32_t rlen_valid, rlen_next;		/* the value this chunk leaves behind (rlen_valid = 0: it loaded no chain, pass the previous one on) */
 } mab_text_info_t;
+/* optional, before the first chunk: the largest chunk the caller will pass (the reference's -N / batch size, minialign.c:6145).  The
+ * context and its clones size their device buffers for it at once; without it they follow the chunks they see, and growing a buffer
+ * later waits for the whole device. */
+int mab_text_reserve(mab_ctx *ctx, uint64_t max_chunk_bytes);
 int mab_text_begin(mab_ctx *ctx, const char *text, uint64_t n_bytes, uint32_t flags, uint32_t rlen_prev, int rlen_known, mab_text_info_t *info);
 int mab_text_commit(mab_ctx *ctx, uint32_t rlen_prev, mab_text_info_t *info);
 /* sam_out = NULL: the text is left in a pinned buffer owned by the context, *sam_ptr points at it (valid until the next begin) */
@@ -158,6 +162,7 @@ int mab_map_text(mab_ctx *ctx, const char *text, uint64_t n_bytes, uint32_t flag
 uint64_t mab_sam_header_text(const mab_ctx *ctx, const char *version, const char *cmdline, char *out, uint64_t cap);
 /* page-locked host memory for text / SAM buffers (copies from / to pageable memory are staged by the driver and block) */
 void *mab_host_alloc(uint64_t bytes);
+void *mab_host_alloc_on(int device, uint64_t bytes);	/* the same from a thread that has not used a device yet (selects `device` first) */
 void mab_host_free(void *p);
 
 /* ---- stage-level entry points (parity tests; same semantics as the reference functions named above) ---- */

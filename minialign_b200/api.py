@@ -113,6 +113,8 @@ def load_library(lib_path: str | None = None):
     L.mab_selftest.restype = C.c_int
     L.mab_selftest.argtypes = [C.c_void_p, u32p]
     ti = C.POINTER(MabTextInfo)
+    L.mab_text_reserve.restype = C.c_int
+    L.mab_text_reserve.argtypes = [C.c_void_p, C.c_uint64]
     L.mab_text_begin.restype = C.c_int
     L.mab_text_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, ti]
     L.mab_text_commit.restype = C.c_int
@@ -201,6 +203,10 @@ class Mapper:
         self._check(self.lib.mab_map_text(self.h, C.addressof(buf), len(text), flags, None, 0, C.byref(ptr), C.byref(info)), "mab_map_text")
         self.last_info = info
         return C.string_at(ptr.value, info.sam_bytes) if info.sam_bytes else b""
+
+    def text_reserve(self, max_chunk_bytes: int):
+        """announce the largest chunk (bytes) this mapper and its clones will be given: buffers are sized for it at once"""
+        self._check(self.lib.mab_text_reserve(self.h, max_chunk_bytes), "mab_text_reserve")
 
     def text_begin(self, ptr: int, n: int, flags: int = 0, rlen_prev: int = 0, rlen_known: bool = False) -> MabTextInfo:
         info = MabTextInfo()

@@ -339,19 +339,55 @@ int main(int argc, char **argv)
 	}
 	if(!o.w_set) { o.ip.w = (uint32_t)(int)(2.0 / 3.0 * o.ip.k + .499); }							/* default window size when -w is absent (minialign.c:6111) */
 	if(o.pos.size() < (o.dump.empty() ? 2u : 1u)) { fprintf(stderr, "usage: minialign-b200 [-x preset] [-T tags] <ref.fa|ref.mai> <reads.fa> [...] > out.sam\n       minialign-b200 [-x preset] -d <out.mai> <ref.fa>\n"); return 1; }
+	/* the host side of the pipeline below: page-locked chunk and output buffers.  Pinning memory is slow (2-3 GB/s), so a thread
+	 * starts on it right away, next to the index load and the device set-up; readers and workers pick the buffers up as they appear. */
+	const uint64_t chunk_bytes = std::max<uint64_t>(1024, (uint64_t)(o.chunk_mb * 1048576.0));
+	std::vector<int> devices = o.devices.empty() ? std::vector<int>{ o.device } : o.devices;
+	const unsigned n_ctx = std::max(1u, o.contexts) * (unsigned)devices.size();
+	struct Chunk { char *buf = nullptr; uint64_t cap = 0, len = 0; uint64_t id = 0; size_t file = 0; bool last_of_file = false, open_failed = false; };
+	struct Out { char *buf = nullptr; uint64_t cap = 0, len = 0; std::string spill; uint64_t id = 0; unsigned owner = 0; bool busy = false; };	/* buf: page-locked, the SAM text is copied from the device straight into it */
+	std::mutex mu; std::condition_variable cv;
+	std::deque<Chunk *> free_chunks, ready; std::map<uint64_t, Out *> done_outs;
+	bool read_done = false, failed = false, pin_stop = false;
+	std::vector<Chunk> chunk_pool(n_ctx + 2); std::vector<Out> out_pool(2 * n_ctx);			/* two output buffers per context: one being written while the next is filled */
+	for(unsigned i = 0; i < 2 * n_ctx; i++) { out_pool[i].owner = i / 2; }
+	std::thread pinner;
+	if(o.dump.empty()) {
+		pinner = std::thread([&]() {
+			auto stopped = [&]() { std::unique_lock<std::mutex> lk(mu); return pin_stop; };
+			auto give_up = [&]() { fprintf(stderr, "[E::main_align] %s\n", mab_last_error()); std::unique_lock<std::mutex> lk(mu); failed = true; cv.notify_all(); };
+			/* first what the first chunks need (a chunk buffer and an output buffer per context), then the second halves */
+			for(unsigned pass = 0; pass < 2; pass++) {
+				for(size_t i = pass ? std::min<size_t>(n_ctx, chunk_pool.size()) : 0; i < (pass ? chunk_pool.size() : std::min<size_t>(n_ctx, chunk_pool.size())); i++) {
+					if(stopped()) { return; }
+					Chunk &c = chunk_pool[i];
+					uint64_t cap = chunk_bytes + (16 << 20); char *b = (char *)mab_host_alloc_on(devices[0], cap);
+					if(!b) { give_up(); return; }
+					std::unique_lock<std::mutex> lk(mu); c.cap = cap; c.buf = b; free_chunks.push_back(&c); cv.notify_all();
+				}
+				for(unsigned i = pass; i < 2 * n_ctx; i += 2) {
+					if(stopped()) { return; }
+					uint64_t cap = chunk_bytes + chunk_bytes / 2 + (1 << 20); char *b = (char *)mab_host_alloc_on(devices[0], cap);
+					if(!b) { give_up(); return; }
+					std::unique_lock<std::mutex> lk(mu); out_pool[i].cap = cap; out_pool[i].buf = b; cv.notify_all();
+				}
+			}
+		});
+	}
+	auto stop_pinner = [&]() { { std::unique_lock<std::mutex> lk(mu); pin_stop = true; } if(pinner.joinable()) { pinner.join(); } };
 	MaiImage im;
 	if(!load_mai(o.pos[0].c_str(), im)) {															/* not an index: a FASTA reference, build it here */
 		SeqReader rr(o.pos[0].c_str());
-		if(!rr.fp) { fprintf(stderr, "[E::main_align] failed to open index file `%s'. Please check file path and it exists.\n", o.pos[0].c_str()); return 1; }
+		if(!rr.fp) { fprintf(stderr, "[E::main_align] failed to open index file `%s'. Please check file path and it exists.\n", o.pos[0].c_str()); stop_pinner(); return 1; }
 		std::vector<MabIdxSeq> refs; Rec r;
 		while(rr.next(r)) { if(r.seq.empty()) { continue; } MabIdxSeq q; q.name = r.name; q.seq = std::move(r.seq); refs.push_back(std::move(q)); }
 		std::string err;
-		if(!mab_build_index(refs, o.ip, im.own, err)) { fprintf(stderr, "[E::main_index] failed to build index from `%s': %s\n", o.pos[0].c_str(), err.c_str()); return 1; }
+		if(!mab_build_index(refs, o.ip, im.own, err)) { fprintf(stderr, "[E::main_index] failed to build index from `%s': %s\n", o.pos[0].c_str(), err.c_str()); stop_pinner(); return 1; }
 		fprintf(stderr, "[M::main_index::%.3f] built index for %zu target sequence(s).\n", now() - t0, refs.size());
 		im.blob = im.own.data(); im.size = im.own.size();
 	}
 	if(!o.dump.empty()) {
-		if(!mab_write_mai(o.dump.c_str(), std::vector<uint8_t>(im.blob, im.blob + im.size))) { fprintf(stderr, "[E::main_index] failed to write index to `%s'.\n", o.dump.c_str()); return 1; }
+		if(!mab_write_mai(o.dump.c_str(), std::vector<uint8_t>(im.blob, im.blob + im.size))) { fprintf(stderr, "[E::main_index] failed to write index to `%s'.\n", o.dump.c_str()); stop_pinner(); return 1; }
 		fprintf(stderr, "[M::main] Command: %s\n[M::main] Real time: %.3f sec\n", cmdline.c_str(), now() - t0);
 		return 0;
 	}
@@ -364,9 +400,6 @@ int main(int argc, char **argv)
 	 *   writer   one thread: write(2) the SAM text of the chunks in file order
 	 * A chunk the device reader does not take (MAB_EFORMAT: wrapped FASTQ, ...) is parsed on the host and goes through the
 	 * record-level entry point and the host formatter instead. */
-	const uint64_t chunk_bytes = std::max<uint64_t>(1024, (uint64_t)(o.chunk_mb * 1048576.0));
-	std::vector<int> devices = o.devices.empty() ? std::vector<int>{ o.device } : o.devices;
-	const unsigned n_ctx = std::max(1u, o.contexts) * (unsigned)devices.size();
 	double t_idx = now() - t0;
 	if(o.contexts > 1 && getenv("MAB_EXT_CTAS") == nullptr) { setenv("MAB_EXT_CTAS", "4", 1); }	/* contexts that run side by side launch 4 of the 6 possible extend CTAs per SM each */
 	std::vector<mab_ctx *> ctxs(n_ctx, nullptr);
@@ -378,6 +411,7 @@ int main(int argc, char **argv)
 				mab_ctx *p = mab_init(im.blob, im.size, &prm, devices[d]);
 				if(!p) { errs[d] = mab_last_error(); return; }
 				ctxs[d] = p;
+				mab_text_reserve(p, chunk_bytes);									/* clones share it: every context sizes its buffers for a full chunk at once */
 				for(unsigned c = 1; c < std::max(1u, o.contexts); c++) { mab_ctx *q = mab_clone(p); if(!q) { errs[d] = mab_last_error(); return; } ctxs[c * devices.size() + d] = q; }
 				/* what is free next to the index is shared by the contexts of this GPU: 60 % of a context's share for its DP arenas, the
 				 * rest for its text, read block, minimizer records, workspaces, result pool and SAM text */
@@ -389,7 +423,7 @@ int main(int argc, char **argv)
 			});
 		}
 		for(auto &x : th) { x.join(); }
-		for(auto &e : errs) { if(!e.empty()) { fprintf(stderr, "[E::main_align] failed to instanciate alignment context: %s\n", e.c_str()); return 1; } }
+		for(auto &e : errs) { if(!e.empty()) { fprintf(stderr, "[E::main_align] failed to instanciate alignment context: %s\n", e.c_str()); stop_pinner(); return 1; } }
 	}
 	mab_ctx *ctx0 = ctxs[0];
 	uint32_t n_ref = mab_n_ref(ctx0);
@@ -397,14 +431,6 @@ int main(int argc, char **argv)
 	for(uint32_t i = 0; i < n_ref; i++) { mab_ref_info(ctx0, i, &refs[i].name, &refs[i].l_name, &refs[i].l_seq, &refs[i].seq); }
 	fprintf(stderr, "[M::main_align::%.3f] loaded/built index for %u target sequence(s) (index file %.3f s, %u device context(s) on %zu GPU(s) %.3f s).\n", now() - t0, n_ref, t_idx, n_ctx, devices.size(), now() - t0 - t_idx);
 	double tmap = now();
-	struct Chunk { char *buf = nullptr; uint64_t cap = 0, len = 0; uint64_t id = 0; size_t file = 0; bool last_of_file = false, open_failed = false; };
-	struct Out { char *buf = nullptr; uint64_t cap = 0, len = 0; std::string spill; uint64_t id = 0; unsigned owner = 0; bool busy = false; };	/* buf: page-locked, the SAM text is copied from the device straight into it */
-	std::mutex mu; std::condition_variable cv;
-	std::deque<Chunk *> free_chunks, ready; std::map<uint64_t, Out *> done_outs;
-	bool read_done = false, failed = false;
-	std::vector<Chunk> chunk_pool(n_ctx + 2); std::vector<Out> out_pool(2 * n_ctx);			/* two output buffers per context: one being written while the next is filled */
-	for(auto &c : chunk_pool) { c.cap = chunk_bytes + (16 << 20); c.buf = (char *)mab_host_alloc(c.cap); if(!c.buf) { fprintf(stderr, "[E::main_align] %s\n", mab_last_error()); return 1; } free_chunks.push_back(&c); }
-	for(unsigned i = 0; i < 2 * n_ctx; i++) { out_pool[i].owner = i / 2; }
 	struct stat st_out; const bool out_is_file = fstat(1, &st_out) == 0 && S_ISREG(st_out.st_mode);
 	uint64_t out_ofs = out_is_file ? (uint64_t)std::max<off_t>(0, lseek(1, 0, SEEK_CUR)) : 0;	/* regular file: the writers pwrite() concurrently at known offsets */
 	uint64_t next_commit = 0, next_write = 0, tot_bases = 0, tot_reads = 0, n_chunks_total = 0;
@@ -445,7 +471,7 @@ int main(int argc, char **argv)
 		std::unique_lock<std::mutex> lk(mu); read_done = true; n_chunks_total = id; cv.notify_all();
 	});
 	double t_wr = 0;
-	if(write_all(1, header.data(), header.size()) != 0) { fprintf(stderr, "[E::main_align] failed to write the SAM header\n"); return 1; }
+	if(write_all(1, header.data(), header.size()) != 0) { fprintf(stderr, "[E::main_align] failed to write the SAM header\n"); stop_pinner(); return 1; }
 	out_ofs += header.size();
 	auto writer_fn = [&]() {
 		while(true) {
@@ -482,7 +508,7 @@ int main(int argc, char **argv)
 			Chunk *c; Out *x;
 			{
 				std::unique_lock<std::mutex> lk(mu);
-				auto my_out = [&]() -> Out * { for(unsigned i = 0; i < 2; i++) { if(!out_pool[2 * w + i].busy) { return &out_pool[2 * w + i]; } } return nullptr; };
+				auto my_out = [&]() -> Out * { for(unsigned i = 0; i < 2; i++) { if(!out_pool[2 * w + i].busy && out_pool[2 * w + i].buf != nullptr) { return &out_pool[2 * w + i]; } } return nullptr; };
 				cv.wait(lk, [&]() { return (!ready.empty() && my_out() != nullptr) || failed || (read_done && ready.empty()); });
 				if(failed || ready.empty()) { return; }
 				c = ready.front(); ready.pop_front(); x = my_out(); x->busy = true;
@@ -539,7 +565,7 @@ int main(int argc, char **argv)
 	for(auto &x : workers) { x.join(); }
 	{ std::unique_lock<std::mutex> lk(mu); cv.notify_all(); }
 	reader.join(); for(auto &x : writers) { x.join(); }
-	if(failed) { return 1; }
+	if(failed) { stop_pinner(); return 1; }
 	double sb = 0, st = 0, sf = 0; for(unsigned w = 0; w < n_ctx; w++) { sb += t_begin[w]; st += t_turn[w]; sf += t_finish[w]; }
 	fprintf(stderr, "[M::main_align] host pipeline: %u context(s); per context on average: parse+map %.3f s, waiting for its turn %.3f s, post+SAM+copy %.3f s; writer: writing %.3f s; reads re-mapped for the rlen chain: %llu; chunks parsed on the host: %llu\n",
 		n_ctx, sb / n_ctx, st / n_ctx, sf / n_ctx, t_wr, (unsigned long long)n_redo.load(), (unsigned long long)n_fallback.load());

@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <algorithm>
 #include <thread>
+#include <mutex>
 
 using namespace mab;
 
@@ -27,6 +28,20 @@ struct RunState {
 	PipeShape sh; const uint8_t *d_base;
 	uint32_t blk_cap, ext_ctas, seed_ctas, init_ctas, sc_cls[2][MAB_SC_CLASSES], sc_ncls[2], rlen_init, init_known;
 	uint64_t arena_stride;
+};
+
+/* What the contexts of one index have learnt about the workload: output and workspace sizes per input byte, seed counts, the
+ * parser's array sizes.  Shared between a context and its clones, so that a clone's first chunk is sized by what the others
+ * have already seen instead of finding everything out again (a buffer found too small costs a re-run, and re-allocating one
+ * waits for the whole device). */
+struct Calib {
+	std::mutex mu;
+	uint64_t mark_hw = 0, rec_hw = 0;	/* high-water marks of the parser's arrays */
+	double sam_per_byte = 1.3;			/* SAM bytes per input byte (high-water mark, sizes d_sam) */
+	uint32_t sc_c0[2] = { 1280, 1280 };	/* k_sortchain: staging capacity of the smallest size class (median seed bound of the previous batch), per round kind */
+	double ws_per_base = 6.0;			/* workspace estimate: bytes per read base beyond the fixed 20 KB per read (high-water mark) */
+	bool ws_seen = false;				/* ws_per_base is a measurement (a batch has gone through), not the built-in guess */
+	uint64_t reserve_bytes = 0;			/* mab_text_reserve: the largest chunk the caller will pass; buffers are sized for it from the first chunk on */
 };
 
 struct mab_ctx {
@@ -78,11 +93,8 @@ struct mab_ctx {
 	bool thr_ok = false;
 	uint8_t *d_sam = nullptr; uint64_t sam_cap = 0;
 	uint8_t *h_sam = nullptr; uint64_t h_sam_cap = 0;		/* pinned; used when the caller passes no output buffer */
-	uint64_t mark_hw = 0, rec_hw = 0;	/* high-water marks of the parser's arrays */
-	double sam_per_byte = 1.3;			/* SAM bytes per input byte (high-water mark, sizes d_sam) */
-	struct TextState { const uint8_t *d_text; uint64_t n_text, n_kept, sam_total; uint32_t n_rec, flags, stage, rlen_committed; bool rlen_known; TextCounters tc; } tx;
-	uint32_t sc_c0[2] = { 1280, 1280 };	/* k_sortchain: staging capacity of the smallest size class (median seed bound of the previous batch), per round kind */
-	double ws_per_base = 6.0;			/* workspace estimate: bytes per read base beyond the fixed 20 KB per read (high-water mark) */
+	std::shared_ptr<Calib> cal;			/* shared with the clones */
+	struct TextState { const uint8_t *d_text; uint64_t n_text, n_kept, sam_total; uint32_t n_rec, flags, stage, rlen_committed; bool rlen_known; double reserve = 1.0; TextCounters tc; } tx;
 	mab_stats_t stats;
 };
 
@@ -166,6 +178,16 @@ inline uint32_t rd32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v;
 inline uint16_t rd16(const uint8_t *p) { uint16_t v; memcpy(&v, p, 2); return v; }
 }  // namespace
 
+/* MAB_TRACE=1: one stderr line per stage boundary / reallocation (wall clock in ms since the first line; for reading how the
+ * chunks of several contexts interleave on one GPU) */
+static bool trace_on() { static int on = -1; if(on < 0) { const char *e = getenv("MAB_TRACE"); on = e && atoi(e) > 0; } return on != 0; }
+static void trace_line(const void *ctx, const char *what, double a = 0, double b = 0)
+{
+	if(!trace_on()) { return; }
+	static double t0 = RT_WALL_MS();
+	fprintf(stderr, "[T %10.2f ctx %p] %s %.3f %.3f\n", RT_WALL_MS() - t0, ctx, what, a, b);
+}
+
 static int text_init(struct mab_ctx *ctx);
 static void text_destroy(struct mab_ctx *ctx);
 #define CK(call) do { if(!RT_OK(call)) { g_err = std::string(#call) + ": " + RT_ERRSTR(); return MAB_ENODEV; } } while(0)
@@ -204,6 +226,7 @@ extern "C" mab_ctx *mab_init(const void *mai_blob, uint64_t size, const mab_para
 	if(check_params(params) != 0) { g_err = "mab_init: unsupported scoring parameters (combined gap model with validated ranges only)"; return nullptr; }
 	mab_ctx *ctx = new mab_ctx();
 	ctx->device = device; ctx->prm = *params;
+	try { ctx->cal = std::make_shared<Calib>(); } catch(const std::bad_alloc &) { g_err = "host allocation failed"; delete ctx; return nullptr; }
 	memset(&ctx->stats, 0, sizeof(ctx->stats));
 	if(!RT_OK(RT_SET_DEVICE(device))) { g_err = std::string("no usable CUDA device: ") + RT_ERRSTR(); delete ctx; return nullptr; }
 	ctx->n_sm = RT_SM_COUNT(device);
@@ -226,8 +249,10 @@ extern "C" mab_ctx *mab_init(const void *mai_blob, uint64_t size, const mab_para
 	for(int i = 0; i < 16; i++) { if((i & 3) == (i >> 3)) { mc += params->score_matrix[0]; } else { xc += params->score_matrix[0]; } }
 	P.mcoef = mc / 4.0; ctx->xcoef = xc / 12.0; P.xcoef = ctx->xcoef;
 	init_gaba_consts(P, params);
+	trace_line(ctx, "init: enter, index MB", size / 1048576.0);
 	CKP(RT_MALLOC(&ctx->d_idx, size + 256));
 	CKP(RT_MEMCPY_H2D(ctx->d_idx, b, size));
+	trace_line(ctx, "init: index on the device");
 	P.idx = ctx->d_idx;
 	uint8_t nt[128]; memset(nt, 4, sizeof(nt));
 	CKP(RT_MALLOC(&ctx->d_ntail, 256));
@@ -235,6 +260,7 @@ extern "C" mab_ctx *mab_init(const void *mai_blob, uint64_t size, const mab_para
 	if(text_init(ctx) != MAB_OK) { mab_destroy(ctx); return nullptr; }
 	CKP(RT_DEVICE_SYNC());								/* the uploads above ran on the legacy stream: nothing on the context's own (non-blocking) stream may overtake them */
 	if(ctx_private_init(ctx) != MAB_OK) { mab_destroy(ctx); return nullptr; }
+	trace_line(ctx, "init: done");
 	return ctx;
 }
 
@@ -246,11 +272,13 @@ extern "C" mab_ctx *mab_clone(mab_ctx *parent)
 	while(parent->parent != nullptr) { parent = parent->parent; }
 	mab_ctx *ctx = new mab_ctx();
 	ctx->parent = parent; ctx->device = parent->device; ctx->prm = parent->prm; ctx->P = parent->P; ctx->xcoef = parent->xcoef; ctx->n_sm = parent->n_sm;
+	ctx->cal = parent->cal;
 	ctx->blob = parent->blob; ctx->blob_ptr = parent->blob_ptr; ctx->d_idx = parent->d_idx; ctx->d_ntail = parent->d_ntail; ctx->d_thr = parent->d_thr; ctx->thr_ok = parent->thr_ok;
 	memset(&ctx->stats, 0, sizeof(ctx->stats));
 	if(!RT_OK(RT_USE_DEVICE(ctx->device))) { g_err = std::string("no usable CUDA device: ") + RT_ERRSTR(); delete ctx; return nullptr; }
 	CKP(RT_MALLOC(&ctx->d_tc, sizeof(TextCounters)));
 	if(ctx_private_init(ctx) != MAB_OK) { mab_destroy(ctx); return nullptr; }
+	trace_line(ctx, "clone: done");
 	return ctx;
 }
 
@@ -303,10 +331,12 @@ extern "C" int mab_last_stats(const mab_ctx *ctx, mab_stats_t *out) { *out = ctx
 template <class T> static int grow(T **p, uint64_t *cap, uint64_t need_bytes)
 {
 	if(need_bytes <= *cap && *p != nullptr) { return MAB_OK; }
+	double tg = RT_WALL_MS();
 	RT_FREE(*p); *p = nullptr;
 	uint64_t nb = need_bytes + need_bytes / 4 + 4096;
 	if(!RT_OK(RT_MALLOC(p, nb))) { g_err = std::string("device allocation failed: ") + RT_ERRSTR(); *cap = 0; return MAB_ENOMEM; }
 	*cap = nb;
+	trace_line(p, "grow MB, ms", nb / 1048576.0, RT_WALL_MS() - tg);
 	return MAB_OK;
 }
 
@@ -527,6 +557,7 @@ static int pipe_verify(mab_ctx *ctx, uint32_t rlen_init, uint32_t init_known)
 		const BatchCounters &hc = ctx->hc;
 		if((hc.err_any & (MAB_ERR_POOL_OVF | MAB_ERR_WS_OVF)) || hc.pool_top > ctx->pool_cap / 4 || hc.n_redo == 0) { break; }
 		S.n_retry += hc.n_redo;
+		trace_line(ctx, "rlen redo, reads", hc.n_redo);
 		pipe_rounds(ctx, false, false);
 	}
 	return MAB_OK;
@@ -537,7 +568,7 @@ static int pipe_verify(mab_ctx *ctx, uint32_t rlen_init, uint32_t init_known)
  * the first launch and the verification needs the host: workspace offsets, the work order and the `rlen` speculation are
  * computed on the device, buffers are sized from the shape and from high-water marks of earlier batches, and a buffer that
  * turns out too small (result pool, workspace) is grown and the batch re-run.  On return ctx->hc holds the batch counters. */
-static int pipeline_run(mab_ctx *ctx, const uint8_t *d_base, const PipeShape &sh, uint32_t rlen_init, uint32_t init_known, bool timed)
+static int pipeline_run(mab_ctx *ctx, const uint8_t *d_base, const PipeShape &sh, uint32_t rlen_init, uint32_t init_known, bool timed, double reserve = 1.0)
 {
 	const DevParams &P = ctx->P;
 	mab_stats_t &S = ctx->stats;
@@ -545,10 +576,17 @@ static int pipeline_run(mab_ctx *ctx, const uint8_t *d_base, const PipeShape &sh
 	const uint32_t n_seq = sh.n_seq;
 	double t_sub = RT_WALL_MS();
 	R.sh = sh; R.d_base = d_base; R.rlen_init = rlen_init; R.init_known = init_known;
+	/* buffers are sized for `reserve` (>= 1) times this batch: the largest chunk the caller has announced (mab_text_reserve), so
+	 * that a context whose first chunk happens to be a short one does not re-allocate everything on its second */
+	reserve = std::max(1.0, reserve);
+	const uint64_t z_seq = reserve > 1.0 ? (uint64_t)((double)n_seq * reserve * 1.05) + 64 : n_seq;
+	const uint64_t z_span = (uint64_t)((double)sh.span * reserve), z_len = (uint64_t)((double)sh.tot_len * reserve);
+	double ws_per_base; bool ws_seen; uint32_t sc_c0[2];
+	{ std::lock_guard<std::mutex> lk(ctx->cal->mu); ws_per_base = ctx->cal->ws_per_base; ws_seen = ctx->cal->ws_seen; sc_c0[0] = ctx->cal->sc_c0[0]; sc_c0[1] = ctx->cal->sc_c0[1]; }
 	{ int rc = pin_reserve(ctx, ctx->pin_user + 2 * sizeof(BatchCounters) + 256); if(rc) { return rc; } }
-	{ int rc = grow(&ctx->d_recs, &ctx->recs_cap, 16ull * sh.span + 256); if(rc) { return rc; } }
-	{ int rc = grow(&ctx->d_frames, &ctx->frames_cap, 4ull * 8 * MAB_RS_FRAME * ((uint64_t)n_seq + 8)); if(rc) { return rc; } }
-	{ int rc = grow(&ctx->d_order, &ctx->order_cap, 4ull * n_seq); if(rc) { return rc; } }
+	{ int rc = grow(&ctx->d_recs, &ctx->recs_cap, 16ull * z_span + 256); if(rc) { return rc; } }
+	{ int rc = grow(&ctx->d_frames, &ctx->frames_cap, 4ull * 8 * MAB_RS_FRAME * (z_seq + 8)); if(rc) { return rc; } }
+	{ int rc = grow(&ctx->d_order, &ctx->order_cap, 4ull * z_seq); if(rc) { return rc; } }
 	R.blk_cap = dp_blk_cap(sh.maxlen);
 	ArenaLayout AL = arena_layout(R.blk_cap);
 	R.arena_stride = AL.total;
@@ -561,8 +599,8 @@ static int pipeline_run(mab_ctx *ctx, const uint8_t *d_base, const PipeShape &sh
 		if(fit < R.ext_ctas) { R.ext_ctas = (uint32_t)std::max<uint64_t>(1, fit); }
 	}
 	{ int rc = grow(&ctx->d_arenas, &ctx->arenas_cap, AL.total * (uint64_t)R.ext_ctas * MAB_WARPS_PER_CTA); if(rc) { return rc; } }
-	uint64_t pool_need = sh.tot_len / 4 + 64ull * n_seq + (1u << 16);				/* ~2 bits per base and alignment, x4 head room */
-	uint64_t ws_need = (uint64_t)(ctx->ws_per_base * (double)sh.tot_len) + 20480ull * n_seq + 4096;
+	uint64_t pool_need = z_len / 4 + 64ull * z_seq + (1u << 16);					/* ~2 bits per base and alignment, x4 head room */
+	uint64_t ws_need = (uint64_t)(ws_per_base * (double)z_len) + 20480ull * z_seq + 4096;
 	R.seed_ctas = std::max<uint32_t>(1, std::min<uint32_t>((n_seq + MAB_WARPS_PER_CTA - 1) / MAB_WARPS_PER_CTA, ctx->n_sm * 8));
 	R.init_ctas = std::max<uint32_t>(1, std::min<uint32_t>((n_seq + 255) / 256, ctx->n_sm * 4));
 	/* k_sortchain size classes, per round kind (round 0 stages a read's own seeds, later rounds all of them).  A read's seed array
@@ -570,7 +608,7 @@ static int pipeline_run(mab_ctx *ctx, const uint8_t *d_base, const PipeShape &sh
 	 * its largest member.  Classes: the median seed bound of the previous batch, then steps of x1.4 up to MAB_SC_MAX seeds (96 KB);
 	 * beyond that the read works in global memory. */
 	for(int k = 0; k < 2; k++) {
-		uint32_t c = std::max<uint32_t>(64u, std::min<uint32_t>(ctx->sc_c0[k], MAB_SC_MAX)), n = 0;
+		uint32_t c = std::max<uint32_t>(64u, std::min<uint32_t>(sc_c0[k], MAB_SC_MAX)), n = 0;
 		while(n + 1 < MAB_SC_CLASSES && c < MAB_SC_MAX) { R.sc_cls[k][n++] = c; c = std::min<uint32_t>(MAB_SC_MAX, ((c * 7 / 5) + 63u) & ~63u); }
 		R.sc_cls[k][n++] = MAB_SC_MAX;
 		R.sc_ncls[k] = n;
@@ -593,24 +631,43 @@ static int pipeline_run(mab_ctx *ctx, const uint8_t *d_base, const PipeShape &sh
 		RT_LAUNCH(k_seed_probe, R.seed_ctas, 32 * MAB_WARPS_PER_CTA, 0, ctx->stream, P, ctx->d_reads, n_seq, ctx->d_recs);
 		RT_LAUNCH(k_size, 1, MAB_PIPE_THREADS, 0, ctx->stream, ctx->d_reads, n_seq, ctx->ws_cap, ctx->d_ctr);
 		S.n_launches += 3;
+		if(!ws_seen) {
+			/* first batch on this index: how many seeds a read base yields is not known yet (4 to 40 workspace bytes per base from a
+			 * bacterial to a human index), so the host looks at k_size's total here, before the expensive stages, instead of finding the
+			 * workspace too small after them.  Later batches go through without this wait on the high-water mark. */
+			BatchCounters *pin_ctr = (BatchCounters *)(ctx->pin + ((ctx->pin_user + 127) & ~127ull));
+			CK(RT_MEMCPY_D2H_ASYNC(pin_ctr, ctx->d_ctr, sizeof(BatchCounters), ctx->stream));
+			{ double tw = RT_WALL_MS(); CK(ctx_sync(ctx)); S.ms_wall_wait += (float)(RT_WALL_MS() - tw); }
+			S.d2h_bytes += sizeof(BatchCounters);
+			ws_seen = true;
+			if(pin_ctr->ws_need > ctx->ws_cap) {
+				ws_need = (uint64_t)((double)pin_ctr->ws_need * reserve); ws_need += ws_need / 8 + 4096;
+				trace_line(ctx, "first batch: workspace sized after the seed scan, MB", ws_need / 1048576.0);
+				continue;
+			}
+		}
 		pipe_rounds(ctx, true, timed);
 		S.ms_wall_submit += (float)(RT_WALL_MS() - t_sub);
 		{ int rc = pipe_verify(ctx, rlen_init, init_known); if(rc) { return rc; } }
 		const BatchCounters &hc = ctx->hc;
 		if(hc.ws_need > ctx->ws_cap || (hc.err_any & MAB_ERR_WS_OVF)) {					/* workspace estimate too small: now it is known exactly */
 			ws_need = hc.ws_need + hc.ws_need / 8 + 4096; S.n_retry++;
+			trace_line(ctx, "workspace overflow: re-run, MB", ws_need / 1048576.0);
 			if(attempt >= 3) { g_err = "workspace overflow after retries"; return MAB_EOVERFLOW; }
 			continue;
 		}
 		if((hc.err_any & MAB_ERR_POOL_OVF) || hc.pool_top > ctx->pool_cap / 4) {
 			pool_need = std::max<uint64_t>(4 * pool_need, hc.pool_top + hc.pool_top / 2); S.n_retry++;
+			trace_line(ctx, "pool overflow: re-run, MB", 4.0 * pool_need / 1048576.0);
 			if(attempt >= 3) { g_err = "result pool overflow after retries"; return MAB_EOVERFLOW; }
 			continue;
 		}
 		S.n_vectors += hc.n_vectors; S.n_fill_calls += hc.n_fill; S.n_trace += hc.n_trace;
 		if(sh.tot_len) {																	/* high-water mark for the next batch's estimate */
 			double per_base = ((double)hc.ws_need - 20480.0 * n_seq) / (double)sh.tot_len;
-			if(per_base * 1.25 > ctx->ws_per_base) { ctx->ws_per_base = per_base * 1.25; }
+			std::lock_guard<std::mutex> lk(ctx->cal->mu);
+			if(per_base * 1.25 > ctx->cal->ws_per_base) { ctx->cal->ws_per_base = per_base * 1.25; }
+			ctx->cal->ws_seen = true;
 		}
 		break;
 	}
@@ -627,7 +684,8 @@ static void update_sc_caps(mab_ctx *ctx, const ReadRec *hr, uint32_t n_seq)
 		if(bnd.size() < 16) { continue; }
 		size_t k50 = bnd.size() / 2;
 		std::nth_element(bnd.begin(), bnd.begin() + k50, bnd.end());
-		ctx->sc_c0[kind] = std::max<uint32_t>(64u, std::min<uint32_t>((bnd[k50] + 63u) & ~63u, MAB_SC_SMALL));
+		std::lock_guard<std::mutex> lk(ctx->cal->mu);
+		ctx->cal->sc_c0[kind] = std::max<uint32_t>(64u, std::min<uint32_t>((bnd[k50] + 63u) & ~63u, MAB_SC_SMALL));
 	}
 }
 
@@ -792,8 +850,8 @@ extern "C" uint64_t mab_seed_chain(mab_ctx *ctx, const uint8_t *seq, uint32_t le
 	if(!RT_OK(RT_MALLOC(&d_rec, 16ull * len + 256))) { RT_FREE(d_seq); RT_FREE(d_r); RT_FREE(d_fr); return 0; }
 	RT_LAUNCH(k_seed_scan, 1, 32, 2560, ctx->stream, P, (const uint8_t *)d_seq, d_r, 1u, d_rec);
 	RT_LAUNCH(k_seed_probe, 1, 32, 0, ctx->stream, P, d_r, 1u, d_rec);
-	ctx_sync(ctx);
 	RT_MEMCPY_D2H_ASYNC(&r, d_r, sizeof(r), ctx->stream);
+	ctx_sync(ctx);
 	uint64_t ns = 0;
 	if(r.state == 0) {
 		r.seed_cap = 2 * (r.tot_seeds + 1) + 8; r.root_cap = r.tot_seeds + 8; r.resc_cap = r.tot_resc + 4; r.bin_cap = 2 * r.tot_seeds + 128; r.ws_ofs = 0;
@@ -802,12 +860,13 @@ extern "C" uint64_t mab_seed_chain(mab_ctx *ctx, const uint8_t *seq, uint32_t le
 		RT_MEMCPY_H2D_ASYNC(d_r, &r, sizeof(r), ctx->stream);
 		RT_LAUNCH(k_seed_expand, 1, 32, 0, ctx->stream, P, d_r, 1u, d_ws, (const uint32_t *)d_rec);
 		{ uint32_t sc_cap = std::max<uint32_t>(64u, std::min<uint32_t>(r.tot_seeds + 2, MAB_SC_SMALL)); for(uint32_t i = 0; i <= round && i < P.n_occ; i++) { RT_LAUNCH(k_sortchain, 1, 32, 16 * sc_cap + 2048, ctx->stream, P, d_r, 1u, d_ws, d_fr, i, sc_cap, 0u, 0xffffffffu); } }
-		ctx_sync(ctx);
 		RT_MEMCPY_D2H_ASYNC(&r, d_r, sizeof(r), ctx->stream);
+		ctx_sync(ctx);
 		if(r.n_seed) {
 			ns = r.n_seed; *n_total = r.seed_n; *n_root = r.n_root;
 			if(r.seed_n <= seed_cap) { RT_MEMCPY_D2H_ASYNC(seeds, d_ws + L.seed, 16ull * r.seed_n, ctx->stream); }
 			if(r.n_root && r.n_root <= root_cap) { RT_MEMCPY_D2H_ASYNC(roots, d_ws + L.root, 8ull * r.n_root, ctx->stream); }
+			ctx_sync(ctx);
 		}
 		RT_FREE(d_ws);
 	}

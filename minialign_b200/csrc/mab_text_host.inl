@@ -56,6 +56,11 @@ static void text_destroy(mab_ctx *ctx)
 	RT_HOST_FREE(ctx->h_sam);
 }
 
+extern "C" void *mab_host_alloc_on(int device, uint64_t bytes)
+{
+	if(!RT_OK(RT_USE_DEVICE(device))) { g_err = std::string("no usable CUDA device: ") + RT_ERRSTR(); return nullptr; }
+	return mab_host_alloc(bytes);
+}
 extern "C" void *mab_host_alloc(uint64_t bytes) { void *p = nullptr; if(!RT_OK(RT_HOST_ALLOC(&p, bytes))) { g_err = std::string("pinned host allocation failed: ") + RT_ERRSTR(); return nullptr; } return p; }
 extern "C" void mab_host_free(void *p) { RT_HOST_FREE(p); }
 
@@ -79,6 +84,14 @@ static void text_fill_info(const mab_ctx *ctx, mab_text_info_t *info)
 	info->rlen_valid = ctx->hc.chain_valid; info->rlen_next = ctx->hc.chain_rlen;
 }
 
+extern "C" int mab_text_reserve(mab_ctx *ctx, uint64_t max_chunk_bytes)
+{
+	if(ctx == nullptr || max_chunk_bytes >= 0xfffffff0ull) { g_err = "mab_text_reserve: bad arguments (chunks are limited to 4 GiB)"; return MAB_EINVAL; }
+	std::lock_guard<std::mutex> lk(ctx->cal->mu);
+	ctx->cal->reserve_bytes = max_chunk_bytes;
+	return MAB_OK;
+}
+
 extern "C" int mab_text_begin(mab_ctx *ctx, const char *text, uint64_t n_bytes, uint32_t flags, uint32_t rlen_prev, int rlen_known, mab_text_info_t *info)
 {
 	mab_stats_t &S = ctx->stats;
@@ -89,6 +102,17 @@ extern "C" int mab_text_begin(mab_ctx *ctx, const char *text, uint64_t n_bytes, 
 	if(!ctx->thr_ok) { g_err = "text path unavailable: this host's log10 is not monotone around a MAPQ step"; return MAB_EINVAL; }
 	if(n_bytes >= 0xfffffff0ull) { g_err = "mab_text_begin: chunks are limited to 4 GiB"; return MAB_EINVAL; }
 	CK(RT_USE_DEVICE(ctx->device));
+	trace_line(ctx, "begin: enter, MB", n_bytes / 1048576.0);
+	/* buffer sizes follow the largest chunk the caller announced (mab_text_reserve) when this one is a fair sample of it; a much
+	 * shorter chunk (the tail of a file) is sized as it is */
+	double reserve = 1.0; uint64_t mark_hw, rec_hw;
+	{
+		std::lock_guard<std::mutex> lk(ctx->cal->mu);
+		const uint64_t rb = ctx->cal->reserve_bytes;
+		if(n_bytes != 0 && rb > n_bytes && rb <= 2 * n_bytes) { reserve = (double)rb / (double)n_bytes; }
+		mark_hw = ctx->cal->mark_hw; rec_hw = ctx->cal->rec_hw;
+	}
+	ctx->tx.reserve = reserve;
 	RT_EVENT_RECORD(ctx->ev[0], ctx->stream);
 	if(n_bytes == 0) { ctx->tx.stage = 2; text_fill_info(ctx, info); return MAB_OK; }
 	/* the chunk: on the device, closed by a newline, padded with newlines for the 16-byte loads of the scanner */
@@ -104,7 +128,7 @@ extern "C" int mab_text_begin(mab_ctx *ctx, const char *text, uint64_t n_bytes, 
 		first = fl[0]; last = fl[1];
 		if(last != '\n') { g_err = "mab_text_begin: a device-resident chunk must end with a newline"; return MAB_EINVAL; }
 	} else {
-		{ int rc = grow(&ctx->d_text, &ctx->text_cap, n_bytes + 128); if(rc) { return rc; } }
+		{ int rc = grow(&ctx->d_text, &ctx->text_cap, (uint64_t)((double)n_bytes * reserve) + 128); if(rc) { return rc; } }
 		CK(RT_MEMCPY_H2D_ASYNC(ctx->d_text, text, n_bytes, ctx->stream));
 		CK(RT_MEMSET_ASYNC(ctx->d_text + n_bytes, '\n', 64, ctx->stream));
 		S.h2d_bytes += n_bytes;
@@ -116,9 +140,10 @@ extern "C" int mab_text_begin(mab_ctx *ctx, const char *text, uint64_t n_bytes, 
 	const uint32_t fastq = first == '@';
 	ctx->tx.d_text = d_text; ctx->tx.n_text = n_bytes;
 	const uint32_t n_tiles = (uint32_t)((n_bytes + MAB_TXT_TILE - 1) / MAB_TXT_TILE);
-	{ int rc = grow(&ctx->d_tiles, &ctx->tiles_cap, 4ull * n_tiles + 64); if(rc) { return rc; } }
-	uint64_t mark_cap = std::max<uint64_t>(ctx->mark_hw + ctx->mark_hw / 2, n_bytes / 64 + 1024);
-	uint64_t rec_cap = std::max<uint64_t>(ctx->rec_hw + ctx->rec_hw / 2, n_bytes / 256 + 1024);
+	{ int rc = grow(&ctx->d_tiles, &ctx->tiles_cap, (uint64_t)(4.0 * n_tiles * reserve) + 64); if(rc) { return rc; } }
+	const uint64_t z_bytes = (uint64_t)((double)n_bytes * reserve);
+	uint64_t mark_cap = std::max<uint64_t>(mark_hw + mark_hw / 2, z_bytes / 64 + 1024);
+	uint64_t rec_cap = std::max<uint64_t>(rec_hw + rec_hw / 2, z_bytes / 256 + 1024);
 	{ int rc = pin_reserve(ctx, sizeof(TextCounters) + 2 * sizeof(BatchCounters) + 512); if(rc) { return rc; } }
 	TextCounters *pin_tc = (TextCounters *)ctx->pin;
 	TextCounters tc;
@@ -137,6 +162,7 @@ extern "C" int mab_text_begin(mab_ctx *ctx, const char *text, uint64_t n_bytes, 
 		CK(RT_MEMCPY_D2H_ASYNC(pin_tc, ctx->d_tc, sizeof(TextCounters), ctx->stream));
 		{ double tw = RT_WALL_MS(); CK(ctx_sync(ctx)); S.ms_wall_wait += (float)(RT_WALL_MS() - tw); }
 		tc = *pin_tc;
+		trace_line(ctx, "begin: parsed, reads", tc.n_rec);
 		S.d2h_bytes += sizeof(TextCounters);
 		if(tc.err & (MAB_TXT_EMARKS | MAB_TXT_ERECS)) {
 			if(attempt >= 2) { g_err = "text index arrays overflowed after retries"; return MAB_EOVERFLOW; }
@@ -148,17 +174,21 @@ extern "C" int mab_text_begin(mab_ctx *ctx, const char *text, uint64_t n_bytes, 
 		break;
 	}
 	if(tc.err & MAB_TXT_EFORMAT) { g_err = "mab_text_begin: record layout not handled by the device reader (wrapped FASTQ, blank lines, text before the first record)"; return MAB_EFORMAT; }
-	ctx->mark_hw = std::max<uint64_t>(ctx->mark_hw, tc.n_mark); ctx->rec_hw = std::max<uint64_t>(ctx->rec_hw, tc.n_rec);
+	{
+		std::lock_guard<std::mutex> lk(ctx->cal->mu);
+		ctx->cal->mark_hw = std::max<uint64_t>(ctx->cal->mark_hw, (uint64_t)((double)tc.n_mark * reserve));
+		ctx->cal->rec_hw = std::max<uint64_t>(ctx->cal->rec_hw, (uint64_t)((double)tc.n_rec * reserve));
+	}
 	ctx->tx.tc = tc; ctx->tx.n_rec = tc.n_rec;
 	/* the read block */
-	{ int rc = grow(&ctx->d_base, &ctx->base_cap, tc.span + 256); if(rc) { return rc; } }
+	{ int rc = grow(&ctx->d_base, &ctx->base_cap, (uint64_t)((double)tc.span * reserve) + 256); if(rc) { return rc; } }
 	CK(RT_MEMSET_ASYNC(ctx->d_base, 0, tc.span + 256, ctx->stream));
 	RT_LAUNCH(k_text_pack, ctx->n_sm * 8, 32 * MAB_WARPS_PER_CTA, 0, ctx->stream, d_text, (const TextRec *)ctx->d_trec, (const ReadRec *)ctx->d_reads, tc.n_rec, ctx->d_base);
 	S.n_launches++;
 	PipeShape sh; sh.n_seq = tc.n_rec; sh.maxlen = tc.maxlen; sh.tot_len = tc.tot_len; sh.span = tc.span;
 	ctx->pin_user = sizeof(TextCounters) + 256;
 	if(tc.n_rec != 0) {
-		int rc = pipeline_run(ctx, ctx->d_base, sh, rlen_prev, rlen_known ? 1u : 0u, true);
+		int rc = pipeline_run(ctx, ctx->d_base, sh, rlen_prev, rlen_known ? 1u : 0u, true, reserve);
 		if(rc) { return rc; }
 	}
 	ctx->tx.n_kept = tc.n_rec;						/* dropped (empty) records are counted out in finish, where the records come back */
@@ -166,6 +196,7 @@ extern "C" int mab_text_begin(mab_ctx *ctx, const char *text, uint64_t n_bytes, 
 	if(rlen_known && ctx->hc.chain_valid) { ctx->rlen_last = ctx->hc.chain_rlen; }
 	text_fill_info(ctx, info);
 	S.ms_wall = (float)(RT_WALL_MS() - t_call);
+	trace_line(ctx, "begin: mapped, ms", S.ms_wall);
 	return MAB_OK;
 }
 
@@ -203,10 +234,11 @@ extern "C" int mab_text_finish(mab_ctx *ctx, char *sam_out, uint64_t sam_cap, co
 	if(n == 0) { ctx->tx.sam_total = 0; ctx->tx.stage = 0; text_fill_info(ctx, info); return MAB_OK; }
 	CK(RT_USE_DEVICE(ctx->device));
 	const double t_call = RT_WALL_MS();
+	trace_line(ctx, "finish: enter");
 	const uint32_t flags = ctx->tx.flags, tags = flags & ~(MAB_TEXT_KEEP_QUAL | MAB_TEXT_DEVICE_OUT), keep_qual = (flags & MAB_TEXT_KEEP_QUAL) != 0;
 	const uint32_t ctas = std::max<uint32_t>(1, std::min<uint32_t>((n + MAB_WARPS_PER_CTA - 1) / MAB_WARPS_PER_CTA, ctx->n_sm * 8));
 	const uint64_t rr_bytes = sizeof(ReadRec) * (uint64_t)n;
-	{ int rc = pin_reserve(ctx, sizeof(TextCounters) + 256 + rr_bytes + 2 * sizeof(BatchCounters) + 512); if(rc) { return rc; } }
+	{ int rc = pin_reserve(ctx, sizeof(TextCounters) + 256 + (uint64_t)((double)rr_bytes * ctx->tx.reserve) + 2 * sizeof(BatchCounters) + 512); if(rc) { return rc; } }
 	TextCounters *pin_tc = (TextCounters *)ctx->pin;
 	ReadRec *pin_rr = (ReadRec *)(ctx->pin + sizeof(TextCounters) + 256);
 	RT_EVENT_RECORD(ctx->ev[6], ctx->stream);
@@ -216,13 +248,16 @@ extern "C" int mab_text_finish(mab_ctx *ctx, char *sam_out, uint64_t sam_cap, co
 	S.n_launches += 3;
 	CK(RT_MEMCPY_D2H_ASYNC(pin_tc, ctx->d_tc, sizeof(TextCounters), ctx->stream));
 	/* the output buffer is sized from earlier chunks; the size pass usually confirms it while the write pass is already queued */
-	uint64_t est = (uint64_t)(ctx->sam_per_byte * (double)ctx->tx.n_text) + 512ull * n + 4096;
+	double sam_per_byte;
+	{ std::lock_guard<std::mutex> lk(ctx->cal->mu); sam_per_byte = ctx->cal->sam_per_byte; }
+	uint64_t est = (uint64_t)((sam_per_byte * (double)ctx->tx.n_text + 512.0 * n) * ctx->tx.reserve) + 4096;
 	{ int rc = grow(&ctx->d_sam, &ctx->sam_cap, est); if(rc) { return rc; } }
 	{ double tw = RT_WALL_MS(); CK(ctx_sync(ctx)); S.ms_wall_wait += (float)(RT_WALL_MS() - tw); }
 	const uint64_t total = pin_tc->sam_total;
+	trace_line(ctx, "finish: sized, MB", total / 1048576.0);
 	S.d2h_bytes += sizeof(TextCounters);
 	{ int rc = grow(&ctx->d_sam, &ctx->sam_cap, total + 64); if(rc) { return rc; } }
-	{ double r = (double)total / (double)ctx->tx.n_text; if(r * 1.1 > ctx->sam_per_byte) { ctx->sam_per_byte = r * 1.1; } }
+	{ double r = (double)total / (double)ctx->tx.n_text; std::lock_guard<std::mutex> lk(ctx->cal->mu); if(r * 1.1 > ctx->cal->sam_per_byte) { ctx->cal->sam_per_byte = r * 1.1; } }
 	RT_LAUNCH((k_sam<true>), ctas, 32 * MAB_WARPS_PER_CTA, 0, ctx->stream, ctx->P, (const uint32_t *)ctx->d_pool, (const ReadRec *)ctx->d_reads, ctx->d_trec, n, ctx->tx.d_text, (const uint8_t *)ctx->d_base, tags, keep_qual, ctx->d_sam);
 	S.n_launches++;
 	RT_EVENT_RECORD(ctx->ev[7], ctx->stream);
@@ -266,6 +301,9 @@ extern "C" int mab_text_finish(mab_ctx *ctx, char *sam_out, uint64_t sam_cap, co
 	S.ms_d2h = RT_EVENT_MS(ctx->ev[7], ctx->ev[5]);
 	S.ms_total = RT_EVENT_MS(ctx->ev[0], ctx->ev[5]);
 	S.ms_wall += (float)(RT_WALL_MS() - t_call);
+	trace_line(ctx, "finish: done; device ms sortchain, extend", S.ms_sortchain, S.ms_extend);
+	trace_line(ctx, "finish: done; device ms seed, post", S.ms_seed, S.ms_post);
+	trace_line(ctx, "finish: done; device ms h2d, d2h", S.ms_h2d, S.ms_d2h);
 	ctx->tx.stage = 0;
 	text_fill_info(ctx, info);
 	return MAB_OK;
