@@ -76,10 +76,11 @@ if p.returncode != 0:
 if os.environ.get("HUMAN_TRACE"):             # stage timeline of the CLI (MAB_TRACE lines) for the listed context counts, nothing else
     REP = int(os.environ.get("HUMAN_REPEAT", "3"))
     for nc in [int(x) for x in os.environ["HUMAN_TRACE"].split(",")]:
-        with open(os.devnull, "wb") as f:
-            pc = subprocess.run([CLI, "-xpacbio", f"-c{nc}", idx] + [rd] * REP, stdout=f, stderr=subprocess.PIPE, text=True, env=dict(os.environ, MAB_TRACE="1"))
-        open(os.path.join(OUT, f"trace_c{nc}.log"), "w").write(pc.stderr)
-        log("trace", nc, pc.stderr[-300:])
+        for ctas in os.environ.get("HUMAN_CTAS", "4").split(","):
+            with open(os.devnull, "wb") as f:
+                pc = subprocess.run([CLI, "-xpacbio", f"-c{nc}", idx] + [rd] * REP, stdout=f, stderr=subprocess.PIPE, text=True, env=dict(os.environ, MAB_TRACE="1", MAB_EXT_CTAS=ctas))
+            open(os.path.join(OUT, f"trace_c{nc}_ctas{ctas}.log"), "w").write(pc.stderr)
+            log("trace", nc, ctas, pc.stderr[-300:])
     raise SystemExit(0)
 
 # ---- our CLI, file to SAM ----
