@@ -61,6 +61,19 @@ mab_ctx *mab_init(const void *mai_blob, uint64_t size, const mab_params_t *param
 /* another context on the same device sharing the parent's index image (several batches in flight per GPU cost one index copy);
  * the parent must outlive its clones.  One host thread per context at a time. */
 mab_ctx *mab_clone(mab_ctx *parent);
+/* Staged set-up, for a host that produces the image piece by piece (the .mai container is a sequence of independently deflated
+ * 1 MiB frames, minialign.c:1137-1290, 3128-3167): every piece goes to all the listed devices while the rest is still being
+ * inflated, so a human-sized index (15-17 GB) is on the GPUs when the last frame is done.
+ *   ld = mab_load_begin(max_size, params, devices, n)     device buffers of max_size bytes, a ring of page-locked staging slots
+ *   mab_load_put(ld, offset, src, n)                       any thread, any order; returns when src may be reused
+ *   mab_load_end(ld, blob, size, ctx_out)                  waits for the copies; one context per device (as from mab_init) in ctx_out[n]
+ *   mab_load_abort(ld)                                     instead of mab_load_end: drops everything
+ * mab_load_end consumes the loader whatever it returns. */
+typedef struct mab_loader mab_loader;
+mab_loader *mab_load_begin(uint64_t max_size, const mab_params_t *params, const int *devices, int n_devices);
+int mab_load_put(mab_loader *ld, uint64_t offset, const void *src, uint64_t n);
+int mab_load_end(mab_loader *ld, const void *blob, uint64_t size, mab_ctx **ctx_out);
+void mab_load_abort(mab_loader *ld);
 void mab_destroy(mab_ctx *ctx);
 const char *mab_last_error(void);
 

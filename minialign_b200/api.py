@@ -113,6 +113,14 @@ def load_library(lib_path: str | None = None):
     L.mab_selftest.restype = C.c_int
     L.mab_selftest.argtypes = [C.c_void_p, u32p]
     ti = C.POINTER(MabTextInfo)
+    L.mab_load_begin.restype = C.c_void_p
+    L.mab_load_begin.argtypes = [C.c_uint64, C.POINTER(MabParams), C.POINTER(C.c_int), C.c_int]
+    L.mab_load_put.restype = C.c_int
+    L.mab_load_put.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+    L.mab_load_end.restype = C.c_int
+    L.mab_load_end.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
+    L.mab_load_abort.restype = None
+    L.mab_load_abort.argtypes = [C.c_void_p]
     L.mab_text_reserve.restype = C.c_int
     L.mab_text_reserve.argtypes = [C.c_void_p, C.c_uint64]
     L.mab_text_begin.restype = C.c_int
@@ -153,6 +161,32 @@ class Mapper:
         self.h = self.lib.mab_init(self.blob.ctypes.data, self.blob.size, C.byref(self.params), device)
         if not self.h:
             raise RuntimeError("mab_init failed: " + self.lib.mab_last_error().decode())
+
+    @classmethod
+    def staged(cls, mai_blob: np.ndarray, params: dict | str = "pacbio", devices=(0,), piece: int = 1 << 20, order=None, lib_path: str | None = None):
+        """The staged set-up (mab_load_begin / put / end): the image goes to every listed device piece by piece (`order`: the
+        sequence the pieces are handed over in, default ascending); returns one Mapper per device."""
+        lib = load_library(lib_path)
+        prm = make_params(PRESETS[params] if isinstance(params, str) else params)
+        blob = np.ascontiguousarray(mai_blob, dtype=np.uint8)
+        devs = (C.c_int * len(devices))(*devices)
+        ld = lib.mab_load_begin(blob.size, C.byref(prm), devs, len(devices))
+        if not ld:
+            raise RuntimeError("mab_load_begin failed: " + lib.mab_last_error().decode())
+        starts = list(range(0, blob.size, piece))
+        for k in (order(starts) if order else starts):
+            if lib.mab_load_put(ld, k, blob.ctypes.data + k, min(piece, blob.size - k)) != 0:
+                lib.mab_load_abort(ld)
+                raise RuntimeError("mab_load_put failed: " + lib.mab_last_error().decode())
+        out = (C.c_void_p * len(devices))()
+        if lib.mab_load_end(ld, blob.ctypes.data, blob.size, out) != 0:
+            raise RuntimeError("mab_load_end failed: " + lib.mab_last_error().decode())
+        ms = []
+        for h in out:
+            m = cls.__new__(cls)
+            m.lib, m.params, m.blob, m.h = lib, prm, blob, h
+            ms.append(m)
+        return ms
 
     def clone(self) -> "Mapper":
         """Another context on the same device sharing this one's index image (keep this one alive while the clone is used)."""

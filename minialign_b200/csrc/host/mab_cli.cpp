@@ -27,6 +27,7 @@
 #include <memory>
 #include <mutex>
 #include <thread>
+#include <functional>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -45,7 +46,10 @@ struct MaiImage {
 	std::vector<uint8_t> own;							/* payload built here (FASTA reference) */
 	~MaiImage() { free(raw); }
 };
-static bool load_mai(const char *path, MaiImage &im)
+/* on_size(payload bytes) is called once the header frame is read, on_piece(payload offset, bytes, n) for every inflated frame
+ * from the thread that inflated it: the caller forwards the pieces to the GPUs while the other frames are still in the works */
+struct MaiHooks { std::function<void(uint64_t)> on_size; std::function<void(uint64_t, const uint8_t *, uint64_t)> on_piece; };
+static bool load_mai(const char *path, MaiImage &im, const MaiHooks *hooks = nullptr)
 {
 	int fd = open(path, O_RDONLY);
 	if(fd < 0) { return false; }
@@ -67,16 +71,39 @@ static bool load_mai(const char *path, MaiImage &im)
 	im.raw = (uint8_t *)malloc(frames.size() * BS + 64);
 	if(!im.raw) { munmap((void *)file, fsz); return false; }
 	std::vector<uint32_t> out_len(frames.size(), 0);
-	std::atomic<size_t> next(0); std::atomic<bool> ok(true);
-	auto work = [&]() {
-		for(size_t i; (i = next.fetch_add(1)) < frames.size();) {
-			z_stream zs; memset(&zs, 0, sizeof(zs));
-			zs.next_in = (Bytef *)(file + frames[i].ofs); zs.avail_in = (uInt)frames[i].len; zs.next_out = im.raw + i * BS; zs.avail_out = (uInt)BS;
-			if(inflateInit2(&zs, 15) != Z_OK) { ok = false; return; }
-			int rc = inflate(&zs, Z_FINISH); inflateEnd(&zs);
-			if(rc != Z_STREAM_END) { ok = false; return; }
-			out_len[i] = (uint32_t)(BS - zs.avail_out);
+	std::atomic<size_t> next(1); std::atomic<bool> ok(true);
+	uint64_t payload = 0;																		/* from the header in frame 0 */
+	auto one = [&](size_t i) -> bool {
+		z_stream zs; memset(&zs, 0, sizeof(zs));
+		zs.next_in = (Bytef *)(file + frames[i].ofs); zs.avail_in = (uInt)frames[i].len; zs.next_out = im.raw + i * BS; zs.avail_out = (uInt)BS;
+		if(inflateInit2(&zs, 15) != Z_OK) { return false; }
+		int rc = inflate(&zs, Z_FINISH); inflateEnd(&zs);
+		if(rc != Z_STREAM_END) { return false; }
+		out_len[i] = (uint32_t)(BS - zs.avail_out);
+		if(hooks && payload) {																	/* this frame's share of the payload [0, payload) */
+			uint64_t lo = i * BS, hi = lo + out_len[i];
+			lo = std::max<uint64_t>(lo, 12); hi = std::min<uint64_t>(hi, 12 + payload);
+			if(lo < hi) { hooks->on_piece(lo - 12, im.raw + lo, hi - lo); }
 		}
+		return true;
+	};
+	{	/* frame 0 first: it holds the {magic, size} header the device buffers are sized by */
+		z_stream zs; memset(&zs, 0, sizeof(zs));
+		zs.next_in = (Bytef *)(file + frames[0].ofs); zs.avail_in = (uInt)frames[0].len; zs.next_out = im.raw; zs.avail_out = (uInt)BS;
+		bool good = inflateInit2(&zs, 15) == Z_OK;
+		if(good) { int rc = inflate(&zs, Z_FINISH); inflateEnd(&zs); good = rc == Z_STREAM_END; }
+		out_len[0] = good ? (uint32_t)(BS - zs.avail_out) : 0;
+		uint32_t magic = 0; uint64_t size = 0;
+		if(good && out_len[0] >= 12) { memcpy(&magic, im.raw, 4); memcpy(&size, im.raw + 4, 8); }
+		if(!good || magic != 0x0849414du || size + 12 > frames.size() * BS) { munmap((void *)file, fsz); return false; }
+		if(hooks) {
+			payload = size; hooks->on_size(size);
+			uint64_t hi = std::min<uint64_t>(out_len[0], 12 + payload);
+			if(hi > 12) { hooks->on_piece(0, im.raw + 12, hi - 12); }
+		}
+	}
+	auto work = [&]() {
+		for(size_t i; (i = next.fetch_add(1)) < frames.size();) { if(!one(i)) { ok = false; return; } }
 	};
 	unsigned nth = std::max(1u, std::min(std::thread::hardware_concurrency(), 64u));
 	std::vector<std::thread> th;
@@ -376,7 +403,15 @@ int main(int argc, char **argv)
 	}
 	auto stop_pinner = [&]() { { std::unique_lock<std::mutex> lk(mu); pin_stop = true; } if(pinner.joinable()) { pinner.join(); } };
 	MaiImage im;
-	if(!load_mai(o.pos[0].c_str(), im)) {															/* not an index: a FASTA reference, build it here */
+	/* a .mai index goes to the GPUs frame by frame while the other frames are still being inflated (mab_load_*) */
+	mab_loader *ld = nullptr; std::atomic<bool> ld_failed(false);
+	mab_params_t ld_prm = o.p; ld_prm.flags |= MAB_FLAG_BORROW_INDEX;								/* `im` outlives the contexts */
+	MaiHooks hooks;
+	hooks.on_size = [&](uint64_t size) { ld = mab_load_begin(size, &ld_prm, devices.data(), (int)devices.size()); if(!ld) { ld_failed = true; } };
+	hooks.on_piece = [&](uint64_t off, const uint8_t *p, uint64_t n) { if(ld && !ld_failed && mab_load_put(ld, off, p, n) != MAB_OK) { ld_failed = true; } };
+	const bool is_mai = load_mai(o.pos[0].c_str(), im, o.dump.empty() && getenv("MAB_NO_STAGED_LOAD") == nullptr ? &hooks : nullptr);
+	if(ld && (!is_mai || ld_failed)) { mab_load_abort(ld); ld = nullptr; }								/* the plain path below reports what is wrong */
+	if(!is_mai) {															/* not an index: a FASTA reference, build it here */
 		SeqReader rr(o.pos[0].c_str());
 		if(!rr.fp) { fprintf(stderr, "[E::main_align] failed to open index file `%s'. Please check file path and it exists.\n", o.pos[0].c_str()); stop_pinner(); return 1; }
 		std::vector<MabIdxSeq> refs; Rec r;
@@ -405,10 +440,14 @@ int main(int argc, char **argv)
 	std::vector<mab_ctx *> ctxs(n_ctx, nullptr);
 	{	/* one parent context per device (uploads the index), clones share its image; devices are set up in parallel */
 		std::vector<std::thread> th; std::vector<std::string> errs(devices.size());
+		std::vector<mab_ctx *> parents(devices.size(), nullptr);
+		if(ld) {
+			if(mab_load_end(ld, im.blob, im.size, parents.data()) != MAB_OK) { fprintf(stderr, "[E::main_align] failed to instanciate alignment context: %s\n", mab_last_error()); stop_pinner(); return 1; }
+			ld = nullptr;
+		}
 		for(size_t d = 0; d < devices.size(); d++) {
 			th.emplace_back([&, d]() {
-				mab_params_t prm = o.p; prm.flags |= MAB_FLAG_BORROW_INDEX;			/* `im` outlives the contexts */
-				mab_ctx *p = mab_init(im.blob, im.size, &prm, devices[d]);
+				mab_ctx *p = parents[d] ? parents[d] : mab_init(im.blob, im.size, &ld_prm, devices[d]);
 				if(!p) { errs[d] = mab_last_error(); return; }
 				ctxs[d] = p;
 				mab_text_reserve(p, chunk_bytes);									/* clones share it: every context sizes its buffers for a full chunk at once */

@@ -220,9 +220,10 @@ static int ctx_private_init(mab_ctx *ctx)
 	return MAB_OK;
 }
 
-extern "C" mab_ctx *mab_init(const void *mai_blob, uint64_t size, const mab_params_t *params, int device)
+/* the host part of a context's set-up: parameters, the header of the index image, the GABA constants */
+static mab_ctx *ctx_new(const uint8_t *b, uint64_t size, const mab_params_t *params, int device)
 {
-	if(mai_blob == nullptr || size < 64 || params == nullptr) { g_err = "mab_init: bad arguments"; return nullptr; }
+	if(b == nullptr || size < 64 || params == nullptr) { g_err = "mab_init: bad arguments"; return nullptr; }
 	if(check_params(params) != 0) { g_err = "mab_init: unsupported scoring parameters (combined gap model with validated ranges only)"; return nullptr; }
 	mab_ctx *ctx = new mab_ctx();
 	ctx->device = device; ctx->prm = *params;
@@ -230,7 +231,6 @@ extern "C" mab_ctx *mab_init(const void *mai_blob, uint64_t size, const mab_para
 	memset(&ctx->stats, 0, sizeof(ctx->stats));
 	if(!RT_OK(RT_SET_DEVICE(device))) { g_err = std::string("no usable CUDA device: ") + RT_ERRSTR(); delete ctx; return nullptr; }
 	ctx->n_sm = RT_SM_COUNT(device);
-	const uint8_t *b = (const uint8_t *)mai_blob;
 	if(params->flags & MAB_FLAG_BORROW_INDEX) { ctx->blob_ptr = b; }
 	else {
 		try { ctx->blob = std::make_shared<std::vector<uint8_t>>(b, b + size); } catch(const std::bad_alloc &) { g_err = "host allocation failed"; delete ctx; return nullptr; }
@@ -249,11 +249,13 @@ extern "C" mab_ctx *mab_init(const void *mai_blob, uint64_t size, const mab_para
 	for(int i = 0; i < 16; i++) { if((i & 3) == (i >> 3)) { mc += params->score_matrix[0]; } else { xc += params->score_matrix[0]; } }
 	P.mcoef = mc / 4.0; ctx->xcoef = xc / 12.0; P.xcoef = ctx->xcoef;
 	init_gaba_consts(P, params);
-	trace_line(ctx, "init: enter, index MB", size / 1048576.0);
-	CKP(RT_MALLOC(&ctx->d_idx, size + 256));
-	CKP(RT_MEMCPY_H2D(ctx->d_idx, b, size));
-	trace_line(ctx, "init: index on the device");
-	P.idx = ctx->d_idx;
+	return ctx;
+}
+
+/* the device part after the index image is in place (ctx->d_idx) */
+static mab_ctx *ctx_finish(mab_ctx *ctx)
+{
+	ctx->P.idx = ctx->d_idx;
 	uint8_t nt[128]; memset(nt, 4, sizeof(nt));
 	CKP(RT_MALLOC(&ctx->d_ntail, 256));
 	CKP(RT_MEMCPY_H2D(ctx->d_ntail, nt, 128));
@@ -262,6 +264,147 @@ extern "C" mab_ctx *mab_init(const void *mai_blob, uint64_t size, const mab_para
 	if(ctx_private_init(ctx) != MAB_OK) { mab_destroy(ctx); return nullptr; }
 	trace_line(ctx, "init: done");
 	return ctx;
+}
+
+extern "C" mab_ctx *mab_init(const void *mai_blob, uint64_t size, const mab_params_t *params, int device)
+{
+	mab_ctx *ctx = ctx_new((const uint8_t *)mai_blob, size, params, device);
+	if(ctx == nullptr) { return nullptr; }
+	trace_line(ctx, "init: enter, index MB", size / 1048576.0);
+	CKP(RT_MALLOC(&ctx->d_idx, size + 256));
+	CKP(RT_MEMCPY_H2D(ctx->d_idx, ctx->blob_ptr, size));
+	trace_line(ctx, "init: index on the device");
+	return ctx_finish(ctx);
+}
+
+/* ---- staged set-up: the index image goes to the device(s) in pieces while the caller is still producing it ----
+ * A .mai file is a sequence of deflated 1 MiB frames (minialign.c:1137-1290); inflating a human-sized index takes seconds on all
+ * host cores and copying 15-17 GB from pageable memory takes as long again.  Here every piece is handed over as soon as it exists:
+ * mab_load_put stages it in a ring of page-locked slots and queues one asynchronous copy per device, so the upload runs under the
+ * inflation and every GPU of the process gets its copy from the same staging slot. */
+struct mab_loader {
+	std::vector<int> devices;
+	std::vector<uint8_t *> d_idx;
+	std::vector<RT_STREAM> streams;
+	mab_params_t prm;
+	uint64_t cap = 0;
+	uint8_t *ring = nullptr;
+	static constexpr uint32_t SLOTS = 64;
+	static constexpr uint64_t SLOT_BYTES = 1ull << 20;
+	std::mutex slot_mu[SLOTS];
+	std::vector<RT_EVENT> slot_ev;			/* [slot][device] */
+	std::vector<uint8_t> slot_used;			/* [slot] */
+	std::mutex mu; uint32_t next = 0;
+	bool failed = false;
+};
+
+extern "C" void mab_load_abort(mab_loader *ld)
+{
+	if(ld == nullptr) { return; }
+	for(size_t d = 0; d < ld->devices.size(); d++) {
+		RT_USE_DEVICE(ld->devices[d]);
+		if(d < ld->streams.size()) { RT_STREAM_SYNC(ld->streams[d]); RT_STREAM_DESTROY(ld->streams[d]); }
+		for(uint32_t sl = 0; sl < mab_loader::SLOTS; sl++) { size_t e = sl * ld->devices.size() + d; if(e < ld->slot_ev.size()) { RT_EVENT_DESTROY(ld->slot_ev[e]); } }
+		if(d < ld->d_idx.size()) { RT_FREE(ld->d_idx[d]); }
+	}
+	RT_HOST_FREE(ld->ring);
+	delete ld;
+}
+
+extern "C" mab_loader *mab_load_begin(uint64_t max_size, const mab_params_t *params, const int *devices, int n_devices)
+{
+	if(params == nullptr || devices == nullptr || n_devices <= 0 || max_size < 64) { g_err = "mab_load_begin: bad arguments"; return nullptr; }
+	if(check_params(params) != 0) { g_err = "mab_init: unsupported scoring parameters (combined gap model with validated ranges only)"; return nullptr; }
+	mab_loader *ld = new mab_loader();
+	ld->prm = *params; ld->cap = max_size; ld->devices.assign(devices, devices + n_devices);
+	ld->slot_used.assign(mab_loader::SLOTS, 0);
+	/* the devices in parallel: creating a CUDA context takes a few hundred milliseconds each */
+	ld->d_idx.assign(n_devices, nullptr); ld->streams.resize(n_devices);
+	ld->slot_ev.resize((size_t)mab_loader::SLOTS * n_devices);
+	std::vector<std::string> errs(n_devices); std::vector<int> n_ev(n_devices, 0), have_stream(n_devices, 0);
+	{
+		std::vector<std::thread> th;
+		for(int d = 0; d < n_devices; d++) {
+			th.emplace_back([&, d]() {
+				if(!RT_OK(RT_SET_DEVICE(devices[d]))) { errs[d] = std::string("no usable CUDA device: ") + RT_ERRSTR(); return; }
+				if(!RT_OK(RT_MALLOC(&ld->d_idx[d], max_size + 256))) { errs[d] = std::string("device allocation failed: ") + RT_ERRSTR(); ld->d_idx[d] = nullptr; return; }
+				if(!RT_OK(RT_STREAM_CREATE(&ld->streams[d]))) { errs[d] = std::string("stream creation failed: ") + RT_ERRSTR(); return; }
+				have_stream[d] = 1;
+				for(uint32_t sl = 0; sl < mab_loader::SLOTS; sl++) {
+					if(!RT_OK(RT_SYNC_EVENT_CREATE(&ld->slot_ev[(size_t)sl * n_devices + d]))) { errs[d] = std::string("event creation failed: ") + RT_ERRSTR(); return; }
+					n_ev[d]++;
+				}
+			});
+		}
+		for(auto &t : th) { t.join(); }
+	}
+	for(int d = 0; d < n_devices; d++) {
+		if(errs[d].empty()) { continue; }
+		g_err = errs[d];
+		for(int e = 0; e < n_devices; e++) {										/* partial set-up: undo by hand */
+			RT_USE_DEVICE(devices[e]);
+			for(int sl = 0; sl < n_ev[e]; sl++) { RT_EVENT_DESTROY(ld->slot_ev[(size_t)sl * n_devices + e]); }
+			if(have_stream[e]) { RT_STREAM_DESTROY(ld->streams[e]); }
+			RT_FREE(ld->d_idx[e]);
+		}
+		delete ld;
+		return nullptr;
+	}
+	RT_USE_DEVICE(devices[0]);
+	if(!RT_OK(RT_HOST_ALLOC(&ld->ring, mab_loader::SLOTS * mab_loader::SLOT_BYTES))) { g_err = std::string("pinned host allocation failed: ") + RT_ERRSTR(); mab_load_abort(ld); return nullptr; }
+	trace_line(ld, "load: begin, index MB", max_size / 1048576.0);
+	return ld;
+}
+
+/* bytes [offset, offset + n) of the image; any thread, any order.  Returns once the bytes are staged (src may be reused). */
+extern "C" int mab_load_put(mab_loader *ld, uint64_t offset, const void *src, uint64_t n)
+{
+	if(ld == nullptr || src == nullptr || offset + n > ld->cap) { g_err = "mab_load_put: bad arguments"; return MAB_EINVAL; }
+	const uint8_t *s = (const uint8_t *)src;
+	const size_t nd = ld->devices.size();
+	while(n > 0) {
+		const uint64_t m = std::min<uint64_t>(n, mab_loader::SLOT_BYTES);
+		uint32_t sl;
+		{ std::lock_guard<std::mutex> lk(ld->mu); sl = ld->next++ % mab_loader::SLOTS; }
+		std::lock_guard<std::mutex> lk(ld->slot_mu[sl]);
+		uint8_t *stage = ld->ring + (uint64_t)sl * mab_loader::SLOT_BYTES;
+		if(ld->slot_used[sl]) { for(size_t d = 0; d < nd; d++) { CK(RT_EVENT_SYNC(ld->slot_ev[sl * nd + d])); } }	/* the slot's previous copies */
+		memcpy(stage, s, m);
+		for(size_t d = 0; d < nd; d++) {
+			CK(RT_USE_DEVICE(ld->devices[d]));
+			CK(RT_MEMCPY_H2D_ASYNC(ld->d_idx[d] + offset, stage, m, ld->streams[d]));
+			RT_EVENT_RECORD(ld->slot_ev[sl * nd + d], ld->streams[d]);
+		}
+		ld->slot_used[sl] = 1;
+		s += m; offset += m; n -= m;
+	}
+	return MAB_OK;
+}
+
+/* all pieces are in: waits for the copies and builds one context per device around the uploaded image.  blob = the complete
+ * host image of `size` bytes (kept or borrowed like in mab_init).  The loader is gone afterwards, whatever the outcome. */
+extern "C" int mab_load_end(mab_loader *ld, const void *blob, uint64_t size, mab_ctx **ctx_out)
+{
+	if(ld == nullptr || blob == nullptr || ctx_out == nullptr || size > ld->cap) { g_err = "mab_load_end: bad arguments"; mab_load_abort(ld); return MAB_EINVAL; }
+	const size_t nd = ld->devices.size();
+	int rc = MAB_OK;
+	for(size_t d = 0; d < nd; d++) { ctx_out[d] = nullptr; }
+	for(size_t d = 0; d < nd && rc == MAB_OK; d++) {
+		RT_USE_DEVICE(ld->devices[d]);
+		if(!RT_OK(RT_STREAM_SYNC(ld->streams[d]))) { g_err = std::string("index upload failed: ") + RT_ERRSTR(); rc = MAB_ENODEV; }
+	}
+	trace_line(ld, "load: index on the device(s)");
+	for(size_t d = 0; d < nd && rc == MAB_OK; d++) {
+		mab_ctx *ctx = ctx_new((const uint8_t *)blob, size, &ld->prm, ld->devices[d]);
+		if(ctx == nullptr) { rc = MAB_EINVAL; break; }
+		ctx->d_idx = ld->d_idx[d]; ld->d_idx[d] = nullptr;			/* the context owns it from here */
+		ctx = ctx_finish(ctx);
+		if(ctx == nullptr) { rc = MAB_ENODEV; break; }
+		ctx_out[d] = ctx;
+	}
+	if(rc != MAB_OK) { for(size_t d = 0; d < nd; d++) { if(ctx_out[d]) { mab_destroy(ctx_out[d]); ctx_out[d] = nullptr; } } }
+	mab_load_abort(ld);
+	return rc;
 }
 
 /* a second (third, ...) context on the parent's device that shares its index image: batches in flight at the same time cost one

@@ -154,3 +154,23 @@ def test_emu_text_chunks_on_several_contexts_chain_rlen(tmp_path):
         out += C.string_at(ptr, info.sam_bytes).decode()
         m.close()
     assert out == exp
+
+
+def test_emu_staged_load_and_reserve(gold):
+    """mab_load_begin / put / end with the pieces out of order gives the context mab_init gives; with a chunk size announced
+    (mab_text_reserve) a short chunk followed by a long one maps like without it"""
+    so = build_emu()
+    n = 0
+    while n < len(gold["enc"]) and sum(s.size for s in gold["enc"][:n + 1]) <= 40000:
+        n += 1
+    short, long_ = _fasta(gold["reads"][:3]), _fasta(gold["reads"][:n])
+    m0 = api.Mapper(gold["blob"], "pacbio", lib_path=so)
+    exp = [m0.map_text(short), m0.map_text(long_)]
+    m0.close()
+    (m1,) = api.Mapper.staged(gold["blob"], "pacbio", piece=70001, order=lambda st: st[::-1], lib_path=so)
+    m1.text_reserve(len(long_) + 100)
+    c = m1.clone()
+    got = [m1.map_text(short), m1.map_text(long_)]
+    assert got == exp
+    assert c.map_text(long_) == api.Mapper(gold["blob"], "pacbio", lib_path=so).map_text(long_)
+    c.close(); m1.close()
