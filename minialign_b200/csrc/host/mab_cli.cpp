@@ -106,6 +106,7 @@ static bool load_mai(const char *path, MaiImage &im, const MaiHooks *hooks = nul
 		for(size_t i; (i = next.fetch_add(1)) < frames.size();) { if(!one(i)) { ok = false; return; } }
 	};
 	unsigned nth = std::max(1u, std::min(std::thread::hardware_concurrency(), 64u));
+	if(hooks && nth > 2) { nth--; }															/* a core for the thread that brings the devices up meanwhile */
 	std::vector<std::thread> th;
 	for(unsigned t = 1; t < nth; t++) { th.emplace_back(work); }
 	work();
@@ -366,8 +367,8 @@ int main(int argc, char **argv)
 	}
 	if(!o.w_set) { o.ip.w = (uint32_t)(int)(2.0 / 3.0 * o.ip.k + .499); }							/* default window size when -w is absent (minialign.c:6111) */
 	if(o.pos.size() < (o.dump.empty() ? 2u : 1u)) { fprintf(stderr, "usage: minialign-b200 [-x preset] [-T tags] <ref.fa|ref.mai> <reads.fa> [...] > out.sam\n       minialign-b200 [-x preset] -d <out.mai> <ref.fa>\n"); return 1; }
-	/* the host side of the pipeline below: page-locked chunk and output buffers.  Pinning memory is slow (2-3 GB/s), so a thread
-	 * starts on it right away, next to the index load and the device set-up; readers and workers pick the buffers up as they appear. */
+	/* the host side of the pipeline below: page-locked chunk and output buffers.  Pinning memory is slow (1.5-2.5 GB/s), so a thread
+	 * of its own does it while the first chunks are already being read and mapped; readers and workers pick the buffers up as they appear. */
 	const uint64_t chunk_bytes = std::max<uint64_t>(1024, (uint64_t)(o.chunk_mb * 1048576.0));
 	std::vector<int> devices = o.devices.empty() ? std::vector<int>{ o.device } : o.devices;
 	const unsigned n_ctx = std::max(1u, o.contexts) * (unsigned)devices.size();
@@ -375,13 +376,18 @@ int main(int argc, char **argv)
 	struct Out { char *buf = nullptr; uint64_t cap = 0, len = 0; std::string spill; uint64_t id = 0; unsigned owner = 0; bool busy = false; };	/* buf: page-locked, the SAM text is copied from the device straight into it */
 	std::mutex mu; std::condition_variable cv;
 	std::deque<Chunk *> free_chunks, ready; std::map<uint64_t, Out *> done_outs;
-	bool read_done = false, failed = false, pin_stop = false;
+	bool read_done = false, failed = false, pin_stop = false, pin_go = false;
 	std::vector<Chunk> chunk_pool(n_ctx + 2); std::vector<Out> out_pool(2 * n_ctx);			/* two output buffers per context: one being written while the next is filled */
 	for(unsigned i = 0; i < 2 * n_ctx; i++) { out_pool[i].owner = i / 2; }
 	std::thread pinner;
 	if(o.dump.empty()) {
 		pinner = std::thread([&]() {
 			auto stopped = [&]() { std::unique_lock<std::mutex> lk(mu); return pin_stop; };
+			/* not before the contexts stand: pinning pages holds up every other CUDA call of the process, and doing it while the CUDA
+			 * contexts come up and the index frames are copied costs more than it saves (measured: device set-up 1.3 -> 2.4-4.3 s,
+			 * upload 2.5 -> 4.3 s, context set-up 0.01 -> 1.7 s) */
+			{ std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&]() { return pin_go || pin_stop; }); }
+			if(getenv("MAB_TRACE")) { fprintf(stderr, "[pinner %.3f] start\n", now() - t0); }
 			auto give_up = [&]() { fprintf(stderr, "[E::main_align] %s\n", mab_last_error()); std::unique_lock<std::mutex> lk(mu); failed = true; cv.notify_all(); };
 			/* first what the first chunks need (a chunk buffer and an output buffer per context), then the second halves */
 			for(unsigned pass = 0; pass < 2; pass++) {
@@ -392,6 +398,7 @@ int main(int argc, char **argv)
 					if(!b) { give_up(); return; }
 					std::unique_lock<std::mutex> lk(mu); c.cap = cap; c.buf = b; free_chunks.push_back(&c); cv.notify_all();
 				}
+				if(getenv("MAB_TRACE")) { fprintf(stderr, "[pinner %.3f] pass %u: chunk buffers done\n", now() - t0, pass); }
 				for(unsigned i = pass; i < 2 * n_ctx; i += 2) {
 					if(stopped()) { return; }
 					uint64_t cap = chunk_bytes + chunk_bytes / 2 + (1 << 20); char *b = (char *)mab_host_alloc_on(devices[0], cap);
@@ -401,15 +408,47 @@ int main(int argc, char **argv)
 			}
 		});
 	}
-	auto stop_pinner = [&]() { { std::unique_lock<std::mutex> lk(mu); pin_stop = true; } if(pinner.joinable()) { pinner.join(); } };
+	auto stop_pinner = [&]() { { std::unique_lock<std::mutex> lk(mu); pin_stop = true; cv.notify_all(); } if(pinner.joinable()) { pinner.join(); } };
 	MaiImage im;
-	/* a .mai index goes to the GPUs frame by frame while the other frames are still being inflated (mab_load_*) */
+	/* a .mai index goes to the GPUs frame by frame while the other frames are still being inflated (mab_load_*).  The devices are
+	 * set up (CUDA context, buffers: a second or more) by a thread of their own next to the inflation; frames finished before they
+	 * are ready wait in a list, which every inflating thread helps to empty afterwards. */
 	mab_loader *ld = nullptr; std::atomic<bool> ld_failed(false);
 	mab_params_t ld_prm = o.p; ld_prm.flags |= MAB_FLAG_BORROW_INDEX;								/* `im` outlives the contexts */
+	struct Piece { uint64_t off; const uint8_t *p; uint64_t n; };
+	std::mutex ld_mu; std::deque<Piece> backlog; bool ld_ready = false; std::thread ld_thread;
+	auto drain = [&]() {
+		for(;;) {
+			Piece q;
+			{ std::unique_lock<std::mutex> lk(ld_mu); if(!ld_ready || backlog.empty()) { return; } q = backlog.front(); backlog.pop_front(); }
+			if(ld && !ld_failed && mab_load_put(ld, q.off, q.p, q.n) != MAB_OK) { ld_failed = true; }
+		}
+	};
 	MaiHooks hooks;
-	hooks.on_size = [&](uint64_t size) { ld = mab_load_begin(size, &ld_prm, devices.data(), (int)devices.size()); if(!ld) { ld_failed = true; } };
-	hooks.on_piece = [&](uint64_t off, const uint8_t *p, uint64_t n) { if(ld && !ld_failed && mab_load_put(ld, off, p, n) != MAB_OK) { ld_failed = true; } };
+	hooks.on_size = [&](uint64_t size) {
+		ld_thread = std::thread([&, size]() {
+			mab_loader *l = mab_load_begin(size, &ld_prm, devices.data(), (int)devices.size());
+			if(getenv("MAB_TRACE")) { fprintf(stderr, "[loader %.3f] devices ready\n", now() - t0); }
+			{ std::unique_lock<std::mutex> lk(ld_mu); ld = l; if(!l) { ld_failed = true; } ld_ready = true; }
+			drain();
+		});
+	};
+	hooks.on_piece = [&](uint64_t off, const uint8_t *p, uint64_t n) {
+		{ std::unique_lock<std::mutex> lk(ld_mu); backlog.push_back({ off, p, n }); }
+		drain();
+	};
 	const bool is_mai = load_mai(o.pos[0].c_str(), im, o.dump.empty() && getenv("MAB_NO_STAGED_LOAD") == nullptr ? &hooks : nullptr);
+	if(getenv("MAB_TRACE")) { fprintf(stderr, "[main %.3f] index file read\n", now() - t0); }
+	if(ld_thread.joinable()) {
+		ld_thread.join();
+		size_t left; { std::unique_lock<std::mutex> lk(ld_mu); left = backlog.size(); }
+		if(left > 64) {																			/* the devices came up late: the rest of the list on all cores */
+			std::vector<std::thread> th;
+			for(unsigned t = 1; t < std::max(1u, std::min(std::thread::hardware_concurrency(), 32u)); t++) { th.emplace_back(drain); }
+			drain();
+			for(auto &x : th) { x.join(); }
+		} else { drain(); }
+	}
 	if(ld && (!is_mai || ld_failed)) { mab_load_abort(ld); ld = nullptr; }								/* the plain path below reports what is wrong */
 	if(!is_mai) {															/* not an index: a FASTA reference, build it here */
 		SeqReader rr(o.pos[0].c_str());
@@ -464,6 +503,7 @@ int main(int argc, char **argv)
 		for(auto &x : th) { x.join(); }
 		for(auto &e : errs) { if(!e.empty()) { fprintf(stderr, "[E::main_align] failed to instanciate alignment context: %s\n", e.c_str()); stop_pinner(); return 1; } }
 	}
+	{ std::unique_lock<std::mutex> lk(mu); pin_go = true; cv.notify_all(); }
 	mab_ctx *ctx0 = ctxs[0];
 	uint32_t n_ref = mab_n_ref(ctx0);
 	std::vector<MabSamRef> refs(n_ref);

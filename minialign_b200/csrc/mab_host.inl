@@ -316,6 +316,7 @@ extern "C" mab_loader *mab_load_begin(uint64_t max_size, const mab_params_t *par
 	if(params == nullptr || devices == nullptr || n_devices <= 0 || max_size < 64) { g_err = "mab_load_begin: bad arguments"; return nullptr; }
 	if(check_params(params) != 0) { g_err = "mab_init: unsupported scoring parameters (combined gap model with validated ranges only)"; return nullptr; }
 	mab_loader *ld = new mab_loader();
+	trace_line(ld, "load: enter");
 	ld->prm = *params; ld->cap = max_size; ld->devices.assign(devices, devices + n_devices);
 	ld->slot_used.assign(mab_loader::SLOTS, 0);
 	/* the devices in parallel: creating a CUDA context takes a few hundred milliseconds each */
@@ -331,7 +332,7 @@ extern "C" mab_loader *mab_load_begin(uint64_t max_size, const mab_params_t *par
 				if(!RT_OK(RT_STREAM_CREATE(&ld->streams[d]))) { errs[d] = std::string("stream creation failed: ") + RT_ERRSTR(); return; }
 				have_stream[d] = 1;
 				for(uint32_t sl = 0; sl < mab_loader::SLOTS; sl++) {
-					if(!RT_OK(RT_SYNC_EVENT_CREATE(&ld->slot_ev[(size_t)sl * n_devices + d]))) { errs[d] = std::string("event creation failed: ") + RT_ERRSTR(); return; }
+					if(!RT_OK(RT_EVENT_CREATE(&ld->slot_ev[(size_t)sl * n_devices + d]))) { errs[d] = std::string("event creation failed: ") + RT_ERRSTR(); return; }
 					n_ev[d]++;
 				}
 			});
@@ -350,6 +351,7 @@ extern "C" mab_loader *mab_load_begin(uint64_t max_size, const mab_params_t *par
 		delete ld;
 		return nullptr;
 	}
+	trace_line(ld, "load: devices ready");
 	RT_USE_DEVICE(devices[0]);
 	if(!RT_OK(RT_HOST_ALLOC(&ld->ring, mab_loader::SLOTS * mab_loader::SLOT_BYTES))) { g_err = std::string("pinned host allocation failed: ") + RT_ERRSTR(); mab_load_abort(ld); return nullptr; }
 	trace_line(ld, "load: begin, index MB", max_size / 1048576.0);

@@ -78,7 +78,7 @@ if os.environ.get("HUMAN_TRACE"):             # stage timeline of the CLI (MAB_T
     for nc in [int(x) for x in os.environ["HUMAN_TRACE"].split(",")]:
         for ctas in os.environ.get("HUMAN_CTAS", "4").split(","):
             with open(os.devnull, "wb") as f:
-                pc = subprocess.run([CLI, "-xpacbio", f"-c{nc}", idx] + [rd] * REP, stdout=f, stderr=subprocess.PIPE, text=True, env=dict(os.environ, MAB_TRACE="1", MAB_EXT_CTAS=ctas))
+                pc = subprocess.run([CLI, "-xpacbio", f"-c{nc}", idx] + [rd] * REP, stdout=f, stderr=subprocess.PIPE, text=True, env=dict(os.environ, MAB_TRACE="1", MAB_EXT_CTAS=ctas.rstrip("d"), **({"MAB_PIN_DELAY": "1"} if ctas.endswith("d") else {})))
             open(os.path.join(OUT, f"trace_c{nc}_ctas{ctas}.log"), "w").write(pc.stderr)
             log("trace", nc, ctas, pc.stderr[-300:])
     raise SystemExit(0)
