@@ -184,6 +184,9 @@ uint64_t mab_sketch(mab_ctx *ctx, const uint8_t *seq, uint32_t len, uint64_t *ou
 /* seeds (+ leaves) and roots after rounds 0..round of mm_seed + mm_chain; returns n_seed */
 uint64_t mab_seed_chain(mab_ctx *ctx, const uint8_t *seq, uint32_t len, uint32_t round,
 	uint32_t *seeds, uint64_t seed_cap, uint64_t *n_total, uint32_t *roots, uint64_t root_cap, uint64_t *n_root);
+/* n <= 32767 elements of 16 bytes (key = the first 8) through the reference's unstable sort (ksort.h:82-131) as k_sortchain walks
+ * it and through the parallel form k_sort uses: both must give the reference's order, ties included */
+int mab_sort_check(mab_ctx *ctx, const uint32_t *elems, uint32_t n, uint32_t *out_exact, uint32_t *out_walk);
 /* n independent extension problems: pair i = (a_i, b_i, apos, bpos, brev, narrow); res = 16 u32 per pair, alignment in
  * the flat layout above at aln_out + aln_ofs[i] (aln_ofs[n] = total).  See oracle/ref_harness.c refh_extend. */
 typedef struct {

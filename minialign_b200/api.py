@@ -287,6 +287,16 @@ class Mapper:
             raise RuntimeError("mab_selftest failed: " + self.lib.mab_last_error().decode())
         return out.reshape(64, 32)
 
+    def sort_check(self, elems: np.ndarray):
+        """elems: (n, 4) uint32 -> (cycle-walking sort, parallel form), both (n, 4)"""
+        e = np.ascontiguousarray(elems, dtype=np.uint32)
+        a, b = np.zeros_like(e), np.zeros_like(e)
+        u32p = C.POINTER(C.c_uint32)
+        self.lib.mab_sort_check.restype = C.c_int
+        self.lib.mab_sort_check.argtypes = [C.c_void_p, u32p, C.c_uint32, u32p, u32p]
+        self._check(self.lib.mab_sort_check(self.h, e.ctypes.data_as(u32p), e.shape[0], a.ctypes.data_as(u32p), b.ctypes.data_as(u32p)), "mab_sort_check")
+        return a, b
+
     # ---- stage-level entry points (parity tests) ----
     def sketch(self, seq: np.ndarray) -> np.ndarray:
         buf = np.zeros(seq.size + 128, dtype=np.uint8)

@@ -81,6 +81,7 @@ struct mab_ctx {
 	BatchCounters hc;					/* counters of the last batch */
 	RunState rs;
 	uint64_t arena_budget = 40ull << 30;	/* HBM the DP arenas of this context may take (mab_set_arena_budget) */
+	bool sort_walk = true;				/* MAB_SORT_WALK=0: the fused k_sortchain (sort by cycle-walking in shared memory) instead of k_sort + k_chain (A/B switch) */
 	bool ext_wide = true;				/* MAB_EXT_WIDE=0: always the 80-register build of k_extend (A/B switch) */
 	/* text path (mab_text_*): the chunk, its index, the packed read block, the SAM text */
 	uint8_t *d_text = nullptr; uint64_t text_cap = 0;
@@ -211,6 +212,10 @@ static int ctx_private_init(mab_ctx *ctx)
 	for(int i = 0; i < 24; i++) { CK(RT_EVENT_CREATE(&ctx->rev[i])); ctx->n_ev++; }
 	CK(RT_SYNC_EVENT_CREATE(&ctx->sync_ev)); ctx->have_sync_ev = true;
 	RT_FUNC_MAX_SMEM(k_sortchain, 16 * MAB_SC_MAX + 2048);
+	RT_FUNC_MAX_SMEM(k_chain, 16 * MAB_SC_MAX + 2048);
+	RT_FUNC_MAX_SMEM(k_sort, 4 * MAB_WK_SM_WORDS + 32768);
+	RT_FUNC_MAX_SMEM(k_sort_check, 4 * MAB_WK_SM_WORDS + 32768);
+	if(const char *e = getenv("MAB_SORT_WALK")) { ctx->sort_walk = atoi(e) != 0; }
 	ctx->n_slots = RT_EXTEND_SLOTS(ctx->n_sm);
 	if(const char *e = getenv("MAB_EXT_WIDE")) { ctx->ext_wide = atoi(e) != 0; }
 	if(const char *e = getenv("MAB_EXT_CTAS")) {										/* resident k_extend CTAs per SM actually launched (<= MAB_EXT_CTAS_PER_SM) */
@@ -661,10 +666,26 @@ static void pipe_rounds(mab_ctx *ctx, bool first, bool timed)
 		bool ev = timed && first && round < 8;
 		if(ev) { RT_EVENT_RECORD(ctx->rev[3 * round], ctx->stream); }
 		int kind = round == 0 ? 0 : 1;
-		for(uint32_t ci = 0, lo = 0; ci < R.sc_ncls[kind]; ci++) {					/* one launch per size class: shared memory cut to the class */
-			const uint32_t cap = R.sc_cls[kind][ci], hi = ci + 1 == R.sc_ncls[kind] ? 0xffffffffu : cap;
-			RT_LAUNCH(k_sortchain, n_seq, 32, 16 * cap + 2048, ctx->stream, P, ctx->d_reads, n_seq, ctx->d_ws, ctx->d_frames, round, cap, lo, hi);
-			lo = cap; S.n_launches++;
+		if(ctx->sort_walk) {
+			/* sort (elements in global memory, a byte of shared memory per element: classes of x2), then chaining on the sorted array
+			 * staged in shared memory (16 B per seed: the classes sized from the previous batch) */
+			for(uint32_t cap = 1024, lo = 0; ; cap *= 2) {
+				const bool last = cap >= 32768;
+				RT_LAUNCH(k_sort, n_seq, 32, 4 * MAB_WK_SM_WORDS + cap, ctx->stream, P, ctx->d_reads, (const uint32_t *)ctx->d_order, n_seq, ctx->d_ws, ctx->d_frames, round, cap, lo, last ? 0xffffffffu : cap);
+				S.n_launches++; lo = cap;
+				if(last) { break; }
+			}
+			for(uint32_t ci = 0, lo = 0; ci < R.sc_ncls[kind]; ci++) {
+				const uint32_t cap = R.sc_cls[kind][ci], hi = ci + 1 == R.sc_ncls[kind] ? 0xffffffffu : cap;
+				RT_LAUNCH(k_chain, n_seq, 32, 16 * cap + 2048, ctx->stream, P, ctx->d_reads, (const uint32_t *)ctx->d_order, n_seq, ctx->d_ws, ctx->d_frames, cap, lo, hi);
+				lo = cap; S.n_launches++;
+			}
+		} else {
+			for(uint32_t ci = 0, lo = 0; ci < R.sc_ncls[kind]; ci++) {				/* one launch per size class: shared memory cut to the class */
+				const uint32_t cap = R.sc_cls[kind][ci], hi = ci + 1 == R.sc_ncls[kind] ? 0xffffffffu : cap;
+				RT_LAUNCH(k_sortchain, n_seq, 32, 16 * cap + 2048, ctx->stream, P, ctx->d_reads, n_seq, ctx->d_ws, ctx->d_frames, round, cap, lo, hi);
+				lo = cap; S.n_launches++;
+			}
 		}
 		if(first && round == 0) { RT_LAUNCH(k_rlen_predict, 1, MAB_PIPE_THREADS, 0, ctx->stream, P, ctx->d_reads, n_seq, (const uint8_t *)ctx->d_ws, R.rlen_init, R.init_known); S.n_launches++; }
 		RT_MEMSET_ASYNC(&ctx->d_ctr->work_next, 0, sizeof(unsigned int), ctx->stream);
@@ -1004,7 +1025,18 @@ extern "C" uint64_t mab_seed_chain(mab_ctx *ctx, const uint8_t *seq, uint32_t le
 		RT_MALLOC(&d_ws, L.total + 256);
 		RT_MEMCPY_H2D_ASYNC(d_r, &r, sizeof(r), ctx->stream);
 		RT_LAUNCH(k_seed_expand, 1, 32, 0, ctx->stream, P, d_r, 1u, d_ws, (const uint32_t *)d_rec);
-		{ uint32_t sc_cap = std::max<uint32_t>(64u, std::min<uint32_t>(r.tot_seeds + 2, MAB_SC_SMALL)); for(uint32_t i = 0; i <= round && i < P.n_occ; i++) { RT_LAUNCH(k_sortchain, 1, 32, 16 * sc_cap + 2048, ctx->stream, P, d_r, 1u, d_ws, d_fr, i, sc_cap, 0u, 0xffffffffu); } }
+		{
+			uint32_t sc_cap = std::max<uint32_t>(64u, std::min<uint32_t>(r.tot_seeds + 2, MAB_SC_SMALL));
+			uint32_t *d_ord = nullptr; RT_MALLOC(&d_ord, 64); RT_MEMSET_ASYNC(d_ord, 0, 64, ctx->stream);
+			for(uint32_t i = 0; i <= round && i < P.n_occ; i++) {
+				if(ctx->sort_walk) {
+					uint32_t cap = 1024; while(cap < r.tot_seeds + 2 && cap < 32768) { cap *= 2; }
+					RT_LAUNCH(k_sort, 1, 32, 4 * MAB_WK_SM_WORDS + cap, ctx->stream, P, d_r, (const uint32_t *)d_ord, 1u, d_ws, d_fr, i, cap, 0u, 0xffffffffu);
+					RT_LAUNCH(k_chain, 1, 32, 16 * sc_cap + 2048, ctx->stream, P, d_r, (const uint32_t *)d_ord, 1u, d_ws, d_fr, sc_cap, 0u, 0xffffffffu);
+				} else { RT_LAUNCH(k_sortchain, 1, 32, 16 * sc_cap + 2048, ctx->stream, P, d_r, 1u, d_ws, d_fr, i, sc_cap, 0u, 0xffffffffu); }
+			}
+			ctx_sync(ctx); RT_FREE(d_ord);
+		}
 		RT_MEMCPY_D2H_ASYNC(&r, d_r, sizeof(r), ctx->stream);
 		ctx_sync(ctx);
 		if(r.n_seed) {
@@ -1098,7 +1130,27 @@ extern "C" int mab_selftest(mab_ctx *ctx, uint32_t *out)
 	RT_LAUNCH(k_selftest, 1, 32, 0, ctx->stream, d);
 	CK(ctx_sync(ctx));
 	CK(RT_MEMCPY_D2H_ASYNC(out, d, 4ull * 64 * 32, ctx->stream));
+	CK(ctx_sync(ctx));
 	RT_FREE(d);
+	return MAB_OK;
+}
+
+/* test entry: n 16-byte elements (key = words 1:0) sorted by the reference's sort as the device walks it (out_exact) and by its
+ * parallel form (out_walk); n <= 32767 */
+extern "C" int mab_sort_check(mab_ctx *ctx, const uint32_t *elems, uint32_t n, uint32_t *out_exact, uint32_t *out_walk)
+{
+	if(n == 0 || n > 32767) { g_err = "mab_sort_check: 1..32767 elements"; return MAB_EINVAL; }
+	CK(RT_USE_DEVICE(ctx->device));
+	uint32_t *a = nullptr, *b = nullptr, *fr = nullptr, *e = nullptr; uint16_t *sc = nullptr;
+	CK(RT_MALLOC(&a, 16ull * n)); CK(RT_MALLOC(&b, 32ull * n)); CK(RT_MALLOC(&fr, 4ull * 8 * MAB_RS_FRAME)); CK(RT_MALLOC(&sc, 4ull * (n + 16))); CK(RT_MALLOC(&e, 64));
+	CK(RT_MEMCPY_H2D(a, elems, 16ull * n)); CK(RT_MEMCPY_H2D(b, elems, 16ull * n));
+	CK(RT_DEVICE_SYNC());
+	RT_LAUNCH(k_sort_check, 1, 32, 4 * MAB_WK_SM_WORDS + 32768, ctx->stream, a, b, n, fr, sc, e);
+	CK(ctx_sync(ctx));
+	uint32_t err = 0;
+	CK(RT_MEMCPY_D2H(out_exact, a, 16ull * n)); CK(RT_MEMCPY_D2H(out_walk, b, 16ull * n)); CK(RT_MEMCPY_D2H(&err, e, 4));
+	RT_FREE(a); RT_FREE(b); RT_FREE(fr); RT_FREE(sc); RT_FREE(e);
+	if(err) { g_err = "mab_sort_check: frame stack overflow"; return MAB_EOVERFLOW; }
 	return MAB_OK;
 }
 

@@ -349,6 +349,120 @@ __global__ void k_sortchain(DevParams P, ReadRec *reads, uint32_t n_reads, uint8
 	else { sortchain_read<false>(P, r, ws, fr, round, sm, sseed, lane); }
 }
 
+/* ---------------------------------------------------------------- k_sort + k_chain */
+/* The two halves of k_sortchain as kernels of their own.  k_sort: rescue-round seeding and the exact sort in its parallel form
+ * (radix_sort_walk_warp: elements stay in global memory, shared memory holds a byte per element, so a few dozen reads are
+ * resident per SM).  k_chain: chaining + root sort on the sorted array staged in shared memory.  One warp per read in both;
+ * reads are taken longest first (order[]). */
+__global__ void k_sort(DevParams P, ReadRec *reads, const uint32_t *order, uint32_t n_reads, uint8_t *ws, uint32_t *frames, uint32_t round, uint32_t cap, uint32_t lo_cap, uint32_t hi_cap)
+{
+	MAB_DYN_SMEM(smem);
+	int lane = threadIdx.x & 31;
+	uint32_t *sm = (uint32_t *)smem;
+	uint8_t *fdig = (uint8_t *)(sm + MAB_WK_SM_WORDS);
+	uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if(slot >= n_reads) { return; }
+	uint32_t i = order[slot];
+	ReadRec *r = &reads[i];
+	if(r->state != 0) { return; }
+	uint32_t bound = (round == 0 ? r->tot_seeds0 : r->tot_seeds) + 2;
+	if(bound <= lo_cap || bound > hi_cap) { return; }
+	uint32_t *fr = frames + (uint64_t)i * 8 * MAB_RS_FRAME;
+	WsLayout L = ws_layout(r->seed_cap, r->root_cap, r->resc_cap, r->bin_cap);
+	uint32_t *seed = (uint32_t *)(ws + r->ws_ofs + L.seed), *root = (uint32_t *)(ws + r->ws_ofs + L.root), *resc = (uint32_t *)(ws + r->ws_ofs + L.resc);
+	uint32_t n = r->n_seed, sort_err = 0;
+	if(round > 0) {																/* mm_seed, cnt > 0 (3510-3526) */
+		if(round == 1) { radix_sort_exact_warp<4>(resc, r->n_resc, fr, sm, lane, &sort_err); }
+		for(uint32_t s = lane; s < n; s += 32) { seed[4ull * s + 3] = 0x7fffffffu; }
+		__syncwarp();
+		uint32_t p = r->presc; const uint32_t n_resc = r->n_resc;
+		bool ovf = false;
+		while(p < n_resc && resc[4ull * p + 1] <= P.occ[round]) {					/* warp-uniform; the occurrences of an entry spread over the lanes */
+			const uint32_t *e = resc + 4ull * p;
+			const uint32_t ne = e[1], qs = e[0];
+			const uint8_t *occ = P.idx + ((uint64_t)e[2] | (uint64_t)e[3] << 32);
+			if(n + ne + 2 > r->seed_cap / 2) { ovf = true; break; }
+			for(uint32_t t = lane; t < ne; t += 32) { make_seed(P, seed + 4ull * (n + t), ldg32(occ + 8ull * t), ldg32(occ + 8ull * t + 4), qs); }
+			n += ne; p++;
+		}
+		__syncwarp();
+		if(lane == 0) { r->presc = p; if(ovf) { r->err |= MAB_ERR_SEED_OVF; } }
+	}
+	if(lane == 0) {
+		r->n_root = 0; r->n_next = 0; r->n_seed = n;
+		if(n == 0) { r->seed_n = 0; }
+		else { uint32_t *s = seed + 4ull * n; s[0] = 0x80000000u; s[1] = 0x7fffffffu; s[2] = 0x80000000u; s[3] = 0x7fffffffu; }	/* sentinel (3531) */
+	}
+	__syncwarp();
+	if(n == 0) { return; }
+	if(n + 1 <= 32767u && n + 1 <= cap) {
+		uint16_t *fpos = (uint16_t *)root, *where = fpos + ((n + 8u) & ~7u);		/* the root / next arrays are free until the chaining */
+		radix_sort_walk_warp(seed, seed + 4ull * (n + 1), n + 1, fr, sm, fdig, fpos, where, lane, &sort_err);
+	} else { radix_sort_exact_warp<4>(seed, n + 1, fr, sm, lane, &sort_err); }
+	if(__any_sync(0xffffffffu, sort_err != 0) && lane == 0) { r->err |= MAB_ERR_SEED_OVF; }
+}
+
+template <bool STAGED>
+__device__ __forceinline__ void chain_read(const DevParams &P, ReadRec *r, uint8_t *ws, uint32_t *fr, uint32_t *sm, uint32_t *sseed, int lane)
+{
+	WsLayout L = ws_layout(r->seed_cap, r->root_cap, r->resc_cap, r->bin_cap);
+	uint32_t *seed = (uint32_t *)(ws + r->ws_ofs + L.seed), *root = (uint32_t *)(ws + r->ws_ofs + L.root);
+	const uint32_t n = r->n_seed;
+	uint32_t sort_err = 0;
+	if(n == 0) { return; }
+	uint32_t *sd = STAGED ? sseed : seed;
+	if(STAGED) {
+		for(uint32_t t = lane; t < n + 1; t += 32) { ((uint4 *)sseed)[t] = ((const uint4 *)seed)[t]; }
+		__syncwarp();
+	}
+	uint32_t nc = 0;
+	if(lane == 0) {
+		uint32_t seed_n = 0;
+		nc = chain_seeds(P, sd, seed, n, root, &seed_n);							/* mm_chain (3702-3721); circular refs unsupported */
+		r->seed_n = seed_n;
+	}
+	nc = __shfl_sync(0xffffffffu, nc, 0);
+	if(STAGED) {
+		__syncwarp();
+		for(uint32_t t = lane; t < n + 1; t += 32) { ((uint4 *)seed)[t] = ((const uint4 *)sseed)[t]; }
+	}
+	if(nc != 0) {
+		radix_sort_exact_warp<2>(root, nc, fr, sm, lane, &sort_err);
+		if(lane == 0) { r->n_root = nc; }
+	}
+	if(__any_sync(0xffffffffu, sort_err != 0) && lane == 0) { r->err |= MAB_ERR_SEED_OVF; }
+}
+
+__global__ void k_chain(DevParams P, ReadRec *reads, const uint32_t *order, uint32_t n_reads, uint8_t *ws, uint32_t *frames, uint32_t sc_cap, uint32_t lo_cap, uint32_t hi_cap)
+{
+	MAB_DYN_SMEM(smem);
+	int lane = threadIdx.x & 31;
+	uint32_t *sm = (uint32_t *)smem, *sseed = sm + 512;
+	uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if(slot >= n_reads) { return; }
+	uint32_t i = order[slot];
+	ReadRec *r = &reads[i];
+	if(r->state != 0) { return; }
+	uint32_t bound = r->n_seed + 2;												/* the sorted array, sentinel included */
+	if(bound <= lo_cap || bound > hi_cap) { return; }
+	uint32_t *fr = frames + (uint64_t)i * 8 * MAB_RS_FRAME;
+	if(bound <= sc_cap) { chain_read<true>(P, r, ws, fr, sm, sseed, lane); }
+	else { chain_read<false>(P, r, ws, fr, sm, sseed, lane); }
+}
+
+/* test kernel: the same array through the cycle-walking sort (a) and its parallel form (b; b holds 2 n elements) */
+__global__ void k_sort_check(uint32_t *a, uint32_t *b, uint32_t n, uint32_t *frames, uint16_t *scratch, uint32_t *err_out)
+{
+	MAB_DYN_SMEM(smem);
+	int lane = threadIdx.x & 31;
+	uint32_t *sm = (uint32_t *)smem;
+	uint32_t err = 0;
+	radix_sort_exact_warp<4>(a, n, frames, sm, lane, &err);
+	__syncwarp();
+	radix_sort_walk_warp(b, b + 4ull * n, n, frames, sm, (uint8_t *)(sm + MAB_WK_SM_WORDS), scratch, scratch + ((n + 8u) & ~7u), lane, &err);
+	if(lane == 0) { *err_out = err; }
+}
+
 /* ---------------------------------------------------------------- mm_extend state machine, lane-0 routines */
 #define MAB_CREM 50000u
 #define MAB_SREM 8u

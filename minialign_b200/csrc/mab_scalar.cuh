@@ -179,6 +179,188 @@ __device__ __forceinline__ void radix_sort_exact_warp(uint32_t *a, uint32_t n, u
 	}
 }
 
+/* ---------------------------------------------------------------- the same sort, parallel form */
+/* One distribution pass of the reference's sort moves every element once, but in an order that depends on the data: bucket k's
+ * pointer walks its region, an element that belongs elsewhere starts a cycle of swaps that ends with the first element belonging
+ * to k (ksort.h:97-118).  What the order of equal keys after the pass depends on is only WHICH element ends up in which slot, and
+ * that follows from much less than the elements themselves.  Call an element foreign when it sits in another bucket's region.
+ * Then (tests/test_sort_model.py checks this against the literal pass):
+ *   - the walk only ever touches foreign elements, region by region in position order: an arrival in bucket l (from a cycle that
+ *     started in an earlier bucket) takes the slot at l's pointer, the natives between it and l's next foreign element move up by
+ *     one, and that foreign element is the next to travel; in bucket k's own phase a foreign element at the pointer starts a
+ *     cycle and the element that closes the cycle lands in its slot, natives stay;
+ *   - so the a-th early arrival in l lands at l's begin (a = 1) or one behind l's (a-1)-th foreign slot, a closing element lands
+ *     in the slot its cycle started from, a native moves up by one iff it sits in front of the t-th foreign slot of its region,
+ *     t = the number of early arrivals (the region's pointer position when its own phase begins).
+ * The sequential part is therefore a walk over one byte per foreign element (its destination digit) and a 16-bit counter per
+ * bucket: two dependent shared-memory loads per element instead of a 16-byte swap through three, and a footprint of n bytes
+ * instead of 16 n, so that 3-5 times as many reads are resident per SM while the elements themselves stay in global memory and
+ * are only streamed (histogram, classification, placement: coalesced loads, one scattered 16-byte store per element and pass).
+ * Elements ping-pong between two global buffers A (the seed array) and B (the free second half of it); small buckets are
+ * insertion-sorted in a shared-memory tile like before and always end in A.
+ * sm: 1280 u32 {begin[256], end[256], q[256] = foreign-list start | popped << 16, qe[256] u16, tl[256] u16} + tile (256 elements)
+ * + fdig (cap bytes).  fpos / where: 2 x cap u16 of global scratch.  Frames of more than 32767 elements are not taken (caller). */
+#define MAB_WK_TILE 256u
+#define MAB_WK_SM_WORDS (256u * 3u + 256u + 4u * MAB_WK_TILE)
+__device__ __forceinline__ void wk_copy_range(uint32_t *dst, const uint32_t *src, uint32_t cnt, int lane)
+{
+	for(uint32_t t = lane; t < cnt; t += 32) { ((uint4 *)dst)[t] = ((const uint4 *)src)[t]; }
+}
+__device__ __forceinline__ void radix_sort_walk_warp(uint32_t *A, uint32_t *Bf, uint32_t n, uint32_t *stack, uint32_t *sm, uint8_t *fdig, uint16_t *fpos, uint16_t *where, int lane, uint32_t *err)
+{
+	uint32_t *begin = sm, *end = sm + 256, *q = sm + 512;
+	uint16_t *qe = (uint16_t *)(sm + 768), *tl = qe + 256;
+	uint32_t *tile = sm + 1024;
+	if(n <= 64) {
+		if(n > 1) {
+			wk_copy_range(tile, A, n, lane); __syncwarp();
+			if(lane == 0) { rs_insertion<4>(tile, n); }
+			__syncwarp(); wk_copy_range(A, tile, n, lane); __syncwarp();
+		}
+		return;
+	}
+	uint32_t sp = 1;
+	if(lane == 0) { stack[0] = 0; stack[1] = n | (7u << 29); }						/* {beg, cnt | in B << 28 | shift / 8 << 29} */
+	__syncwarp();
+	while(sp > 0) {
+		sp--;
+		const uint32_t beg = stack[2 * sp], w1 = stack[2 * sp + 1];
+		const uint32_t cnt = w1 & 0xffffu, inb = (w1 >> 28) & 1u;
+		uint32_t s = (w1 >> 29) * 8;
+		uint32_t *X = (inb ? Bf : A) + 4ull * beg, *Y = (inb ? A : Bf) + 4ull * beg, *Af = A + 4ull * beg;
+		__syncwarp();
+		uint64_t k0 = rs_key<4>(X), diff = 0;
+		for(uint32_t i = 1 + lane; i < cnt; i += 32) { diff |= rs_key<4>(X + 4 * i) ^ k0; }
+		uint32_t dlo = __reduce_or_sync(0xffffffffu, (uint32_t)diff), dhi = __reduce_or_sync(0xffffffffu, (uint32_t)(diff >> 32));
+		diff = (uint64_t)dhi << 32 | dlo;
+		while(s > 0 && ((diff >> s) & 0xff) == 0) { s -= 8; }
+		if(((diff >> s) & 0xff) == 0) {												/* nothing left to order: final where it is */
+			if(inb) { wk_copy_range(Af, X, cnt, lane); }
+			__syncwarp();
+			continue;
+		}
+		for(int k = lane; k < 256; k += 32) { end[k] = 0; }
+		__syncwarp();
+		for(uint32_t i0 = 0; i0 < cnt; i0 += 32) {									/* digit histogram (leader of each digit group adds) */
+			uint32_t i = i0 + lane;
+			uint32_t d = i < cnt ? (uint32_t)((rs_key<4>(X + 4 * i) >> s) & 0xff) : 0x100u + (uint32_t)lane;
+			uint32_t m = __match_any_sync(0xffffffffu, d);
+			if(d < 0x100u && lane == __ffs((int)m) - 1) { end[d] += (uint32_t)__popc(m); }
+			__syncwarp();
+		}
+		{	/* bucket ends (inclusive prefix sum) and begins */
+			uint32_t loc[8], sum = 0;
+			for(int j = 0; j < 8; j++) { sum += end[8 * lane + j]; loc[j] = sum; }
+			uint32_t inc = sum;
+			for(int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, inc, d); if(lane >= d) { inc += y; } }
+			uint32_t excl = inc - sum;
+			__syncwarp();
+			for(int j = 0; j < 8; j++) { uint32_t e = excl + loc[j]; end[8 * lane + j] = e; begin[8 * lane + j] = e - (loc[j] - (j ? loc[j - 1] : 0)); q[8 * lane + j] = 0; qe[8 * lane + j] = 0; tl[8 * lane + j] = 0; }
+			__syncwarp();
+		}
+		/* classification: the region of a position is the first bucket whose end lies behind it; foreign elements are listed in
+		 * position order (their destination digit and their position), each region notes where its part of the list starts and ends */
+		uint32_t nf = 0;
+		for(uint32_t i0 = 0; i0 < cnt; i0 += 32) {
+			uint32_t i = i0 + lane, d = 0, r = 0;
+			bool in = i < cnt;
+			if(in) {
+				d = (uint32_t)((rs_key<4>(X + 4 * i) >> s) & 0xff);
+				uint32_t lo = 0, hi = 255;											/* first r with end[r] > i */
+				while(lo < hi) { uint32_t mid = (lo + hi) >> 1; if(end[mid] > i) { hi = mid; } else { lo = mid + 1; } }
+				r = lo;
+			}
+			bool foreign = in && d != r;
+			uint32_t fm = __ballot_sync(0xffffffffu, foreign);
+			uint32_t j = nf + (uint32_t)__popc(fm & ((1u << lane) - 1u));
+			if(foreign) { fdig[j] = (uint8_t)d; fpos[j] = (uint16_t)i; }
+			if(in && i == begin[r]) { q[r] = j; }
+			if(in && i + 1 == end[r]) { qe[r] = (uint16_t)(j + (foreign ? 1u : 0u)); }
+			nf += (uint32_t)__popc(fm);
+		}
+		__syncwarp();
+		if(lane == 0) {																/* the walk */
+			for(uint32_t k = 0; k < 256; k++) {
+				if(begin[k] == end[k]) { continue; }
+				uint32_t wq = q[k]; const uint32_t qs_k = wq & 0xffffu, qe_k = qe[k];
+				uint32_t qh_k = wq >> 16;
+				tl[k] = (uint16_t)qh_k;
+				while(qs_k + qh_k < qe_k) {
+					const uint32_t js = qs_k + qh_k; qh_k++;
+					uint32_t cur = js;
+					for(;;) {
+						const uint32_t l = fdig[cur];
+						if(l == k) { where[cur] = (uint16_t)(0x8000u | js); break; }
+						const uint32_t wl = q[l], j2 = (wl & 0xffffu) + (wl >> 16);
+						q[l] = wl + 0x10000u;
+						where[cur] = (uint16_t)j2;
+						cur = j2;
+					}
+				}
+			}
+		}
+		__syncwarp();
+		/* tl[r] becomes the position in front of which the natives of region r move up by one (0: none do) */
+		for(int j = 0; j < 8; j++) { int k = 8 * lane + j; uint32_t t = tl[k]; tl[k] = t ? fpos[(q[k] & 0xffffu) + t - 1] : 0; }
+		__syncwarp();
+		nf = 0;
+		for(uint32_t i0 = 0; i0 < cnt; i0 += 32) {									/* placement */
+			uint32_t i = i0 + lane, d = 0, r = 0, dst = 0;
+			bool in = i < cnt;
+			uint4 e; e.x = 0; e.y = 0; e.z = 0; e.w = 0;
+			if(in) {
+				e = ((const uint4 *)X)[i];
+				d = (uint32_t)((((uint64_t)e.y << 32 | e.x) >> s) & 0xff);
+				uint32_t lo = 0, hi = 255;
+				while(lo < hi) { uint32_t mid = (lo + hi) >> 1; if(end[mid] > i) { hi = mid; } else { lo = mid + 1; } }
+				r = lo;
+			}
+			bool foreign = in && d != r;
+			uint32_t fm = __ballot_sync(0xffffffffu, foreign);
+			uint32_t j = nf + (uint32_t)__popc(fm & ((1u << lane) - 1u));
+			nf += (uint32_t)__popc(fm);
+			if(foreign) {
+				uint32_t w = where[j];
+				if(w & 0x8000u) { dst = fpos[w & 0x7fffu]; }
+				else { dst = w == (q[d] & 0xffffu) ? begin[d] : (uint32_t)fpos[w - 1] + 1u; }
+			} else if(in) { dst = i + (i < (uint32_t)tl[r] ? 1u : 0u); }
+			if(in) { ((uint4 *)Y)[dst] = e; }
+		}
+		__syncwarp();
+		if(s == 0) {																	/* buckets of equal keys: final */
+			if(!inb) { wk_copy_range(Af, Y, cnt, lane); __syncwarp(); }
+			continue;
+		}
+		/* the buckets: large ones go on the stack (they now live in the other buffer), runs of small ones are insertion-sorted in
+		 * the shared-memory tile, one bucket per lane, and written to A */
+		const uint32_t ns = s - 8, y_in_b = inb ^ 1u;
+		uint32_t k = 0;
+		while(k < 256) {
+			uint32_t sz = end[k] - begin[k];
+			if(sz > 64) {
+				if(sp < MAB_RS_STACK) { if(lane == 0) { stack[2 * sp] = beg + begin[k]; stack[2 * sp + 1] = sz | (y_in_b << 28) | ((ns >> 3) << 29); } sp++; }
+				else { *err |= 1u; }
+				k++;
+				continue;
+			}
+			uint32_t k1 = k, tot = 0; bool work = false;
+			while(k1 < 256 && end[k1] - begin[k1] <= 64 && tot + (end[k1] - begin[k1]) <= MAB_WK_TILE) { uint32_t z = end[k1] - begin[k1]; tot += z; work |= z > 1; k1++; }
+			if(tot != 0 && (work || y_in_b)) {
+				const uint32_t t0 = begin[k];
+				if(work) {
+					wk_copy_range(tile, Y + 4ull * t0, tot, lane); __syncwarp();
+					for(uint32_t kk = k + lane; kk < k1; kk += 32) { uint32_t z = end[kk] - begin[kk]; if(z > 1) { rs_insertion<4>(tile + 4 * (begin[kk] - t0), z); } }
+					__syncwarp();
+					wk_copy_range(Af + 4ull * t0, tile, tot, lane);
+				} else { wk_copy_range(Af + 4ull * t0, Y + 4ull * t0, tot, lane); }
+				__syncwarp();
+			}
+			k = k1;
+		}
+		__syncwarp();
+	}
+}
+
 /* ---------------------------------------------------------------- seeds and chaining (minialign.c:3340-3625) */
 __device__ __forceinline__ uint32_t u_of(uint32_t x, uint32_t y) { return ((x << 1) - y) + MAB_OFS0; }
 __device__ __forceinline__ uint32_t v_of(uint32_t x, uint32_t y) { return ((y << 1) - x) + MAB_OFS0; }
