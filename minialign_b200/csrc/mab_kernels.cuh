@@ -415,17 +415,14 @@ __device__ __forceinline__ void chain_read(const DevParams &P, ReadRec *r, uint8
 		for(uint32_t t = lane; t < n + 1; t += 32) { ((uint4 *)sseed)[t] = ((const uint4 *)seed)[t]; }
 		__syncwarp();
 	}
-	uint32_t nc = 0;
-	if(lane == 0) {
-		uint32_t seed_n = 0;
-		nc = chain_seeds(P, sd, seed, n, root, &seed_n);							/* mm_chain (3702-3721); circular refs unsupported */
-		r->seed_n = seed_n;
-	}
-	nc = __shfl_sync(0xffffffffu, nc, 0);
+	uint32_t seed_n = 0;
+	uint32_t nc = chain_seeds_warp(P, sd, seed, n, root, &seed_n, lane);			/* mm_chain (3702-3721); circular refs unsupported */
+	if(lane == 0) { r->seed_n = seed_n; }
 	if(STAGED) {
 		__syncwarp();
 		for(uint32_t t = lane; t < n + 1; t += 32) { ((uint4 *)seed)[t] = ((const uint4 *)sseed)[t]; }
 	}
+	__syncwarp();
 	if(nc != 0) {
 		radix_sort_exact_warp<2>(root, nc, fr, sm, lane, &sort_err);
 		if(lane == 0) { r->n_root = nc; }

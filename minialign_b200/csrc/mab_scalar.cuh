@@ -453,6 +453,81 @@ __device__ inline uint32_t chain_seeds(const DevParams &P, uint32_t *s, uint32_t
 	return ncid;
 }
 
+/* The same, warp-wide.  What takes the time in mm_chain_seeds is the window scan: from every seed that joins a chain, the seeds
+ * behind it are tested against a window that shrinks whenever one of them lies inside it, until one lies beyond its upper u
+ * bound.  Here the 32 lanes test 32 candidates at a time against the current window; the events that change state are taken in
+ * order out of the ballots (the first candidate inside the window narrows it and the lanes behind it are tested again; a
+ * candidate beyond the bound ends the scan), so the result is the sequential scan's.  Everything else is computed redundantly
+ * by all lanes (warp-uniform), lane 0 writes. */
+__device__ inline uint32_t chain_seeds_warp(const DevParams &P, uint32_t *s, uint32_t *lfb, uint32_t n_seed, uint32_t *c, uint32_t *seed_n, int lane)
+{
+	uint32_t ncid = 0, nlid = n_seed + 1, nlsid = 0, tsid = n_seed;
+	while(nlsid < tsid) {
+		uint32_t lid = nlid++;
+		uint32_t *lf = lfb + 4ull * lid;						/* leaf: {rsid, rid, lsid, cid} */
+		uint32_t lf_lsid = nlsid;
+		if(lane == 0) { lf[0] = nlsid; lf[2] = nlsid; lf[1] = s[4ull * nlsid + 1]; lf[3] = 0xffffffffu; }
+		__syncwarp();
+		uint32_t plen = s[4ull * nlsid] + s[4ull * nlsid + 2], scnt = 1;
+		uint64_t nrsid = nlsid; nlsid = 0xffffffffu;
+		while(1) {
+			uint32_t rsid = (uint32_t)nrsid; nrsid = 0;
+			V4 wv = load_wv(s + 4ull * rsid, P.twlen);
+			uint32_t sid0 = rsid + 1;
+			for(bool done = false; !done; sid0 += 32) {
+				uint32_t sid = sid0 + (uint32_t)lane;
+				V4 fv = load_pv(s + 4ull * (sid < n_seed ? sid : n_seed));		/* behind the sentinel: the sentinel again (it ends the scan) */
+				uint32_t from = 0;
+				while(from < 32) {
+					uint32_t m = inside_mask(wv, fv);
+					bool ins = m == 0xf000u, brk = !ins && (m & 0xffu) != 0;
+					uint32_t lm = 0xffffffffu << from;
+					uint32_t Im = __ballot_sync(0xffffffffu, ins) & lm, Bm = __ballot_sync(0xffffffffu, brk) & lm, Nm = __ballot_sync(0xffffffffu, !ins) & lm;
+					uint32_t fi = Im ? (uint32_t)__ffs((int)Im) - 1u : 32u, fb = Bm ? (uint32_t)__ffs((int)Bm) - 1u : 32u;
+					uint32_t upto = fb < fi ? fb + 1u : fi;								/* lanes [from, upto) are passed over in order */
+					uint32_t Ns = Nm & (upto >= 32 ? 0xffffffffu : (1u << upto) - 1u);
+					if(Ns) { uint32_t f = sid0 + (uint32_t)__ffs((int)Ns) - 1u; nlsid = nlsid < f ? nlsid : f; }
+					if(fb < fi) { done = true; break; }
+					if(fi == 32) { break; }
+					V4 f;
+					f.l0 = __shfl_sync(0xffffffffu, fv.l0, (int)fi); f.l1 = __shfl_sync(0xffffffffu, fv.l1, (int)fi); f.l2 = __shfl_sync(0xffffffffu, fv.l2, (int)fi); f.l3 = f.l2;
+					wv = update_wv(wv, f);
+					int64_t di = (int64_t)(((uint64_t)(int64_t)pdiff_wv(wv, f) << 32) | (sid0 + fi));
+					nrsid = (uint64_t)((int64_t)nrsid > di ? (int64_t)nrsid : di);
+					from = fi + 1;
+				}
+			}
+			if(nrsid == 0) { nrsid = rsid; break; }
+			if(s[4ull * (uint32_t)nrsid + 3] != 0x7fffffffu) { nrsid = (uint32_t)nrsid; break; }
+			__syncwarp();
+			if(lane == 0) { s[4ull * (uint32_t)nrsid + 3] = lid; }
+			__syncwarp();
+			scnt++;
+			if((uint64_t)nlsid <= nrsid) { nlsid = 0xffffffffu; }
+		}
+		if(nrsid == lf_lsid) { continue; }
+		uint32_t cid = 0xffffffffu;
+		__syncwarp();
+		if(s[4ull * nrsid + 3] < lid) {
+			nrsid = lfb[4ull * s[4ull * nrsid + 3] + 0];
+			cid = lfb[4ull * s[4ull * nrsid + 3] + 3];
+		}
+		uint32_t c0 = 0, c1 = 0;
+		bool fresh = cid == 0xffffffffu;
+		if(fresh) { cid = ncid++; c0 = MAB_OFS0; c1 = lid; } else { c0 = c[2ull * cid]; c1 = c[2ull * cid + 1]; }
+		uint32_t ps = s[4ull * nrsid] + s[4ull * nrsid + 2];
+		double frac = __dsub_rn(1.0, __ddiv_rn(1.0, (double)scnt));
+		double dl = __dmul_rn(frac, (double)(uint32_t)(ps - plen));
+		plen = (uint32_t)((int32_t)MAB_OFS0 - (int32_t)(uint32_t)(int64_t)__double2ll_rz(dl));
+		if(plen < c0) { c0 = plen; c1 = lid; }
+		__syncwarp();
+		if(lane == 0) { lf[3] = cid; lf[0] = (uint32_t)nrsid; c[2ull * cid] = c0; c[2ull * cid + 1] = c1; }
+		__syncwarp();
+	}
+	*seed_n = nlid;
+	return ncid;
+}
+
 /* ---------------------------------------------------------------- position hash (kh_t, minialign.c:346-613) */
 #define MAB_KH_EMPTY	0xffffffffffffffffull
 #define MAB_KH_MOVED	0xfffffffffffffffeull
