@@ -53,6 +53,8 @@ static inline cudaError_t RT_DEVICE_SYNC() { return cudaDeviceSynchronize(); }
 static inline cudaError_t RT_EVENT_SYNC(RT_EVENT e) { cudaError_t r = cudaEventSynchronize(e); if(r == cudaSuccess) { r = cudaGetLastError(); } return r; }
 static inline cudaError_t RT_SYNC_EVENT_CREATE(RT_EVENT *e) { return cudaEventCreateWithFlags(e, cudaEventBlockingSync | cudaEventDisableTiming); }
 static inline void RT_EVENT_RECORD(RT_EVENT e, RT_STREAM s) { cudaEventRecord(e, s); }
+static inline void RT_STREAM_WAIT(RT_STREAM s, RT_EVENT e) { cudaStreamWaitEvent(s, e, 0); }
+static inline cudaError_t RT_LIGHT_EVENT_CREATE(RT_EVENT *e) { return cudaEventCreateWithFlags(e, cudaEventDisableTiming); }
 static inline float RT_EVENT_MS(RT_EVENT a, RT_EVENT b) { float ms = 0.f; if(cudaEventElapsedTime(&ms, a, b) != cudaSuccess) { ms = 0.f; cudaGetLastError(); } return ms; }
 static inline double RT_WALL_MS() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 #define RT_FUNC_MAX_SMEM(kernel, bytes) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))

@@ -65,6 +65,7 @@ struct mab_ctx {
 	uint32_t *d_pool = nullptr; uint64_t pool_cap = 0;
 	BatchCounters *d_ctr = nullptr;
 	RT_STREAM stream; bool have_stream = false; int n_ev = 0;
+	RT_STREAM side[MAB_SC_CLASSES]; RT_EVENT fork_ev, join_ev[MAB_SC_CLASSES]; int n_side = 0; bool have_fork_ev = false;	/* the size classes of k_sort / k_chain run side by side */
 	RT_EVENT sync_ev; bool have_sync_ev = false;	/* the host waits on this one asleep (blocking-sync event) instead of spinning in a stream synchronize */
 	RT_EVENT ev[8];
 	RT_EVENT rev[24];					/* per-round kernel boundaries: [3r] sortchain start, [3r+1] extend start, [3r+2] extend end */
@@ -81,6 +82,8 @@ struct mab_ctx {
 	BatchCounters hc;					/* counters of the last batch */
 	RunState rs;
 	uint64_t arena_budget = 40ull << 30;	/* HBM the DP arenas of this context may take (mab_set_arena_budget) */
+	bool chain_warp = false;				/* MAB_CHAIN_WARP=1: the chaining's window scan 32 candidates at a time (pays off with long scans only: 15.8 vs 9.9 ms per chunk on the E.coli-like workload) */
+	bool class_streams = true;			/* MAB_CLASS_STREAMS=0: the size classes one after the other on the context's stream (A/B switch) */
 	bool sort_walk = true;				/* MAB_SORT_WALK=0: the fused k_sortchain (sort by cycle-walking in shared memory) instead of k_sort + k_chain (A/B switch) */
 	bool ext_wide = true;				/* MAB_EXT_WIDE=0: always the 80-register build of k_extend (A/B switch) */
 	/* text path (mab_text_*): the chunk, its index, the packed read block, the SAM text */
@@ -211,6 +214,10 @@ static int ctx_private_init(mab_ctx *ctx)
 	for(int i = 0; i < 8; i++) { CK(RT_EVENT_CREATE(&ctx->ev[i])); ctx->n_ev++; }
 	for(int i = 0; i < 24; i++) { CK(RT_EVENT_CREATE(&ctx->rev[i])); ctx->n_ev++; }
 	CK(RT_SYNC_EVENT_CREATE(&ctx->sync_ev)); ctx->have_sync_ev = true;
+	CK(RT_LIGHT_EVENT_CREATE(&ctx->fork_ev)); ctx->have_fork_ev = true;
+	for(int i = 0; i < MAB_SC_CLASSES; i++) { CK(RT_STREAM_CREATE(&ctx->side[i])); CK(RT_LIGHT_EVENT_CREATE(&ctx->join_ev[i])); ctx->n_side++; }
+	if(const char *e = getenv("MAB_CHAIN_WARP")) { ctx->chain_warp = atoi(e) != 0; }
+	if(const char *e = getenv("MAB_CLASS_STREAMS")) { ctx->class_streams = atoi(e) != 0; }
 	RT_FUNC_MAX_SMEM(k_sortchain, 16 * MAB_SC_MAX + 2048);
 	RT_FUNC_MAX_SMEM(k_chain, 16 * MAB_SC_MAX + 2048);
 	RT_FUNC_MAX_SMEM(k_sort, 4 * MAB_WK_SM_WORDS + 32768);
@@ -438,6 +445,8 @@ extern "C" void mab_destroy(mab_ctx *ctx)
 	RT_USE_DEVICE(ctx->device);
 	if(ctx->parent != nullptr) { ctx->d_idx = nullptr; ctx->d_ntail = nullptr; ctx->d_thr = nullptr; }	/* the parent's */
 	if(ctx->have_sync_ev) { RT_EVENT_DESTROY(ctx->sync_ev); }
+	if(ctx->have_fork_ev) { RT_EVENT_DESTROY(ctx->fork_ev); }
+	for(int i = 0; i < ctx->n_side; i++) { RT_STREAM_DESTROY(ctx->side[i]); RT_EVENT_DESTROY(ctx->join_ev[i]); }
 	RT_FREE(ctx->d_idx); RT_FREE(ctx->d_ntail); RT_FREE(ctx->d_ctr); RT_FREE(ctx->d_seq); RT_FREE(ctx->d_reads); RT_FREE(ctx->d_ws);
 	RT_FREE(ctx->d_frames); RT_FREE(ctx->d_order); RT_FREE(ctx->d_recs); RT_FREE(ctx->d_arenas); RT_FREE(ctx->d_pool); RT_FREE(ctx->d_io);
 	RT_HOST_FREE(ctx->h_pool); RT_HOST_FREE(ctx->pin); delete[] ctx->res_words;
@@ -668,18 +677,32 @@ static void pipe_rounds(mab_ctx *ctx, bool first, bool timed)
 		int kind = round == 0 ? 0 : 1;
 		if(ctx->sort_walk) {
 			/* sort (elements in global memory, a byte of shared memory per element: classes of x2), then chaining on the sorted array
-			 * staged in shared memory (16 B per seed: the classes sized from the previous batch) */
-			for(uint32_t cap = 1024, lo = 0; ; cap *= 2) {
-				const bool last = cap >= 32768;
-				RT_LAUNCH(k_sort, n_seq, 32, 4 * MAB_WK_SM_WORDS + cap, ctx->stream, P, ctx->d_reads, (const uint32_t *)ctx->d_order, n_seq, ctx->d_ws, ctx->d_frames, round, cap, lo, last ? 0xffffffffu : cap);
-				S.n_launches++; lo = cap;
+			 * staged in shared memory (16 B per seed: the classes sized from the previous batch).  A class is as long as its slowest
+			 * read (one warp per read, latency-bound), so the classes run side by side on streams of their own, forked off and
+			 * joined back into the context's stream. */
+			const bool par = ctx->class_streams;
+			uint32_t used = 0;
+			if(par) { RT_EVENT_RECORD(ctx->fork_ev, ctx->stream); }
+			for(uint32_t cap = 32768, ci = 0; ; cap /= 2, ci++) {						/* the seed-rich classes first: they take longest */
+				const bool first = cap >= 32768, last = cap <= 1024;
+				RT_STREAM st = par ? ctx->side[ci] : ctx->stream;
+				if(par) { RT_STREAM_WAIT(st, ctx->fork_ev); }
+				RT_LAUNCH(k_sort, n_seq, 32, 4 * MAB_WK_SM_WORDS + cap, st, P, ctx->d_reads, (const uint32_t *)ctx->d_order, n_seq, ctx->d_ws, ctx->d_frames, round, cap, last ? 0u : cap / 2, first ? 0xffffffffu : cap);
+				if(par) { RT_EVENT_RECORD(ctx->join_ev[ci], st); }
+				S.n_launches++; used = ci + 1;
 				if(last) { break; }
 			}
-			for(uint32_t ci = 0, lo = 0; ci < R.sc_ncls[kind]; ci++) {
-				const uint32_t cap = R.sc_cls[kind][ci], hi = ci + 1 == R.sc_ncls[kind] ? 0xffffffffu : cap;
-				RT_LAUNCH(k_chain, n_seq, 32, 16 * cap + 2048, ctx->stream, P, ctx->d_reads, (const uint32_t *)ctx->d_order, n_seq, ctx->d_ws, ctx->d_frames, cap, lo, hi);
-				lo = cap; S.n_launches++;
+			if(par) { for(uint32_t ci = 0; ci < used; ci++) { RT_STREAM_WAIT(ctx->stream, ctx->join_ev[ci]); } RT_EVENT_RECORD(ctx->fork_ev, ctx->stream); }
+			for(uint32_t k = 0; k < R.sc_ncls[kind]; k++) {
+				const uint32_t ci = R.sc_ncls[kind] - 1 - k;
+				const uint32_t cap = R.sc_cls[kind][ci], lo = ci == 0 ? 0u : R.sc_cls[kind][ci - 1], hi = ci + 1 == R.sc_ncls[kind] ? 0xffffffffu : cap;
+				RT_STREAM st = par ? ctx->side[k] : ctx->stream;
+				if(par) { RT_STREAM_WAIT(st, ctx->fork_ev); }
+				RT_LAUNCH(k_chain, n_seq, 32, 16 * cap + 2048, st, P, ctx->d_reads, (const uint32_t *)ctx->d_order, n_seq, ctx->d_ws, ctx->d_frames, cap, lo, hi, ctx->chain_warp ? 1u : 0u);
+				if(par) { RT_EVENT_RECORD(ctx->join_ev[k], st); }
+				S.n_launches++;
 			}
+			if(par) { for(uint32_t k = 0; k < R.sc_ncls[kind]; k++) { RT_STREAM_WAIT(ctx->stream, ctx->join_ev[k]); } }
 		} else {
 			for(uint32_t ci = 0, lo = 0; ci < R.sc_ncls[kind]; ci++) {				/* one launch per size class: shared memory cut to the class */
 				const uint32_t cap = R.sc_cls[kind][ci], hi = ci + 1 == R.sc_ncls[kind] ? 0xffffffffu : cap;
@@ -1032,7 +1055,7 @@ extern "C" uint64_t mab_seed_chain(mab_ctx *ctx, const uint8_t *seq, uint32_t le
 				if(ctx->sort_walk) {
 					uint32_t cap = 1024; while(cap < r.tot_seeds + 2 && cap < 32768) { cap *= 2; }
 					RT_LAUNCH(k_sort, 1, 32, 4 * MAB_WK_SM_WORDS + cap, ctx->stream, P, d_r, (const uint32_t *)d_ord, 1u, d_ws, d_fr, i, cap, 0u, 0xffffffffu);
-					RT_LAUNCH(k_chain, 1, 32, 16 * sc_cap + 2048, ctx->stream, P, d_r, (const uint32_t *)d_ord, 1u, d_ws, d_fr, sc_cap, 0u, 0xffffffffu);
+					RT_LAUNCH(k_chain, 1, 32, 16 * sc_cap + 2048, ctx->stream, P, d_r, (const uint32_t *)d_ord, 1u, d_ws, d_fr, sc_cap, 0u, 0xffffffffu, ctx->chain_warp ? 1u : 0u);
 				} else { RT_LAUNCH(k_sortchain, 1, 32, 16 * sc_cap + 2048, ctx->stream, P, d_r, 1u, d_ws, d_fr, i, sc_cap, 0u, 0xffffffffu); }
 			}
 			ctx_sync(ctx); RT_FREE(d_ord);

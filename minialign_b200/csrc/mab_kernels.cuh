@@ -403,7 +403,7 @@ __global__ void k_sort(DevParams P, ReadRec *reads, const uint32_t *order, uint3
 }
 
 template <bool STAGED>
-__device__ __forceinline__ void chain_read(const DevParams &P, ReadRec *r, uint8_t *ws, uint32_t *fr, uint32_t *sm, uint32_t *sseed, int lane)
+__device__ __forceinline__ void chain_read(const DevParams &P, ReadRec *r, uint8_t *ws, uint32_t *fr, uint32_t *sm, uint32_t *sseed, int lane, uint32_t wide)
 {
 	WsLayout L = ws_layout(r->seed_cap, r->root_cap, r->resc_cap, r->bin_cap);
 	uint32_t *seed = (uint32_t *)(ws + r->ws_ofs + L.seed), *root = (uint32_t *)(ws + r->ws_ofs + L.root);
@@ -415,8 +415,12 @@ __device__ __forceinline__ void chain_read(const DevParams &P, ReadRec *r, uint8
 		for(uint32_t t = lane; t < n + 1; t += 32) { ((uint4 *)sseed)[t] = ((const uint4 *)seed)[t]; }
 		__syncwarp();
 	}
-	uint32_t seed_n = 0;
-	uint32_t nc = chain_seeds_warp(P, sd, seed, n, root, &seed_n, lane);			/* mm_chain (3702-3721); circular refs unsupported */
+	uint32_t seed_n = 0, nc = 0;													/* mm_chain (3702-3721); circular refs unsupported */
+	if(wide) { nc = chain_seeds_warp(P, sd, seed, n, root, &seed_n, lane); }
+	else {
+		if(lane == 0) { nc = chain_seeds(P, sd, seed, n, root, &seed_n); }
+		nc = __shfl_sync(0xffffffffu, nc, 0);
+	}
 	if(lane == 0) { r->seed_n = seed_n; }
 	if(STAGED) {
 		__syncwarp();
@@ -430,7 +434,7 @@ __device__ __forceinline__ void chain_read(const DevParams &P, ReadRec *r, uint8
 	if(__any_sync(0xffffffffu, sort_err != 0) && lane == 0) { r->err |= MAB_ERR_SEED_OVF; }
 }
 
-__global__ void k_chain(DevParams P, ReadRec *reads, const uint32_t *order, uint32_t n_reads, uint8_t *ws, uint32_t *frames, uint32_t sc_cap, uint32_t lo_cap, uint32_t hi_cap)
+__global__ void k_chain(DevParams P, ReadRec *reads, const uint32_t *order, uint32_t n_reads, uint8_t *ws, uint32_t *frames, uint32_t sc_cap, uint32_t lo_cap, uint32_t hi_cap, uint32_t wide)
 {
 	MAB_DYN_SMEM(smem);
 	int lane = threadIdx.x & 31;
@@ -443,8 +447,8 @@ __global__ void k_chain(DevParams P, ReadRec *reads, const uint32_t *order, uint
 	uint32_t bound = r->n_seed + 2;												/* the sorted array, sentinel included */
 	if(bound <= lo_cap || bound > hi_cap) { return; }
 	uint32_t *fr = frames + (uint64_t)i * 8 * MAB_RS_FRAME;
-	if(bound <= sc_cap) { chain_read<true>(P, r, ws, fr, sm, sseed, lane); }
-	else { chain_read<false>(P, r, ws, fr, sm, sseed, lane); }
+	if(bound <= sc_cap) { chain_read<true>(P, r, ws, fr, sm, sseed, lane, wide); }
+	else { chain_read<false>(P, r, ws, fr, sm, sseed, lane, wide); }
 }
 
 /* test kernel: the same array through the cycle-walking sort (a) and its parallel form (b; b holds 2 n elements) */

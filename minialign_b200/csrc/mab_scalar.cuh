@@ -230,6 +230,7 @@ __device__ __forceinline__ void radix_sort_walk_warp(uint32_t *A, uint32_t *Bf, 
 		uint32_t *X = (inb ? Bf : A) + 4ull * beg, *Y = (inb ? A : Bf) + 4ull * beg, *Af = A + 4ull * beg;
 		__syncwarp();
 		uint64_t k0 = rs_key<4>(X), diff = 0;
+		#pragma unroll 4
 		for(uint32_t i = 1 + lane; i < cnt; i += 32) { diff |= rs_key<4>(X + 4 * i) ^ k0; }
 		uint32_t dlo = __reduce_or_sync(0xffffffffu, (uint32_t)diff), dhi = __reduce_or_sync(0xffffffffu, (uint32_t)(diff >> 32));
 		diff = (uint64_t)dhi << 32 | dlo;
@@ -241,12 +242,18 @@ __device__ __forceinline__ void radix_sort_walk_warp(uint32_t *A, uint32_t *Bf, 
 		}
 		for(int k = lane; k < 256; k += 32) { end[k] = 0; }
 		__syncwarp();
-		for(uint32_t i0 = 0; i0 < cnt; i0 += 32) {									/* digit histogram (leader of each digit group adds) */
-			uint32_t i = i0 + lane;
-			uint32_t d = i < cnt ? (uint32_t)((rs_key<4>(X + 4 * i) >> s) & 0xff) : 0x100u + (uint32_t)lane;
-			uint32_t m = __match_any_sync(0xffffffffu, d);
-			if(d < 0x100u && lane == __ffs((int)m) - 1) { end[d] += (uint32_t)__popc(m); }
-			__syncwarp();
+		for(uint32_t i0 = 0; i0 < cnt; i0 += 128) {									/* digit histogram (leader of each digit group adds); the loads of four steps up front */
+			uint32_t dd[4];
+			#pragma unroll
+			for(int u = 0; u < 4; u++) { uint32_t i = i0 + 32u * u + lane; dd[u] = i < cnt ? (uint32_t)((rs_key<4>(X + 4 * i) >> s) & 0xff) : 0x100u + (uint32_t)lane; }
+			#pragma unroll
+			for(int u = 0; u < 4; u++) {
+				if(i0 + 32u * u >= cnt) { break; }
+				uint32_t d = dd[u];
+				uint32_t m = __match_any_sync(0xffffffffu, d);
+				if(d < 0x100u && lane == __ffs((int)m) - 1) { end[d] += (uint32_t)__popc(m); }
+				__syncwarp();
+			}
 		}
 		{	/* bucket ends (inclusive prefix sum) and begins */
 			uint32_t loc[8], sum = 0;
@@ -261,22 +268,28 @@ __device__ __forceinline__ void radix_sort_walk_warp(uint32_t *A, uint32_t *Bf, 
 		/* classification: the region of a position is the first bucket whose end lies behind it; foreign elements are listed in
 		 * position order (their destination digit and their position), each region notes where its part of the list starts and ends */
 		uint32_t nf = 0;
-		for(uint32_t i0 = 0; i0 < cnt; i0 += 32) {
-			uint32_t i = i0 + lane, d = 0, r = 0;
-			bool in = i < cnt;
-			if(in) {
-				d = (uint32_t)((rs_key<4>(X + 4 * i) >> s) & 0xff);
-				uint32_t lo = 0, hi = 255;											/* first r with end[r] > i */
-				while(lo < hi) { uint32_t mid = (lo + hi) >> 1; if(end[mid] > i) { hi = mid; } else { lo = mid + 1; } }
-				r = lo;
+		for(uint32_t i0 = 0; i0 < cnt; i0 += 128) {
+			uint32_t dd[4];
+			#pragma unroll
+			for(int u = 0; u < 4; u++) { uint32_t i = i0 + 32u * u + lane; dd[u] = i < cnt ? (uint32_t)((rs_key<4>(X + 4 * i) >> s) & 0xff) : 0u; }
+			#pragma unroll
+			for(int u = 0; u < 4; u++) {
+				if(i0 + 32u * u >= cnt) { break; }
+				uint32_t i = i0 + 32u * u + lane, d = dd[u], r = 0;
+				bool in = i < cnt;
+				if(in) {
+					uint32_t lo = 0, hi = 255;										/* first r with end[r] > i */
+					while(lo < hi) { uint32_t mid = (lo + hi) >> 1; if(end[mid] > i) { hi = mid; } else { lo = mid + 1; } }
+					r = lo;
+				}
+				bool foreign = in && d != r;
+				uint32_t fm = __ballot_sync(0xffffffffu, foreign);
+				uint32_t j = nf + (uint32_t)__popc(fm & ((1u << lane) - 1u));
+				if(foreign) { fdig[j] = (uint8_t)d; fpos[j] = (uint16_t)i; }
+				if(in && i == begin[r]) { q[r] = j; }
+				if(in && i + 1 == end[r]) { qe[r] = (uint16_t)(j + (foreign ? 1u : 0u)); }
+				nf += (uint32_t)__popc(fm);
 			}
-			bool foreign = in && d != r;
-			uint32_t fm = __ballot_sync(0xffffffffu, foreign);
-			uint32_t j = nf + (uint32_t)__popc(fm & ((1u << lane) - 1u));
-			if(foreign) { fdig[j] = (uint8_t)d; fpos[j] = (uint16_t)i; }
-			if(in && i == begin[r]) { q[r] = j; }
-			if(in && i + 1 == end[r]) { qe[r] = (uint16_t)(j + (foreign ? 1u : 0u)); }
-			nf += (uint32_t)__popc(fm);
 		}
 		__syncwarp();
 		if(lane == 0) {																/* the walk */
@@ -304,27 +317,33 @@ __device__ __forceinline__ void radix_sort_walk_warp(uint32_t *A, uint32_t *Bf, 
 		for(int j = 0; j < 8; j++) { int k = 8 * lane + j; uint32_t t = tl[k]; tl[k] = t ? fpos[(q[k] & 0xffffu) + t - 1] : 0; }
 		__syncwarp();
 		nf = 0;
-		for(uint32_t i0 = 0; i0 < cnt; i0 += 32) {									/* placement */
-			uint32_t i = i0 + lane, d = 0, r = 0, dst = 0;
-			bool in = i < cnt;
-			uint4 e; e.x = 0; e.y = 0; e.z = 0; e.w = 0;
-			if(in) {
-				e = ((const uint4 *)X)[i];
-				d = (uint32_t)((((uint64_t)e.y << 32 | e.x) >> s) & 0xff);
-				uint32_t lo = 0, hi = 255;
-				while(lo < hi) { uint32_t mid = (lo + hi) >> 1; if(end[mid] > i) { hi = mid; } else { lo = mid + 1; } }
-				r = lo;
+		for(uint32_t i0 = 0; i0 < cnt; i0 += 128) {									/* placement */
+			uint4 ee[4];
+			#pragma unroll
+			for(int u = 0; u < 4; u++) { uint32_t i = i0 + 32u * u + lane; if(i < cnt) { ee[u] = ((const uint4 *)X)[i]; } else { ee[u].x = 0; ee[u].y = 0; ee[u].z = 0; ee[u].w = 0; } }
+			#pragma unroll
+			for(int u = 0; u < 4; u++) {
+				if(i0 + 32u * u >= cnt) { break; }
+				uint32_t i = i0 + 32u * u + lane, d = 0, r = 0, dst = 0;
+				bool in = i < cnt;
+				const uint4 e = ee[u];
+				if(in) {
+					d = (uint32_t)((((uint64_t)e.y << 32 | e.x) >> s) & 0xff);
+					uint32_t lo = 0, hi = 255;
+					while(lo < hi) { uint32_t mid = (lo + hi) >> 1; if(end[mid] > i) { hi = mid; } else { lo = mid + 1; } }
+					r = lo;
+				}
+				bool foreign = in && d != r;
+				uint32_t fm = __ballot_sync(0xffffffffu, foreign);
+				uint32_t j = nf + (uint32_t)__popc(fm & ((1u << lane) - 1u));
+				nf += (uint32_t)__popc(fm);
+				if(foreign) {
+					uint32_t w = where[j];
+					if(w & 0x8000u) { dst = fpos[w & 0x7fffu]; }
+					else { dst = w == (q[d] & 0xffffu) ? begin[d] : (uint32_t)fpos[w - 1] + 1u; }
+				} else if(in) { dst = i + (i < (uint32_t)tl[r] ? 1u : 0u); }
+				if(in) { ((uint4 *)Y)[dst] = e; }
 			}
-			bool foreign = in && d != r;
-			uint32_t fm = __ballot_sync(0xffffffffu, foreign);
-			uint32_t j = nf + (uint32_t)__popc(fm & ((1u << lane) - 1u));
-			nf += (uint32_t)__popc(fm);
-			if(foreign) {
-				uint32_t w = where[j];
-				if(w & 0x8000u) { dst = fpos[w & 0x7fffu]; }
-				else { dst = w == (q[d] & 0xffffu) ? begin[d] : (uint32_t)fpos[w - 1] + 1u; }
-			} else if(in) { dst = i + (i < (uint32_t)tl[r] ? 1u : 0u); }
-			if(in) { ((uint4 *)Y)[dst] = e; }
 		}
 		__syncwarp();
 		if(s == 0) {																	/* buckets of equal keys: final */

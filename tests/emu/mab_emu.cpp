@@ -33,6 +33,8 @@ static inline int RT_DEVICE_SYNC() { return 0; }
 static inline int RT_EVENT_SYNC(RT_EVENT) { return 0; }
 static inline int RT_SYNC_EVENT_CREATE(RT_EVENT *e) { *e = 0; return 0; }
 static inline void RT_EVENT_RECORD(RT_EVENT, RT_STREAM) {}
+static inline void RT_STREAM_WAIT(RT_STREAM, RT_EVENT) {}
+static inline int RT_LIGHT_EVENT_CREATE(RT_EVENT *e) { *e = 0; return 0; }
 static inline float RT_EVENT_MS(RT_EVENT, RT_EVENT) { return 0.f; }
 static inline double RT_WALL_MS() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 #define RT_FUNC_MAX_SMEM(kernel, bytes) do {} while(0)

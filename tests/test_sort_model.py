@@ -152,3 +152,21 @@ def test_gpu_parallel_sort_equals_cycle_walking_sort(gold):
         a, b = m.sort_check(e)
         assert np.array_equal(a, b), (n, kind, int(np.argmax(np.any(a != b, axis=1))))
     m.close()
+
+
+def test_emu_wide_chain_scan_equals_single_lane(gold, monkeypatch):
+    """MAB_CHAIN_WARP=1 (window scan 32 candidates at a time) and the fused k_sortchain (MAB_SORT_WALK=0) give the default's chains"""
+    so = build_emu()
+    idx = [i for i, s in enumerate(gold["enc"]) if s.size <= 12000][:12]
+    m = api.Mapper(gold["blob"], "pacbio", lib_path=so)
+    exp = [m.seed_chain(gold["enc"][i], 2) for i in idx]
+    m.close()
+    for var, val in (("MAB_CHAIN_WARP", "1"), ("MAB_SORT_WALK", "0")):
+        monkeypatch.setenv(var, val)
+        m = api.Mapper(gold["blob"], "pacbio", lib_path=so)
+        got = [m.seed_chain(gold["enc"][i], 2) for i in idx]
+        m.close()
+        monkeypatch.delenv(var)
+        assert sum(e[0] for e in exp) > 1000
+        for e, g in zip(exp, got):
+            assert e[0] == g[0] and np.array_equal(e[1], g[1]) and np.array_equal(e[2], g[2])
