@@ -83,6 +83,7 @@ struct mab_ctx {
 	RunState rs;
 	uint64_t arena_budget = 40ull << 30;	/* HBM the DP arenas of this context may take (mab_set_arena_budget) */
 	bool chain_warp = false;				/* MAB_CHAIN_WARP=1: the chaining's window scan 32 candidates at a time (pays off with long scans only: 15.8 vs 9.9 ms per chunk on the E.coli-like workload) */
+	bool chain_staged = false;			/* MAB_CHAIN_STAGED=1: k_chain on a shared-memory copy of the seed array, one launch per size class (A/B switch) */
 	bool class_streams = true;			/* MAB_CLASS_STREAMS=0: the size classes one after the other on the context's stream (A/B switch) */
 	bool sort_walk = true;				/* MAB_SORT_WALK=0: the fused k_sortchain (sort by cycle-walking in shared memory) instead of k_sort + k_chain (A/B switch) */
 	bool ext_wide = true;				/* MAB_EXT_WIDE=0: always the 80-register build of k_extend (A/B switch) */
@@ -218,6 +219,7 @@ static int ctx_private_init(mab_ctx *ctx)
 	for(int i = 0; i < MAB_SC_CLASSES; i++) { CK(RT_STREAM_CREATE(&ctx->side[i])); CK(RT_LIGHT_EVENT_CREATE(&ctx->join_ev[i])); ctx->n_side++; }
 	if(const char *e = getenv("MAB_CHAIN_WARP")) { ctx->chain_warp = atoi(e) != 0; }
 	if(const char *e = getenv("MAB_CLASS_STREAMS")) { ctx->class_streams = atoi(e) != 0; }
+	if(const char *e = getenv("MAB_CHAIN_STAGED")) { ctx->chain_staged = atoi(e) != 0; }
 	RT_FUNC_MAX_SMEM(k_sortchain, 16 * MAB_SC_MAX + 2048);
 	RT_FUNC_MAX_SMEM(k_chain, 16 * MAB_SC_MAX + 2048);
 	RT_FUNC_MAX_SMEM(k_sort, 4 * MAB_WK_SM_WORDS + 32768);
@@ -692,17 +694,23 @@ static void pipe_rounds(mab_ctx *ctx, bool first, bool timed)
 				S.n_launches++; used = ci + 1;
 				if(last) { break; }
 			}
-			if(par) { for(uint32_t ci = 0; ci < used; ci++) { RT_STREAM_WAIT(ctx->stream, ctx->join_ev[ci]); } RT_EVENT_RECORD(ctx->fork_ev, ctx->stream); }
-			for(uint32_t k = 0; k < R.sc_ncls[kind]; k++) {
-				const uint32_t ci = R.sc_ncls[kind] - 1 - k;
-				const uint32_t cap = R.sc_cls[kind][ci], lo = ci == 0 ? 0u : R.sc_cls[kind][ci - 1], hi = ci + 1 == R.sc_ncls[kind] ? 0xffffffffu : cap;
-				RT_STREAM st = par ? ctx->side[k] : ctx->stream;
-				if(par) { RT_STREAM_WAIT(st, ctx->fork_ev); }
-				RT_LAUNCH(k_chain, n_seq, 32, 16 * cap + 2048, st, P, ctx->d_reads, (const uint32_t *)ctx->d_order, n_seq, ctx->d_ws, ctx->d_frames, cap, lo, hi, ctx->chain_warp ? 1u : 0u);
-				if(par) { RT_EVENT_RECORD(ctx->join_ev[k], st); }
+			if(par) { for(uint32_t ci = 0; ci < used; ci++) { RT_STREAM_WAIT(ctx->stream, ctx->join_ev[ci]); } }
+			if(!ctx->chain_staged) {
+				RT_LAUNCH(k_chain, (n_seq + MAB_WARPS_PER_CTA - 1) / MAB_WARPS_PER_CTA, 32 * MAB_WARPS_PER_CTA, 2048 * MAB_WARPS_PER_CTA, ctx->stream, P, ctx->d_reads, (const uint32_t *)ctx->d_order, n_seq, ctx->d_ws, ctx->d_frames, 0u, 0u, 0xffffffffu, ctx->chain_warp ? 1u : 0u);
 				S.n_launches++;
+			} else {
+				if(par) { RT_EVENT_RECORD(ctx->fork_ev, ctx->stream); }
+				for(uint32_t k = 0; k < R.sc_ncls[kind]; k++) {
+					const uint32_t ci = R.sc_ncls[kind] - 1 - k;
+					const uint32_t cap = R.sc_cls[kind][ci], lo = ci == 0 ? 0u : R.sc_cls[kind][ci - 1], hi = ci + 1 == R.sc_ncls[kind] ? 0xffffffffu : cap;
+					RT_STREAM st = par ? ctx->side[k] : ctx->stream;
+					if(par) { RT_STREAM_WAIT(st, ctx->fork_ev); }
+					RT_LAUNCH(k_chain, n_seq, 32, 16 * cap + 2048, st, P, ctx->d_reads, (const uint32_t *)ctx->d_order, n_seq, ctx->d_ws, ctx->d_frames, cap, lo, hi, ctx->chain_warp ? 1u : 0u);
+					if(par) { RT_EVENT_RECORD(ctx->join_ev[k], st); }
+					S.n_launches++;
+				}
+				if(par) { for(uint32_t k = 0; k < R.sc_ncls[kind]; k++) { RT_STREAM_WAIT(ctx->stream, ctx->join_ev[k]); } }
 			}
-			if(par) { for(uint32_t k = 0; k < R.sc_ncls[kind]; k++) { RT_STREAM_WAIT(ctx->stream, ctx->join_ev[k]); } }
 		} else {
 			for(uint32_t ci = 0, lo = 0; ci < R.sc_ncls[kind]; ci++) {				/* one launch per size class: shared memory cut to the class */
 				const uint32_t cap = R.sc_cls[kind][ci], hi = ci + 1 == R.sc_ncls[kind] ? 0xffffffffu : cap;

@@ -352,8 +352,10 @@ __global__ void k_sortchain(DevParams P, ReadRec *reads, uint32_t n_reads, uint8
 /* ---------------------------------------------------------------- k_sort + k_chain */
 /* The two halves of k_sortchain as kernels of their own.  k_sort: rescue-round seeding and the exact sort in its parallel form
  * (radix_sort_walk_warp: elements stay in global memory, shared memory holds a byte per element, so a few dozen reads are
- * resident per SM).  k_chain: chaining + root sort on the sorted array staged in shared memory.  One warp per read in both;
- * reads are taken longest first (order[]). */
+ * resident per SM).  k_chain: chaining + root sort.  One warp per read in both; reads are taken longest first (order[]).
+ * k_chain by default works on the sorted array where it lies (sc_cap = 0: 64 warps per SM, the scans are sequential and hit
+ * L1): measured against staging it in shared memory (16 B per seed: 2-20 warps per SM) that is 7.4 vs 8.9 ms per chunk on the
+ * E.coli-like workload and 23 vs 45 ms on the human-sized one; MAB_CHAIN_STAGED=1 keeps the staged classes for comparison. */
 __global__ void k_sort(DevParams P, ReadRec *reads, const uint32_t *order, uint32_t n_reads, uint8_t *ws, uint32_t *frames, uint32_t round, uint32_t cap, uint32_t lo_cap, uint32_t hi_cap)
 {
 	MAB_DYN_SMEM(smem);
@@ -437,8 +439,8 @@ __device__ __forceinline__ void chain_read(const DevParams &P, ReadRec *r, uint8
 __global__ void k_chain(DevParams P, ReadRec *reads, const uint32_t *order, uint32_t n_reads, uint8_t *ws, uint32_t *frames, uint32_t sc_cap, uint32_t lo_cap, uint32_t hi_cap, uint32_t wide)
 {
 	MAB_DYN_SMEM(smem);
-	int lane = threadIdx.x & 31;
-	uint32_t *sm = (uint32_t *)smem, *sseed = sm + 512;
+	int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	uint32_t *sm = (uint32_t *)smem + (uint64_t)(512u + 4u * sc_cap) * wib, *sseed = sm + 512;
 	uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if(slot >= n_reads) { return; }
 	uint32_t i = order[slot];

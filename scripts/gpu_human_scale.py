@@ -77,10 +77,13 @@ if os.environ.get("HUMAN_TRACE"):             # stage timeline of the CLI (MAB_T
     REP = int(os.environ.get("HUMAN_REPEAT", "3"))
     for nc in [int(x) for x in os.environ["HUMAN_TRACE"].split(",")]:
         for ctas in os.environ.get("HUMAN_CTAS", "4").split(","):
-            with open(os.devnull, "wb") as f:
-                pc = subprocess.run([CLI, "-xpacbio", f"-c{nc}", idx] + [rd] * REP, stdout=f, stderr=subprocess.PIPE, text=True, env=dict(os.environ, MAB_TRACE="1", MAB_EXT_CTAS=ctas.rstrip("d"), **({"MAB_PIN_DELAY": "1"} if ctas.endswith("d") else {})))
-            open(os.path.join(OUT, f"trace_c{nc}_ctas{ctas}.log"), "w").write(pc.stderr)
-            log("trace", nc, ctas, pc.stderr[-300:])
+            for var in os.environ.get("HUMAN_ENVS", "").split(";"):           # e.g. "MAB_SORT_WALK=0;MAB_SORT_WALK=1"
+                extra = dict(kv.split("=") for kv in var.split(",") if kv)
+                with open(os.devnull, "wb") as f:
+                    pc = subprocess.run([CLI, "-xpacbio", f"-c{nc}", idx] + [rd] * REP, stdout=f, stderr=subprocess.PIPE, text=True, env=dict(os.environ, MAB_TRACE="1", MAB_EXT_CTAS=ctas, **extra))
+                tag = f"c{nc}_ctas{ctas}" + ("_" + var.replace("=", "").replace(",", "_") if var else "")
+                open(os.path.join(OUT, f"trace_{tag}.log"), "w").write(pc.stderr)
+                log("trace", tag, pc.stderr[-300:])
     raise SystemExit(0)
 
 # ---- our CLI, file to SAM ----

@@ -155,13 +155,13 @@ def test_gpu_parallel_sort_equals_cycle_walking_sort(gold):
 
 
 def test_emu_wide_chain_scan_equals_single_lane(gold, monkeypatch):
-    """MAB_CHAIN_WARP=1 (window scan 32 candidates at a time) and the fused k_sortchain (MAB_SORT_WALK=0) give the default's chains"""
+    """the A/B switches -- window scan 32 candidates at a time, the fused k_sortchain, k_chain on a shared-memory copy -- give the default's chains"""
     so = build_emu()
     idx = [i for i, s in enumerate(gold["enc"]) if s.size <= 12000][:12]
     m = api.Mapper(gold["blob"], "pacbio", lib_path=so)
     exp = [m.seed_chain(gold["enc"][i], 2) for i in idx]
     m.close()
-    for var, val in (("MAB_CHAIN_WARP", "1"), ("MAB_SORT_WALK", "0")):
+    for var, val in (("MAB_CHAIN_WARP", "1"), ("MAB_SORT_WALK", "0"), ("MAB_CHAIN_STAGED", "1"), ("MAB_CLASS_STREAMS", "0")):
         monkeypatch.setenv(var, val)
         m = api.Mapper(gold["blob"], "pacbio", lib_path=so)
         got = [m.seed_chain(gold["enc"][i], 2) for i in idx]
