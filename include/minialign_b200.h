@@ -177,6 +177,10 @@ uint64_t mab_sam_header_text(const mab_ctx *ctx, const char *version, const char
 void *mab_host_alloc(uint64_t bytes);
 void *mab_host_alloc_on(int device, uint64_t bytes);	/* the same from a thread that has not used a device yet (selects `device` first) */
 void mab_host_free(void *p);
+/* page-lock memory of the caller's own (page-aligned; touch it first, on as many threads as you like: that is the slow part and
+ * unlike mab_host_alloc it does not hold up the other CUDA calls of the process) */
+int mab_host_register(int device, void *p, uint64_t bytes);
+void mab_host_unregister(void *p);
 
 /* ---- stage-level entry points (parity tests; same semantics as the reference functions named above) ---- */
 /* sketch of one read: writes the minimizer words followed by the 4-word cap; returns #words (may exceed cap) */

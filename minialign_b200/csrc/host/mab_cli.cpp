@@ -383,29 +383,52 @@ int main(int argc, char **argv)
 	if(o.dump.empty()) {
 		pinner = std::thread([&]() {
 			auto stopped = [&]() { std::unique_lock<std::mutex> lk(mu); return pin_stop; };
-			/* not before the contexts stand: pinning pages holds up every other CUDA call of the process, and doing it while the CUDA
-			 * contexts come up and the index frames are copied costs more than it saves (measured: device set-up 1.3 -> 2.4-4.3 s,
-			 * upload 2.5 -> 4.3 s, context set-up 0.01 -> 1.7 s) */
+			auto give_up = [&]() { fprintf(stderr, "[E::main_align] %s\n", mab_last_error()); std::unique_lock<std::mutex> lk(mu); failed = true; cv.notify_all(); };
+			/* Page-locking in two steps.  Now, next to the index load: map the buffers and touch every page on a few threads (no
+			 * CUDA involved).  Once the contexts stand: register them with the driver one by one in the order they are needed
+			 * (0.15 s per GB, and other CUDA calls get through meanwhile).  cudaHostAlloc does both in one call at 0.4-0.6 s per GB
+			 * and holds up every other CUDA call of the process for its duration: measured on the CLI that delayed the device
+			 * set-up from 1.3 to 2.4-4.3 s when done early and the first chunk by 1.7 s when done late. */
+			const uint64_t ccap = chunk_bytes + (16 << 20), ocap = chunk_bytes + chunk_bytes / 2 + (1 << 20);
+			const size_t nc = chunk_pool.size(), no = out_pool.size();
+			const uint64_t total = (ccap + 4096) * nc + (ocap + 4096) * no;
+			char *arena = (char *)mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+			if(arena == (char *)MAP_FAILED) { arena = nullptr; }
+			std::vector<char *> cb(nc, nullptr), ob(no, nullptr);
+			if(arena) {
+				char *p = arena;
+				for(size_t i = 0; i < nc; i++) { cb[i] = p; p += (ccap + 4095) & ~4095ull; }
+				for(size_t i = 0; i < no; i++) { ob[i] = p; p += (ocap + 4095) & ~4095ull; }
+				std::atomic<uint64_t> nextpg(0); const uint64_t step = 64ull << 20;
+				auto touch = [&]() { for(uint64_t a; (a = nextpg.fetch_add(step)) < total && !stopped();) { memset(arena + a, 0, std::min<uint64_t>(step, total - a)); } };
+				std::vector<std::thread> th; for(int t = 0; t < 3; t++) { th.emplace_back(touch); }
+				touch(); for(auto &x : th) { x.join(); }
+			}
+			if(getenv("MAB_TRACE")) { fprintf(stderr, "[pinner %.3f] pages touched\n", now() - t0); }
 			{ std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&]() { return pin_go || pin_stop; }); }
 			if(getenv("MAB_TRACE")) { fprintf(stderr, "[pinner %.3f] start\n", now() - t0); }
-			auto give_up = [&]() { fprintf(stderr, "[E::main_align] %s\n", mab_last_error()); std::unique_lock<std::mutex> lk(mu); failed = true; cv.notify_all(); };
+			auto lock = [&](char *pre, uint64_t cap) -> char * {
+				if(pre && mab_host_register(devices[0], pre, cap) == MAB_OK) { return pre; }
+				return (char *)mab_host_alloc_on(devices[0], cap);
+			};
 			/* first what the first chunks need (a chunk buffer and an output buffer per context), then the second halves */
 			for(unsigned pass = 0; pass < 2; pass++) {
-				for(size_t i = pass ? std::min<size_t>(n_ctx, chunk_pool.size()) : 0; i < (pass ? chunk_pool.size() : std::min<size_t>(n_ctx, chunk_pool.size())); i++) {
+				for(size_t i = pass ? std::min<size_t>(n_ctx, nc) : 0; i < (pass ? nc : std::min<size_t>(n_ctx, nc)); i++) {
 					if(stopped()) { return; }
 					Chunk &c = chunk_pool[i];
-					uint64_t cap = chunk_bytes + (16 << 20); char *b = (char *)mab_host_alloc_on(devices[0], cap);
+					char *b = lock(cb[i], ccap);
 					if(!b) { give_up(); return; }
-					std::unique_lock<std::mutex> lk(mu); c.cap = cap; c.buf = b; free_chunks.push_back(&c); cv.notify_all();
+					std::unique_lock<std::mutex> lk(mu); c.cap = ccap; c.buf = b; free_chunks.push_back(&c); cv.notify_all();
 				}
 				if(getenv("MAB_TRACE")) { fprintf(stderr, "[pinner %.3f] pass %u: chunk buffers done\n", now() - t0, pass); }
 				for(unsigned i = pass; i < 2 * n_ctx; i += 2) {
 					if(stopped()) { return; }
-					uint64_t cap = chunk_bytes + chunk_bytes / 2 + (1 << 20); char *b = (char *)mab_host_alloc_on(devices[0], cap);
+					char *b = lock(ob[i], ocap);
 					if(!b) { give_up(); return; }
-					std::unique_lock<std::mutex> lk(mu); out_pool[i].cap = cap; out_pool[i].buf = b; cv.notify_all();
+					std::unique_lock<std::mutex> lk(mu); out_pool[i].cap = ocap; out_pool[i].buf = b; cv.notify_all();
 				}
 			}
+			if(getenv("MAB_TRACE")) { fprintf(stderr, "[pinner %.3f] done\n", now() - t0); }
 		});
 	}
 	auto stop_pinner = [&]() { { std::unique_lock<std::mutex> lk(mu); pin_stop = true; cv.notify_all(); } if(pinner.joinable()) { pinner.join(); } };
@@ -620,7 +643,7 @@ int main(int argc, char **argv)
 				if(x->buf == nullptr) { x->cap = c->len + c->len / 2 + (1 << 20); x->buf = (char *)mab_host_alloc(x->cap); if(!x->buf) { fail(std::string("[E::main_align] ") + mab_last_error()); return; } }
 				rc = mab_text_finish(ctx, x->buf, x->cap, &ptr, &info);		/* device -> this page-locked buffer; the context is free for the next chunk afterwards */
 				if(rc == MAB_ENOMEM && info.sam_bytes > x->cap) {			/* more text than estimated: a larger buffer, format again */
-					mab_host_free(x->buf); x->cap = info.sam_bytes + info.sam_bytes / 8 + (1 << 20); x->buf = (char *)mab_host_alloc(x->cap);
+					x->cap = info.sam_bytes + info.sam_bytes / 8 + (1 << 20); x->buf = (char *)mab_host_alloc(x->cap);	/* (the smaller buffer stays behind: it is part of the pinner's arena) */
 					if(!x->buf) { fail(std::string("[E::main_align] ") + mab_last_error()); return; }
 					rc = mab_text_finish(ctx, x->buf, x->cap, &ptr, &info);
 				}

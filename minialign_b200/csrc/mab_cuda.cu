@@ -37,6 +37,8 @@ static inline unsigned RT_EXTEND_SLOTS(unsigned n_sm) { return n_sm * 4 * MAB_EX
 template <class T> static inline cudaError_t RT_MALLOC(T **p, uint64_t n) { return cudaMalloc((void **)p, n); }
 template <class T> static inline cudaError_t RT_HOST_ALLOC(T **p, uint64_t n) { return cudaHostAlloc((void **)p, n, cudaHostAllocDefault); }
 template <class T> static inline void RT_HOST_FREE(T *p) { if(p) { cudaFreeHost((void *)p); } }
+static inline cudaError_t RT_HOST_REGISTER(void *p, uint64_t n) { return cudaHostRegister(p, n, cudaHostRegisterDefault); }
+static inline void RT_HOST_UNREGISTER(void *p) { cudaHostUnregister(p); }
 template <class T> static inline void RT_FREE(T *p) { if(p) { cudaFree((void *)p); } }
 static inline cudaError_t RT_MEMCPY_H2D(void *d, const void *s, uint64_t n) { return cudaMemcpy(d, s, n, cudaMemcpyHostToDevice); }
 static inline cudaError_t RT_MEMCPY_D2H(void *d, const void *s, uint64_t n) { return cudaMemcpy(d, s, n, cudaMemcpyDeviceToHost); }

@@ -56,6 +56,15 @@ static void text_destroy(mab_ctx *ctx)
 	RT_HOST_FREE(ctx->h_sam);
 }
 
+/* page-locks memory the caller allocated (and, better, already touched: populating pages is the slow part of pinning and can be
+ * done on several threads without holding up the CUDA calls of the rest of the process, which cudaHostAlloc does) */
+extern "C" int mab_host_register(int device, void *p, uint64_t bytes)
+{
+	if(!RT_OK(RT_USE_DEVICE(device))) { g_err = std::string("no usable CUDA device: ") + RT_ERRSTR(); return MAB_ENODEV; }
+	if(!RT_OK(RT_HOST_REGISTER(p, bytes))) { g_err = std::string("page-locking host memory failed: ") + RT_ERRSTR(); return MAB_ENOMEM; }
+	return MAB_OK;
+}
+extern "C" void mab_host_unregister(void *p) { RT_HOST_UNREGISTER(p); }
 extern "C" void *mab_host_alloc_on(int device, uint64_t bytes)
 {
 	if(!RT_OK(RT_USE_DEVICE(device))) { g_err = std::string("no usable CUDA device: ") + RT_ERRSTR(); return nullptr; }

@@ -18,6 +18,8 @@ template <class T> static inline int RT_MALLOC(T **p, uint64_t n) { *p = (T *)al
 template <class T> static inline void RT_FREE(T *p) { free((void *)p); }
 template <class T> static inline int RT_HOST_ALLOC(T **p, uint64_t n) { *p = (T *)malloc(n); return *p ? 0 : 1; }
 template <class T> static inline void RT_HOST_FREE(T *p) { free((void *)p); }
+static inline int RT_HOST_REGISTER(void *, uint64_t) { return 0; }
+static inline void RT_HOST_UNREGISTER(void *) {}
 static inline int RT_MEMCPY_H2D(void *d, const void *s, uint64_t n) { memcpy(d, s, n); return 0; }
 static inline int RT_MEMCPY_D2H(void *d, const void *s, uint64_t n) { memcpy(d, s, n); return 0; }
 static inline int RT_MEMCPY_H2D_ASYNC(void *d, const void *s, uint64_t n, RT_STREAM) { memcpy(d, s, n); return 0; }
