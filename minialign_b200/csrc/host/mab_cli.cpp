@@ -216,10 +216,10 @@ struct ByteSource {
 /* [0, cut) = whole records of buf[0, fill): the start of the last record header that can be told for sure.  FASTA: the last
  * '>' at a line start.  FASTQ: the last '@' at a line start whose line after next starts with '+' (a quality line may start
  * with '@' too, but then the line after next is a sequence).  0 = no such place. */
-static uint64_t record_cut(const char *buf, uint64_t fill)
+static uint64_t record_cut(const char *buf, uint64_t fill, char delim = 0)
 {
 	if(fill < 2) { return 0; }
-	const char delim = buf[0];
+	if(delim == 0) { delim = buf[0]; }
 	for(uint64_t p = fill - 1; p > 0; p--) {
 		if(buf[p] != delim || buf[p - 1] != '\n') { continue; }
 		if(delim != '@') { return p; }
@@ -546,6 +546,62 @@ int main(int argc, char **argv)
 			ByteSource src(o.pos[qi].c_str());
 			if(!src.ok()) { std::unique_lock<std::mutex> lk(mu); Chunk *c = nullptr; cv.wait(lk, [&]() { return !free_chunks.empty() || failed; }); if(failed) { return; } c = free_chunks.front(); free_chunks.pop_front(); c->len = 0; c->id = id++; c->file = qi; c->open_failed = true; c->last_of_file = true; ready.push_back(c); cv.notify_all(); break; }
 			bool eof = false; carry.clear();
+			if(src.fd >= 0 && n_ctx > 1) {
+				/* a plain file is read by several threads: the chunk boundaries (any record start will do) are found first from a few small
+				 * reads around the multiples of the chunk size, then the chunks are pread() side by side -- one thread copies 4-6 GB/s out
+				 * of the page cache, which several GPUs outrun.  Buffers are granted and chunks released in id order (a context waits
+				 * for its turn in file order, so a later chunk must never hold what an earlier one still needs). */
+				struct stat fs; std::vector<uint64_t> cuts;
+				char first = 0;
+				if(fstat(src.fd, &fs) == 0 && S_ISREG(fs.st_mode) && fs.st_size > 0 && pread(src.fd, &first, 1, 0) == 1 && (first == '>' || first == '@')) {
+					const uint64_t F = (uint64_t)fs.st_size, W = 4ull << 20;
+					std::vector<char> win(W);
+					cuts.push_back(0);
+					bool good = true;
+					for(uint64_t x = chunk_bytes; x < F && good; x += chunk_bytes) {
+						uint64_t lo = std::max(x > W ? x - W : 0, cuts.back());
+						int64_t n = pread(src.fd, win.data(), (size_t)std::min<uint64_t>(W, F - lo), (off_t)lo);
+						uint64_t c = n > 2 ? record_cut(win.data(), std::min<uint64_t>((uint64_t)n, x - lo), first) : 0;
+						if(c == 0 || lo + c <= cuts.back()) { good = false; break; }			/* a record longer than the window, ...: the sequential reader sorts it out */
+						cuts.push_back(lo + c);
+					}
+					uint64_t end = F;															/* blank lines at the end of the file */
+					if(good) {
+						char tail[64]; int64_t n = pread(src.fd, tail, (size_t)std::min<uint64_t>(64, F), (off_t)(F - std::min<uint64_t>(64, F)));
+						while(n > 1 && tail[n - 1] == '\n' && tail[n - 2] == '\n' && end > cuts.back() + 1) { n--; end--; }
+						cuts.push_back(end);
+					} else { cuts.clear(); }
+				}
+				if(!cuts.empty()) {
+					const size_t nch = cuts.size() - 1;
+					size_t next_k = 0; uint64_t next_release = id; std::map<uint64_t, Chunk *> pending; bool rd_failed = false;
+					auto rd = [&]() {
+						for(;;) {
+							Chunk *c; size_t k;
+							{
+								std::unique_lock<std::mutex> lk(mu);
+								cv.wait(lk, [&]() { return !free_chunks.empty() || failed || rd_failed || next_k >= nch; });
+								if(failed || rd_failed || next_k >= nch) { return; }
+								k = next_k++; c = free_chunks.front(); free_chunks.pop_front();
+							}
+							const uint64_t len = cuts[k + 1] - cuts[k];
+							uint64_t got = 0;
+							if(len <= c->cap) { while(got < len) { ssize_t n = pread(src.fd, c->buf + got, (size_t)std::min<uint64_t>(len - got, 1u << 30), (off_t)(cuts[k] + got)); if(n <= 0) { break; } got += (uint64_t)n; } }
+							std::unique_lock<std::mutex> lk(mu);
+							if(got != len) { rd_failed = true; fprintf(stderr, "[E::main_align] failed to read sequence file `%s'.\n", o.pos[qi].c_str()); failed = true; cv.notify_all(); return; }
+							c->len = len; c->id = id + k; c->file = qi; c->last_of_file = k + 1 == nch; c->open_failed = false;
+							pending[c->id] = c;
+							while(!pending.empty() && pending.begin()->first == next_release) { ready.push_back(pending.begin()->second); pending.erase(pending.begin()); next_release++; }
+							cv.notify_all();
+						}
+					};
+					std::vector<std::thread> th; for(unsigned t = 0; t < std::min<unsigned>(4, (unsigned)nch); t++) { th.emplace_back(rd); }
+					for(auto &x : th) { x.join(); }
+					{ std::unique_lock<std::mutex> lk(mu); if(failed) { return; } }
+					id += nch;
+					continue;
+				}
+			}
 			while(!eof) {
 				Chunk *c;
 				{ std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&]() { return !free_chunks.empty() || failed; }); if(failed) { return; } c = free_chunks.front(); free_chunks.pop_front(); }
