@@ -24,6 +24,8 @@ import argparse
 import ctypes as C
 import json
 import os
+
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # hardware queues: several contexts x (stream + side streams) + NCCL; at the default 8 they share queues and wait for each other's kernels
 import re
 import subprocess
 import sys

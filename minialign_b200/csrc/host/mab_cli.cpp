@@ -352,6 +352,7 @@ static bool map_chunk_on_host(mab_ctx *ctx, const char *buf, uint64_t len, const
 int main(int argc, char **argv)
 {
 	double t0 = now();
+	setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);				/* hardware queues per device: the contexts' streams (and their side streams) share 8 by default and then wait for each other's kernels */
 	Opts o; memset(&o.p, 0, sizeof(o.p));
 	o.p.wlen = 7000; o.p.glen = 7000; o.p.min_score = 50; o.p.min_ratio = 0.3f; o.p.xdrop = 50;	/* defaults, minialign.c:6152-6158 */
 	set_match(o.p, 1); set_mismatch(o.p, 1); o.p.gi = 1; o.p.ge = 1;

@@ -44,6 +44,10 @@ struct Calib {
 	uint64_t reserve_bytes = 0;			/* mab_text_reserve: the largest chunk the caller will pass; buffers are sized for it from the first chunk on */
 };
 
+/* streams the size classes of k_sort are spread over.  Few on purpose: a process has 8 hardware queues by default
+ * (CUDA_DEVICE_MAX_CONNECTIONS; the hosts here raise it to 32) and streams that share one wait for each other's kernels. */
+#define MAB_SIDE_STREAMS 3
+
 struct mab_ctx {
 	int device;
 	DevParams P;
@@ -65,7 +69,7 @@ struct mab_ctx {
 	uint32_t *d_pool = nullptr; uint64_t pool_cap = 0;
 	BatchCounters *d_ctr = nullptr;
 	RT_STREAM stream; bool have_stream = false; int n_ev = 0;
-	RT_STREAM side[MAB_SC_CLASSES]; RT_EVENT fork_ev, join_ev[MAB_SC_CLASSES]; int n_side = 0; bool have_fork_ev = false;	/* the size classes of k_sort / k_chain run side by side */
+	RT_STREAM side[MAB_SIDE_STREAMS]; RT_EVENT fork_ev, join_ev[MAB_SIDE_STREAMS]; int n_side = 0; bool have_fork_ev = false;	/* the size classes of k_sort / k_chain run side by side */
 	RT_EVENT sync_ev; bool have_sync_ev = false;	/* the host waits on this one asleep (blocking-sync event) instead of spinning in a stream synchronize */
 	RT_EVENT ev[8];
 	RT_EVENT rev[24];					/* per-round kernel boundaries: [3r] sortchain start, [3r+1] extend start, [3r+2] extend end */
@@ -216,7 +220,7 @@ static int ctx_private_init(mab_ctx *ctx)
 	for(int i = 0; i < 24; i++) { CK(RT_EVENT_CREATE(&ctx->rev[i])); ctx->n_ev++; }
 	CK(RT_SYNC_EVENT_CREATE(&ctx->sync_ev)); ctx->have_sync_ev = true;
 	CK(RT_LIGHT_EVENT_CREATE(&ctx->fork_ev)); ctx->have_fork_ev = true;
-	for(int i = 0; i < MAB_SC_CLASSES; i++) { CK(RT_STREAM_CREATE(&ctx->side[i])); CK(RT_LIGHT_EVENT_CREATE(&ctx->join_ev[i])); ctx->n_side++; }
+	for(int i = 0; i < MAB_SIDE_STREAMS; i++) { CK(RT_STREAM_CREATE(&ctx->side[i])); CK(RT_LIGHT_EVENT_CREATE(&ctx->join_ev[i])); ctx->n_side++; }
 	if(const char *e = getenv("MAB_CHAIN_WARP")) { ctx->chain_warp = atoi(e) != 0; }
 	if(const char *e = getenv("MAB_CLASS_STREAMS")) { ctx->class_streams = atoi(e) != 0; }
 	if(const char *e = getenv("MAB_CHAIN_STAGED")) { ctx->chain_staged = atoi(e) != 0; }
@@ -687,14 +691,13 @@ static void pipe_rounds(mab_ctx *ctx, bool first, bool timed)
 			if(par) { RT_EVENT_RECORD(ctx->fork_ev, ctx->stream); }
 			for(uint32_t cap = 32768, ci = 0; ; cap /= 2, ci++) {						/* the seed-rich classes first: they take longest */
 				const bool first = cap >= 32768, last = cap <= 1024;
-				RT_STREAM st = par ? ctx->side[ci] : ctx->stream;
-				if(par) { RT_STREAM_WAIT(st, ctx->fork_ev); }
+				RT_STREAM st = par ? ctx->side[ci % MAB_SIDE_STREAMS] : ctx->stream;
+				if(par && ci < MAB_SIDE_STREAMS) { RT_STREAM_WAIT(st, ctx->fork_ev); }
 				RT_LAUNCH(k_sort, n_seq, 32, 4 * MAB_WK_SM_WORDS + cap, st, P, ctx->d_reads, (const uint32_t *)ctx->d_order, n_seq, ctx->d_ws, ctx->d_frames, round, cap, last ? 0u : cap / 2, first ? 0xffffffffu : cap);
-				if(par) { RT_EVENT_RECORD(ctx->join_ev[ci], st); }
 				S.n_launches++; used = ci + 1;
 				if(last) { break; }
 			}
-			if(par) { for(uint32_t ci = 0; ci < used; ci++) { RT_STREAM_WAIT(ctx->stream, ctx->join_ev[ci]); } }
+			if(par) { for(uint32_t k = 0; k < std::min<uint32_t>(used, MAB_SIDE_STREAMS); k++) { RT_EVENT_RECORD(ctx->join_ev[k], ctx->side[k]); RT_STREAM_WAIT(ctx->stream, ctx->join_ev[k]); } }
 			if(!ctx->chain_staged) {
 				RT_LAUNCH(k_chain, (n_seq + MAB_WARPS_PER_CTA - 1) / MAB_WARPS_PER_CTA, 32 * MAB_WARPS_PER_CTA, 2048 * MAB_WARPS_PER_CTA, ctx->stream, P, ctx->d_reads, (const uint32_t *)ctx->d_order, n_seq, ctx->d_ws, ctx->d_frames, 0u, 0u, 0xffffffffu, ctx->chain_warp ? 1u : 0u);
 				S.n_launches++;
@@ -703,13 +706,12 @@ static void pipe_rounds(mab_ctx *ctx, bool first, bool timed)
 				for(uint32_t k = 0; k < R.sc_ncls[kind]; k++) {
 					const uint32_t ci = R.sc_ncls[kind] - 1 - k;
 					const uint32_t cap = R.sc_cls[kind][ci], lo = ci == 0 ? 0u : R.sc_cls[kind][ci - 1], hi = ci + 1 == R.sc_ncls[kind] ? 0xffffffffu : cap;
-					RT_STREAM st = par ? ctx->side[k] : ctx->stream;
-					if(par) { RT_STREAM_WAIT(st, ctx->fork_ev); }
+					RT_STREAM st = par ? ctx->side[k % MAB_SIDE_STREAMS] : ctx->stream;
+					if(par && k < MAB_SIDE_STREAMS) { RT_STREAM_WAIT(st, ctx->fork_ev); }
 					RT_LAUNCH(k_chain, n_seq, 32, 16 * cap + 2048, st, P, ctx->d_reads, (const uint32_t *)ctx->d_order, n_seq, ctx->d_ws, ctx->d_frames, cap, lo, hi, ctx->chain_warp ? 1u : 0u);
-					if(par) { RT_EVENT_RECORD(ctx->join_ev[k], st); }
 					S.n_launches++;
 				}
-				if(par) { for(uint32_t k = 0; k < R.sc_ncls[kind]; k++) { RT_STREAM_WAIT(ctx->stream, ctx->join_ev[k]); } }
+				if(par) { for(uint32_t k = 0; k < std::min<uint32_t>(R.sc_ncls[kind], MAB_SIDE_STREAMS); k++) { RT_EVENT_RECORD(ctx->join_ev[k], ctx->side[k]); RT_STREAM_WAIT(ctx->stream, ctx->join_ev[k]); } }
 			}
 		} else {
 			for(uint32_t ci = 0, lo = 0; ci < R.sc_ncls[kind]; ci++) {				/* one launch per size class: shared memory cut to the class */

@@ -17,6 +17,8 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # before CUDA starts: see DESIGN.md section 6
 import sys
 import time
 
