@@ -312,6 +312,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    cpu_binding = shard.bind_near_gpu(local) if world > 1 else "unchanged (one rank)"
     host_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -339,6 +340,7 @@ def main():
     m0 = api.Mapper(blob, PRESET, device=local)
     ms = [m0] + [m0.clone() for _ in range(max(1, args.contexts) - 1)]
     config["extend_ctas_per_sm"] = int(ext_pipe)
+    config["cpu_binding"] = cpu_binding
 
     def barrier():
         torch.cuda.synchronize()

@@ -171,6 +171,8 @@ def main(argv=None):
     if backend == "nccl":
         torch.cuda.set_device(local)
         dev = torch.device("cuda", local)
+        if world > 1:
+            shard.bind_near_gpu(local)
     if world > 1:
         dist.init_process_group(backend, **({"device_id": dev} if dev is not None else {}))
     blob = mai.load_mai(o["pos"][0])

@@ -73,6 +73,42 @@ save()
 if p.returncode != 0:
     raise SystemExit("index build failed: " + p.stderr[-500:])
 
+if os.environ.get("HUMAN_GPUS"):               # the whole box: one process, all GPUs (BASELINE configs[4] in shape: REP x 0.3x coverage ~ 3x)
+    ng = int(os.environ["HUMAN_GPUS"]); REP = int(os.environ.get("HUMAN_REPEAT", "10"))
+    glist = ",".join(str(i) for i in range(ng))
+    args = [CLI, "-xpacbio", "-g" + glist, "-c" + os.environ.get("HUMAN_CTX", "2"), "-N" + os.environ.get("HUMAN_CHUNK_MB", "160"), idx]
+    for tag, files, out in (("x%d" % REP, [rd] * REP, os.devnull), ("x1_file", [rd], os.path.join(WORK, "ours8.sam"))):
+        t1 = time.time()
+        with open(out, "wb") as f:
+            pc = subprocess.run(args + files, stdout=f, stderr=subprocess.PIPE, text=True)
+        S["ours_%dgpu_%s_wall_s" % (ng, tag)] = time.time() - t1; S["ours_%dgpu_%s_stderr" % (ng, tag)] = pc.stderr[-1200:]
+        mm = re.search(r"mapped (\d+) reads / ([0-9.]+) Mbases in ([0-9.]+) sec \(([0-9.]+) Mbases/s\)", pc.stderr)
+        if mm:
+            S["ours_%dgpu_%s_map_s" % (ng, tag)], S["ours_%dgpu_%s_mbases_per_s" % (ng, tag)] = float(mm.group(3)), float(mm.group(4))
+        log("ours", ng, tag, S["ours_%dgpu_%s_wall_s" % (ng, tag)], pc.stderr[-400:])
+        save()
+    t1 = time.time()
+    with open(os.devnull, "wb") as f:
+        pr = subprocess.run([REF, "-xpacbio", f"-t{thr}", idx] + [rd] * REP, stdout=f, stderr=subprocess.PIPE, text=True)
+    S["ref_x%d_wall_s" % REP] = time.time() - t1; S["ref_x%d_stderr" % REP] = pr.stderr[-600:]; S["ref_threads"] = thr
+    log("reference", S["ref_x%d_wall_s" % REP], pr.stderr[-300:])
+    save()
+    ns = int(os.environ.get("HUMAN_PARITY_READS", "1000"))
+    synth.write_fasta(srd, sample[:ns])
+    pr1 = subprocess.run([REF, "-xpacbio", "-t1", idx, srd], capture_output=True)
+    exp = [l for l in pr1.stdout.split(b"\n") if l and not l.startswith(b"@")]
+    got = []
+    with open(os.path.join(WORK, "ours8.sam"), "rb") as f:
+        for l in f:
+            if not l.startswith(b"@"):
+                got.append(l.rstrip(b"\n"))
+                if len(got) >= len(exp):
+                    break
+    S["parity_%dgpu" % ng] = {"reads": ns, "sam_lines": len(exp), "identical": got == exp, "against": "oracle/_ref/minialign -xpacbio -t1 on the first reads of the file; ours: ONE SAM written by %d GPUs" % ng}
+    log("parity", S["parity_%dgpu" % ng])
+    save()
+    raise SystemExit(0)
+
 if os.environ.get("HUMAN_TRACE"):             # stage timeline of the CLI (MAB_TRACE lines) for the listed context counts, nothing else
     REP = int(os.environ.get("HUMAN_REPEAT", "3"))
     for nc in [int(x) for x in os.environ["HUMAN_TRACE"].split(",")]:
