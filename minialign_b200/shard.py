@@ -118,14 +118,19 @@ class WaveExchange:
 
 
 def bind_near_gpu(device_index: int) -> str:
-    """Pin this process to the cores next to its GPU (sysfs local_cpulist of the device's PCI function, cut down to the cores the
-    process may use at all) BEFORE it allocates page-locked buffers and starts threads: pinned pages are then first touched on the
-    GPU's own NUMA node and every host<->device copy of the text path (0.8 GB per chunk) stays off the inter-socket link.  Returns
-    what was done, for the record; does nothing when the topology cannot be read or the node has fewer than four usable cores."""
+    """Put this process next to its GPU BEFORE it allocates page-locked buffers and starts threads: (1) its threads on the cores
+    of the GPU's NUMA node (sysfs local_cpulist of the device's PCI function, cut down to the cores the process may use at all),
+    (2) its memory preferably on that node (set_mempolicy(MPOL_PREFERRED): a soft preference, also when the cores cannot follow
+    -- a container whose cores all sit on one socket still has the other socket's GPUs copy 0.8 GB per chunk across the
+    inter-socket link otherwise).  Returns what was done, for the record; leaves things alone when the topology cannot be read."""
+    done = []
     try:
         import torch
         p = torch.cuda.get_device_properties(device_index)
         bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+    except Exception as e:
+        return f"unchanged ({type(e).__name__})"
+    try:
         with open(f"/sys/bus/pci/devices/{bus}/local_cpulist") as f:
             txt = f.read().strip()
         near = set()
@@ -136,8 +141,26 @@ def bind_near_gpu(device_index: int) -> str:
         allowed = os.sched_getaffinity(0)
         use = sorted(near & allowed)
         if len(use) < 4 or len(use) == len(allowed):
-            return f"unchanged ({len(allowed)} cores allowed, {len(use)} of them near {bus})"
-        os.sched_setaffinity(0, use)
-        return f"{len(use)} of {len(allowed)} cores, near {bus}"
-    except Exception as e:          # no sysfs, no such attribute, ...: leave the scheduler alone
-        return f"unchanged ({type(e).__name__})"
+            done.append(f"cores unchanged ({len(allowed)} allowed, {len(use)} of them near {bus})")
+        else:
+            os.sched_setaffinity(0, use)
+            done.append(f"{len(use)} of {len(allowed)} cores, near {bus}")
+    except Exception as e:          # no sysfs, ...: leave the scheduler alone
+        done.append(f"cores unchanged ({type(e).__name__})")
+    try:
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        import platform
+        if platform.machine() != "x86_64":
+            done.append("memory policy unchanged (syscall number known for x86-64 only)")
+        elif 0 <= node < 64:
+            import ctypes
+            libc = ctypes.CDLL(None, use_errno=True)
+            mask = ctypes.c_ulong(1 << node)
+            rc = libc.syscall(238, 1, ctypes.byref(mask), 65)       # x86-64 set_mempolicy(MPOL_PREFERRED, &mask, maxnode)
+            done.append(f"memory preferred on node {node}" if rc == 0 else f"memory policy unchanged (errno {ctypes.get_errno()})")
+        else:
+            done.append("memory policy unchanged (no NUMA node reported)")
+    except Exception as e:
+        done.append(f"memory policy unchanged ({type(e).__name__})")
+    return "; ".join(done)
