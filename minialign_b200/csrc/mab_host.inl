@@ -243,7 +243,8 @@ static mab_ctx *ctx_new(const uint8_t *b, uint64_t size, const mab_params_t *par
 {
 	if(b == nullptr || size < 64 || params == nullptr) { g_err = "mab_init: bad arguments"; return nullptr; }
 	if(check_params(params) != 0) { g_err = "mab_init: unsupported scoring parameters (combined gap model with validated ranges only)"; return nullptr; }
-	mab_ctx *ctx = new mab_ctx();
+	mab_ctx *ctx = new (std::nothrow) mab_ctx();
+	if(ctx == nullptr) { g_err = "host allocation failed"; return nullptr; }
 	ctx->device = device; ctx->prm = *params;
 	try { ctx->cal = std::make_shared<Calib>(); } catch(const std::bad_alloc &) { g_err = "host allocation failed"; delete ctx; return nullptr; }
 	memset(&ctx->stats, 0, sizeof(ctx->stats));
@@ -333,8 +334,10 @@ extern "C" mab_loader *mab_load_begin(uint64_t max_size, const mab_params_t *par
 {
 	if(params == nullptr || devices == nullptr || n_devices <= 0 || max_size < 64) { g_err = "mab_load_begin: bad arguments"; return nullptr; }
 	if(check_params(params) != 0) { g_err = "mab_init: unsupported scoring parameters (combined gap model with validated ranges only)"; return nullptr; }
-	mab_loader *ld = new mab_loader();
+	mab_loader *ld = new (std::nothrow) mab_loader();
+	if(ld == nullptr) { g_err = "host allocation failed"; return nullptr; }
 	trace_line(ld, "load: enter");
+	try {
 	ld->prm = *params; ld->cap = max_size; ld->devices.assign(devices, devices + n_devices);
 	ld->slot_used.assign(mab_loader::SLOTS, 0);
 	/* the devices in parallel: creating a CUDA context takes a few hundred milliseconds each */
@@ -374,6 +377,11 @@ extern "C" mab_loader *mab_load_begin(uint64_t max_size, const mab_params_t *par
 	if(!RT_OK(RT_HOST_ALLOC(&ld->ring, mab_loader::SLOTS * mab_loader::SLOT_BYTES))) { g_err = std::string("pinned host allocation failed: ") + RT_ERRSTR(); mab_load_abort(ld); return nullptr; }
 	trace_line(ld, "load: begin, index MB", max_size / 1048576.0);
 	return ld;
+	} catch(const std::exception &e) {									/* vectors, threads: nothing may be thrown across the C ABI */
+		g_err = std::string("mab_load_begin: ") + e.what();
+		delete ld;
+		return nullptr;
+	}
 }
 
 /* bytes [offset, offset + n) of the image; any thread, any order.  Returns once the bytes are staged (src may be reused). */
@@ -433,7 +441,8 @@ extern "C" mab_ctx *mab_clone(mab_ctx *parent)
 {
 	if(parent == nullptr) { g_err = "mab_clone: bad arguments"; return nullptr; }
 	while(parent->parent != nullptr) { parent = parent->parent; }
-	mab_ctx *ctx = new mab_ctx();
+	mab_ctx *ctx = new (std::nothrow) mab_ctx();
+	if(ctx == nullptr) { g_err = "host allocation failed"; return nullptr; }
 	ctx->parent = parent; ctx->device = parent->device; ctx->prm = parent->prm; ctx->P = parent->P; ctx->xcoef = parent->xcoef; ctx->n_sm = parent->n_sm;
 	ctx->cal = parent->cal;
 	ctx->blob = parent->blob; ctx->blob_ptr = parent->blob_ptr; ctx->d_idx = parent->d_idx; ctx->d_ntail = parent->d_ntail; ctx->d_thr = parent->d_thr; ctx->thr_ok = parent->thr_ok;
