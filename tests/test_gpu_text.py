@@ -51,6 +51,26 @@ def test_map_text_matches_golden_sam(gold, golden, taglist):
     assert st["n_launches"] >= 12 and st["n_failed"] == 0
 
 
+def test_staged_set_up_and_announced_chunk_size(gold):
+    """mab_load_begin / put / end (pieces out of order, every visible device) gives the contexts mab_init gives; with the chunk
+    size announced a short chunk followed by the whole file maps like without"""
+    import torch
+    text = open(os.path.join(GOLD, "reads.fa"), "rb").read()
+    short = text[: text.index(b">", 4000)]
+    m0 = api.Mapper(gold["blob"], "pacbio")
+    exp = [m0.map_text(short), m0.map_text(text)]
+    m0.close()
+    devs = tuple(range(min(2, torch.cuda.device_count())))
+    ms = api.Mapper.staged(gold["blob"], "pacbio", devices=devs, piece=(1 << 20) + 4096, order=lambda st: st[::-1])
+    for m in ms:
+        m.text_reserve(len(text) + 1000)
+        c = m.clone()
+        assert [m.map_text(short), m.map_text(text)] == exp and c.map_text(text) == exp[1]
+        c.close()
+    for m in ms:
+        m.close()
+
+
 def test_map_text_device_resident_io(gold):
     """device-input + device-output mode (bench.py's kernel-side arm): same byte count as the host-buffer mode"""
     import torch
