@@ -1,11 +1,14 @@
 /*
  * mab_kernels.cuh -- the kernels of the mapping path.
  *
- *   k_seed<COUNT>   one warp per read: (w,k)-minimizer sketch (mm_sketch, minialign.c:2410-2435) computed position-parallel,
- *                   ordered ballot compaction, one index probe per lane (mm_idx_get, 2727-2748), occurrence expansion to
- *                   (u,v) seeds (mm_collect_seed / mm_expand, 3420-3493).  COUNT=true only sizes the workspaces.
- *   k_sortchain     one thread per read: rescue-round seeding (mm_seed, 3500-3541), the reference's exact radix sort,
- *                   array chaining (mm_chain, 3702-3721).
+ *   k_seed_scan     one warp per read: (w,k)-minimizer sketch (mm_sketch, minialign.c:2410-2435) computed position-parallel,
+ *                   ordered ballot compaction into 16-byte minimizer records.
+ *   k_seed_probe    one index probe per lane over those records (mm_idx_get, 2727-2748).
+ *   k_seed_expand   occurrence expansion to (u,v) seeds and rescue entries (mm_collect_seed / mm_expand, 3420-3493).
+ *   k_sort          one warp per read: rescue-round seeding (mm_seed, 3500-3541) and the reference's exact (unstable) radix sort
+ *                   in its parallel form (radix_sort_walk_warp, mab_scalar.cuh).
+ *   k_chain         one warp per read: array chaining (mm_chain, 3702-3721) and the root sort.
+ *   k_sortchain     both in one kernel on a shared-memory copy, the sort by walking the permutation cycles (the earlier form; A/B).
  *   k_extend        persistent warps, one read at a time (longest reads first: `order`, so that the reads still running when the
  *                   work list is empty are the short ones): the mm_extend state machine (4118-4173) on lane 0, the GABA
  *                   fill / search / trace (mab_dp.cuh) on all 32 lanes.
