@@ -188,6 +188,43 @@ class Mapper:
             ms.append(m)
         return ms
 
+    @classmethod
+    def from_mai(cls, path: str, params: dict | str = "pacbio", device: int = 0, lib_path: str | None = None) -> "Mapper":
+        """Context from a .mai file with the upload running under the inflation (mai.inflate_mai + the staged set-up): a
+        human-sized index is on the GPU when its last frame is inflated."""
+        from . import mai
+        lib = load_library(lib_path)
+        prm = make_params(PRESETS[params] if isinstance(params, str) else params)
+        prm.flags |= 1                      # MAB_FLAG_BORROW_INDEX: the image stays with the Mapper (self.blob), no second host copy
+        st = {"ld": None, "err": None}
+        devs = (C.c_int * 1)(device)
+
+        def on_size(size):
+            st["ld"] = lib.mab_load_begin(size, C.byref(prm), devs, 1)
+            if not st["ld"]:
+                st["err"] = "mab_load_begin failed: " + lib.mab_last_error().decode()
+
+        def on_piece(off, addr, n):
+            if st["ld"] and st["err"] is None and lib.mab_load_put(st["ld"], off, addr, n) != 0:
+                st["err"] = "mab_load_put failed: " + lib.mab_last_error().decode()
+
+        try:
+            blob = mai.inflate_mai(path, on_size, on_piece)
+        except Exception:
+            if st["ld"]:
+                lib.mab_load_abort(st["ld"])
+            raise
+        if st["err"] is not None:
+            if st["ld"]:
+                lib.mab_load_abort(st["ld"])
+            raise RuntimeError(st["err"])
+        out = (C.c_void_p * 1)()
+        if lib.mab_load_end(st["ld"], blob.ctypes.data, blob.size, out) != 0:
+            raise RuntimeError("mab_load_end failed: " + lib.mab_last_error().decode())
+        m = cls.__new__(cls)
+        m.lib, m.params, m.blob, m.h = lib, prm, blob, out[0]
+        return m
+
     def clone(self) -> "Mapper":
         """Another context on the same device sharing this one's index image (keep this one alive while the clone is used)."""
         m = Mapper.__new__(Mapper)

@@ -175,8 +175,7 @@ def main(argv=None):
             shard.bind_near_gpu(local)
     if world > 1:
         dist.init_process_group(backend, **({"device_id": dev} if dev is not None else {}))
-    blob = mai.load_mai(o["pos"][0])
-    m0 = api.Mapper(blob, o["prm"], device=local if backend == "nccl" else 0, lib_path=o["lib"])
+    m0 = api.Mapper.from_mai(o["pos"][0], o["prm"], device=local if backend == "nccl" else 0, lib_path=o["lib"])    # upload under the inflation
     ms = [m0] + [m0.clone() for _ in range(o["contexts"] - 1)]
     cmdline = "minialign-b200 " + " ".join(sys.argv[1:] if argv is None else argv)
     header = m0.sam_header(cmdline)
@@ -193,6 +192,7 @@ def main(argv=None):
     ex = shard.WaveExchange(device=dev, host_group=host_group)
     ex.out_base = len(header)
     chunk_bytes = max(1024, int(o["chunk_mb"] * 1048576))
+    m0.text_reserve(min(chunk_bytes + (16 << 20), 0xfffffff0 - 1))       # every context sizes its buffers for a full chunk at once
     tot = dict(reads=0, bases=0)
     for path in o["pos"][1:]:
         with open(path, "rb") as f:

@@ -174,3 +174,26 @@ def test_emu_staged_load_and_reserve(gold):
     assert got == exp
     assert c.map_text(long_) == api.Mapper(gold["blob"], "pacbio", lib_path=so).map_text(long_)
     c.close(); m1.close()
+
+
+def test_emu_mapper_from_mai_file(tmp_path, gold):
+    """mai.inflate_mai (frames on a thread pool, pieces handed to the staged set-up as they appear) gives load_mai's payload, and
+    Mapper.from_mai a context that maps like one from mab_init"""
+    import subprocess
+    from conftest import ROOT
+    from minialign_b200 import mai, synth
+    cli = os.path.join(ROOT, "minialign_b200", "minialign-b200")
+    g = synth.make_genome(2_300_000, 3, seed=5)           # > 2 frames of 1 MiB
+    fa, idx = str(tmp_path / "g.fa"), str(tmp_path / "g.mai")
+    synth.write_fasta(fa, g, 80)
+    subprocess.check_call([cli, "-xpacbio", "-d", idx, fa], stderr=subprocess.DEVNULL)
+    a, pieces = mai.load_mai(idx), []
+    b = mai.inflate_mai(idx, None, lambda off, addr, n: pieces.append((off, n)))
+    assert np.array_equal(a, b) and sum(n for _, n in pieces) == a.size and len(pieces) >= 3
+    reads = synth.make_reads(g, 60_000, seed=6)
+    text = _fasta(reads)
+    so = build_emu()
+    m0 = api.Mapper(a, "pacbio", lib_path=so)
+    m1 = api.Mapper.from_mai(idx, "pacbio", lib_path=so)
+    assert m0.map_text(text) == m1.map_text(text)
+    m0.close(); m1.close()
