@@ -332,10 +332,11 @@ def main():
         pinned.append(p)
     log(f"[rank {rank}] workload ready in {time.time() - t0:.1f}s: {n_distinct} chunks x {args.batch_reads} reads, {len(texts[0]) / 1e6:.0f} MB of FASTA each")
     # four mapper contexts per GPU, each driven by its own host thread (pipeline.py): while one chunk is being parsed / copied / printed,
-    # another one's extension runs.  The pipelined contexts launch 4 of the 6 possible k_extend CTAs per SM: the registers / shared
-    # memory left over let the other chunks' kernels (and the next chunk's extension) run under the current one; alone, 6 is faster
-    # (sweep under profiles/r02_sweep_contexts.txt)
-    ext_pipe = os.environ.get("MAB_EXT_CTAS", "4" if args.contexts > 1 else "6")
+    # another one's extension runs.  The pipelined contexts launch 3 of the 6 possible k_extend CTAs per SM (the 128-register build):
+    # at 4 the persistent kernel holds every register of the SM and the other chunks' parser / seeding / sort kernels wait for it to
+    # end; at 3 they run underneath (value 3945 -> 3918, e2e 3546 -> 3762 Mbases/s); alone, 6 is faster
+    # (profiles/r02_sweep_contexts.txt)
+    ext_pipe = os.environ.get("MAB_EXT_CTAS", "3" if args.contexts > 1 else "6")
     os.environ["MAB_EXT_CTAS"] = ext_pipe
     m0 = api.Mapper(blob, PRESET, device=local)
     ms = [m0] + [m0.clone() for _ in range(max(1, args.contexts) - 1)]

@@ -499,7 +499,7 @@ int main(int argc, char **argv)
 	 * A chunk the device reader does not take (MAB_EFORMAT: wrapped FASTQ, ...) is parsed on the host and goes through the
 	 * record-level entry point and the host formatter instead. */
 	double t_idx = now() - t0;
-	if(o.contexts > 1 && getenv("MAB_EXT_CTAS") == nullptr) { setenv("MAB_EXT_CTAS", "4", 1); }	/* contexts that run side by side launch 4 of the 6 possible extend CTAs per SM each */
+	if(o.contexts > 1 && getenv("MAB_EXT_CTAS") == nullptr) { setenv("MAB_EXT_CTAS", "3", 1); }	/* contexts that run side by side launch 3 of the 6 possible extend CTAs per SM each: the other chunks' small kernels need registers to run underneath */
 	std::vector<mab_ctx *> ctxs(n_ctx, nullptr);
 	{	/* one parent context per device (uploads the index), clones share its image; devices are set up in parallel */
 		std::vector<std::thread> th; std::vector<std::string> errs(devices.size());

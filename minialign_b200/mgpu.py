@@ -175,6 +175,8 @@ def main(argv=None):
             shard.bind_near_gpu(local)
     if world > 1:
         dist.init_process_group(backend, **({"device_id": dev} if dev is not None else {}))
+    if o["contexts"] > 1:
+        os.environ.setdefault("MAB_EXT_CTAS", "3")     # contexts that run side by side leave registers for each other's small kernels
     m0 = api.Mapper.from_mai(o["pos"][0], o["prm"], device=local if backend == "nccl" else 0, lib_path=o["lib"])    # upload under the inflation
     ms = [m0] + [m0.clone() for _ in range(o["contexts"] - 1)]
     cmdline = "minialign-b200 " + " ".join(sys.argv[1:] if argv is None else argv)
